@@ -1,0 +1,62 @@
+// Shared host-side declarations for libairfe (error reporting, plans for the tcgen05 GEMM, pointwise kernel launchers).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace airfe {
+
+// Thread-local last-error string surfaced through airfe_last_error() (include/airfe_c.h).
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define AIRFE_CUDA_OK(expr)                                                                              \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) {                                                                              \
+      airfe::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);      \
+      return false;                                                                                       \
+    }                                                                                                     \
+  } while (0)
+
+struct TcGemmParams;
+
+// Description of one dense contraction for tc_gemm_plan().
+struct TcGemmDesc {
+  // A: NHWC fp16 view (element strides), a_C valid channels
+  const void* a = nullptr;
+  int a_C = 0, W = 0, H = 1, B = 1;
+  long long a_sx = 0, a_sy = 0, a_sb = 0;
+  // Bw: [n_rows][k_total] K-major fp16 (or MN-major [k_total][n_rows]); optional batch
+  const void* bw = nullptr;
+  int k_total = 0, n_rows = 0;
+  long long bw_sn = 0, bw_sbatch = 0;
+  int b_batches = 0, b_mn_major = 0;
+  int taps = 1, c_in_pad = 64;
+  int block_n = 64;
+  const float* bias = nullptr;
+  int relu = 0, out_f32 = 0;
+  void* out = nullptr;
+  long long out_sb = 0, out_sy = 0, out_sx = 0;
+  int n_valid = 0;
+  int tw = 128, th = 1, tb = 1;
+};
+
+}  // namespace airfe
+
+#include "tc_gemm_params.h"
+
+namespace airfe {
+struct TcGemmPlan {
+  TcGemmParams p;
+  int grid = 0;
+  int smem_bytes = 0;
+  double flops = 0;
+};
+bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan);
+bool tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream);
+}  // namespace airfe

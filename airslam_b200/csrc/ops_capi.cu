@@ -1,0 +1,29 @@
+// Low-level operator entry points of the C ABI (device pointers in, device pointers out).  These are what the
+// per-kernel parity tests call; the frame-level entry points live in airfe_capi.cu.
+#include "common.h"
+#include "../../include/airfe_c.h"
+
+using namespace airfe;
+
+extern "C" {
+
+const char* airfe_last_error(void) { return get_error(); }
+
+int airfe_op_tc_gemm(const void* a, int a_C, int W, int H, int B, long long a_sx, long long a_sy, long long a_sb,
+                     const void* bw, int k_total, int n_rows, long long bw_sn, long long bw_sbatch, int b_batches, int b_mn_major,
+                     int taps, int c_in_pad, int block_n, const float* bias, int relu, int out_f32,
+                     void* out, long long out_sb, long long out_sy, long long out_sx, int n_valid,
+                     int tw, int th, int tb, void* stream) {
+  TcGemmDesc d;
+  d.a = a; d.a_C = a_C; d.W = W; d.H = H; d.B = B; d.a_sx = a_sx; d.a_sy = a_sy; d.a_sb = a_sb;
+  d.bw = bw; d.k_total = k_total; d.n_rows = n_rows; d.bw_sn = bw_sn; d.bw_sbatch = bw_sbatch; d.b_batches = b_batches;
+  d.b_mn_major = b_mn_major; d.taps = taps; d.c_in_pad = c_in_pad; d.block_n = block_n; d.bias = bias; d.relu = relu;
+  d.out_f32 = out_f32; d.out = out; d.out_sb = out_sb; d.out_sy = out_sy; d.out_sx = out_sx; d.n_valid = n_valid;
+  d.tw = tw; d.th = th; d.tb = tb;
+  TcGemmPlan plan;
+  if (!tc_gemm_plan(d, &plan)) return AIRFE_ERR_INVALID;
+  if (!tc_gemm_launch(plan, (cudaStream_t)stream)) return AIRFE_ERR_CUDA;
+  return AIRFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// Host side of the tcgen05 implicit-GEMM kernel: TMA tensor-map construction, tiling plan, launch.
+
+#include "common.h"
+#include "tc_gemm.cuh"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace airfe {
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+  });
+  return fn;
+}
+
+// fp16 tensor map, `rank` dims, dims[0] innermost (contiguous); strides_bytes[i] for dims 1..rank-1.
+bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return false;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: code %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1],
+              rank > 2 ? box[2] : 0);
+    return false;
+  }
+  return true;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
+  TcGemmParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  if (d.tw * d.th * d.tb != kTileM) { set_error("tc_gemm: tile box %dx%dx%d != 128 pixels", d.tw, d.th, d.tb); return false; }
+  if (d.block_n % 16 || d.block_n < 16 || d.block_n > 256) { set_error("tc_gemm: bad block_n %d", d.block_n); return false; }
+  if (d.b_mn_major && d.block_n != 64) { set_error("tc_gemm: MN-major B needs block_n == 64"); return false; }
+  {
+    uint64_t dims[4] = {(uint64_t)d.a_C, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
+    uint64_t str[3] = {(uint64_t)d.a_sx * 2, (uint64_t)d.a_sy * 2, (uint64_t)d.a_sb * 2};
+    uint32_t box[4] = {64, (uint32_t)d.tw, (uint32_t)d.th, (uint32_t)d.tb};
+    if (!make_tmap_f16(&p.tmA, d.a, 4, dims, str, box)) return false;
+  }
+  {
+    const int nb = d.b_batches > 0 ? d.b_batches : 1;
+    if (d.b_mn_major) {
+      uint64_t dims[3] = {(uint64_t)d.n_rows, (uint64_t)d.k_total, (uint64_t)nb};
+      uint64_t str[2] = {(uint64_t)d.bw_sn * 2, (uint64_t)(nb > 1 ? d.bw_sbatch : d.bw_sn * d.k_total) * 2};
+      uint32_t box[3] = {64, 64, 1};
+      if (!make_tmap_f16(&p.tmB, d.bw, 3, dims, str, box)) return false;
+    } else {
+      uint64_t dims[3] = {(uint64_t)d.k_total, (uint64_t)d.n_rows, (uint64_t)nb};
+      uint64_t str[2] = {(uint64_t)d.bw_sn * 2, (uint64_t)(nb > 1 ? d.bw_sbatch : d.bw_sn * d.n_rows) * 2};
+      uint32_t box[3] = {64, (uint32_t)d.block_n, 1};
+      if (!make_tmap_f16(&p.tmB, d.bw, 3, dims, str, box)) return false;
+    }
+  }
+  p.taps = d.taps;
+  p.c_in_pad = d.c_in_pad;
+  p.kblocks = d.c_in_pad / kBlockK;
+  p.tw = d.tw; p.th = d.th; p.tb = d.tb;
+  p.tiles_x = (d.W + d.tw - 1) / d.tw;
+  p.tiles_y = (d.H + d.th - 1) / d.th;
+  p.tiles_b = (d.B + d.tb - 1) / d.tb;
+  p.block_n = d.block_n;
+  p.n_tiles = (d.n_valid + d.block_n - 1) / d.block_n;
+  p.W = d.W; p.H = d.H; p.B = d.B;
+  p.b_batched = d.b_batches > 1;
+  p.b_mn_major = d.b_mn_major;
+  p.bias = d.bias;
+  p.relu = d.relu;
+  p.out_f32 = d.out_f32;
+  p.out = d.out;
+  p.out_sb = d.out_sb; p.out_sy = d.out_sy; p.out_sx = d.out_sx;
+  p.n_valid = d.n_valid;
+  const int stage_bytes = kABytes + tc_b_bytes(d.block_n, d.b_mn_major);
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  plan->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 16;
+  const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+  plan->grid = total < num_sms() ? total : num_sms();
+  plan->flops = 2.0 * (double)d.W * d.H * d.B * (double)d.n_valid * (double)d.taps * (double)d.a_C;
+  return true;
+}
+
+bool tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(tc_gemm_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return false;
+    }
+    attr_set = true;
+  }
+  if (plan.grid <= 0) return true;
+  tc_gemm_kernel<<<plan.grid, kTcThreads, plan.smem_bytes, stream>>>(plan.p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("tc_gemm launch failed: %s", cudaGetErrorString(e));
+    return false;
+  }
+  return true;
+}
+
+}  // namespace airfe

@@ -1,0 +1,202 @@
+// tcgen05 implicit-GEMM convolution / batched GEMM for sm_100a.
+//
+// One kernel covers every dense contraction on the hot path (SURVEY.md §7.2 K2, K3, K11-MLP, K14 products, K15, K17):
+//   D[pixel, n] = sum_{tap, c} A[pixel + offset(tap), c] * Bw[n, tap*C_pad + c]   (+ bias, ReLU)  -> fp16 / fp32 store
+//  * A is an NHWC fp16 tensor seen through a 4-D TMA map (C, W, H, B); a tile of 128 output pixels is a
+//    (tw x th x tb) box, and a 3x3 tap is the same box shifted by (dx,dy): TMA's out-of-bounds zero fill IS the
+//    convolution padding.  The 128B-swizzled box lands in shared memory exactly in the K-major SWIZZLE_128B
+//    canonical layout tcgen05.mma wants (128 rows x 64 fp16), so no repacking is ever done by threads.
+//  * Bw is [N, K] K-major (weights packed tap-major) or, for attention P.V, an MN-major [K, N=64] tile.
+//  * Accumulators live in TMEM (double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1).
+//  * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+ TMEM owner), warps 2-5 = epilogue.
+//  * Persistent: grid = min(#tiles, #SMs); tiles are strided over CTAs.
+#pragma once
+#include "ptx.cuh"
+#include "tc_gemm_params.h"
+
+namespace airfe {
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A | B)] | barriers | tmem slot
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = tc_b_bytes(p.block_n, p.b_mn_major);
+  const int stage_bytes = kABytes + b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int ksteps = p.taps * p.kblocks;
+  const uint32_t tmem_cols = tc_tmem_cols(p.block_n);
+  const uint32_t acc_stride = tc_acc_stride(p.block_n);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA);
+    ptx::prefetch_tmap(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full[s], 1);
+      ptx::mbar_init(&tmem_empty[s], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = kABytes + (p.b_mn_major ? 64 * 128 : p.block_n * 128);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles;
+        const int mt = t / p.n_tiles;
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int tz = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.tw, y0 = ty * p.th, b0 = tz * p.tb;
+        const int bb = p.b_batched ? b0 : 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+          const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * stage_bytes;
+            uint8_t* sb = sa + kABytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+            ptx::tma_load_4d(sa, &p.tmA, &full_bar[stage], kb * kBlockK, x0 + dx, y0 + dy, b0);
+            const int koff = tap * p.c_in_pad + kb * kBlockK;
+            if (p.b_mn_major)
+              ptx::tma_load_3d(sb, &p.tmB, &full_bar[stage], nt * p.block_n, koff, bb);
+            else
+              ptx::tma_load_3d(sb, &p.tmB, &full_bar[stage], koff, nt * p.block_n, bb);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = ptx::make_idesc_f16(kTileM, p.block_n, p.b_mn_major);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = ptx::make_smem_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t db = p.b_mn_major ? ptx::make_smem_desc(sb + k * 2048, 8192, 1024, 2)
+                                             : ptx::make_smem_desc(sb + k * 32, 16, 1024, 2);
+            ptx::umma_f16(d_tmem, da, db, idesc, (ks | k) != 0);
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> (+bias, ReLU) -> global =====
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.n_tiles;
+      const int mt = t / p.n_tiles;
+      const int tx = mt % p.tiles_x;
+      const int ty = (mt / p.tiles_x) % p.tiles_y;
+      const int tz = mt / (p.tiles_x * p.tiles_y);
+      const int x = tx * p.tw + row % p.tw;
+      const int y = ty * p.th + (row / p.tw) % p.th;
+      const int b = tz * p.tb + row / (p.tw * p.th);
+      const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
+      const long long off = (long long)b * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(quarter * 32) << 16);
+      const int n0 = nt * p.block_n;
+      for (int c = 0; c < p.block_n; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld16(taddr + c, r);
+        ptx::tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float f = __uint_as_float(r[i]);
+          if (p.bias && n0 + c + i < p.n_valid) f += __ldg(p.bias + n0 + c + i);
+          if (p.relu) f = fmaxf(f, 0.f);
+          v[i] = f;
+        }
+        const int nbase = n0 + c;
+        if (valid && nbase < p.n_valid) {
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + off + nbase;
+            if (nbase + 16 <= p.n_valid) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+              for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) o[i] = v[i];
+            }
+          } else {
+            __half* o = reinterpret_cast<__half*>(p.out) + off + nbase;
+            if (nbase + 16 <= p.n_valid) {
+              uint32_t h[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                h[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+            } else {
+              for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) o[i] = __float2half_rn(v[i]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace airfe

@@ -1,0 +1,42 @@
+// Parameter block of the tcgen05 implicit-GEMM kernel (see tc_gemm.cuh for the kernel itself).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace airfe {
+
+struct TcGemmParams {
+  CUtensorMap tmA;  // 4-D (C, W, H, B)   box (64, tw, th, tb)   SWIZZLE_128B
+  CUtensorMap tmB;  // 3-D (K, N, batch)  box (64, block_n, 1)   SWIZZLE_128B   [MN-major: (N, K, batch), box (64, 64, 1)]
+  int taps;         // 1 or 9
+  int kblocks;      // 64-wide K blocks per tap
+  int c_in_pad;     // kblocks * 64 (K offset between taps in Bw)
+  int tw, th, tb;   // tile box, tw*th*tb == 128
+  int tiles_x, tiles_y, tiles_b;
+  int n_tiles, block_n;
+  int W, H, B;      // valid output extents
+  int b_batched;    // Bw batch coordinate follows the tile's batch index
+  int b_mn_major;   // Bw tile is MN-major (block_n must be 64)
+  const float* bias;
+  int relu;
+  int out_f32;
+  void* out;        // element (b,y,x,n) at out[b*out_sb + y*out_sy + x*out_sx + n]  (ch offset folded into `out`)
+  long long out_sb, out_sy, out_sx;
+  int n_valid;
+  int stages;
+};
+
+constexpr int kTcThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
+
+__host__ __device__ inline int tc_b_bytes(int block_n, int mn_major) { return mn_major ? 64 * 128 : ((block_n * 128 + 1023) / 1024) * 1024; }
+__host__ __device__ inline int tc_acc_stride(int block_n) { return (block_n + 31) / 32 * 32; }
+__host__ __device__ inline int tc_tmem_cols(int block_n) {
+  int need = 2 * tc_acc_stride(block_n), c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+
+}  // namespace airfe
