@@ -39,3 +39,105 @@ def _declare(L):
                                    i32, i32, i32, f32p, i32, i32,
                                    vp, i64, i64, i64, i32, i32, i32, i32, vp]
     L.airfe_op_tc_gemm.restype = i32
+
+
+class Config(C.Structure):
+    _fields_ = [("weights_dir", C.c_char_p), ("max_batch", i32), ("max_keypoints", i32), ("keypoint_threshold", C.c_float),
+                ("remove_borders", i32), ("line_threshold", C.c_float), ("line_length_threshold", C.c_float),
+                ("image_width", i32), ("image_height", i32), ("enable_superpoint", i32), ("enable_plnet", i32),
+                ("enable_lightglue", i32), ("enable_superglue", i32)]
+
+
+NET_SUPERPOINT, NET_PLNET = 0, 1
+MATCHER_LIGHTGLUE, MATCHER_SUPERGLUE = 0, 1
+WEIGHTS_DIR = os.path.join(os.path.dirname(HERE), "weights")
+
+
+def _declare_frame(L):
+    L.airfe_default_config.argtypes = [C.POINTER(Config)]
+    L.airfe_create.argtypes = [C.POINTER(Config), i32, C.POINTER(vp)]
+    L.airfe_create.restype = i32
+    L.airfe_destroy.argtypes = [vp]
+    L.airfe_stream.argtypes = [vp]
+    L.airfe_stream.restype = vp
+    L.airfe_detect_batch.argtypes = [vp, i32, i32, vp, i32, i32, i32, i64, vp, i32, vp, vp, i32, vp, vp, i32, vp]
+    L.airfe_detect_batch.restype = i32
+    L.airfe_debug_read.argtypes = [vp, i32, C.c_char_p, i32, vp, i64]
+    L.airfe_debug_read.restype = i64
+
+
+_declare_base = _declare
+
+
+def _declare(L):  # noqa: F811
+    _declare_base(L)
+    _declare_frame(L)
+    if hasattr(L, "airfe_match_batch"):
+        _declare_match(L)
+
+
+def _declare_match(L):
+    L.airfe_match_batch.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp]
+    L.airfe_match_batch.restype = i32
+
+
+class Context:
+    """Owns one airfe_ctx.  numpy in / numpy out; every call goes through the C ABI with host buffers."""
+
+    def __init__(self, device=0, **kw):
+        import numpy as np  # noqa: F401
+        L = lib()
+        self.cfg = Config()
+        L.airfe_default_config(C.byref(self.cfg))
+        self._wd = WEIGHTS_DIR.encode()
+        self.cfg.weights_dir = self._wd
+        for k, v in kw.items():
+            if not hasattr(self.cfg, k):
+                raise AirfeError("unknown config field " + k)
+            setattr(self.cfg, k, v)
+        self.h = vp()
+        check(L.airfe_create(C.byref(self.cfg), device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().airfe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return lib().airfe_stream(self.h)
+
+    def detect_batch(self, net, images, lines=False, junctions=False, feat_cap=None, line_cap=4096, junc_cap=1024):
+        """images: uint8 [B,H,W] contiguous.  Returns list of (feat [259,N], lines [L,4] float64 | None, junc [259,J] | None)."""
+        import numpy as np
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        b, h, w = images.shape
+        feat_cap = feat_cap or self.cfg.max_keypoints
+        feat = np.zeros((b, feat_cap, 259), dtype=np.float32)
+        n_feat = np.zeros(b, dtype=np.int32)
+        ln = np.zeros((b, line_cap, 4), dtype=np.float64) if lines else None
+        n_ln = np.zeros(b, dtype=np.int32)
+        jn = np.zeros((b, junc_cap, 259), dtype=np.float32) if junctions else None
+        n_jn = np.zeros(b, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(vp) if a is not None else None
+        check(lib().airfe_detect_batch(self.h, net, b, p(images), w, h, w, h * w, p(feat), feat_cap, p(n_feat), p(ln), line_cap,
+                                       p(n_ln), p(jn), junc_cap, p(n_jn)))
+        out = []
+        for i in range(b):
+            out.append((feat[i, :n_feat[i]].T.copy(), ln[i, :n_ln[i]].copy() if lines else None,
+                        jn[i, :n_jn[i]].T.copy() if junctions else None))
+        return out
+
+    def debug_read(self, net, name, index, dtype, shape):
+        import numpy as np
+        out = np.zeros(shape, dtype=dtype)
+        n = lib().airfe_debug_read(self.h, net, name.encode(), index, out.ctypes.data_as(vp), out.nbytes)
+        if n < 0:
+            check(int(n))
+        return out

@@ -43,6 +43,7 @@ struct TcGemmDesc {
   long long out_sb = 0, out_sy = 0, out_sx = 0;
   int n_valid = 0;
   int tw = 128, th = 1, tb = 1;
+  const int* dyn_w = nullptr;
 };
 
 }  // namespace airfe

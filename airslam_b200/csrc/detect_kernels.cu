@@ -1,0 +1,452 @@
+// Hand-written sm_100a kernels for the detector's non-GEMM stages: resize, first conv, pool / upsample, detector softmax,
+// NMS, keypoint selection, descriptor sampling.  All are HBM/L2-bandwidth kernels: coalesced, vectorised (16-byte
+// accesses where the layout allows), warp-shuffle reductions, no tensor cores.
+#include "kernels.h"
+#include <math.h>
+
+namespace airfe {
+
+// =====================================================================================================================
+// K1 resize.  Bit-exact restatement of OpenCV's 8-bit INTER_LINEAR (fixed-point, 11-bit coefficients), SURVEY.md App. B9.
+// The per-column / per-row coefficient tables are built on the host with the same float/double casts as OpenCV.
+// =====================================================================================================================
+void build_resize_tables_host(int src_w, int src_h, int* sx, int* a0, int* a1, int* sy, int* b0, int* b1) {
+  const double scale_x = (double)src_w / 512.0, scale_y = (double)src_h / 512.0;
+  for (int x = 0; x < 512; ++x) {
+    float fx = (float)((x + 0.5) * scale_x - 0.5);
+    int s = (int)floorf(fx);
+    fx -= (float)s;
+    if (s < 0) { s = 0; fx = 0.f; }
+    if (s >= src_w - 1) { s = src_w - 1; fx = 0.f; }
+    sx[x] = s;
+    a0[x] = (int)rintf((1.f - fx) * 2048.f);
+    a1[x] = (int)rintf(fx * 2048.f);
+  }
+  for (int y = 0; y < 512; ++y) {
+    float fy = (float)((y + 0.5) * scale_y - 0.5);
+    int s = (int)floorf(fy);
+    fy -= (float)s;
+    sy[y] = s;
+    b0[y] = (int)rintf((1.f - fy) * 2048.f);
+    b1[y] = (int)rintf(fy * 2048.f);
+  }
+}
+
+__global__ void resize_kernel(const uint8_t* __restrict__ src, int src_w, int src_h, int src_stride, long long src_img_stride,
+                              ResizeTables t, __half* __restrict__ dst, uint8_t* __restrict__ dst_u8) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (x >= 512) return;
+  const uint8_t* img = src + (long long)b * src_img_stride;
+  const int s0 = t.sx[x], s1 = min(s0 + 1, src_w - 1);
+  const int a0 = t.a0[x], a1 = t.a1[x];
+  const int r0 = min(max(t.sy[y], 0), src_h - 1), r1 = min(max(t.sy[y] + 1, 0), src_h - 1);
+  const int h0 = (int)img[(long long)r0 * src_stride + s0] * a0 + (int)img[(long long)r0 * src_stride + s1] * a1;
+  const int h1 = (int)img[(long long)r1 * src_stride + s0] * a0 + (int)img[(long long)r1 * src_stride + s1] * a1;
+  int v = (((t.b0[y] * (h0 >> 4)) >> 16) + ((t.b1[y] * (h1 >> 4)) >> 16) + 2) >> 2;
+  v = min(max(v, 0), 255);
+  const long long o = ((long long)b * 512 + y) * 512 + x;
+  // reference: float(u8) / 255.0 evaluated in double, stored as float (src/plnet.cpp:264); then the fp16 operand rounding
+  dst[o] = __float2half_rn((float)((double)v / 255.0));
+  if (dst_u8) dst_u8[o] = (uint8_t)v;
+}
+
+void launch_resize_u8_to_f16(const uint8_t* src, int src_w, int src_h, int src_stride, long long src_img_stride, int batch,
+                             ResizeTables t, __half* dst, uint8_t* dst_u8, cudaStream_t st) {
+  dim3 grid(512 / 128, 512, batch);
+  resize_kernel<<<grid, 128, 0, st>>>(src, src_w, src_h, src_stride, src_img_stride, t, dst, dst_u8);
+}
+
+// =====================================================================================================================
+// First layer: 3x3, 1 -> 64 channels.  K = 9 is no tensor-core shape; the layer is bound by its 32 MiB/frame NHWC store.
+// Thread = (pixel, group of 8 output channels): consecutive threads write consecutive 16-byte vectors.
+// =====================================================================================================================
+__global__ void conv1a_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
+                              __half* __restrict__ out, int H, int W, long long total) {
+  __shared__ float sw[64 * 9];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 576; i += blockDim.x) sw[i] = __half2float(w[i]);
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cg = (int)(gid & 7);
+  const long long pix = gid >> 3;
+  const int xx = (int)(pix % W);
+  const int yy = (int)((pix / W) % H);
+  const long long img = pix / ((long long)W * H);
+  const __half* xi = x + img * (long long)W * H;
+  float in[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int y2 = yy + ky - 1, x2 = xx + kx - 1;
+      in[ky * 3 + kx] = (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? __half2float(xi[(long long)y2 * W + x2]) : 0.f;
+    }
+  uint32_t packed[4];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    float acc[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = cg * 8 + j + u;
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a = fmaf(in[k], sw[c * 9 + k], a);
+      acc[u] = fmaxf(a + sb[c], 0.f);
+    }
+    __half2 h2 = __floats2half2_rn(acc[0], acc[1]);
+    packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+  *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+void launch_conv1a(const __half* x, const __half* w, const float* bias, __half* out, int batch, int H, int W, cudaStream_t st) {
+  const long long total = (long long)batch * H * W * 8;
+  conv1a_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, w, bias, out, H, W, total);
+}
+
+// =====================================================================================================================
+// 2x2 max-pool / nearest 2x upsample, NHWC fp16, 8 channels (16 bytes) per thread.
+// =====================================================================================================================
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+  uint4 r;
+  __half2* ra = reinterpret_cast<__half2*>(&a);
+  __half2* rb = reinterpret_cast<__half2*>(&b);
+  __half2* rr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rr[i] = __hmax2(ra[i], rb[i]);
+  return r;
+}
+
+__global__ void maxpool2_kernel(const __half* __restrict__ in, int C8, int H, int W, long long in_ps, __half* __restrict__ out,
+                                long long out_ps, long long total) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c = (int)(gid % C8);
+  const long long p = gid / C8;
+  const int Wo = W >> 1, Ho = H >> 1;
+  const int xo = (int)(p % Wo);
+  const int yo = (int)((p / Wo) % Ho);
+  const long long b = p / ((long long)Wo * Ho);
+  const __half* base = in + ((b * H + 2 * yo) * (long long)W + 2 * xo) * in_ps + c * 8;
+  uint4 v00 = *reinterpret_cast<const uint4*>(base);
+  uint4 v01 = *reinterpret_cast<const uint4*>(base + in_ps);
+  uint4 v10 = *reinterpret_cast<const uint4*>(base + (long long)W * in_ps);
+  uint4 v11 = *reinterpret_cast<const uint4*>(base + (long long)W * in_ps + in_ps);
+  *reinterpret_cast<uint4*>(out + p * out_ps + c * 8) = hmax8(hmax8(v00, v01), hmax8(v10, v11));
+}
+
+void launch_maxpool2(const __half* in, int C, int H, int W, int batch, long long in_ps, __half* out, long long out_ps, cudaStream_t st) {
+  const long long total = (long long)batch * (H / 2) * (W / 2) * (C / 8);
+  maxpool2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C / 8, H, W, in_ps, out, out_ps, total);
+}
+
+__global__ void upsample2_kernel(const __half* __restrict__ in, int C8, int H, int W, long long in_ps, __half* __restrict__ out,
+                                 long long out_ps, long long total) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c = (int)(gid % C8);
+  const long long p = gid / C8;  // output pixel
+  const int Wo = W * 2, Ho = H * 2;
+  const int xo = (int)(p % Wo);
+  const int yo = (int)((p / Wo) % Ho);
+  const long long b = p / ((long long)Wo * Ho);
+  const uint4 v = *reinterpret_cast<const uint4*>(in + ((b * H + (yo >> 1)) * (long long)W + (xo >> 1)) * in_ps + c * 8);
+  *reinterpret_cast<uint4*>(out + p * out_ps + c * 8) = v;
+}
+
+void launch_upsample2(const __half* in, int C, int H, int W, int batch, long long in_ps, __half* out, long long out_ps, cudaStream_t st) {
+  const long long total = (long long)batch * (H * 2) * (W * 2) * (C / 8);
+  upsample2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, C / 8, H, W, in_ps, out, out_ps, total);
+}
+
+// =====================================================================================================================
+// K4 detector head: softmax over 65 logits per 8x8 cell, drop the dustbin, depth-to-space into the 512x512 heat map.
+// One warp per cell: lanes hold logits {l, l+32, (64 on lane 0)}; shuffle max / sum; lane l writes pixels l and l+32.
+// =====================================================================================================================
+__global__ void softmax_d2s_kernel(const float* __restrict__ logits, int ld, float* __restrict__ heat, int cells) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= cells) return;
+  const float* l = logits + (long long)warp * ld;
+  const float v0 = l[lane], v1 = l[lane + 32];
+  const float v2 = (lane == 0) ? l[64] : -INFINITY;
+  float m = fmaxf(fmaxf(v0, v1), v2);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float e0 = expf(v0 - m), e1 = expf(v1 - m), e2 = (lane == 0) ? expf(v2 - m) : 0.f;
+  float s = e0 + e1 + e2;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int b = warp >> 12, cy = (warp >> 6) & 63, cx = warp & 63;
+  float* h = heat + (long long)b * 262144;
+  // channel c -> (dy = c / 8, dx = c % 8)
+  h[(cy * 8 + (lane >> 3)) * 512 + cx * 8 + (lane & 7)] = e0 / s;
+  h[(cy * 8 + 4 + (lane >> 3)) * 512 + cx * 8 + (lane & 7)] = e1 / s;
+}
+
+void launch_softmax_d2s(const float* logits, int ld, float* heat, int batch, cudaStream_t st) {
+  const int cells = batch * 4096;
+  softmax_d2s_kernel<<<(cells * 32 + 255) / 256, 256, 0, st>>>(logits, ld, heat, cells);
+}
+
+// =====================================================================================================================
+// K5 simple_nms (radius 4).  App. B1:  M = (S == mp9(S));  2x { Sup = mp9(M) > 0; S' = Sup ? 0 : S;
+//                                      M |= (S' == mp9(S')) & ~Sup };  out = M ? S : 0.   Padding acts as -inf.
+// Round kernel: one CTA computes a 32x32 output tile from a (32+16)^2 input tile of (S, M) held in shared memory;
+// 9x9 max = separable row-max then column-max.
+// =====================================================================================================================
+constexpr int NT = 32;
+
+__global__ void nms_init_kernel(const float* __restrict__ heat, uint8_t* __restrict__ mask) {
+  __shared__ float s[NT + 8][NT + 8];
+  __shared__ float r[NT + 8][NT];
+  const int b = blockIdx.z, x0 = blockIdx.x * NT, y0 = blockIdx.y * NT;
+  const float* h = heat + (long long)b * 262144;
+  for (int i = threadIdx.x; i < (NT + 8) * (NT + 8); i += blockDim.x) {
+    const int yy = i / (NT + 8), xx = i % (NT + 8);
+    const int gy = y0 + yy - 4, gx = x0 + xx - 4;
+    s[yy][xx] = (gy >= 0 && gy < 512 && gx >= 0 && gx < 512) ? h[gy * 512 + gx] : -INFINITY;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (NT + 8) * NT; i += blockDim.x) {
+    const int yy = i / NT, xx = i % NT;
+    float m = s[yy][xx];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) m = fmaxf(m, s[yy][xx + k]);
+    r[yy][xx] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NT * NT; i += blockDim.x) {
+    const int yy = i / NT, xx = i % NT;
+    float m = r[yy][xx];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) m = fmaxf(m, r[yy + k][xx]);
+    mask[(long long)b * 262144 + (y0 + yy) * 512 + x0 + xx] = (s[yy + 4][xx + 4] == m) ? 1 : 0;
+  }
+}
+
+__global__ void nms_round_kernel(const float* __restrict__ heat, const uint8_t* __restrict__ mask_in, uint8_t* __restrict__ mask_out,
+                                 float* __restrict__ scores_out /* non-null on the last round */) {
+  constexpr int T16 = NT + 16, T8 = NT + 8;
+  __shared__ float s[T16][T16];       // S on tile + 8 halo (-inf outside the image)
+  __shared__ uint8_t mk[T16][T16];    // M on tile + 8 halo (0 outside)
+  __shared__ float t1[T16][T8];       // row pass scratch
+  __shared__ float sp[T8][T8];        // S' on tile + 4 halo (-inf outside the image)
+  __shared__ uint8_t sup[T8][T8];
+  const int b = blockIdx.z, x0 = blockIdx.x * NT, y0 = blockIdx.y * NT;
+  const float* h = heat + (long long)b * 262144;
+  const uint8_t* mi = mask_in + (long long)b * 262144;
+  for (int i = threadIdx.x; i < T16 * T16; i += blockDim.x) {
+    const int yy = i / T16, xx = i % T16;
+    const int gy = y0 + yy - 8, gx = x0 + xx - 8;
+    const bool in = (gy >= 0 && gy < 512 && gx >= 0 && gx < 512);
+    s[yy][xx] = in ? h[gy * 512 + gx] : -INFINITY;
+    mk[yy][xx] = in ? mi[gy * 512 + gx] : 0;
+  }
+  __syncthreads();
+  // Sup = mp9(float(M)) > 0 on tile+4: separable OR
+  for (int i = threadIdx.x; i < T16 * T8; i += blockDim.x) {
+    const int yy = i / T8, xx = i % T8;
+    int a = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a |= mk[yy][xx + k];
+    t1[yy][xx] = (float)a;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T8 * T8; i += blockDim.x) {
+    const int yy = i / T8, xx = i % T8;
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a = fmaxf(a, t1[yy + k][xx]);
+    const int gy = y0 + yy - 4, gx = x0 + xx - 4;
+    const bool in = (gy >= 0 && gy < 512 && gx >= 0 && gx < 512);
+    const bool su = a > 0.f;
+    sup[yy][xx] = su;
+    sp[yy][xx] = in ? (su ? 0.f : s[yy + 4][xx + 4]) : -INFINITY;
+  }
+  __syncthreads();
+  // mp9(S') on the tile
+  float (*t2)[T8] = t1;  // reuse: rows 0..T8-1, cols 0..NT-1
+  for (int i = threadIdx.x; i < T8 * NT; i += blockDim.x) {
+    const int yy = i / NT, xx = i % NT;
+    float m = sp[yy][xx];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) m = fmaxf(m, sp[yy][xx + k]);
+    t2[yy][xx] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NT * NT; i += blockDim.x) {
+    const int yy = i / NT, xx = i % NT;
+    float m = t2[yy][xx];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) m = fmaxf(m, t2[yy + k][xx]);
+    const bool su = sup[yy + 4][xx + 4];
+    const bool newm = mk[yy + 8][xx + 8] | ((sp[yy + 4][xx + 4] == m) && !su);
+    const long long o = (long long)b * 262144 + (y0 + yy) * 512 + x0 + xx;
+    mask_out[o] = newm;
+    if (scores_out) scores_out[o] = newm ? s[yy + 8][xx + 8] : 0.f;
+  }
+}
+
+void launch_simple_nms(const float* heat, float* scores, uint8_t* mask_a, uint8_t* mask_b, int batch, cudaStream_t st) {
+  dim3 grid(512 / NT, 512 / NT, batch);
+  nms_init_kernel<<<grid, 256, 0, st>>>(heat, mask_a);
+  nms_round_kernel<<<grid, 256, 0, st>>>(heat, mask_a, mask_b, nullptr);
+  nms_round_kernel<<<grid, 256, 0, st>>>(heat, mask_b, mask_a, scores);
+}
+
+// =====================================================================================================================
+// K6 keypoint selection (detect_point, src/plnet.cpp:309-355): score >= thr, border <= x <= W-border (inclusive), same for y;
+// if more than top_k survive: top_k by (score desc, raster index asc) -- the tie order this build defines -- else raster order.
+// Stage 1: unordered compaction with one atomic per warp.  Stage 2: O(n^2) rank (n <= ~10k after radius-4 NMS): each
+// candidate counts the candidates that precede it in BOTH orders; no sort, deterministic output positions.
+// =====================================================================================================================
+__global__ void kp_compact_kernel(const float* __restrict__ scores, float thr, int border, int* __restrict__ cand, int cap,
+                                  int* __restrict__ count) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..262143
+  const float s = scores[(long long)b * 262144 + i];
+  const int y = i >> 9, x = i & 511;
+  const bool ok = (s >= thr) && !(x < border || x > 512 - border || y < border || y > 512 - border);
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if (!m) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(count + b, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (ok) {
+    const int pos = base + __popc(m & ((1u << lane) - 1));
+    if (pos < cap) cand[(long long)b * cap + pos] = i;
+  }
+}
+
+__global__ void kp_rank_kernel(const float* __restrict__ scores, const int* __restrict__ cand, int cap, const int* __restrict__ count,
+                               int top_k, float* __restrict__ kp_out, int kp_cap, int* __restrict__ kp_count) {
+  const int b = blockIdx.y;
+  const int n = min(count[b], cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_idx[256];
+  __shared__ float s_val[256];
+  const float* sc = scores + (long long)b * 262144;
+  const int* cd = cand + (long long)b * cap;
+  int my_idx = 0;
+  float my_val = 0.f;
+  if (i < n) { my_idx = cd[i]; my_val = sc[my_idx]; }
+  int r_score = 0, r_idx = 0;
+  for (int base = 0; base < n; base += 256) {
+    const int j = base + threadIdx.x;
+    __syncthreads();
+    if (j < n) { const int id = cd[j]; s_idx[threadIdx.x] = id; s_val[threadIdx.x] = sc[id]; }
+    __syncthreads();
+    const int lim = min(256, n - base);
+    if (i < n) {
+      for (int k = 0; k < lim; ++k) {
+        const float v = s_val[k];
+        const int id = s_idx[k];
+        r_score += (v > my_val) || (v == my_val && id < my_idx);
+        r_idx += (id < my_idx);
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) kp_count[b] = min(n, min(top_k, kp_cap));
+  if (i < n) {
+    const int pos = (n > top_k) ? r_score : r_idx;
+    if (pos < top_k && pos < kp_cap) {
+      float* o = kp_out + ((long long)b * kp_cap + pos) * 3;
+      o[0] = my_val;
+      o[1] = (float)(my_idx & 511);
+      o[2] = (float)(my_idx >> 9);
+    }
+  }
+}
+
+void launch_select_keypoints(const float* scores, int batch, float threshold, int border, int top_k, int* cand_idx, int cand_cap,
+                             int* cand_count, float* kp_out, int kp_cap, int* kp_count, cudaStream_t st) {
+  cudaMemsetAsync(cand_count, 0, sizeof(int) * batch, st);
+  kp_compact_kernel<<<dim3(262144 / 256, batch), 256, 0, st>>>(scores, threshold, border, cand_idx, cand_cap, cand_count);
+  kp_rank_kernel<<<dim3((cand_cap + 255) / 256, batch), 256, 0, st>>>(scores, cand_idx, cand_cap, cand_count, top_k, kp_out, kp_cap,
+                                                                      kp_count);
+}
+
+// =====================================================================================================================
+// K7+K8 descriptor sampling (extract_descriptors, src/plnet.cpp:369-417).  One warp per keypoint, 8 channels per lane.
+// The dense map is L2-normalised per pixel first (graph: D / clip(||D||, 1e-12)), which is folded into the gather: the
+// four neighbours' norms are warp-reduced on the fly, so the normalised dense map is never written to HBM.
+// =====================================================================================================================
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void sample_desc_kernel(const float* __restrict__ desc_raw, const float* __restrict__ kp, const int* __restrict__ kp_count,
+                                   int kp_cap, float w_scale, float h_scale, float* __restrict__ feat) {
+  const int b = blockIdx.y;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= kp_count[b]) return;
+  const float* k = kp + ((long long)b * kp_cap + j) * 3;
+  const float score = k[0], px = k[1], py = k[2];
+  // constants for s = 8, w = h = 64: note `s / 2` is integer division in the reference
+  const float den = (float)(64 * 8 - 8 / 2 - 0.5);
+  const float sx = 2.f / den;
+  const float bx = (float)((1 - 8) / (64 * 8 - 8 / 2 - 0.5) - 1);
+  const float nx = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, sx), bx), 1.f), 0.5f);
+  const float ny = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(py, sx), bx), 1.f), 0.5f);
+  const float ix = __fmul_rn(nx, 63.f), iy = __fmul_rn(ny, 63.f);
+  auto clip = [](int v) { return v < 0 ? 0 : (v > 63 ? 63 : v); };
+  const int x_nw = clip((int)floorf(ix)), y_nw = clip((int)floorf(iy));
+  const int x_ne = clip(x_nw + 1), y_ne = y_nw;
+  const int x_sw = x_nw, y_sw = clip(y_nw + 1);
+  const int x_se = clip(x_nw + 1), y_se = clip(y_nw + 1);
+  const float w_nw = __fmul_rn(__fsub_rn((float)x_se, ix), __fsub_rn((float)y_se, iy));
+  const float w_ne = __fmul_rn(__fsub_rn(ix, (float)x_sw), __fsub_rn((float)y_sw, iy));
+  const float w_sw = __fmul_rn(__fsub_rn((float)x_ne, ix), __fsub_rn(iy, (float)y_ne));
+  const float w_se = __fmul_rn(__fsub_rn(ix, (float)x_nw), __fsub_rn(iy, (float)y_nw));
+  const float* base = desc_raw + (long long)b * 4096 * 256;
+  const float* p_nw = base + (y_nw * 64 + x_nw) * 256 + lane * 8;
+  const float* p_ne = base + (y_ne * 64 + x_ne) * 256 + lane * 8;
+  const float* p_sw = base + (y_sw * 64 + x_sw) * 256 + lane * 8;
+  const float* p_se = base + (y_se * 64 + x_se) * 256 + lane * 8;
+  float v[4][8];
+  float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* ps[4] = {p_nw, p_ne, p_sw, p_se};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(ps[q]);
+    const float4 c = *reinterpret_cast<const float4*>(ps[q] + 4);
+    v[q][0] = a.x; v[q][1] = a.y; v[q][2] = a.z; v[q][3] = a.w; v[q][4] = c.x; v[q][5] = c.y; v[q][6] = c.z; v[q][7] = c.w;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) nrm[q] = fmaf(v[q][e], v[q][e], nrm[q]);
+    nrm[q] = fmaxf(sqrtf(warp_sum(nrm[q])), 1e-12f);
+  }
+  float o[8];
+  float ss = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float acc = __fmul_rn(__fdiv_rn(v[0][e], nrm[0]), w_nw);
+    acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(v[1][e], nrm[1]), w_ne));
+    acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(v[2][e], nrm[2]), w_sw));
+    acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(v[3][e], nrm[3]), w_se));
+    o[e] = acc;
+    ss = fmaf(acc, acc, ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = ss > 0.f ? 1.f / sqrtf(ss) : 1.f;   // Eigen normalize(): all-zero column stays zero
+  float* f = feat + ((long long)b * kp_cap + j) * 259;
+  if (lane == 0) { f[0] = score; f[1] = __fmul_rn(px, w_scale); f[2] = __fmul_rn(py, h_scale); }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[3 + lane * 8 + e] = ss > 0.f ? __fmul_rn(o[e], inv) : o[e];
+}
+
+void launch_sample_descriptors(const float* desc_raw, const float* kp, const int* kp_count, int kp_cap, int batch, float w_scale,
+                               float h_scale, float* feat_out, cudaStream_t st) {
+  dim3 grid((kp_cap * 32 + 255) / 256, batch);
+  sample_desc_kernel<<<grid, 256, 0, st>>>(desc_raw, kp, kp_count, kp_cap, w_scale, h_scale, feat_out);
+}
+
+}  // namespace airfe

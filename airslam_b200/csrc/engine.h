@@ -1,0 +1,96 @@
+// Host runtime of libairfe: weight containers, device arena, op lists (the replacement for the reference's
+// TensorRT engines + tensorrt_buffer::BufferManager, 3rdparty/tensorrtbuffer/include/buffers.h:237-417, which
+// cudaMalloc/cudaFree every binding on every infer() call; here everything is allocated once per context).
+#pragma once
+#include "common.h"
+#include "kernels.h"
+
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace airfe {
+
+// ---- AIRFEW01 weight container (tools/make_weights.py) -----------------------------------------------------------
+struct WTensor {
+  int dtype = 0;  // 0 f32, 1 f16, 2 i32
+  int ndim = 0;
+  int dims[4] = {1, 1, 1, 1};
+  const uint8_t* data = nullptr;
+  size_t nbytes = 0;
+  size_t numel() const { return (size_t)dims[0] * dims[1] * dims[2] * dims[3]; }
+};
+class WeightFile {
+ public:
+  bool load(const std::string& path);
+  const WTensor* find(const std::string& name) const;
+  bool has(const std::string& name) const { return find(name) != nullptr; }
+  // fetch as float (converting fp16), empty vector on error
+  bool get_f32(const std::string& name, std::vector<float>* out) const;
+ private:
+  std::vector<uint8_t> blob_;
+  std::map<std::string, WTensor> index_;
+};
+
+// ---- bump allocator over one cudaMalloc --------------------------------------------------------------------------
+class Arena {
+ public:
+  ~Arena();
+  bool init(size_t bytes);
+  void* alloc(size_t bytes, size_t align = 1024);
+  template <typename T> T* alloc_n(size_t n) { return reinterpret_cast<T*>(alloc(n * sizeof(T))); }
+  size_t used() const { return off_; }
+  bool ok() const { return !failed_; }
+ private:
+  uint8_t* base_ = nullptr;
+  size_t cap_ = 0, off_ = 0;
+  bool failed_ = false;
+};
+
+// ---- packed weights of one dense layer (device) -------------------------------------------------------------------
+struct DenseW {
+  __half* w = nullptr;    // [n_rows][taps * c_in_pad]
+  float* bias = nullptr;  // [n_rows]
+  int n_rows = 0, c_in = 0, c_in_pad = 0, taps = 1;
+};
+
+// NHWC fp16/fp32 activation view on a [Bmax, H, W, ps] buffer (channel offset folded into p)
+struct Act {
+  void* p = nullptr;
+  int C = 0, H = 0, W = 0;
+  long long ps = 0;  // pixel stride in elements
+  bool f32 = false;
+  Act slice(int c0, int c) const {
+    Act a = *this;
+    a.p = (uint8_t*)p + (size_t)c0 * (f32 ? 4 : 2);
+    a.C = c;
+    return a;
+  }
+};
+
+using Op = std::function<bool(cudaStream_t)>;
+struct OpList {
+  std::vector<Op> ops;
+  double tc_flops = 0;   // algorithmic FLOPs of the tensor-core ops in this list
+  int launches = 0;
+  bool run(cudaStream_t st) const {
+    for (auto& o : ops)
+      if (!o(st)) return false;
+    return true;
+  }
+};
+
+// Pack helpers (host): conv OIHW / linear [out,in] fp16 -> tap-major K-major rows, several sources concatenated along N.
+struct PackSrc {
+  std::string weight, bias;  // tensor names in the container (bias may be empty)
+  int in_offset = 0;         // place this source's input channels at [in_offset, in_offset + c_in) of the packed K (block-diagonal / concat remap)
+};
+bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in_total, Arena* arena, DenseW* out,
+                const std::vector<int>* in_perm = nullptr);
+
+// Append a tcgen05 conv / GEMM op.
+bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int batch, bool relu, int n_valid = -1, int block_n = 0,
+               const int* dyn_rows = nullptr);
+
+}  // namespace airfe

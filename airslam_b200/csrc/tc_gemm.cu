@@ -106,6 +106,7 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   p.out = d.out;
   p.out_sb = d.out_sb; p.out_sy = d.out_sy; p.out_sx = d.out_sx;
   p.n_valid = d.n_valid;
+  p.dyn_w = d.dyn_w;
   const int stage_bytes = kABytes + tc_b_bytes(d.block_n, d.b_mn_major);
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int tiles_x = p.tiles_x;
+  const int m_tiles = tiles_x * p.tiles_y * p.tiles_b;
   const int total_tiles = m_tiles * p.n_tiles;
   const int ksteps = p.taps * p.kblocks;
   const uint32_t tmem_cols = tc_tmem_cols(p.block_n);
@@ -67,10 +68,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % p.n_tiles;
         const int mt = t / p.n_tiles;
-        const int tx = mt % p.tiles_x;
-        const int ty = (mt / p.tiles_x) % p.tiles_y;
-        const int tz = mt / (p.tiles_x * p.tiles_y);
+        const int tx = mt % tiles_x;
+        const int ty = (mt / tiles_x) % p.tiles_y;
+        const int tz = mt / (tiles_x * p.tiles_y);
         const int x0 = tx * p.tw, y0 = ty * p.th, b0 = tz * p.tb;
+        if (p.dyn_w && x0 >= __ldg(p.dyn_w + b0)) continue;   // rows beyond the device-side count: all roles skip alike
         const int bb = p.b_batched ? b0 : 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
@@ -100,6 +102,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        if (p.dyn_w) {
+          const int mt = t / p.n_tiles;
+          if ((mt % tiles_x) * p.tw >= __ldg(p.dyn_w + (mt / (tiles_x * p.tiles_y)) * p.tb)) continue;
+        }
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
@@ -132,13 +138,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t % p.n_tiles;
       const int mt = t / p.n_tiles;
-      const int tx = mt % p.tiles_x;
-      const int ty = (mt / p.tiles_x) % p.tiles_y;
-      const int tz = mt / (p.tiles_x * p.tiles_y);
+      const int tx = mt % tiles_x;
+      const int ty = (mt / tiles_x) % p.tiles_y;
+      const int tz = mt / (tiles_x * p.tiles_y);
       const int x = tx * p.tw + row % p.tw;
       const int y = ty * p.th + (row / p.tw) % p.th;
       const int b = tz * p.tb + row / (p.tw * p.th);
-      const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
+      const int vW = p.dyn_w ? min(__ldg(p.dyn_w + tz * p.tb), p.W) : p.W;
+      if (p.dyn_w && tx * p.tw >= vW) continue;
+      const bool valid = (x < vW) && (y < p.H) && (b < p.B);
       const long long off = (long long)b * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();

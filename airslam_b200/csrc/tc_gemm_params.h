@@ -24,6 +24,7 @@ struct TcGemmParams {
   long long out_sb, out_sy, out_sx;
   int n_valid;
   int stages;
+  const int* dyn_w;  // optional: per-batch-index valid W (rows of a plain GEMM), read from device memory (tb must be 1)
 };
 
 constexpr int kTcThreads = 192;

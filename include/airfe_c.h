@@ -38,6 +38,58 @@ int airfe_op_tc_gemm(const void* a, int a_C, int W, int H, int B, long long a_sx
                      void* out, long long out_sb, long long out_sy, long long out_sx, int n_valid,
                      int tw, int th, int tb, void* stream);
 
+/* ---- frame-level entry points (host buffers in, host buffers out; pinned staging is internal) ---- */
+
+typedef struct airfe_ctx airfe_ctx; /* one per (device, model set); NOT thread-safe, like the reference's classes */
+
+typedef struct airfe_config {
+  const char* weights_dir;        /* directory holding *.afw (converted once from the reference's ONNX files) */
+  int max_batch;                  /* images per detect call / pairs per match call */
+  /* PLNetConfig / SuperPointConfig fields (include/read_configs.h:9-83) */
+  int max_keypoints;
+  float keypoint_threshold;
+  int remove_borders;
+  float line_threshold;
+  float line_length_threshold;
+  /* PointMatcherConfig fields (include/read_configs.h:85-103) */
+  int image_width, image_height;
+  /* which networks to load */
+  int enable_superpoint;          /* G1 */
+  int enable_plnet;               /* G2 + G3 */
+  int enable_lightglue;           /* G4 */
+  int enable_superglue;           /* G5: 0 off, 1 indoor, 2 outdoor */
+} airfe_config;
+
+#define AIRFE_NET_SUPERPOINT 0
+#define AIRFE_NET_PLNET 1
+#define AIRFE_MATCHER_LIGHTGLUE 0
+#define AIRFE_MATCHER_SUPERGLUE 1
+#define AIRFE_FEAT_DIM 259
+
+void airfe_default_config(airfe_config* cfg);
+int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out);
+void airfe_destroy(airfe_ctx* ctx);
+
+/* Detect on `batch` 8-bit gray images of identical size (image i at gray + i * image_stride_bytes, rows `stride` bytes apart).
+ * Replaces SuperPoint::infer / PLNet::infer.  Outputs per image i:
+ *   feat    + i*feat_cap*259 : column-major 259 x n_feat[i] (score, x, y, 256-d descriptor), image-pixel coordinates
+ *   lines   + i*line_cap*4   : n_lines[i] x (x1,y1,x2,y2) doubles (NULL => no line detection; requires net = PLNET)
+ *   junc    + i*junc_cap*259 : junction features, as feat (NULL => junction_detection = false) */
+int airfe_detect_batch(airfe_ctx* ctx, int net, int batch, const uint8_t* gray, int width, int height, int stride,
+                       long long image_stride_bytes, float* feat, int feat_cap, int* n_feat, double* lines, int line_cap,
+                       int* n_lines, float* junc, int junc_cap, int* n_junc);
+
+/* Single image convenience (SURVEY.md 8b signature). */
+int airfe_detect(airfe_ctx* ctx, int net, const uint8_t* gray, int width, int height, int stride, float* feat259_colmajor,
+                 int feat_cap, int* n_feat, double* lines_xyxy, int line_cap, int* n_lines, float* junc259_colmajor, int junc_cap,
+                 int* n_junc);
+
+/* Parity taps: copy a named intermediate of the last detect call (image `index`) to `dst`; returns bytes, <0 on error. */
+long long airfe_debug_read(airfe_ctx* ctx, int net, const char* name, int index, void* dst, long long dst_bytes);
+
+/* The CUDA stream all work of this context is issued on (cudaStream_t), for event timing by the caller. */
+void* airfe_stream(airfe_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif
