@@ -79,6 +79,15 @@ def _declare(L):  # noqa: F811
 def _declare_match(L):
     L.airfe_match_batch.argtypes = [vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp]
     L.airfe_match_batch.restype = i32
+    L.airfe_detect_match_stereo_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, i32, i64, vp, i32, vp, vp, i32, vp, vp, i32, vp,
+                                                  vp, vp, vp, i32, vp]
+    L.airfe_detect_match_stereo_batch.restype = i32
+    L.airfe_stereo_device.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i64, i32, i32]
+    L.airfe_stereo_device.restype = i32
+    L.airfe_profile_stereo.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i64, i32, i32, vp, i64]
+    L.airfe_profile_stereo.restype = i64
+    L.airfe_stereo_cost.argtypes = [vp, i32, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(i32)]
+    L.airfe_stereo_cost.restype = i32
 
 
 class Context:
@@ -140,4 +149,72 @@ class Context:
         n = lib().airfe_debug_read(self.h, net, name.encode(), index, out.ctypes.data_as(vp), out.nbytes)
         if n < 0:
             check(int(n))
+        return out
+
+    def match_batch(self, matcher, feats0, feats1, match_cap=1024):
+        """feats0/feats1: lists of [259,N] float32 arrays (image-pixel keypoints).  Returns list of (idx [K,2] int32, score [K])."""
+        import numpy as np
+        p = len(feats0)
+        cap = max(max(f.shape[1] for f in feats0), max(f.shape[1] for f in feats1), 1)
+        f0 = np.zeros((p, cap, 259), dtype=np.float32)
+        f1 = np.zeros((p, cap, 259), dtype=np.float32)
+        n0 = np.array([f.shape[1] for f in feats0], dtype=np.int32)
+        n1 = np.array([f.shape[1] for f in feats1], dtype=np.int32)
+        for i in range(p):
+            f0[i, :n0[i]] = feats0[i].T
+            f1[i, :n1[i]] = feats1[i].T
+        i0 = np.zeros((p, match_cap), dtype=np.int32)
+        i1 = np.zeros((p, match_cap), dtype=np.int32)
+        sc = np.zeros((p, match_cap), dtype=np.float32)
+        nm = np.zeros(p, dtype=np.int32)
+        q = lambda a: a.ctypes.data_as(vp)
+        check(lib().airfe_match_batch(self.h, matcher, p, q(f0), q(n0), q(f1), q(n1), cap, q(i0), q(i1), q(sc), match_cap, q(nm)))
+        return [(np.stack([i0[i, :nm[i]], i1[i, :nm[i]]], axis=1), sc[i, :nm[i]].copy()) for i in range(p)]
+
+    def stereo_batch(self, net, matcher, left, right, lines=False, junctions=False, line_cap=4096, junc_cap=1024, match_cap=1024):
+        """left/right: uint8 [P,H,W].  Returns per pair dict(feat_l, feat_r, lines_l, lines_r, junc, matches (idx, score))."""
+        import numpy as np
+        left = np.ascontiguousarray(left, dtype=np.uint8)
+        right = np.ascontiguousarray(right, dtype=np.uint8)
+        p, h, w = left.shape
+        fc = self.cfg.max_keypoints
+        feat = np.zeros((2 * p, fc, 259), dtype=np.float32)
+        nf = np.zeros(2 * p, dtype=np.int32)
+        ln = np.zeros((2 * p, line_cap, 4), dtype=np.float64) if lines else None
+        nl = np.zeros(2 * p, dtype=np.int32)
+        jn = np.zeros((p, junc_cap, 259), dtype=np.float32) if junctions else None
+        nj = np.zeros(p, dtype=np.int32)
+        i0 = np.zeros((p, match_cap), dtype=np.int32)
+        i1 = np.zeros((p, match_cap), dtype=np.int32)
+        sc = np.zeros((p, match_cap), dtype=np.float32)
+        nm = np.zeros(p, dtype=np.int32)
+        q = lambda a: a.ctypes.data_as(vp) if a is not None else None
+        check(lib().airfe_detect_match_stereo_batch(self.h, net, matcher, p, q(left), q(right), w, h, w, h * w, q(feat), fc, q(nf), q(ln), line_cap,
+                                                    q(nl), q(jn), junc_cap, q(nj), q(i0), q(i1), q(sc), match_cap, q(nm)))
+        out = []
+        for i in range(p):
+            out.append(dict(feat_l=feat[2 * i, :nf[2 * i]].T.copy(), feat_r=feat[2 * i + 1, :nf[2 * i + 1]].T.copy(),
+                            lines_l=ln[2 * i, :nl[2 * i]].copy() if lines else None, lines_r=ln[2 * i + 1, :nl[2 * i + 1]].copy() if lines else None,
+                            junc=jn[i, :nj[i]].T.copy() if junctions else None,
+                            matches=(np.stack([i0[i, :nm[i]], i1[i, :nm[i]]], axis=1), sc[i, :nm[i]].copy())))
+        return out
+
+    def stereo_device(self, net, matcher, pairs, d_images_ptr, w, h, stride, img_stride, lines=True, junctions=True):
+        check(lib().airfe_stereo_device(self.h, net, matcher, pairs, d_images_ptr, w, h, stride, img_stride, int(lines), int(junctions)))
+
+    def stereo_cost(self, net, matcher, pairs, lines=True):
+        fl, ln = C.c_double(0), i32(0)
+        check(lib().airfe_stereo_cost(self.h, net, matcher, pairs, int(lines), C.byref(fl), C.byref(ln)))
+        return fl.value, ln.value
+
+    def profile_stereo(self, net, matcher, pairs, d_images_ptr, w, h, stride, img_stride, lines=True, junctions=True):
+        """One profiled step; returns list of (name, flops, ms)."""
+        buf = C.create_string_buffer(1 << 18)
+        n = lib().airfe_profile_stereo(self.h, net, matcher, pairs, d_images_ptr, w, h, stride, img_stride, int(lines), int(junctions), buf, len(buf))
+        if n < 0:
+            check(int(n))
+        out = []
+        for line in buf.value.decode().splitlines():
+            nm, fl, ms = line.split("\t")
+            out.append((nm, float(fl), float(ms)))
         return out

@@ -2,8 +2,11 @@
 // is asynchronous on the context's stream and synchronised once per call, right before results are handed back.
 #include "../../include/airfe_c.h"
 #include "detector.h"
+#include "matcher.h"
 
 #include <memory>
+#include <stdlib.h>
+#include <vector>
 
 using namespace airfe;
 
@@ -12,6 +15,9 @@ struct airfe_ctx {
   airfe_config cfg;
   cudaStream_t stream = nullptr;
   std::unique_ptr<Detector> sp, pl;
+  std::unique_ptr<LightGlue> lg;
+  float* d_mfeat = nullptr; int* d_mn = nullptr;   // staging for host-provided features [2*max_batch][kKpCap][259]
+  float* h_mfeat = nullptr; int* h_mn = nullptr; int* h_midx = nullptr; float* h_mscore = nullptr; int* h_mcount = nullptr;
   // pinned staging
   uint8_t* h_img = nullptr; size_t h_img_bytes = 0;
   float* h_feat = nullptr; float* h_junc = nullptr; float* h_lines = nullptr;
@@ -51,7 +57,7 @@ int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out) {
   c->cfg = *cfg;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return AIRFE_ERR_CUDA; }
   DetectorConfig dc;
-  dc.max_batch = cfg->max_batch;
+  dc.max_batch = 2 * cfg->max_batch;   // a stereo batch of max_batch pairs = 2*max_batch images
   dc.max_keypoints = cfg->max_keypoints;
   dc.keypoint_threshold = cfg->keypoint_threshold;
   dc.remove_borders = cfg->remove_borders;
@@ -68,9 +74,26 @@ int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out) {
     dc.enable_lines = true;
     if (!c->pl->init(dc, wdir, true)) return AIRFE_ERR_IO;
   }
+  if (cfg->enable_lightglue) {
+    MatcherConfig mc;
+    mc.max_pairs = cfg->max_batch;
+    mc.cap = cfg->max_keypoints <= 512 ? 512 : 1024;
+    mc.image_width = cfg->image_width;
+    mc.image_height = cfg->image_height;
+    c->lg.reset(new LightGlue);
+    if (!c->lg->init(mc, wdir)) return AIRFE_ERR_IO;
+    const size_t S = 2 * (size_t)cfg->max_batch;
+    if (cudaMalloc(&c->d_mfeat, S * kKpCap * 259 * 4) != cudaSuccess || cudaMalloc(&c->d_mn, S * 4) != cudaSuccess ||
+        cudaMallocHost(&c->h_mfeat, S * kKpCap * 259 * 4) != cudaSuccess || cudaMallocHost(&c->h_mn, S * 4) != cudaSuccess ||
+        cudaMallocHost(&c->h_midx, (size_t)cfg->max_batch * 1024 * 2 * 4) != cudaSuccess ||
+        cudaMallocHost(&c->h_mscore, (size_t)cfg->max_batch * 1024 * 4) != cudaSuccess || cudaMallocHost(&c->h_mcount, (size_t)cfg->max_batch * 4) != cudaSuccess) {
+      set_error("matcher staging allocation failed");
+      return AIRFE_ERR_CUDA;
+    }
+  }
   const int B = cfg->max_batch;
-  if (cudaMallocHost(&c->h_feat, (size_t)B * kKpCap * 259 * 4) != cudaSuccess || cudaMallocHost(&c->h_junc, (size_t)B * kKpCap * 259 * 4) != cudaSuccess ||
-      cudaMallocHost(&c->h_lines, (size_t)B * kLineCap * 4 * 4) != cudaSuccess || cudaMallocHost(&c->h_counts, (size_t)3 * B * 4) != cudaSuccess) {
+  if (cudaMallocHost(&c->h_feat, (size_t)2 * B * kKpCap * 259 * 4) != cudaSuccess || cudaMallocHost(&c->h_junc, (size_t)2 * B * kKpCap * 259 * 4) != cudaSuccess ||
+      cudaMallocHost(&c->h_lines, (size_t)2 * B * kLineCap * 4 * 4) != cudaSuccess || cudaMallocHost(&c->h_counts, (size_t)6 * B * 4) != cudaSuccess) {
     set_error("pinned allocation failed");
     return AIRFE_ERR_CUDA;
   }
@@ -84,6 +107,14 @@ void airfe_destroy(airfe_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->sp.reset();
   c->pl.reset();
+  c->lg.reset();
+  if (c->d_mfeat) cudaFree(c->d_mfeat);
+  if (c->d_mn) cudaFree(c->d_mn);
+  if (c->h_mfeat) cudaFreeHost(c->h_mfeat);
+  if (c->h_mn) cudaFreeHost(c->h_mn);
+  if (c->h_midx) cudaFreeHost(c->h_midx);
+  if (c->h_mscore) cudaFreeHost(c->h_mscore);
+  if (c->h_mcount) cudaFreeHost(c->h_mcount);
   if (c->h_img) cudaFreeHost(c->h_img);
   if (c->h_feat) cudaFreeHost(c->h_feat);
   if (c->h_junc) cudaFreeHost(c->h_junc);
@@ -109,7 +140,7 @@ int airfe_detect_batch(airfe_ctx* c, int net, int batch, const uint8_t* gray, in
   if (w <= 1 || h <= 1 || stride < w) { set_error("empty image"); return AIRFE_ERR_INVALID; }   // image.empty() -> false (plnet.cpp:247)
   Detector* d = pick(c, net);
   if (!d) return AIRFE_ERR_INVALID;
-  if (batch < 1 || batch > c->cfg.max_batch) { set_error("batch %d outside [1,%d]", batch, c->cfg.max_batch); return AIRFE_ERR_INVALID; }
+  if (batch < 1 || batch > 2 * c->cfg.max_batch) { set_error("batch %d outside [1,%d]", batch, 2 * c->cfg.max_batch); return AIRFE_ERR_INVALID; }
   if ((lines || junc) && net != AIRFE_NET_PLNET) { set_error("lines / junctions need the PLNet network"); return AIRFE_ERR_INVALID; }
   if (junc && !lines) { set_error("junction detection needs line detection"); return AIRFE_ERR_INVALID; }
   cudaSetDevice(c->device);
@@ -126,7 +157,7 @@ int airfe_detect_batch(airfe_ctx* c, int net, int batch, const uint8_t* gray, in
   if (cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return AIRFE_ERR_CUDA; }
   if (!d->run(c->d_img, batch, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return AIRFE_ERR_CUDA;
   const DetectOutputs& o = d->out();
-  const int B = c->cfg.max_batch;
+  const int B = 2 * c->cfg.max_batch;
   int* hc = c->h_counts;
   cudaMemcpyAsync(hc, o.n_feat, 4 * batch, cudaMemcpyDeviceToHost, st);
   if (lines) cudaMemcpyAsync(hc + B, o.n_lines, 4 * batch, cudaMemcpyDeviceToHost, st);
@@ -173,7 +204,178 @@ int airfe_detect(airfe_ctx* c, int net, const uint8_t* gray, int w, int h, int s
   return airfe_detect_batch(c, net, 1, gray, w, h, stride, 0, feat, feat_cap, n_feat, lines, line_cap, n_lines, junc, junc_cap, n_junc);
 }
 
+static int fetch_matches(airfe_ctx* c, int pairs, int* idx0, int* idx1, float* score, int match_cap, int* n_match, const int* zero_mask) {
+  const MatchOutputs& mo = c->lg->out();
+  const int cap = c->lg->cap();
+  cudaStream_t st = c->stream;
+  cudaMemcpyAsync(c->h_mcount, mo.count, 4 * pairs, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(c->h_midx, mo.idx, (size_t)pairs * cap * 8, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(c->h_mscore, mo.score, (size_t)pairs * cap * 4, cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("match failed: %s", cudaGetErrorString(cudaGetLastError())); return AIRFE_ERR_CUDA; }
+  for (int p = 0; p < pairs; ++p) {
+    int n = c->h_mcount[p];
+    if (zero_mask && zero_mask[p]) n = 0;      // features0.cols() < 1 || features1.cols() < 1 -> return 0 (point_matcher.cc:53-55)
+    if (n > match_cap) n = match_cap;
+    n_match[p] = n;
+    for (int k = 0; k < n; ++k) {
+      idx0[(size_t)p * match_cap + k] = c->h_midx[((size_t)p * cap + k) * 2];
+      idx1[(size_t)p * match_cap + k] = c->h_midx[((size_t)p * cap + k) * 2 + 1];
+      score[(size_t)p * match_cap + k] = c->h_mscore[(size_t)p * cap + k];
+    }
+  }
+  return AIRFE_OK;
+}
+
+int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1,
+                      int feat_cap, int* idx0, int* idx1, float* score, int match_cap, int* n_match) {
+  if (!c || !feat0 || !feat1 || !n0 || !n1 || !idx0 || !idx1 || !score || !n_match) { set_error("null argument"); return AIRFE_ERR_INVALID; }
+  if (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
+  if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return AIRFE_ERR_INVALID; }
+  cudaSetDevice(c->device);
+  const int cap = c->lg->cap();
+  std::vector<int> zero(pairs, 0);
+  for (int p = 0; p < pairs; ++p) {
+    if (n0[p] > cap || n1[p] > cap || n0[p] > feat_cap || n1[p] > feat_cap) { set_error("pair %d: %d/%d keypoints exceed capacity %d", p, n0[p], n1[p], cap); return AIRFE_ERR_CAPACITY; }
+    zero[p] = (n0[p] < 1 || n1[p] < 1);
+    c->h_mn[2 * p] = n0[p];
+    c->h_mn[2 * p + 1] = n1[p];
+    memcpy(c->h_mfeat + (size_t)(2 * p) * kKpCap * 259, feat0 + (size_t)p * feat_cap * 259, (size_t)n0[p] * 259 * 4);
+    memcpy(c->h_mfeat + (size_t)(2 * p + 1) * kKpCap * 259, feat1 + (size_t)p * feat_cap * 259, (size_t)n1[p] * 259 * 4);
+  }
+  cudaStream_t st = c->stream;
+  for (int s = 0; s < 2 * pairs; ++s)
+    if (c->h_mn[s] > 0)
+      cudaMemcpyAsync(c->d_mfeat + (size_t)s * kKpCap * 259, c->h_mfeat + (size_t)s * kKpCap * 259, (size_t)c->h_mn[s] * 259 * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(c->d_mn, c->h_mn, 8 * pairs, cudaMemcpyHostToDevice, st);
+  if (!c->lg->run(c->d_mfeat, c->d_mn, kKpCap, pairs, getenv("AIRFE_DEBUG_DENSE") != nullptr, st)) return AIRFE_ERR_CUDA;
+  return fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, zero.data());
+}
+
+int airfe_stereo_device(airfe_ctx* c, int net, int matcher, int pairs, const void* d_images, int w, int h, int stride, long long img_stride,
+                        int lines, int junctions) {
+  Detector* d = pick(c, net);
+  if (!d) return AIRFE_ERR_INVALID;
+  if (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
+  if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return AIRFE_ERR_INVALID; }
+  cudaSetDevice(c->device);
+  if (!d->run((const uint8_t*)d_images, 2 * pairs, w, h, stride, img_stride, lines != 0, junctions != 0, c->stream)) return AIRFE_ERR_CUDA;
+  const DetectOutputs& o = d->out();
+  if (!c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream)) return AIRFE_ERR_CUDA;
+  return AIRFE_OK;
+}
+
+long long airfe_profile_stereo(airfe_ctx* c, int net, int matcher, int pairs, const void* d_images, int w, int h, int stride, long long img_stride,
+                               int lines, int junctions, char* out, long long cap) {
+  cudaStreamSynchronize(c->stream);
+  profiler().begin();
+  int rc = airfe_stereo_device(c, net, matcher, pairs, d_images, w, h, stride, img_stride, lines, junctions);
+  profiler().finish();
+  if (rc != AIRFE_OK) return rc;
+  long long off = 0;
+  for (auto& r : profiler().recs) {
+    char line[256];
+    int n = snprintf(line, sizeof(line), "%s\t%.0f\t%.6f\n", r.name.c_str(), r.flops, r.ms);
+    if (off + n >= cap) break;
+    memcpy(out + off, line, n);
+    off += n;
+  }
+  if (off < cap) out[off] = 0;
+  return off;
+}
+
+int airfe_stereo_cost(airfe_ctx* c, int net, int matcher, int pairs, int lines, double* tc_flops, int* launches) {
+  Detector* d = pick(c, net);
+  if (!d || !c->lg) { set_error("networks not enabled"); return AIRFE_ERR_INVALID; }
+  if (tc_flops) *tc_flops = d->tc_flops(2 * pairs, lines != 0) + c->lg->tc_flops(pairs);
+  if (launches) *launches = d->launches(2 * pairs, lines != 0) + c->lg->launches(pairs) + 12;
+  return AIRFE_OK;
+}
+
+int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pairs, const uint8_t* left, const uint8_t* right, int w, int h,
+                                    int stride, long long img_stride, float* feat, int feat_cap, int* n_feat, double* lines, int line_cap,
+                                    int* n_lines, float* junc, int junc_cap, int* n_junc, int* idx0, int* idx1, float* score, int match_cap,
+                                    int* n_match) {
+  if (!c || !left || !right || !feat || !n_feat || !idx0 || !idx1 || !score || !n_match) { set_error("null argument"); return AIRFE_ERR_INVALID; }
+  if (w <= 1 || h <= 1 || stride < w) { set_error("empty image"); return AIRFE_ERR_INVALID; }
+  Detector* d = pick(c, net);
+  if (!d) return AIRFE_ERR_INVALID;
+  if (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
+  if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return AIRFE_ERR_INVALID; }
+  if ((lines || junc) && net != AIRFE_NET_PLNET) { set_error("lines / junctions need the PLNet network"); return AIRFE_ERR_INVALID; }
+  cudaSetDevice(c->device);
+  const size_t one = (size_t)h * stride, need = one * 2 * pairs;
+  if (need > c->h_img_bytes) {
+    if (c->h_img) cudaFreeHost(c->h_img);
+    if (c->d_img) cudaFree(c->d_img);
+    if (cudaMallocHost(&c->h_img, need) != cudaSuccess || cudaMalloc(&c->d_img, need) != cudaSuccess) { set_error("staging allocation failed"); return AIRFE_ERR_CUDA; }
+    c->h_img_bytes = c->d_img_bytes = need;
+  }
+  for (int p = 0; p < pairs; ++p) {
+    memcpy(c->h_img + one * (2 * p), left + (size_t)img_stride * p, one);
+    memcpy(c->h_img + one * (2 * p + 1), right + (size_t)img_stride * p, one);
+  }
+  cudaStream_t st = c->stream;
+  cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st);
+  if (!d->run(c->d_img, 2 * pairs, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return AIRFE_ERR_CUDA;
+  const DetectOutputs& o = d->out();
+  if (!c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, st)) return AIRFE_ERR_CUDA;
+  // results: features of 2*pairs images, lines, left junctions, matches
+  const int B = 2 * c->cfg.max_batch, S = 2 * pairs;
+  int* hc = c->h_counts;
+  cudaMemcpyAsync(hc, o.n_feat, 4 * S, cudaMemcpyDeviceToHost, st);
+  if (lines) cudaMemcpyAsync(hc + B, o.n_lines, 4 * S, cudaMemcpyDeviceToHost, st);
+  if (junc) cudaMemcpyAsync(hc + 2 * B, o.n_junc, 4 * S, cudaMemcpyDeviceToHost, st);
+  const int kmax = c->cfg.max_keypoints;
+  for (int i = 0; i < S; ++i)
+    cudaMemcpyAsync(c->h_feat + (size_t)i * kKpCap * 259, o.feat + (size_t)i * kKpCap * 259, (size_t)kmax * 259 * 4, cudaMemcpyDeviceToHost, st);
+  int rc = fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, nullptr);   // synchronises the stream
+  if (rc != AIRFE_OK) return rc;
+  for (int i = 0; i < S; ++i) {
+    const int n = hc[i] < feat_cap ? hc[i] : feat_cap;
+    n_feat[i] = n;
+    memcpy(feat + (size_t)i * feat_cap * 259, c->h_feat + (size_t)i * kKpCap * 259, (size_t)n * 259 * 4);
+  }
+  for (int p = 0; p < pairs; ++p)
+    if (hc[2 * p] < 1 || hc[2 * p + 1] < 1) n_match[p] = 0;
+  if (lines) {
+    const double ws = (double)((float)w / 512.f), hs = (double)((float)h / 512.f);
+    for (int i = 0; i < S; ++i) {
+      const int n = hc[B + i] < line_cap ? hc[B + i] : line_cap;
+      n_lines[i] = n;
+      if (n) cudaMemcpyAsync(c->h_lines + (size_t)i * kLineCap * 4, o.lines + (size_t)i * kLineCap * 4, (size_t)n * 16, cudaMemcpyDeviceToHost, st);
+    }
+    if (junc)
+      for (int p = 0; p < pairs; ++p) {
+        const int n = hc[2 * B + 2 * p] < junc_cap ? hc[2 * B + 2 * p] : junc_cap;
+        n_junc[p] = n;
+        if (n) cudaMemcpyAsync(c->h_junc + (size_t)p * kKpCap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)n * 259 * 4, cudaMemcpyDeviceToHost, st);
+      }
+    cudaStreamSynchronize(st);
+    for (int i = 0; i < S; ++i) {
+      const float* l = c->h_lines + (size_t)i * kLineCap * 4;
+      double* dl = lines + (size_t)i * line_cap * 4;
+      for (int k = 0; k < n_lines[i]; ++k) {
+        dl[k * 4 + 0] = (double)l[k * 4 + 0] * ws; dl[k * 4 + 1] = (double)l[k * 4 + 1] * hs;
+        dl[k * 4 + 2] = (double)l[k * 4 + 2] * ws; dl[k * 4 + 3] = (double)l[k * 4 + 3] * hs;
+      }
+    }
+    if (junc)
+      for (int p = 0; p < pairs; ++p) memcpy(junc + (size_t)p * junc_cap * 259, c->h_junc + (size_t)p * kKpCap * 259, (size_t)n_junc[p] * 259 * 4);
+  }
+  return AIRFE_OK;
+}
+
 long long airfe_debug_read(airfe_ctx* c, int net, const char* name, int index, void* dst, long long dst_bytes) {
+  if (net == 100) {   // LightGlue taps: "lg_scores" = dense log-assignment [cap][cap] of pair `index` (needs AIRFE_DEBUG_DENSE=1)
+    if (!c->lg) { set_error("lightglue not enabled"); return AIRFE_ERR_INVALID; }
+    const long long cap = c->lg->cap(), nb = cap * cap * 4;
+    if (nb > dst_bytes) { set_error("tap needs %lld bytes", nb); return AIRFE_ERR_CAPACITY; }
+    cudaStreamSynchronize(c->stream);
+    const float* src = !strcmp(name, "lg_scores") ? c->lg->out().dense + (size_t)index * cap * cap : nullptr;
+    if (!src) { set_error("unknown tap %s", name); return AIRFE_ERR_INVALID; }
+    if (cudaMemcpy(dst, src, (size_t)nb, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("debug read failed"); return AIRFE_ERR_CUDA; }
+    return nb;
+  }
   Detector* d = pick(c, net);
   if (!d) return AIRFE_ERR_INVALID;
   auto it = d->taps.find(name);

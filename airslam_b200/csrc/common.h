@@ -34,16 +34,22 @@ struct TcGemmDesc {
   const void* bw = nullptr;
   int k_total = 0, n_rows = 0;
   long long bw_sn = 0, bw_sbatch = 0;
-  int b_batches = 0, b_mn_major = 0;
+  int b_batches = 0, b_mn_major = 0;   // b_batches > 1: Bw has a batch dim (stride bw_sbatch) indexed by the tile batch
+  int b_heads = 0; long long bw_shead = 0; // with b_batches: Bw head dim (indexed by the tile's y) and its stride
+  int b_batch_xor = 0;
   int taps = 1, c_in_pad = 64;
   int block_n = 64;
   const float* bias = nullptr;
+  float scale = 1.f; int scale_cols = 0;
+  const float* resid = nullptr;
+  void* out2 = nullptr; long long out2_sb = 0, out2_sy = 0, out2_sx = 0;
   int relu = 0, out_f32 = 0;
   void* out = nullptr;
   long long out_sb = 0, out_sy = 0, out_sx = 0;
   int n_valid = 0;
   int tw = 128, th = 1, tb = 1;
   const int* dyn_w = nullptr;
+  int dyn_w_stride = 1;
 };
 
 }  // namespace airfe

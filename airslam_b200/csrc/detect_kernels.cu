@@ -62,8 +62,9 @@ void launch_resize_u8_to_f16(const uint8_t* src, int src_w, int src_h, int src_s
 // First layer: 3x3, 1 -> 64 channels.  K = 9 is no tensor-core shape; the layer is bound by its 32 MiB/frame NHWC store.
 // Thread = (pixel, group of 8 output channels): consecutive threads write consecutive 16-byte vectors.
 // =====================================================================================================================
-__global__ void conv1a_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
-                              __half* __restrict__ out, int H, int W, long long total) {
+constexpr int kC1Px = 8;   // pixels along x per thread: the 72 weights of a thread's 8 channels live in registers
+__global__ void __launch_bounds__(256) conv1a_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
+                                                     __half* __restrict__ out, int H, int W, long long total) {
   __shared__ float sw[64 * 9];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 576; i += blockDim.x) sw[i] = __half2float(w[i]);
@@ -72,39 +73,54 @@ __global__ void conv1a_kernel(const __half* __restrict__ x, const __half* __rest
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   const int cg = (int)(gid & 7);
-  const long long pix = gid >> 3;
-  const int xx = (int)(pix % W);
-  const int yy = (int)((pix / W) % H);
-  const long long img = pix / ((long long)W * H);
+  const long long grp = gid >> 3;                 // group of kC1Px pixels
+  const int gpr = W / kC1Px;                      // groups per row
+  const int x0 = (int)(grp % gpr) * kC1Px;
+  const int yy = (int)((grp / gpr) % H);
+  const long long img = grp / ((long long)gpr * H);
   const __half* xi = x + img * (long long)W * H;
-  float in[9];
+  float wr[8][9], br[8];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+  for (int j = 0; j < 8; ++j) {
+    br[j] = sb[cg * 8 + j];
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int y2 = yy + ky - 1, x2 = xx + kx - 1;
-      in[ky * 3 + kx] = (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? __half2float(xi[(long long)y2 * W + x2]) : 0.f;
-    }
-  uint32_t packed[4];
-#pragma unroll
-  for (int j = 0; j < 8; j += 2) {
-    float acc[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = cg * 8 + j + u;
-      float a = 0.f;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) a = fmaf(in[k], sw[c * 9 + k], a);
-      acc[u] = fmaxf(a + sb[c], 0.f);
-    }
-    __half2 h2 = __floats2half2_rn(acc[0], acc[1]);
-    packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+    for (int k = 0; k < 9; ++k) wr[j][k] = sw[(cg * 8 + j) * 9 + k];
   }
-  *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  float in[3][kC1Px + 2];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int y2 = yy + ky - 1;
+#pragma unroll
+    for (int c = 0; c < kC1Px + 2; ++c) {
+      const int x2 = x0 + c - 1;
+      in[ky][c] = (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? __half2float(xi[(long long)y2 * W + x2]) : 0.f;
+    }
+  }
+  __half* o = out + ((img * H + yy) * (long long)W + x0) * 64 + cg * 8;
+#pragma unroll
+  for (int px = 0; px < kC1Px; ++px) {
+    uint32_t packed[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      float acc[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float a = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) a = fmaf(in[ky][px + kx], wr[j + u][ky * 3 + kx], a);
+        acc[u] = fmaxf(a + br[j + u], 0.f);
+      }
+      __half2 h2 = __floats2half2_rn(acc[0], acc[1]);
+      packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(o + (long long)px * 64) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
 }
 
 void launch_conv1a(const __half* x, const __half* w, const float* bias, __half* out, int batch, int H, int W, cudaStream_t st) {
-  const long long total = (long long)batch * H * W * 8;
+  const long long total = (long long)batch * H * (W / kC1Px) * 8;
   conv1a_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, w, bias, out, H, W, total);
 }
 

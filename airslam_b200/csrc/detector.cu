@@ -220,18 +220,18 @@ bool Detector::build_ops(int B) {
   const bool lines = plnet_ && cfg_.enable_lines;
   auto pool = [&](OpList* ol, const Act& in, const Act& out) {
     const Act i = in, o = out;
-    ol->ops.push_back([=](cudaStream_t st) { launch_maxpool2((const __half*)i.p, i.C, i.H, i.W, B, i.ps, (__half*)o.p, o.ps, st); return true; });
+    ol->push("maxpool2", 0, [=](cudaStream_t st) { launch_maxpool2((const __half*)i.p, i.C, i.H, i.W, B, i.ps, (__half*)o.p, o.ps, st); return true; });
     ol->launches++;
   };
   auto up = [&](OpList* ol, const Act& in, const Act& out) {
     const Act i = in, o = out;
-    ol->ops.push_back([=](cudaStream_t st) { launch_upsample2((const __half*)i.p, i.C, i.H, i.W, B, i.ps, (__half*)o.p, o.ps, st); return true; });
+    ol->push("upsample2", 0, [=](cudaStream_t st) { launch_upsample2((const __half*)i.p, i.C, i.H, i.W, B, i.ps, (__half*)o.p, o.ps, st); return true; });
     ol->launches++;
   };
   // SuperPoint trunk + heads (G1; G2 /backbone/point_detector/*)
   {
     const __half* x = x16_; const __half* w = w_conv1a_; const float* bb = b_conv1a_; __half* o = (__half*)a1_.p;
-    t.ops.push_back([=](cudaStream_t st) { launch_conv1a(x, w, bb, o, B, 512, 512, st); return true; });
+    t.push("conv1a 1->64", 0, [=](cudaStream_t st) { launch_conv1a(x, w, bb, o, B, 512, 512, st); return true; });
     t.launches++;
   }
   const Act r3 = cat2_.slice(32, 64), r5 = cat3_.slice(128, 128);
@@ -247,7 +247,7 @@ bool Detector::build_ops(int B) {
   if (!add_dense(&t, pd_.slice(256, 256), wDb_, descraw_, B, false)) return false;
   {
     const float* lg = (const float*)logits_.p; float* heat = heat_; float* sc = scores_; uint8_t* ma = mask_a_; uint8_t* mb = mask_b_;
-    t.ops.push_back([=](cudaStream_t st) { launch_softmax_d2s(lg, 80, heat, B, st); launch_simple_nms(heat, sc, ma, mb, B, st); return true; });
+    t.push("softmax_d2s+nms", 0, [=](cudaStream_t st) { launch_softmax_d2s(lg, 80, heat, B, st); launch_simple_nms(heat, sc, ma, mb, B, st); return true; });
     t.launches += 4;
   }
   trunk_ops_[B] = std::move(t);
@@ -297,25 +297,31 @@ bool Detector::run(const uint8_t* d_images, int B, int w, int h, int stride, lon
   if (B < 1 || B > cfg_.max_batch) { set_error("batch %d outside [1,%d]", B, cfg_.max_batch); return false; }
   lines = lines && plnet_ && cfg_.enable_lines;
   if (!ensure_tables(w, h) || !build_ops(B)) return false;
-  launch_resize_u8_to_f16(d_images, w, h, stride, img_stride, B, tables_[{w, h}], x16_, nullptr, st);
+  timed("resize", st, [&] { launch_resize_u8_to_f16(d_images, w, h, stride, img_stride, B, tables_[{w, h}], x16_, nullptr, st); });
   if (!trunk_ops_[B].run(st)) return false;
   const float w_scale = (float)w / 512.f, h_scale = (float)h / 512.f;
-  launch_select_keypoints(scores_, B, cfg_.keypoint_threshold, cfg_.remove_borders, cfg_.max_keypoints, cand_, kCandCap, cand_count_, kp_,
-                          kKpCap, out_.n_feat, st);
-  launch_sample_descriptors(desc_raw_, kp_, out_.n_feat, kKpCap, B, w_scale, h_scale, out_.feat, st);
+  timed("select_keypoints", st, [&] {
+    launch_select_keypoints(scores_, B, cfg_.keypoint_threshold, cfg_.remove_borders, cfg_.max_keypoints, cand_, kCandCap, cand_count_, kp_,
+                            kKpCap, out_.n_feat, st);
+  });
+  timed("sample_descriptors", st, [&] { launch_sample_descriptors(desc_raw_, kp_, out_.n_feat, kKpCap, B, w_scale, h_scale, out_.feat, st); });
   if (lines) {
     if (!line_ops_[B].run(st)) return false;
     const float* heads = (const float*)heads9_o_.p;
-    launch_hafm_decode(heads, 16, lines_pred_, jloc_, B, st);
+    timed("hafm_decode", st, [&] { launch_hafm_decode(heads, 16, lines_pred_, jloc_, B, st); });
     // scratch: peaks list reuses cand_ (ints, >= 16384 per image), is_peak reuses mask_b_
-    launch_junctions(jloc_, heads, 16, cand_, cand_count_, mask_b_, juncs_, junc_idx_, B, st);
-    launch_association(lines_pred_, juncs_, imin_, imax_, iskeep_, pair_table_, uid_pairs_, uid_first_, n_unique_, kLineCap, B, st);
-    launch_loi_gather((const float*)loi_o_.p, 128, (const float*)thinaux_o_.p, 8, juncs_, lines_pred_, uid_pairs_, uid_first_, n_unique_, kLineCap,
-                      s1_tspan_, (__half*)feat496_.p, adj_, B, st);
+    timed("junction_topk", st, [&] { launch_junctions(jloc_, heads, 16, cand_, cand_count_, mask_b_, juncs_, junc_idx_, B, st); });
+    timed("association+unique", st, [&] { launch_association(lines_pred_, juncs_, imin_, imax_, iskeep_, pair_table_, uid_pairs_, uid_first_, n_unique_, kLineCap, B, st); });
+    timed("loi_gather", st, [&] {
+      launch_loi_gather((const float*)loi_o_.p, 128, (const float*)thinaux_o_.p, 8, juncs_, lines_pred_, uid_pairs_, uid_first_, n_unique_, kLineCap,
+                        s1_tspan_, (__half*)feat496_.p, adj_, B, st);
+    });
     if (!mlp_ops_[B].run(st)) return false;      // stage-1 MLP on tensor cores; row counts are read on the device
+    timed("line_head+accept", st, [&] {
     launch_line_head((const float*)mlp_c_.p, (const float*)mlp_r_.p, s1_head_w_, s1_head_b_, n_unique_, kLineCap, line_score_, B, st);
     launch_line_accept(adj_, line_score_, n_unique_, kLineCap, cfg_.line_threshold, cfg_.line_length_threshold,
                        cfg_.remove_borders > 0 ? cfg_.remove_borders : 0, junc_map_, out_.lines, out_.n_lines, B, st);
+    });
     if (junctions) {
       launch_junction_scan(junc_map_, scores_, cfg_.remove_borders > 0 ? cfg_.remove_borders : 0, jkp_, kKpCap, jkp_count_, B, st);
       launch_sample_descriptors(desc_raw_, jkp_, jkp_count_, kKpCap, B, w_scale, h_scale, out_.junc, st);

@@ -70,7 +70,7 @@ void* Arena::alloc(size_t bytes, size_t align) {
 
 // ---- packing --------------------------------------------------------------------------------------------------------------
 bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in_total, Arena* arena, DenseW* out,
-                const std::vector<int>* in_perm) {
+                const std::vector<int>* in_perm, const std::vector<int>* out_perm) {
   int n_rows = 0, taps = 0;
   for (auto& s : srcs) {
     const WTensor* t = wf.find(s.weight);
@@ -95,12 +95,13 @@ bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in
         for (int tp = 0; tp < taps; ++tp) {
           int cdst = s.in_offset + c;
           if (in_perm) cdst = (*in_perm)[cdst];
-          hw[(size_t)(row0 + r) * k_total + (size_t)tp * c_pad + cdst] = src[((size_t)r * ci + c) * taps + tp];
+          const int rdst = out_perm ? (*out_perm)[row0 + r] : row0 + r;
+          hw[(size_t)rdst * k_total + (size_t)tp * c_pad + cdst] = src[((size_t)r * ci + c) * taps + tp];
         }
     if (!s.bias.empty()) {
       std::vector<float> b;
       if (!wf.get_f32(s.bias, &b)) return false;
-      for (int r = 0; r < o; ++r) hb[row0 + r] = b[r];
+      for (int r = 0; r < o; ++r) hb[out_perm ? (*out_perm)[row0 + r] : row0 + r] = b[r];
     }
     row0 += o;
   }
@@ -113,9 +114,45 @@ bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in
   return true;
 }
 
+// ---- profiler ---------------------------------------------------------------------------------------------------------------
+Profiler& profiler() { static Profiler p; return p; }
+void Profiler::record(const std::string& name, double fl, cudaStream_t st, const std::function<bool(cudaStream_t)>& fn, bool* ok) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, st);
+  *ok = fn(st);
+  cudaEventRecord(b, st);
+  OpProfile r;
+  r.name = name; r.flops = fl;
+  recs.push_back(r);
+  evs.push_back({a, b});
+}
+void Profiler::finish() {
+  for (size_t i = 0; i < evs.size(); ++i) {
+    cudaEventSynchronize(evs[i].second);
+    cudaEventElapsedTime(&recs[i].ms, evs[i].first, evs[i].second);
+    cudaEventDestroy(evs[i].first);
+    cudaEventDestroy(evs[i].second);
+  }
+  evs.clear();
+  on = false;
+}
+
 // ---- op construction -----------------------------------------------------------------------------------------------------
+bool add_gemm(OpList* ol, const TcGemmDesc& d, double flops) {
+  TcGemmPlan plan;
+  if (!tc_gemm_plan(d, &plan)) return false;
+  ol->tc_flops += flops;
+  ol->launches += 1;
+  char nm[160];
+  snprintf(nm, sizeof(nm), "tc_gemm attn M=%dx%dx%d K=%d N=%d%s", d.W, d.H, d.B, d.c_in_pad, d.n_valid, d.b_mn_major ? " (P.V)" : "");
+  ol->push(nm, flops, [plan](cudaStream_t st) { return tc_gemm_launch(plan, st); });
+  return true;
+}
+
 bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int batch, bool relu, int n_valid, int block_n,
-               const int* dyn_rows) {
+               const int* dyn_rows, float scale, const float* resid, const Act* out2) {
   TcGemmDesc d;
   d.a = in.p; d.a_C = in.C; d.W = in.W; d.H = in.H; d.B = batch;
   d.a_sx = in.ps; d.a_sy = in.ps * in.W; d.a_sb = in.ps * in.W * in.H;
@@ -125,7 +162,8 @@ bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int b
   d.n_valid = n_valid;
   if (!block_n) {
     const int n16 = (n_valid + 15) / 16 * 16;
-    if (n16 <= 256) block_n = n16;
+    if (in.H == 1 && n16 >= 256 && n16 % 128 == 0) block_n = 128;   // row GEMMs of the matchers: more CTAs beat wider tiles
+    else if (n16 <= 256) block_n = n16;
     else if (n16 % 256 == 0) block_n = 256;
     else if (n16 % 160 == 0) block_n = 160;
     else if (n16 % 128 == 0) block_n = 128;
@@ -138,12 +176,18 @@ bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int b
   else if (in.W >= 16) { d.tw = 16; d.th = 8; d.tb = 1; }
   else { d.tw = 8; d.th = 8; d.tb = 2; }
   d.dyn_w = dyn_rows;
+  if (scale != 1.f) { d.scale = scale; d.scale_cols = n_valid; }
+  d.resid = resid;
+  if (out2) { d.out2 = out2->p; d.out2_sx = out2->ps; d.out2_sy = out2->ps * out2->W; d.out2_sb = out2->ps * out2->W * out2->H; }
   if (in.C > w.c_in_pad || in.C < w.c_in) { set_error("add_dense: activation has %d channels, weights expect %d", in.C, w.c_in); return false; }
   TcGemmPlan plan;
   if (!tc_gemm_plan(d, &plan)) return false;
-  ol->tc_flops += 2.0 * (double)in.W * in.H * batch * (double)n_valid * w.taps * w.c_in;
+  const double fl = 2.0 * (double)in.W * in.H * batch * (double)n_valid * w.taps * w.c_in;
+  ol->tc_flops += fl;
   ol->launches += 1;
-  ol->ops.push_back([plan](cudaStream_t st) { return tc_gemm_launch(plan, st); });
+  char nm[160];
+  snprintf(nm, sizeof(nm), "tc_gemm %s %d->%d @%dx%dx%d", w.taps == 9 ? "conv3x3" : (in.H == 1 ? "linear" : "conv1x1"), w.c_in, n_valid, in.W, in.H, batch);
+  ol->push(nm, fl, [plan](cudaStream_t st) { return tc_gemm_launch(plan, st); });
   return true;
 }
 

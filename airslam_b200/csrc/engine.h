@@ -70,16 +70,54 @@ struct Act {
 };
 
 using Op = std::function<bool(cudaStream_t)>;
+struct OpProfile {            // filled when profiling is on (airfe_profile_begin): one record per executed op
+  std::string name;
+  double flops = 0;           // algorithmic tensor-core FLOPs (0 for non-GEMM ops)
+  float ms = 0;
+};
+struct Profiler {
+  bool on = false;
+  std::vector<OpProfile> recs;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
+  void begin() { on = true; recs.clear(); }
+  void record(const std::string& name, double flops, cudaStream_t st, const std::function<bool(cudaStream_t)>& fn, bool* ok);
+  void finish();              // synchronises and converts events to milliseconds
+};
+Profiler& profiler();
+
 struct OpList {
   std::vector<Op> ops;
+  std::vector<std::string> names;   // parallel to ops (tensor-core ops carry their shape in the name)
+  std::vector<double> flops;        // parallel to ops
   double tc_flops = 0;   // algorithmic FLOPs of the tensor-core ops in this list
   int launches = 0;
+  void push(const std::string& name, double fl, Op op) { ops.push_back(std::move(op)); names.push_back(name); flops.push_back(fl); }
   bool run(cudaStream_t st) const {
-    for (auto& o : ops)
-      if (!o(st)) return false;
+    Profiler& pr = profiler();
+    for (size_t i = 0; i < ops.size(); ++i) {
+      if (pr.on) {
+        bool ok = true;
+        pr.record(i < names.size() ? names[i] : "op", i < flops.size() ? flops[i] : 0.0, st, ops[i], &ok);
+        if (!ok) return false;
+      } else if (!ops[i](st)) {
+        return false;
+      }
+    }
     return true;
   }
 };
+
+// Run `f()` (a group of plain kernel launches on `st`), recording it as one profiled op when profiling is on.
+template <class F>
+inline void timed(const char* name, cudaStream_t st, F&& f) {
+  Profiler& pr = profiler();
+  if (pr.on) {
+    bool ok = true;
+    pr.record(name, 0.0, st, [&](cudaStream_t) { f(); return true; }, &ok);
+  } else {
+    f();
+  }
+}
 
 // Pack helpers (host): conv OIHW / linear [out,in] fp16 -> tap-major K-major rows, several sources concatenated along N.
 struct PackSrc {
@@ -87,10 +125,12 @@ struct PackSrc {
   int in_offset = 0;         // place this source's input channels at [in_offset, in_offset + c_in) of the packed K (block-diagonal / concat remap)
 };
 bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in_total, Arena* arena, DenseW* out,
-                const std::vector<int>* in_perm = nullptr);
+                const std::vector<int>* in_perm = nullptr, const std::vector<int>* out_perm = nullptr /* old row -> new row */);
 
 // Append a tcgen05 conv / GEMM op.
 bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int batch, bool relu, int n_valid = -1, int block_n = 0,
-               const int* dyn_rows = nullptr);
+               const int* dyn_rows = nullptr, float scale = 1.f, const float* resid = nullptr, const Act* out2 = nullptr);
+// Append a raw tcgen05 GEMM described by `d` (attention products).
+bool add_gemm(OpList* ol, const TcGemmDesc& d, double flops);
 
 }  // namespace airfe

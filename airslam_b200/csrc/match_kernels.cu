@@ -1,0 +1,317 @@
+// Hand-written sm_100a kernels for the matchers' non-GEMM stages.
+// Data layout: "slot" s = 2 * pair + side owns rows [s*CAP, s*CAP + n[s]) of every [rows, C] matrix; all kernels read the
+// per-slot keypoint counts n[] from device memory, so nothing here depends on host-side knowledge of N.
+#include "match_kernels.h"
+#include <math.h>
+
+namespace airfe {
+
+__device__ __forceinline__ float warp_sum_(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- K13: unpack 259xN host features -> normalised keypoints, fp32 state x, fp16 operand copy, rotary table ---------------
+// NormalizeKeypoints (src/point_matcher.cc:39-48): (x - width/2) * L_inv with integer width/2; L_inv = float(1.0/max(w,h)*scale).
+__global__ void lg_prepare_kernel(const float* __restrict__ feat, const int* __restrict__ n, int cap, int feat_cap, int width, int height,
+                                  float l_inv, const __half* __restrict__ wr /*[32][2]*/, float* __restrict__ x, __half* __restrict__ cat16,
+                                  float* __restrict__ rot /*[slots][cap][64] cos | sin interleaved as (cos,sin) per freq*/) {
+  const int s = blockIdx.y;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n[s]) return;
+  const float* f = feat + ((long long)s * feat_cap + r) * 259;
+  const float kx = __fmul_rn(__fsub_rn(f[1], (float)(width / 2)), l_inv);
+  const float ky = __fmul_rn(__fsub_rn(f[2], (float)(height / 2)), l_inv);
+  const long long row = (long long)s * cap + r;
+  // descriptors: fp32 residual stream + fp16 operand copy (cols 0..255 of the [x | msg] concat buffer)
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float v = f[3 + lane * 8 + e];
+    x[row * 256 + lane * 8 + e] = v;
+    cat16[row * 512 + lane * 8 + e] = __float2half_rn(v);
+  }
+  // rotary: freq f_j = kpt . Wr[j] (operands rounded to fp16, fp32 accumulate), j = lane
+  const float kxr = __half2float(__float2half_rn(kx)), kyr = __half2float(__float2half_rn(ky));
+  const float fr = kxr * __half2float(wr[lane * 2]) + kyr * __half2float(wr[lane * 2 + 1]);
+  rot[row * 64 + lane * 2] = cosf(fr);
+  rot[row * 64 + lane * 2 + 1] = sinf(fr);
+}
+
+// ---- K14a: rotary + 64^-1/4 scaling of q,k ; v passthrough.  qkv fp32 [rows][768] = [q | k | v] (weights pre-permuted) ------
+__global__ void lg_rotary_kernel(const float* __restrict__ qkv, const float* __restrict__ rot, const int* __restrict__ n, int cap,
+                                 __half* __restrict__ q16, __half* __restrict__ k16, __half* __restrict__ v16, float sc) {
+  const int s = blockIdx.y;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n[s]) return;
+  const long long row = (long long)s * cap + r;
+  const float c = rot[row * 64 + lane * 2], sn = rot[row * 64 + lane * 2 + 1];   // pair index j = lane within a head
+  const float* in = qkv + row * 768;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const int o = h * 64 + lane * 2;
+    const float q0 = in[o], q1 = in[o + 1];
+    const float k0 = in[256 + o], k1 = in[256 + o + 1];
+    // q*cos + rot_half(q)*sin with rot_half(x0,x1) = (-x1, x0)
+    const float rq0 = (q0 * c + (-q1) * sn) * sc, rq1 = (q1 * c + q0 * sn) * sc;
+    const float rk0 = (k0 * c + (-k1) * sn) * sc, rk1 = (k1 * c + k0 * sn) * sc;
+    *reinterpret_cast<__half2*>(q16 + row * 256 + o) = __floats2half2_rn(rq0, rq1);
+    *reinterpret_cast<__half2*>(k16 + row * 256 + o) = __floats2half2_rn(rk0, rk1);
+    *reinterpret_cast<__half2*>(v16 + row * 256 + o) = __floats2half2_rn(in[512 + o], in[512 + o + 1]);
+  }
+}
+
+// ---- K14b: row softmax of attention scores S fp32 [slot][head][cap][cap] -> P fp16, zero beyond the valid columns ------------
+// One warp per row.  Valid columns = n[slot ^ col_xor] (cross attention looks at the partner's keypoints).
+__global__ void softmax_rows_kernel(const float* __restrict__ S, __half* __restrict__ P, const int* __restrict__ n, int cap, int col_xor) {
+  const int s = blockIdx.z, h = blockIdx.y;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n[s]) return;
+  const int nc = n[s ^ col_xor];
+  const long long base = (((long long)s * 4 + h) * cap + r) * cap;
+  const float* in = S + base;
+  float m = -INFINITY;
+  for (int j = lane; j < nc; j += 32) m = fmaxf(m, in[j]);
+  m = warp_max_(m);
+  float sum = 0.f;
+  for (int j = lane; j < nc; j += 32) sum += expf(in[j] - m);
+  sum = warp_sum_(sum);
+  const float inv = 1.f / sum;
+  __half* out = P + base;
+  const int ncp = (nc + 63) / 64 * 64;
+  for (int j = lane; j < ncp; j += 32) out[j] = __float2half_rn(j < nc ? expf(in[j] - m) * inv : 0.f);
+}
+
+// ---- FFN middle: LayerNorm(512, eps 1e-5) + exact GELU, fp32 in -> fp16 operand out.  One warp per row. -----------------------
+__global__ void ln_gelu_kernel(const float* __restrict__ h, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const int* __restrict__ n, int cap, __half* __restrict__ out) {
+  const int s = blockIdx.y;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n[s]) return;
+  const long long row = (long long)s * cap + r;
+  const float* in = h + row * 512;
+  float v[16];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 a = *reinterpret_cast<const float4*>(in + i * 128 + lane * 4);
+    v[i * 4] = a.x; v[i * 4 + 1] = a.y; v[i * 4 + 2] = a.z; v[i * 4 + 3] = a.w;
+    sum += a.x + a.y + a.z + a.w;
+  }
+  const float mean = warp_sum_(sum) * (1.f / 512.f);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; var += d * d; }
+  var = warp_sum_(var) * (1.f / 512.f);
+  const float rstd = 1.f / sqrtf(var + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = i * 128 + lane * 4 + e;
+      const float y = (v[i * 4 + e] - mean) * rstd * gamma[c] + beta[c];
+      o[e] = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+    }
+    __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+    *reinterpret_cast<uint2*>(out + row * 512 + i * 128 + lane * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  }
+}
+
+// ---- K15: log assignment.  sim fp32 [pair][cap][cap] (rows = image 0, cols = image 1); z = matchability logit ------------------
+__global__ void matchability_kernel(const float* __restrict__ x, const __half* __restrict__ w /*[256]*/, float bias, const int* __restrict__ n,
+                                    int cap, float* __restrict__ logsig) {
+  const int s = blockIdx.y;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n[s]) return;
+  const long long row = (long long)s * cap + r;
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc += __half2float(__float2half_rn(x[row * 256 + lane * 8 + e])) * __half2float(w[lane * 8 + e]);
+  acc = warp_sum_(acc) + bias;
+  // logsigmoid(z) = min(z,0) - log1p(exp(-|z|))
+  if (lane == 0) logsig[row] = fminf(acc, 0.f) - log1pf(expf(-fabsf(acc)));
+}
+
+__global__ void row_lse_kernel(const float* __restrict__ sim, const int* __restrict__ n, int cap, float* __restrict__ lse) {
+  const int p = blockIdx.y;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n[2 * p]) return;
+  const int nc = n[2 * p + 1];
+  const float* in = sim + ((long long)p * cap + r) * cap;
+  float m = -INFINITY;
+  for (int j = lane; j < nc; j += 32) m = fmaxf(m, in[j]);
+  m = warp_max_(m);
+  float sum = 0.f;
+  for (int j = lane; j < nc; j += 32) sum += expf(in[j] - m);
+  sum = warp_sum_(sum);
+  if (lane == 0) lse[(long long)(2 * p) * cap + r] = m + logf(sum);
+}
+
+// column LSE: block of 32x8 threads sweeps rows; thread (tx) owns column, ty strides rows; smem combine
+__global__ void col_lse_kernel(const float* __restrict__ sim, const int* __restrict__ n, int cap, float* __restrict__ lse) {
+  const int p = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int nr = n[2 * p], nc = n[2 * p + 1];
+  __shared__ float sm[8][33], ss[8][33];
+  const float* in = sim + (long long)p * cap * cap;
+  float m = -INFINITY;
+  if (c < nc) for (int r = threadIdx.y; r < nr; r += 8) m = fmaxf(m, in[(long long)r * cap + c]);
+  sm[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  float mm = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mm = fmaxf(mm, sm[k][threadIdx.x]);
+  float sum = 0.f;
+  if (c < nc) for (int r = threadIdx.y; r < nr; r += 8) sum += expf(in[(long long)r * cap + c] - mm);
+  ss[threadIdx.y][threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < nc) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += ss[k][threadIdx.x];
+    lse[(long long)(2 * p + 1) * cap + c] = mm + logf(t);
+  }
+}
+
+// scores(i,j) = (sim - rowlse_i) + (sim - collse_j) + ls0_i + ls1_j   (graph: log_softmax(dim cols) + log_softmax(dim rows) + ...)
+__device__ __forceinline__ float lg_score(float sim, float rl, float cl, float l0, float l1) {
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fsub_rn(sim, rl), __fsub_rn(sim, cl)), l0), l1);
+}
+
+// ---- K16: mutual nearest neighbour + threshold (filter_matches, src/light_glue.cpp:214-266) -----------------------------------
+__global__ void lg_rowmax_kernel(const float* __restrict__ sim, const float* __restrict__ lse, const float* __restrict__ logsig,
+                                 const int* __restrict__ n, int cap, int* __restrict__ row_arg, float* __restrict__ row_val,
+                                 float* __restrict__ scores_out /*optional dense [pair][cap][cap]*/) {
+  const int p = blockIdx.y;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n[2 * p]) return;
+  const int nc = n[2 * p + 1];
+  const float* in = sim + ((long long)p * cap + r) * cap;
+  const float rl = lse[(long long)(2 * p) * cap + r], l0 = logsig[(long long)(2 * p) * cap + r];
+  const float* cl = lse + (long long)(2 * p + 1) * cap;
+  const float* l1 = logsig + (long long)(2 * p + 1) * cap;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int j = lane; j < nc; j += 32) {
+    const float v = lg_score(in[j], rl, cl[j], l0, l1[j]);
+    if (scores_out) scores_out[((long long)p * cap + r) * cap + j] = v;
+    if (v > best) { best = v; arg = j; }   // ascending j per lane: first max kept
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  if (lane == 0) { row_arg[(long long)p * cap + r] = arg; row_val[(long long)p * cap + r] = best; }
+}
+
+__global__ void lg_colmax_kernel(const float* __restrict__ sim, const float* __restrict__ lse, const float* __restrict__ logsig,
+                                 const int* __restrict__ n, int cap, int* __restrict__ col_arg) {
+  const int p = blockIdx.y;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int nr = n[2 * p], nc = n[2 * p + 1];
+  __shared__ float sv[8][33];
+  __shared__ int sa[8][33];
+  const float* in = sim + (long long)p * cap * cap;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  if (c < nc) {
+    const float cl = lse[(long long)(2 * p + 1) * cap + c], l1 = logsig[(long long)(2 * p + 1) * cap + c];
+    for (int r = threadIdx.y; r < nr; r += 8) {
+      const float v = lg_score(in[(long long)r * cap + c], lse[(long long)(2 * p) * cap + r], cl, logsig[(long long)(2 * p) * cap + r], l1);
+      if (v > best) { best = v; arg = r; }
+    }
+  }
+  sv[threadIdx.y][threadIdx.x] = best;
+  sa[threadIdx.y][threadIdx.x] = arg;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < nc) {
+    for (int k = 1; k < 8; ++k) {
+      const float ob = sv[k][threadIdx.x];
+      const int oa = sa[k][threadIdx.x];
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    col_arg[(long long)p * cap + c] = arg;
+  }
+}
+
+// ordered compaction of mutual matches with exp(score) > threshold; one CTA (1024 threads) per pair; cap <= 1024
+__global__ void __launch_bounds__(1024) lg_filter_kernel(const int* __restrict__ row_arg, const float* __restrict__ row_val,
+                                                         const int* __restrict__ col_arg, const int* __restrict__ n, int cap, float thr,
+                                                         int* __restrict__ m_idx /*[pair][cap][2]*/, float* __restrict__ m_score,
+                                                         int* __restrict__ m_count) {
+  const int p = blockIdx.x;
+  const int r = threadIdx.x;
+  const int nr = n[2 * p];
+  bool ok = false;
+  int j = 0;
+  float e = 0.f;
+  if (r < nr && r < cap) {
+    j = row_arg[(long long)p * cap + r];
+    if (col_arg[(long long)p * cap + j] == r) {
+      e = expf(row_val[(long long)p * cap + r]);
+      ok = e > thr;
+    }
+  }
+  // block exclusive scan of `ok`
+  __shared__ int ws[32];
+  const int lane = r & 31, warp = r >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) ws[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    int w = ws[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    ws[lane] = w;
+  }
+  __syncthreads();
+  const int pos = (warp ? ws[warp - 1] : 0) + __popc(bal & ((1u << lane) - 1));
+  if (ok) {
+    m_idx[((long long)p * cap + pos) * 2] = r;
+    m_idx[((long long)p * cap + pos) * 2 + 1] = j;
+    m_score[(long long)p * cap + pos] = e;
+  }
+  if (r == 0) m_count[p] = ws[31];
+}
+
+// ---- launchers ------------------------------------------------------------------------------------------------------------------
+void launch_lg_prepare(const float* feat, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, const __half* wr,
+                       float* x, __half* cat16, float* rot, cudaStream_t st) {
+  lg_prepare_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(feat, n, cap, feat_cap, width, height, l_inv, wr, x, cat16, rot);
+}
+void launch_lg_rotary(const float* qkv, const float* rot, const int* n, int slots, int cap, __half* q16, __half* k16, __half* v16, cudaStream_t st) {
+  lg_rotary_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(qkv, rot, n, cap, q16, k16, v16, 0.35355339059327379f /* 64^-1/4 */);
+}
+void launch_softmax_rows(const float* S, __half* P, const int* n, int slots, int cap, int col_xor, cudaStream_t st) {
+  softmax_rows_kernel<<<dim3((cap + 7) / 8, 4, slots), 256, 0, st>>>(S, P, n, cap, col_xor);
+}
+void launch_ln_gelu(const float* h, const float* gamma, const float* beta, const int* n, int slots, int cap, __half* out, cudaStream_t st) {
+  ln_gelu_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(h, gamma, beta, n, cap, out);
+}
+void launch_lg_assignment(const float* sim, const float* x, const __half* wm, float bm, const int* n, int pairs, int cap, float* logsig,
+                          float* lse, int* row_arg, float* row_val, int* col_arg, float thr, int* m_idx, float* m_score, int* m_count,
+                          float* scores_out, cudaStream_t st) {
+  matchability_kernel<<<dim3((cap + 7) / 8, 2 * pairs), 256, 0, st>>>(x, wm, bm, n, cap, logsig);
+  row_lse_kernel<<<dim3((cap + 7) / 8, pairs), 256, 0, st>>>(sim, n, cap, lse);
+  col_lse_kernel<<<dim3((cap + 31) / 32, pairs), dim3(32, 8), 0, st>>>(sim, n, cap, lse);
+  lg_rowmax_kernel<<<dim3((cap + 7) / 8, pairs), 256, 0, st>>>(sim, lse, logsig, n, cap, row_arg, row_val, scores_out);
+  lg_colmax_kernel<<<dim3((cap + 31) / 32, pairs), dim3(32, 8), 0, st>>>(sim, lse, logsig, n, cap, col_arg);
+  lg_filter_kernel<<<pairs, 1024, 0, st>>>(row_arg, row_val, col_arg, n, cap, thr, m_idx, m_score, m_count);
+}
+
+}  // namespace airfe

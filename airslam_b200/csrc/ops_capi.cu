@@ -16,7 +16,7 @@ int airfe_op_tc_gemm(const void* a, int a_C, int W, int H, int B, long long a_sx
                      int tw, int th, int tb, void* stream) {
   TcGemmDesc d;
   d.a = a; d.a_C = a_C; d.W = W; d.H = H; d.B = B; d.a_sx = a_sx; d.a_sy = a_sy; d.a_sb = a_sb;
-  d.bw = bw; d.k_total = k_total; d.n_rows = n_rows; d.bw_sn = bw_sn; d.bw_sbatch = bw_sbatch; d.b_batches = b_batches;
+  d.bw = bw; d.k_total = k_total; d.n_rows = n_rows; d.bw_sn = bw_sn; d.bw_sbatch = bw_sbatch; d.b_batches = b_batches; if (H > 1 && b_batches > 1) { d.b_heads = 0; }
   d.b_mn_major = b_mn_major; d.taps = taps; d.c_in_pad = c_in_pad; d.block_n = block_n; d.bias = bias; d.relu = relu;
   d.out_f32 = out_f32; d.out = out; d.out_sb = out_sb; d.out_sy = out_sy; d.out_sx = out_sx; d.n_valid = n_valid;
   d.tw = tw; d.th = th; d.tb = tb;

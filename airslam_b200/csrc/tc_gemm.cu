@@ -76,16 +76,20 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   }
   {
     const int nb = d.b_batches > 0 ? d.b_batches : 1;
+    const int nh = d.b_heads > 0 ? d.b_heads : 1;
+    const uint64_t rows = d.b_mn_major ? (uint64_t)d.k_total : (uint64_t)d.n_rows;
+    const uint64_t s_head = (uint64_t)(nh > 1 ? d.bw_shead : d.bw_sn * (long long)rows) * 2;
+    const uint64_t s_batch = (uint64_t)(nb > 1 ? d.bw_sbatch : d.bw_sn * (long long)rows * nh) * 2;
     if (d.b_mn_major) {
-      uint64_t dims[3] = {(uint64_t)d.n_rows, (uint64_t)d.k_total, (uint64_t)nb};
-      uint64_t str[2] = {(uint64_t)d.bw_sn * 2, (uint64_t)(nb > 1 ? d.bw_sbatch : d.bw_sn * d.k_total) * 2};
-      uint32_t box[3] = {64, 64, 1};
-      if (!make_tmap_f16(&p.tmB, d.bw, 3, dims, str, box)) return false;
+      uint64_t dims[4] = {(uint64_t)d.n_rows, (uint64_t)d.k_total, (uint64_t)nh, (uint64_t)nb};
+      uint64_t str[3] = {(uint64_t)d.bw_sn * 2, s_head, s_batch};
+      uint32_t box[4] = {64, 64, 1, 1};
+      if (!make_tmap_f16(&p.tmB, d.bw, 4, dims, str, box)) return false;
     } else {
-      uint64_t dims[3] = {(uint64_t)d.k_total, (uint64_t)d.n_rows, (uint64_t)nb};
-      uint64_t str[2] = {(uint64_t)d.bw_sn * 2, (uint64_t)(nb > 1 ? d.bw_sbatch : d.bw_sn * d.n_rows) * 2};
-      uint32_t box[3] = {64, (uint32_t)d.block_n, 1};
-      if (!make_tmap_f16(&p.tmB, d.bw, 3, dims, str, box)) return false;
+      uint64_t dims[4] = {(uint64_t)d.k_total, (uint64_t)d.n_rows, (uint64_t)nh, (uint64_t)nb};
+      uint64_t str[3] = {(uint64_t)d.bw_sn * 2, s_head, s_batch};
+      uint32_t box[4] = {64, (uint32_t)d.block_n, 1, 1};
+      if (!make_tmap_f16(&p.tmB, d.bw, 4, dims, str, box)) return false;
     }
   }
   p.taps = d.taps;
@@ -98,7 +102,11 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   p.block_n = d.block_n;
   p.n_tiles = (d.n_valid + d.block_n - 1) / d.block_n;
   p.W = d.W; p.H = d.H; p.B = d.B;
-  p.b_batched = d.b_batches > 1;
+  p.b_batched = d.b_batches > 1 || d.b_heads > 1;
+  p.b_batch_xor = d.b_batch_xor;
+  p.scale = d.scale; p.scale_cols = d.scale_cols;
+  p.resid = d.resid;
+  p.out2 = d.out2; p.out2_sb = d.out2_sb; p.out2_sy = d.out2_sy; p.out2_sx = d.out2_sx;
   p.b_mn_major = d.b_mn_major;
   p.bias = d.bias;
   p.relu = d.relu;
@@ -107,6 +115,7 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   p.out_sb = d.out_sb; p.out_sy = d.out_sy; p.out_sx = d.out_sx;
   p.n_valid = d.n_valid;
   p.dyn_w = d.dyn_w;
+  p.dyn_w_stride = d.dyn_w_stride;
   const int stage_bytes = kABytes + tc_b_bytes(d.block_n, d.b_mn_major);
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;

@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
         const int ty = (mt / tiles_x) % p.tiles_y;
         const int tz = mt / (tiles_x * p.tiles_y);
         const int x0 = tx * p.tw, y0 = ty * p.th, b0 = tz * p.tb;
-        if (p.dyn_w && x0 >= __ldg(p.dyn_w + b0)) continue;   // rows beyond the device-side count: all roles skip alike
-        const int bb = p.b_batched ? b0 : 0;
+        if (p.dyn_w && x0 >= __ldg(p.dyn_w + b0 * p.dyn_w_stride)) continue;   // rows beyond the device-side count: all roles skip alike
+        const int bb = p.b_batched ? (b0 ^ p.b_batch_xor) : 0;
+        const int hb = p.b_batched ? y0 : 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
           const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
@@ -85,9 +86,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
             ptx::tma_load_4d(sa, &p.tmA, &full_bar[stage], kb * kBlockK, x0 + dx, y0 + dy, b0);
             const int koff = tap * p.c_in_pad + kb * kBlockK;
             if (p.b_mn_major)
-              ptx::tma_load_3d(sb, &p.tmB, &full_bar[stage], nt * p.block_n, koff, bb);
+              ptx::tma_load_4d(sb, &p.tmB, &full_bar[stage], nt * p.block_n, koff, hb, bb);
             else
-              ptx::tma_load_3d(sb, &p.tmB, &full_bar[stage], koff, nt * p.block_n, bb);
+              ptx::tma_load_4d(sb, &p.tmB, &full_bar[stage], koff, nt * p.block_n, hb, bb);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         if (p.dyn_w) {
           const int mt = t / p.n_tiles;
-          if ((mt % tiles_x) * p.tw >= __ldg(p.dyn_w + (mt / (tiles_x * p.tiles_y)) * p.tb)) continue;
+          if ((mt % tiles_x) * p.tw >= __ldg(p.dyn_w + (mt / (tiles_x * p.tiles_y)) * p.tb * p.dyn_w_stride)) continue;
         }
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       const int x = tx * p.tw + row % p.tw;
       const int y = ty * p.th + (row / p.tw) % p.th;
       const int b = tz * p.tb + row / (p.tw * p.th);
-      const int vW = p.dyn_w ? min(__ldg(p.dyn_w + tz * p.tb), p.W) : p.W;
+      const int vW = p.dyn_w ? min(__ldg(p.dyn_w + tz * p.tb * p.dyn_w_stride), p.W) : p.W;
       if (p.dyn_w && tx * p.tw >= vW) continue;
       const bool valid = (x < vW) && (y < p.H) && (b < p.B);
       const long long off = (long long)b * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx;
@@ -161,11 +162,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
         for (int i = 0; i < 16; ++i) {
           float f = __uint_as_float(r[i]);
           if (p.bias && n0 + c + i < p.n_valid) f += __ldg(p.bias + n0 + c + i);
+          if (n0 + c + i < p.scale_cols) f *= p.scale;
           if (p.relu) f = fmaxf(f, 0.f);
           v[i] = f;
         }
         const int nbase = n0 + c;
         if (valid && nbase < p.n_valid) {
+          if (p.resid) {
+            const float* rs = p.resid + off + nbase;
+            if (nbase + 16 <= p.n_valid) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(rs + i);
+                v[i] += q.x; v[i + 1] += q.y; v[i + 2] += q.z; v[i + 3] += q.w;
+              }
+            } else {
+              for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) v[i] += __ldg(rs + i);
+            }
+          }
+          if (p.out2) {
+            __half* o2 = reinterpret_cast<__half*>(p.out2) + (long long)b * p.out2_sb + (long long)y * p.out2_sy + (long long)x * p.out2_sx + nbase;
+            if (nbase + 16 <= p.n_valid) {
+              uint32_t h[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                h[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(o2) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(o2 + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+            } else {
+              for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) o2[i] = __float2half_rn(v[i]);
+            }
+          }
           if (p.out_f32) {
             float* o = reinterpret_cast<float*>(p.out) + off + nbase;
             if (nbase + 16 <= p.n_valid) {

@@ -7,7 +7,7 @@ namespace airfe {
 
 struct TcGemmParams {
   CUtensorMap tmA;  // 4-D (C, W, H, B)   box (64, tw, th, tb)   SWIZZLE_128B
-  CUtensorMap tmB;  // 3-D (K, N, batch)  box (64, block_n, 1)   SWIZZLE_128B   [MN-major: (N, K, batch), box (64, 64, 1)]
+  CUtensorMap tmB;  // 4-D (K, N, Hb, Bb) box (64, block_n, 1, 1) SWIZZLE_128B  [MN-major: (N, K, Hb, Bb), box (64, 64, 1, 1)]
   int taps;         // 1 or 9
   int kblocks;      // 64-wide K blocks per tap
   int c_in_pad;     // kblocks * 64 (K offset between taps in Bw)
@@ -15,15 +15,22 @@ struct TcGemmParams {
   int tiles_x, tiles_y, tiles_b;
   int n_tiles, block_n;
   int W, H, B;      // valid output extents
-  int b_batched;    // Bw batch coordinate follows the tile's batch index
+  int b_batched;    // Bw coordinates (Hb, Bb) follow the tile's (y, batch) index: per-head / per-image operand
+  int b_batch_xor;  // Bb = tile batch ^ b_batch_xor (cross attention reads the partner image)
   int b_mn_major;   // Bw tile is MN-major (block_n must be 64)
   const float* bias;
+  float scale;      // (acc + bias) * scale for columns < scale_cols (the 64^-1/4 / 256^-1/4 factors of the matchers)
+  int scale_cols;
+  const float* resid;  // optional fp32 residual, same indexing as `out` (which must be fp32): out = resid + acc + bias
+  void* out2;       // optional second store of the same values as fp16 (operand copy for the next GEMM)
+  long long out2_sb, out2_sy, out2_sx;
   int relu;
   int out_f32;
   void* out;        // element (b,y,x,n) at out[b*out_sb + y*out_sy + x*out_sx + n]  (ch offset folded into `out`)
   long long out_sb, out_sy, out_sx;
   int n_valid;
   int stages;
+  int dyn_w_stride; // index = tile batch * dyn_w_stride
   const int* dyn_w;  // optional: per-batch-index valid W (rows of a plain GEMM), read from device memory (tb must be 1)
 };
 

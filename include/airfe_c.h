@@ -84,6 +84,36 @@ int airfe_detect(airfe_ctx* ctx, int net, const uint8_t* gray, int width, int he
                  int feat_cap, int* n_feat, double* lines_xyxy, int line_cap, int* n_lines, float* junc259_colmajor, int junc_cap,
                  int* n_junc);
 
+/* Match `pairs` feature-set pairs.  Replaces PointMatcher::MatchingPoints (without the optional OpenCV RANSAC, which stays a
+ * host hook in include/point_matcher.h).  feat0/feat1: pair p at + p*feat_cap*259, column-major 259 x n (row 0 score, 1-2 x,y in
+ * image pixels, 3.. descriptor); keypoints are normalised internally exactly like PointMatcher::NormalizeKeypoints with the
+ * context's image_width/height.  Outputs per pair p (at + p*match_cap): idx0/idx1 (ascending idx0), score = exp(log-score)
+ * (LightGlue) or (mscores0+mscores1)/2 (SuperGlue); DMatch::distance = 1 - score is formed by the C++ wrapper. */
+int airfe_match_batch(airfe_ctx* ctx, int matcher, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1,
+                      int feat_cap, int* idx0, int* idx1, float* score, int match_cap, int* n_match);
+
+/* The keyframe path of MapBuilder::ExtractFeatureThread (src/map_builder.cc:85-86) for `pairs` stereo pairs at once:
+ * Detect(left, right, ...) + MatchingPoints(left, right).  Features never leave the device between detect and match.
+ * left/right: pair p at + p*image_stride_bytes.  Feature/line outputs as airfe_detect_batch with index 2*p (left), 2*p+1 (right);
+ * junctions are produced for left images only, index p (src/feature_detector.cc:100-101).  lines/junc may be NULL. */
+int airfe_detect_match_stereo_batch(airfe_ctx* ctx, int net, int matcher, int pairs, const uint8_t* left, const uint8_t* right,
+                                    int width, int height, int stride, long long image_stride_bytes, float* feat, int feat_cap,
+                                    int* n_feat, double* lines, int line_cap, int* n_lines, float* junc, int junc_cap, int* n_junc,
+                                    int* idx0, int* idx1, float* score, int match_cap, int* n_match);
+
+/* Same work with the images already resident in device memory (u8, slot s = 2*pair + side at d_images + s*image_stride_bytes) and
+ * results left on the device; asynchronous on airfe_stream(ctx).  Used to time the device pipeline without PCIe. */
+int airfe_stereo_device(airfe_ctx* ctx, int net, int matcher, int pairs, const void* d_images, int width, int height, int stride,
+                        long long image_stride_bytes, int lines, int junctions);
+
+/* One airfe_stereo_device step with CUDA events around every op; writes "name\tflops\tms\n" records into `out`
+ * (returns the number of bytes written, <0 on error).  Used by bench.py for the live roofline numbers. */
+long long airfe_profile_stereo(airfe_ctx* ctx, int net, int matcher, int pairs, const void* d_images, int width, int height, int stride,
+                               long long image_stride_bytes, int lines, int junctions, char* out, long long cap);
+
+/* Algorithmic tensor-core FLOPs and kernel launches of one airfe_stereo_device call (for roofline accounting). */
+int airfe_stereo_cost(airfe_ctx* ctx, int net, int matcher, int pairs, int lines, double* tc_flops, int* launches);
+
 /* Parity taps: copy a named intermediate of the last detect call (image `index`) to `dst`; returns bytes, <0 on error. */
 long long airfe_debug_read(airfe_ctx* ctx, int net, const char* name, int index, void* dst, long long dst_bytes);
 

@@ -27,7 +27,7 @@ def _draw_line(img, x0, y0, x1, y1, val, thick):
             img[yy[ok], xx[ok]] = val
 
 
-def scene(w, h, seed, margin=48):
+def scene(w, h, seed, margin=96):
     """Float64 image [h, w+margin] in 0..255 with texture, rectangles and line segments."""
     rs = np.random.RandomState(seed & 0x7FFFFFFF)
     ww = w + margin
@@ -50,8 +50,8 @@ def stereo_pair(w, h, seed, low_light=False):
     rs = np.random.RandomState((seed * 2654435761 + 12345) & 0x7FFFFFFF)
     sc = scene(w, h, seed)
     disp = int(rs.randint(4, 41))
-    left = sc[:, 44:44 + w].copy()
-    right = sc[:, 44 - disp:44 - disp + w].copy()
+    left = sc[:, 8:8 + w].copy()
+    right = sc[:, 8 + disp:8 + disp + w].copy()      # x_right = x_left - disp (rectified stereo geometry)
     if low_light:
         left, right = left * 0.25, right * 0.25
         left += rs.normal(0, 6.0, left.shape)
@@ -75,6 +75,7 @@ def keypoint_set(n, w, h, seed, perturb_of=None):
         d = rs.normal(0, 1, (256, n))
         f[3:] = d / np.linalg.norm(d, axis=0, keepdims=True)
         return f
+    assert n <= perturb_of.shape[1]
     perm = rs.permutation(perturb_of.shape[1])[:n]
     f = perturb_of[:, perm].copy()
     f[1] += rs.normal(0, 1.0, n) - 12.0

@@ -1,0 +1,82 @@
+"""GPU parity of the LightGlue device pipeline against the oracle (precision-matched 'emul' mode) and of the
+mutual-NN filter (exact, on the GPU's own score matrix).  Also the stereo (detect -> match) entry point."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    os.environ["AIRFE_DEBUG_DENSE"] = "1"
+    from airslam_b200 import capi
+    c = capi.Context(max_batch=3, enable_superpoint=1, enable_plnet=0)
+    yield c
+    c.close()
+
+
+def _pairs():
+    from oracle import synth
+    out = []
+    for k, (n0, n1) in enumerate(((400, 380), (400, 257), (64, 33))):
+        f0 = synth.keypoint_set(n0, 752, 480, 70 + k)
+        f1, perm = synth.keypoint_set(n1, 752, 480, 80 + k, perturb_of=f0)
+        out.append((f0, f1, perm))
+    return out
+
+
+def test_lightglue_scores_and_matches(ctx):
+    from airslam_b200 import capi
+    from oracle import host, weights
+    w = weights.load("lightglue")
+    prs = _pairs()
+    res = ctx.match_batch(capi.MATCHER_LIGHTGLUE, [p[0] for p in prs], [p[1] for p in prs])
+    for i, (f0, f1, perm) in enumerate(prs):
+        n0, n1 = f0.shape[1], f1.shape[1]
+        dense = ctx.debug_read(100, "lg_scores", i, np.float32, (512, 512))[:n0, :n1]
+        a = host.normalize_keypoints(f0, 752, 480, 0.5)
+        b = host.normalize_keypoints(f1, 752, 480, 0.5)
+        idx_o, sc_o, dense_o = host.lightglue_infer(a[1:], b[1:], w, emul=True)
+        # dense log-scores: compare where it matters (exp(score) > 1e-4) in probability space, tolerance 1e-3 abs
+        big = (dense_o > np.log(1e-4)) | (dense > np.log(1e-4))
+        assert np.abs(np.exp(dense[big]) - np.exp(dense_o[big])).max() <= 2e-3
+        # filter on OUR dense matrix: exact indices, scores 1e-6
+        idx_g, sc_g = host.filter_matches(dense)
+        assert np.array_equal(res[i][0], idx_g)
+        assert np.abs(res[i][1] - sc_g).max() <= 1e-6
+        # vs the pure oracle: identical match indices, scores within 2e-3
+        assert np.array_equal(res[i][0], idx_o), (len(res[i][0]), len(idx_o))
+        assert np.abs(res[i][1] - sc_o).max() <= 2e-3
+        # planted correspondences are recovered
+        good = (perm[res[i][0][:, 1]] == res[i][0][:, 0]).mean()
+        assert good > 0.95
+
+
+def test_empty_side_returns_zero_matches(ctx):
+    from airslam_b200 import capi
+    from oracle import synth
+    f0 = synth.keypoint_set(50, 752, 480, 3)
+    res = ctx.match_batch(capi.MATCHER_LIGHTGLUE, [f0], [np.zeros((259, 0), dtype=np.float32)])
+    assert len(res[0][0]) == 0
+
+
+def test_stereo_entry_matches_two_step_path(ctx):
+    """airfe_detect_match_stereo_batch == airfe_detect_batch followed by airfe_match_batch (bit-identical)."""
+    from airslam_b200 import capi
+    from oracle import synth
+    ims = [synth.stereo_pair(752, 480, 31 + k) for k in range(2)]
+    left = np.stack([a for a, _, _ in ims])
+    right = np.stack([b for _, b, _ in ims])
+    st = ctx.stereo_batch(capi.NET_SUPERPOINT, capi.MATCHER_LIGHTGLUE, left, right)
+    det = ctx.detect_batch(capi.NET_SUPERPOINT, np.concatenate([left, right]))
+    mt = ctx.match_batch(capi.MATCHER_LIGHTGLUE, [det[0][0], det[1][0]], [det[2][0], det[3][0]])
+    for p in range(2):
+        assert np.array_equal(st[p]["feat_l"], det[p][0]) and np.array_equal(st[p]["feat_r"], det[2 + p][0])
+        assert np.array_equal(st[p]["matches"][0], mt[p][0])
+        assert np.allclose(st[p]["matches"][1], mt[p][1], atol=1e-6)
+        d = ims[p][2]
+        i0, i1 = st[p]["matches"][0][:, 0], st[p]["matches"][0][:, 1]
+        disp = st[p]["feat_l"][1, i0] - st[p]["feat_r"][1, i1]
+        assert len(i0) > 100 and abs(np.median(disp) - d) < 1.5, (len(i0), np.median(disp), d)
