@@ -82,6 +82,8 @@ def _declare_match(L):
     L.airfe_detect_match_stereo_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, i32, i64, vp, i32, vp, vp, i32, vp, vp, i32, vp,
                                                   vp, vp, vp, i32, vp]
     L.airfe_detect_match_stereo_batch.restype = i32
+    L.airfe_superglue_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32]
+    L.airfe_superglue_batch.restype = i32
     L.airfe_stereo_device.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i64, i32, i32]
     L.airfe_stereo_device.restype = i32
     L.airfe_profile_stereo.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i64, i32, i32, vp, i64]
@@ -218,3 +220,21 @@ class Context:
             nm, fl, ms = line.split("\t")
             out.append((nm, float(fl), float(ms)))
         return out
+
+    def superglue_batch(self, feats0, feats1):
+        """Raw SuperGlue::infer outputs per pair: (indices0, indices1, mscores0, mscores1)."""
+        import numpy as np
+        p = len(feats0)
+        cap = max(max(f.shape[1] for f in feats0), max(f.shape[1] for f in feats1), 1)
+        f0 = np.zeros((p, cap, 259), dtype=np.float32)
+        f1 = np.zeros((p, cap, 259), dtype=np.float32)
+        n0 = np.array([f.shape[1] for f in feats0], dtype=np.int32)
+        n1 = np.array([f.shape[1] for f in feats1], dtype=np.int32)
+        for i in range(p):
+            f0[i, :n0[i]] = feats0[i].T
+            f1[i, :n1[i]] = feats1[i].T
+        i0 = np.zeros((p, cap), dtype=np.int32); i1 = np.zeros((p, cap), dtype=np.int32)
+        m0 = np.zeros((p, cap), dtype=np.float32); m1 = np.zeros((p, cap), dtype=np.float32)
+        q = lambda a: a.ctypes.data_as(vp)
+        check(lib().airfe_superglue_batch(self.h, p, q(f0), q(n0), q(f1), q(n1), cap, q(i0), q(i1), q(m0), q(m1), cap))
+        return [(i0[i, :n0[i]].copy(), i1[i, :n1[i]].copy(), m0[i, :n0[i]].copy(), m1[i, :n1[i]].copy()) for i in range(p)]

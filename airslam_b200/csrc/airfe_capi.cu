@@ -16,6 +16,8 @@ struct airfe_ctx {
   cudaStream_t stream = nullptr;
   std::unique_ptr<Detector> sp, pl;
   std::unique_ptr<LightGlue> lg;
+  std::unique_ptr<SuperGlue> sg;
+  int* h_sgidx = nullptr; float* h_sgms = nullptr;   // [2][max_batch][1024] each
   float* d_mfeat = nullptr; int* d_mn = nullptr;   // staging for host-provided features [2*max_batch][kKpCap][259]
   float* h_mfeat = nullptr; int* h_mn = nullptr; int* h_midx = nullptr; float* h_mscore = nullptr; int* h_mcount = nullptr;
   // pinned staging
@@ -74,14 +76,20 @@ int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out) {
     dc.enable_lines = true;
     if (!c->pl->init(dc, wdir, true)) return AIRFE_ERR_IO;
   }
-  if (cfg->enable_lightglue) {
+  if (cfg->enable_superglue) {
     MatcherConfig mc;
     mc.max_pairs = cfg->max_batch;
     mc.cap = cfg->max_keypoints <= 512 ? 512 : 1024;
     mc.image_width = cfg->image_width;
     mc.image_height = cfg->image_height;
-    c->lg.reset(new LightGlue);
-    if (!c->lg->init(mc, wdir)) return AIRFE_ERR_IO;
+    c->sg.reset(new SuperGlue);
+    if (!c->sg->init(mc, wdir, cfg->enable_superglue == 2)) return AIRFE_ERR_IO;
+    if (cudaMallocHost(&c->h_sgidx, (size_t)2 * cfg->max_batch * 1024 * 4) != cudaSuccess || cudaMallocHost(&c->h_sgms, (size_t)2 * cfg->max_batch * 1024 * 4) != cudaSuccess) {
+      set_error("superglue staging allocation failed");
+      return AIRFE_ERR_CUDA;
+    }
+  }
+  if (cfg->enable_lightglue || cfg->enable_superglue) {
     const size_t S = 2 * (size_t)cfg->max_batch;
     if (cudaMalloc(&c->d_mfeat, S * kKpCap * 259 * 4) != cudaSuccess || cudaMalloc(&c->d_mn, S * 4) != cudaSuccess ||
         cudaMallocHost(&c->h_mfeat, S * kKpCap * 259 * 4) != cudaSuccess || cudaMallocHost(&c->h_mn, S * 4) != cudaSuccess ||
@@ -90,6 +98,15 @@ int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out) {
       set_error("matcher staging allocation failed");
       return AIRFE_ERR_CUDA;
     }
+  }
+  if (cfg->enable_lightglue) {
+    MatcherConfig mc;
+    mc.max_pairs = cfg->max_batch;
+    mc.cap = cfg->max_keypoints <= 512 ? 512 : 1024;
+    mc.image_width = cfg->image_width;
+    mc.image_height = cfg->image_height;
+    c->lg.reset(new LightGlue);
+    if (!c->lg->init(mc, wdir)) return AIRFE_ERR_IO;
   }
   const int B = cfg->max_batch;
   if (cudaMallocHost(&c->h_feat, (size_t)2 * B * kKpCap * 259 * 4) != cudaSuccess || cudaMallocHost(&c->h_junc, (size_t)2 * B * kKpCap * 259 * 4) != cudaSuccess ||
@@ -108,6 +125,9 @@ void airfe_destroy(airfe_ctx* c) {
   c->sp.reset();
   c->pl.reset();
   c->lg.reset();
+  c->sg.reset();
+  if (c->h_sgidx) cudaFreeHost(c->h_sgidx);
+  if (c->h_sgms) cudaFreeHost(c->h_sgms);
   if (c->d_mfeat) cudaFree(c->d_mfeat);
   if (c->d_mn) cudaFree(c->d_mn);
   if (c->h_mfeat) cudaFreeHost(c->h_mfeat);
@@ -204,13 +224,17 @@ int airfe_detect(airfe_ctx* c, int net, const uint8_t* gray, int w, int h, int s
   return airfe_detect_batch(c, net, 1, gray, w, h, stride, 0, feat, feat_cap, n_feat, lines, line_cap, n_lines, junc, junc_cap, n_junc);
 }
 
-static int fetch_matches(airfe_ctx* c, int pairs, int* idx0, int* idx1, float* score, int match_cap, int* n_match, const int* zero_mask) {
-  const MatchOutputs& mo = c->lg->out();
-  const int cap = c->lg->cap();
+static int fetch_matches(airfe_ctx* c, int pairs, int* idx0, int* idx1, float* score, int match_cap, int* n_match, const int* zero_mask,
+                         int matcher = AIRFE_MATCHER_LIGHTGLUE) {
+  const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
+  const int cap = sgm ? c->sg->cap() : c->lg->cap();
+  const int* d_count = sgm ? c->sg->out().m_count : c->lg->out().count;
+  const int* d_idx = sgm ? c->sg->out().m_idx : c->lg->out().idx;
+  const float* d_score = sgm ? c->sg->out().m_score : c->lg->out().score;
   cudaStream_t st = c->stream;
-  cudaMemcpyAsync(c->h_mcount, mo.count, 4 * pairs, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(c->h_midx, mo.idx, (size_t)pairs * cap * 8, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(c->h_mscore, mo.score, (size_t)pairs * cap * 4, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(c->h_mcount, d_count, 4 * pairs, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(c->h_midx, d_idx, (size_t)pairs * cap * 8, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(c->h_mscore, d_score, (size_t)pairs * cap * 4, cudaMemcpyDeviceToHost, st);
   if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("match failed: %s", cudaGetErrorString(cudaGetLastError())); return AIRFE_ERR_CUDA; }
   for (int p = 0; p < pairs; ++p) {
     int n = c->h_mcount[p];
@@ -229,10 +253,11 @@ static int fetch_matches(airfe_ctx* c, int pairs, int* idx0, int* idx1, float* s
 int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1,
                       int feat_cap, int* idx0, int* idx1, float* score, int match_cap, int* n_match) {
   if (!c || !feat0 || !feat1 || !n0 || !n1 || !idx0 || !idx1 || !score || !n_match) { set_error("null argument"); return AIRFE_ERR_INVALID; }
-  if (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
+  const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
+  if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
   if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return AIRFE_ERR_INVALID; }
   cudaSetDevice(c->device);
-  const int cap = c->lg->cap();
+  const int cap = sgm ? c->sg->cap() : c->lg->cap();
   std::vector<int> zero(pairs, 0);
   for (int p = 0; p < pairs; ++p) {
     if (n0[p] > cap || n1[p] > cap || n0[p] > feat_cap || n1[p] > feat_cap) { set_error("pair %d: %d/%d keypoints exceed capacity %d", p, n0[p], n1[p], cap); return AIRFE_ERR_CAPACITY; }
@@ -247,8 +272,32 @@ int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, 
     if (c->h_mn[s] > 0)
       cudaMemcpyAsync(c->d_mfeat + (size_t)s * kKpCap * 259, c->h_mfeat + (size_t)s * kKpCap * 259, (size_t)c->h_mn[s] * 259 * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(c->d_mn, c->h_mn, 8 * pairs, cudaMemcpyHostToDevice, st);
-  if (!c->lg->run(c->d_mfeat, c->d_mn, kKpCap, pairs, getenv("AIRFE_DEBUG_DENSE") != nullptr, st)) return AIRFE_ERR_CUDA;
-  return fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, zero.data());
+  const bool dense = getenv("AIRFE_DEBUG_DENSE") != nullptr;
+  if (sgm ? !c->sg->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st) : !c->lg->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st)) return AIRFE_ERR_CUDA;
+  return fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, zero.data(), matcher);
+}
+
+int airfe_superglue_batch(airfe_ctx* c, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1, int feat_cap,
+                          int* indices0, int* indices1, float* mscores0, float* mscores1, int out_cap) {
+  if (!c || !c->sg) { set_error("superglue not enabled in this context"); return AIRFE_ERR_INVALID; }
+  std::vector<int> i0((size_t)pairs * 1024), i1((size_t)pairs * 1024), nm(pairs);
+  std::vector<float> sc((size_t)pairs * 1024);
+  int rc = airfe_match_batch(c, AIRFE_MATCHER_SUPERGLUE, pairs, feat0, n0, feat1, n1, feat_cap, i0.data(), i1.data(), sc.data(), 1024, nm.data());
+  if (rc != AIRFE_OK) return rc;
+  const SuperGlueOutputs& o = c->sg->out();
+  const int cap = c->sg->cap();
+  const size_t PC = (size_t)pairs * cap;
+  cudaMemcpyAsync(c->h_sgidx, o.idx0, PC * 4, cudaMemcpyDeviceToHost, c->stream);
+  cudaMemcpyAsync(c->h_sgidx + PC, o.idx1, PC * 4, cudaMemcpyDeviceToHost, c->stream);
+  cudaMemcpyAsync(c->h_sgms, o.ms0, PC * 4, cudaMemcpyDeviceToHost, c->stream);
+  cudaMemcpyAsync(c->h_sgms + PC, o.ms1, PC * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("superglue readback failed"); return AIRFE_ERR_CUDA; }
+  for (int p = 0; p < pairs; ++p) {
+    if (n0[p] > out_cap || n1[p] > out_cap) { set_error("output capacity %d too small", out_cap); return AIRFE_ERR_CAPACITY; }
+    for (int k = 0; k < n0[p]; ++k) { indices0[(size_t)p * out_cap + k] = c->h_sgidx[(size_t)p * cap + k]; mscores0[(size_t)p * out_cap + k] = c->h_sgms[(size_t)p * cap + k]; }
+    for (int k = 0; k < n1[p]; ++k) { indices1[(size_t)p * out_cap + k] = c->h_sgidx[PC + (size_t)p * cap + k]; mscores1[(size_t)p * out_cap + k] = c->h_sgms[PC + (size_t)p * cap + k]; }
+  }
+  return AIRFE_OK;
 }
 
 int airfe_stereo_device(airfe_ctx* c, int net, int matcher, int pairs, const void* d_images, int w, int h, int stride, long long img_stride,
@@ -366,6 +415,14 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
 }
 
 long long airfe_debug_read(airfe_ctx* c, int net, const char* name, int index, void* dst, long long dst_bytes) {
+  if (net == 101) {   // SuperGlue tap: "sg_scores" = final [cap+1][cap+1] score matrix of pair `index` (needs AIRFE_DEBUG_DENSE=1)
+    if (!c->sg) { set_error("superglue not enabled"); return AIRFE_ERR_INVALID; }
+    const long long ld = c->sg->cap() + 1, nb = ld * ld * 4;
+    if (nb > dst_bytes) { set_error("tap needs %lld bytes", nb); return AIRFE_ERR_CAPACITY; }
+    cudaStreamSynchronize(c->stream);
+    if (cudaMemcpy(dst, c->sg->out().dense + (size_t)index * ld * ld, (size_t)nb, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("debug read failed"); return AIRFE_ERR_CUDA; }
+    return nb;
+  }
   if (net == 100) {   // LightGlue taps: "lg_scores" = dense log-assignment [cap][cap] of pair `index` (needs AIRFE_DEBUG_DENSE=1)
     if (!c->lg) { set_error("lightglue not enabled"); return AIRFE_ERR_INVALID; }
     const long long cap = c->lg->cap(), nb = cap * cap * 4;

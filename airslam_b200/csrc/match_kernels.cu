@@ -86,8 +86,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, __half* __restr
   sum = warp_sum_(sum);
   const float inv = 1.f / sum;
   __half* out = P + base;
-  const int ncp = (nc + 63) / 64 * 64;
-  for (int j = lane; j < ncp; j += 32) out[j] = __float2half_rn(j < nc ? expf(in[j] - m) * inv : 0.f);
+  // zero the whole padded row: columns beyond nc may hold stale probabilities of an earlier, larger pair
+  for (int j = lane; j < cap; j += 32) out[j] = __float2half_rn(j < nc ? expf(in[j] - m) * inv : 0.f);
 }
 
 // ---- FFN middle: LayerNorm(512, eps 1e-5) + exact GELU, fp32 in -> fp16 operand out.  One warp per row. -----------------------
@@ -216,7 +216,7 @@ __global__ void lg_rowmax_kernel(const float* __restrict__ sim, const float* __r
     const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
     if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
   }
-  if (lane == 0) { row_arg[(long long)p * cap + r] = arg; row_val[(long long)p * cap + r] = best; }
+  if (lane == 0) { row_arg[(long long)p * cap + r] = (arg == 0x7fffffff) ? -1 : arg; row_val[(long long)p * cap + r] = best; }
 }
 
 __global__ void lg_colmax_kernel(const float* __restrict__ sim, const float* __restrict__ lse, const float* __restrict__ logsig,
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(1024) lg_filter_kernel(const int* __restrict__
   float e = 0.f;
   if (r < nr && r < cap) {
     j = row_arg[(long long)p * cap + r];
-    if (col_arg[(long long)p * cap + j] == r) {
+    if (j >= 0 && j < n[2 * p + 1] && col_arg[(long long)p * cap + j] == r) {
       e = expf(row_val[(long long)p * cap + r]);
       ok = e > thr;
     }
@@ -312,6 +312,251 @@ void launch_lg_assignment(const float* sim, const float* x, const __half* wm, fl
   lg_rowmax_kernel<<<dim3((cap + 7) / 8, pairs), 256, 0, st>>>(sim, lse, logsig, n, cap, row_arg, row_val, scores_out);
   lg_colmax_kernel<<<dim3((cap + 31) / 32, pairs), dim3(32, 8), 0, st>>>(sim, lse, logsig, n, cap, col_arg);
   lg_filter_kernel<<<pairs, 1024, 0, st>>>(row_arg, row_val, col_arg, n, cap, thr, m_idx, m_score, m_count);
+}
+
+}  // namespace airfe
+
+// =====================================================================================================================
+// SuperGlue (G5): keypoint-encoder input, log-domain Sinkhorn (App. B7), decode (src/super_glue.cpp:339-367) and the
+// mutual-match extraction of PointMatcher::MatchingPoints (src/point_matcher.cc:73-92).
+// =====================================================================================================================
+namespace airfe {
+
+// kenc input rows [x', y', score, 0...] (fp16, K padded to 64) and residual stream x = descriptors (fp32)
+__global__ void sg_prepare_kernel(const float* __restrict__ feat, const int* __restrict__ n, int cap, int feat_cap, int width, int height,
+                                  float l_inv, float* __restrict__ x, __half* __restrict__ kin16) {
+  const int s = blockIdx.y;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= n[s]) return;
+  const float* f = feat + ((long long)s * feat_cap + r) * 259;
+  const long long row = (long long)s * cap + r;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[row * 256 + lane * 8 + e] = f[3 + lane * 8 + e];
+  __half2 o = __floats2half2_rn(0.f, 0.f);
+  if (lane == 0) o = __floats2half2_rn(__fmul_rn(__fsub_rn(f[1], (float)(width / 2)), l_inv), __fmul_rn(__fsub_rn(f[2], (float)(height / 2)), l_inv));
+  if (lane == 1) o = __floats2half2_rn(f[0], 0.f);
+  *reinterpret_cast<__half2*>(kin16 + row * 64 + lane * 2) = o;
+}
+
+void launch_sg_prepare(const float* feat, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, float* x,
+                       __half* kin16, cudaStream_t st) {
+  sg_prepare_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(feat, n, cap, feat_cap, width, height, l_inv, x, kin16);
+}
+
+// Z = [[S, bin],[bin, bin]] with leading dimension ld = cap + 1; u = v = 0
+__global__ void sg_couplings_kernel(const float* __restrict__ sim, const int* __restrict__ n, int cap, float bin, float* __restrict__ Z,
+                                    float* __restrict__ u, float* __restrict__ v) {
+  const int p = blockIdx.z;
+  const int m = n[2 * p], nn = n[2 * p + 1];
+  const int i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ld = cap + 1;
+  if (i > m || j > nn) return;
+  float val = bin;
+  if (i < m && j < nn) val = sim[((long long)p * cap + i) * cap + j];
+  Z[((long long)p * ld + i) * ld + j] = val;
+  if (j == 0) u[(long long)p * ld + i] = 0.f;
+  if (i == 0) v[(long long)p * ld + j] = 0.f;
+}
+
+// u_i = log_mu_i - LSE_j(Z_ij + v_j): one warp per row
+__global__ void sg_row_pass_kernel(const float* __restrict__ Z, const int* __restrict__ n, int cap, float* __restrict__ u, const float* __restrict__ v) {
+  const int p = blockIdx.y;
+  const int m = n[2 * p], nn = n[2 * p + 1];
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i > m) return;
+  const int ld = cap + 1;
+  const float* z = Z + ((long long)p * ld + i) * ld;
+  const float* vv = v + (long long)p * ld;
+  float mx = -INFINITY;
+  for (int j = lane; j <= nn; j += 32) mx = fmaxf(mx, z[j] + vv[j]);
+  mx = warp_max_(mx);
+  float s = 0.f;
+  for (int j = lane; j <= nn; j += 32) s += expf(z[j] + vv[j] - mx);
+  s = warp_sum_(s);
+  if (lane == 0) {
+    const float norm = -logf((float)(m + nn));
+    const float log_mu = (i < m) ? norm : logf((float)nn) + norm;
+    u[(long long)p * ld + i] = log_mu - (mx + logf(s));
+  }
+}
+
+// v_j = log_nu_j - LSE_i(Z_ij + u_i): 32 columns per block, 8 row-lanes
+__global__ void sg_col_pass_kernel(const float* __restrict__ Z, const int* __restrict__ n, int cap, const float* __restrict__ u, float* __restrict__ v) {
+  const int p = blockIdx.y;
+  const int m = n[2 * p], nn = n[2 * p + 1];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int ld = cap + 1;
+  __shared__ float sm[8][33], ss[8][33];
+  const float* z = Z + (long long)p * ld * ld;
+  const float* uu = u + (long long)p * ld;
+  float mx = -INFINITY;
+  if (j <= nn) for (int i = threadIdx.y; i <= m; i += 8) mx = fmaxf(mx, z[(long long)i * ld + j] + uu[i]);
+  sm[threadIdx.y][threadIdx.x] = mx;
+  __syncthreads();
+  float mm = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mm = fmaxf(mm, sm[k][threadIdx.x]);
+  float s = 0.f;
+  if (j <= nn) for (int i = threadIdx.y; i <= m; i += 8) s += expf(z[(long long)i * ld + j] + uu[i] - mm);
+  ss[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j <= nn) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += ss[k][threadIdx.x];
+    const float norm = -logf((float)(m + nn));
+    const float log_nu = (j < nn) ? norm : logf((float)m) + norm;
+    v[(long long)p * ld + j] = log_nu - (mm + logf(t));
+  }
+}
+
+__device__ __forceinline__ float sg_score(float z, float u, float v, float norm) { return __fsub_rn(__fadd_rn(__fadd_rn(z, u), v), norm); }
+
+// decode: row / column argmax over the inner M x N block of Z + u + v - norm (strict '<' scan: first max)
+__global__ void sg_rowmax_kernel(const float* __restrict__ Z, const float* __restrict__ u, const float* __restrict__ v, const int* __restrict__ n,
+                                 int cap, int* __restrict__ arg0, float* __restrict__ val0, float* __restrict__ dense_out) {
+  const int p = blockIdx.y;
+  const int m = n[2 * p], nn = n[2 * p + 1];
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int ld = cap + 1;
+  if (i > m) return;
+  const float norm = -logf((float)(m + nn));
+  const float* z = Z + ((long long)p * ld + i) * ld;
+  const float ui = u[(long long)p * ld + i];
+  const float* vv = v + (long long)p * ld;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int j = lane; j <= nn; j += 32) {
+    const float s = sg_score(z[j], ui, vv[j], norm);
+    if (dense_out) dense_out[((long long)p * ld + i) * ld + j] = s;
+    if (j < nn && i < m && s > best) { best = s; arg = j; }
+  }
+  if (i >= m) return;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  if (lane == 0) { arg0[(long long)p * cap + i] = arg == 0x7fffffff ? 0 : arg; val0[(long long)p * cap + i] = best; }
+}
+
+__global__ void sg_colmax_kernel(const float* __restrict__ Z, const float* __restrict__ u, const float* __restrict__ v, const int* __restrict__ n,
+                                 int cap, int* __restrict__ arg1) {
+  const int p = blockIdx.y;
+  const int m = n[2 * p], nn = n[2 * p + 1];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int ld = cap + 1;
+  __shared__ float sv[8][33];
+  __shared__ int sa[8][33];
+  const float norm = -logf((float)(m + nn));
+  const float* z = Z + (long long)p * ld * ld;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  if (j < nn) {
+    const float vj = v[(long long)p * ld + j];
+    for (int i = threadIdx.y; i < m; i += 8) {
+      const float s = sg_score(z[(long long)i * ld + j], u[(long long)p * ld + i], vj, norm);
+      if (s > best) { best = s; arg = i; }
+    }
+  }
+  sv[threadIdx.y][threadIdx.x] = best;
+  sa[threadIdx.y][threadIdx.x] = arg;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < nn) {
+    for (int k = 1; k < 8; ++k) {
+      const float ob = sv[k][threadIdx.x];
+      const int oa = sa[k][threadIdx.x];
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    arg1[(long long)p * cap + j] = arg == 0x7fffffff ? 0 : arg;
+  }
+}
+
+// decode() + the mutual filter of MatchingPoints; one CTA of 1024 threads per pair (cap <= 1024)
+__global__ void __launch_bounds__(1024) sg_decode_kernel(const int* __restrict__ arg0, const float* __restrict__ val0, const int* __restrict__ arg1,
+                                                         const int* __restrict__ n, int cap, float thr, int* __restrict__ idx0, int* __restrict__ idx1,
+                                                         float* __restrict__ ms0, float* __restrict__ ms1, int* __restrict__ m_idx,
+                                                         float* __restrict__ m_score, int* __restrict__ m_count) {
+  const int p = blockIdx.x;
+  const int t = threadIdx.x;
+  const int m = n[2 * p], nn = n[2 * p + 1];
+  __shared__ float s_ms0[1024];
+  __shared__ unsigned char s_valid0[1024];
+  __shared__ int s_i1[1024];
+  const long long o = (long long)p * cap;
+  // side 0
+  float my_ms0 = 0.f;
+  bool valid0 = false;
+  int a0 = 0;
+  if (t < m) {
+    a0 = arg0[o + t];
+    const bool mutual0 = (arg1[o + a0] == t);
+    my_ms0 = mutual0 ? expf(val0[o + t]) : 0.f;
+    valid0 = mutual0 && (my_ms0 > thr);
+  }
+  s_ms0[t] = my_ms0;
+  s_valid0[t] = valid0;
+  __syncthreads();
+  if (t < m) { idx0[o + t] = valid0 ? a0 : -1; ms0[o + t] = my_ms0; }
+  // side 1
+  int my_i1 = -1;
+  float my_ms1 = 0.f;
+  if (t < nn) {
+    const int a1 = arg1[o + t];
+    const bool mutual1 = (arg0[o + a1] == t);
+    my_ms1 = mutual1 ? s_ms0[a1] : 0.f;
+    const bool valid1 = mutual1 && s_valid0[a1];
+    my_i1 = valid1 ? a1 : -1;
+    idx1[o + t] = my_i1;
+    ms1[o + t] = my_ms1;
+  }
+  s_i1[t] = my_i1;
+  __syncthreads();
+  // PointMatcher: i with indices0[i] in range and indices1[indices0[i]] == i -> match (i, indices0[i]), score (ms0[i] + ms1[j]) / 2
+  bool ok = false;
+  int j = 0;
+  if (t < m && valid0) {
+    j = a0;
+    ok = (j >= 0 && j < nn && s_i1[j] == t);
+  }
+  __shared__ int ws[32];
+  const int lane = t & 31, warp = t >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) ws[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    int w = ws[lane];
+#pragma unroll
+    for (int q = 1; q < 32; q <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, w, q); if (lane >= q) w += tt; }
+    ws[lane] = w;
+  }
+  __syncthreads();
+  const int pos = (warp ? ws[warp - 1] : 0) + __popc(bal & ((1u << lane) - 1));
+  if (ok) {
+    m_idx[(o + pos) * 2] = t;
+    m_idx[(o + pos) * 2 + 1] = j;
+    // mscores1[j] for a mutual valid pair equals mscores0[i]; keep the reference's expression
+    m_score[o + pos] = (float)(((double)my_ms0 + (double)s_ms0[t]) / 2.0);
+  }
+  if (t == 0) m_count[p] = ws[31];
+}
+
+void launch_sg_sinkhorn_decode(const float* sim, const int* n, int pairs, int cap, float bin_score, int iters, float* Z, float* u, float* v,
+                               float thr, int* arg0, float* val0, int* arg1, int* idx0, int* idx1, float* ms0, float* ms1, int* m_idx,
+                               float* m_score, int* m_count, float* dense_out, cudaStream_t st) {
+  sg_couplings_kernel<<<dim3((cap + 1 + 127) / 128, cap + 1, pairs), 128, 0, st>>>(sim, n, cap, bin_score, Z, u, v);
+  for (int it = 0; it < iters; ++it) {
+    sg_row_pass_kernel<<<dim3((cap + 1 + 7) / 8, pairs), 256, 0, st>>>(Z, n, cap, u, v);
+    sg_col_pass_kernel<<<dim3((cap + 1 + 31) / 32, pairs), dim3(32, 8), 0, st>>>(Z, n, cap, u, v);
+  }
+  sg_rowmax_kernel<<<dim3((cap + 1 + 7) / 8, pairs), 256, 0, st>>>(Z, u, v, n, cap, arg0, val0, dense_out);
+  sg_colmax_kernel<<<dim3((cap + 31) / 32, pairs), dim3(32, 8), 0, st>>>(Z, u, v, n, cap, arg1);
+  sg_decode_kernel<<<pairs, 1024, 0, st>>>(arg0, val0, arg1, n, cap, thr, idx0, idx1, ms0, ms1, m_idx, m_score, m_count);
 }
 
 }  // namespace airfe

@@ -14,3 +14,13 @@ void launch_lg_assignment(const float* sim, const float* x, const __half* wm, fl
                           float* scores_out, cudaStream_t st);
 
 }  // namespace airfe
+
+namespace airfe {
+// ---- SuperGlue (G5) ------------------------------------------------------------------------------------------------------------
+void launch_sg_prepare(const float* feat, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, float* x,
+                       __half* kin16, cudaStream_t st);
+// couplings Z [pair][cap+1][cap+1] from sim (already divided by 16) + bin score; 100 log-Sinkhorn iterations; decode
+void launch_sg_sinkhorn_decode(const float* sim, const int* n, int pairs, int cap, float bin_score, int iters, float* Z, float* u, float* v,
+                               float thr, int* arg0, float* val0, int* arg1, int* idx0, int* idx1, float* ms0, float* ms1, int* m_idx,
+                               float* m_score, int* m_count, float* dense_out, cudaStream_t st);
+}  // namespace airfe

@@ -45,3 +45,43 @@ class LightGlue {
 };
 
 }  // namespace airfe
+
+namespace airfe {
+
+// SuperGlue (G5) device pipeline.  Replaces SuperGlue::infer (src/super_glue.cpp:137-197): process_input (:199-246), the
+// engine (keypoint encoder, 18 GNN layers, final projection, 100 in-graph Sinkhorn iterations) and decode (:339-367).
+struct SuperGlueOutputs {
+  int* idx0 = nullptr;      // [P][cap]  indices0 (-1 = unmatched)
+  int* idx1 = nullptr;      // [P][cap]
+  float* ms0 = nullptr;     // [P][cap]  mscores0
+  float* ms1 = nullptr;
+  int* m_idx = nullptr;     // [P][cap][2] mutual matches as PointMatcher::MatchingPoints forms them
+  float* m_score = nullptr; // (mscores0[i] + mscores1[j]) / 2
+  int* m_count = nullptr;   // [P]
+  float* dense = nullptr;   // [P][cap+1][cap+1] final score matrix (parity tap)
+};
+
+class SuperGlue {
+ public:
+  bool init(const MatcherConfig& cfg, const std::string& weights_dir, bool outdoor);
+  bool run(const float* d_feat, const int* d_n, int feat_cap, int pairs, bool want_dense, cudaStream_t st);
+  const SuperGlueOutputs& out() const { return out_; }
+  int cap() const { return cfg_.cap; }
+  double tc_flops(int pairs) { return build_ops(pairs) ? ops_[pairs].tc_flops : 0.0; }
+  int launches(int pairs) { return build_ops(pairs) ? ops_[pairs].launches + 210 : 0; }
+
+ private:
+  bool build_ops(int pairs);
+  MatcherConfig cfg_;
+  Arena arena_;
+  std::map<int, OpList> ops_;
+  DenseW kenc_[5], final_;
+  struct Layer { DenseW qkv, merge, mlp0, mlp3; } L_[18];
+  float bin_score_ = 0.f;
+  float *x_ = nullptr, *S_ = nullptr, *sim_ = nullptr, *Z_ = nullptr, *u_ = nullptr, *v_ = nullptr, *val0_ = nullptr;
+  __half *kin16_ = nullptr, *k1_ = nullptr, *k2_ = nullptr, *cat16_ = nullptr, *qkv16_ = nullptr, *P_ = nullptr, *ctx16_ = nullptr, *h16_ = nullptr, *md16_ = nullptr;
+  int *n_ = nullptr, *arg0_ = nullptr, *arg1_ = nullptr;
+  SuperGlueOutputs out_;
+};
+
+}  // namespace airfe

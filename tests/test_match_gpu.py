@@ -80,3 +80,51 @@ def test_stereo_entry_matches_two_step_path(ctx):
         i0, i1 = st[p]["matches"][0][:, 0], st[p]["matches"][0][:, 1]
         disp = st[p]["feat_l"][1, i0] - st[p]["feat_r"][1, i1]
         assert len(i0) > 100 and abs(np.median(disp) - d) < 1.5, (len(i0), np.median(disp), d)
+
+
+@pytest.fixture(scope="module")
+def ctx_sg():
+    os.environ["AIRFE_DEBUG_DENSE"] = "1"
+    from airslam_b200 import capi
+    c = capi.Context(max_batch=3, enable_superpoint=0, enable_plnet=0, enable_lightglue=0, enable_superglue=1, image_width=640, image_height=480)
+    yield c
+    c.close()
+
+
+def test_superglue_scores_decode_and_matches(ctx_sg):
+    """G5: kenc + 18 GNN layers + 100 Sinkhorn iterations + decode, against the oracle (config 3: 640x480, SuperGlue-indoor)."""
+    from airslam_b200 import capi
+    from oracle import host, synth, weights
+    w = weights.load("superglue_indoor")
+    prs = []
+    for k, (n0, n1) in enumerate(((400, 380), (300, 150))):
+        f0 = synth.keypoint_set(n0, 640, 480, 170 + k)
+        f1, perm = synth.keypoint_set(n1, 640, 480, 180 + k, perturb_of=f0)
+        prs.append((f0, f1, perm))
+    raw = ctx_sg.superglue_batch([p[0] for p in prs], [p[1] for p in prs])
+    mm = ctx_sg.match_batch(capi.MATCHER_SUPERGLUE, [p[0] for p in prs], [p[1] for p in prs])
+    for i, (f0, f1, perm) in enumerate(prs):
+        n0, n1 = f0.shape[1], f1.shape[1]
+        dense = ctx_sg.debug_read(101, "sg_scores", i, np.float32, (513, 513))[:n0 + 1, :n1 + 1]
+        a = host.normalize_keypoints(f0, 640, 480, 0.7)
+        b = host.normalize_keypoints(f1, 640, 480, 0.7)
+        i0_o, i1_o, m0_o, m1_o, dense_o = host.superglue_infer(a, b, w, emul=True)
+        assert dense_o.shape == dense.shape
+        # 18 attention layers + 200 LSE passes in mixed precision: 5e-3 abs in probability space on the match block,
+        # 2e-3 relative on the dustbin row / column (values up to N)
+        di, do = dense[:n0, :n1], dense_o[:n0, :n1]
+        big = (do > np.log(1e-4)) | (di > np.log(1e-4))
+        assert np.abs(np.exp(di[big]) - np.exp(do[big])).max() <= 5e-3
+        assert np.abs(dense[n0, :] - dense_o[n0, :]).max() <= 2e-3 and np.abs(dense[:, n1] - dense_o[:, n1]).max() <= 2e-3
+        # decode on OUR matrix: exact
+        i0_g, i1_g, m0_g, m1_g = host.superglue_decode(dense)
+        assert np.array_equal(raw[i][0], i0_g) and np.array_equal(raw[i][1], i1_g)
+        assert np.abs(raw[i][2] - m0_g).max() <= 1e-6 and np.abs(raw[i][3] - m1_g).max() <= 1e-6
+        # vs the pure oracle
+        assert np.array_equal(raw[i][0], i0_o) and np.array_equal(raw[i][1], i1_o)
+        assert np.abs(raw[i][2] - m0_o).max() <= 3e-3
+        # PointMatcher::MatchingPoints semantics on top of it
+        exp = [(k, int(i0_g[k])) for k in range(n0) if 0 <= i0_g[k] < n1 and i1_g[i0_g[k]] == k]
+        assert [tuple(r) for r in mm[i][0]] == exp
+        v = raw[i][0] >= 0
+        assert (perm[raw[i][0][v]] == np.nonzero(v)[0]).mean() > 0.95
