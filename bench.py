@@ -173,12 +173,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from airslam_b200 import dist as D
+
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return D.max_over_ranks(x, device="cuda")
 
     P = args.pairs
     W_ = max(args.warmup, 3)

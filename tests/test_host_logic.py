@@ -1,0 +1,95 @@
+"""CPU: restated host semantics of the reference (tie-breaks, inclusive borders, integer divisions, empty inputs)."""
+import numpy as np
+import pytest
+
+from oracle import host, synth
+
+
+def test_cv_resize_bit_exact_against_cv2():
+    cv2 = pytest.importorskip("cv2")
+    for (w, h) in ((752, 480), (640, 480), (1280, 720), (376, 240), (512, 512)):
+        img = synth.stereo_pair(w, h, 3)[0]
+        assert np.array_equal(host.cv_resize_u8(img), cv2.resize(img, (512, 512))), (w, h)
+    noise = np.random.RandomState(0).randint(0, 256, (480, 752)).astype(np.uint8)
+    assert np.array_equal(host.cv_resize_u8(noise), cv2.resize(noise, (512, 512)))
+
+
+def test_process_image_is_double_division_then_float():
+    img = np.arange(512 * 512, dtype=np.uint32).reshape(512, 512).astype(np.uint8)
+    x = host.process_image(img)
+    assert x.dtype == np.float32 and x.shape == (1, 1, 512, 512)
+    assert np.array_equal(x[0, 0], (img.astype(np.float64) / 255.0).astype(np.float32))
+
+
+def test_detect_point_border_is_inclusive_and_ties_are_raster_ordered():
+    heat = np.zeros((512, 512), dtype=np.float32)
+    heat[4, 4] = 0.5       # x == border: kept
+    heat[3, 100] = 0.9     # y < border: dropped
+    heat[508, 508] = 0.5   # x == W - border: kept (reference uses '>' W-border, src/plnet.cpp:332)
+    heat[509, 10] = 0.9    # y > H - border: dropped
+    heat[100, 100] = 0.5
+    pts = host.detect_point(heat, 0.004, 4, 400)
+    assert pts.shape == (3, 3)
+    assert [tuple(p) for p in pts[1:].T] == [(4.0, 4.0), (100.0, 100.0), (508.0, 508.0)]    # raster order when <= top_k
+    pts = host.detect_point(heat, 0.004, 4, 2)
+    assert [tuple(p) for p in pts[1:].T] == [(4.0, 4.0), (100.0, 100.0)]                   # equal scores: lower raster index first
+    assert host.detect_point(np.zeros((512, 512), np.float32), 0.004, 4, 400).shape == (3, 0)
+
+
+def test_extract_descriptors_unit_norm_and_zero_column():
+    rs = np.random.RandomState(1)
+    desc = rs.normal(size=(256, 64, 64)).astype(np.float32)
+    desc[:, :3, :3] = 0
+    pts = np.array([[0.1, 0.2, 0.3], [250.0, 4.0, 508.0], [300.0, 4.0, 4.0]], dtype=np.float32)
+    d = host.extract_descriptors(desc, pts)
+    assert d.shape == (256, 3)
+    assert abs(np.linalg.norm(d[:, 0]) - 1) < 1e-5 and abs(np.linalg.norm(d[:, 2]) - 1) < 1e-5
+    assert np.all(d[:, 1] == 0)      # all-zero neighbourhood stays zero (Eigen normalize() guard), no NaN
+
+
+def test_wireframe_matcher_first_seen_order_and_swap():
+    keep = np.array([0, 1, 1, 0, 1, 1, 1], dtype=np.float32)
+    imin = np.array([0, 5, 2, 0, 5, 1, 2], dtype=np.float32)
+    imax = np.array([0, 9, 7, 0, 9, 3, 7], dtype=np.float32)
+    ki, inv, pairs = host.wireframe_matcher(keep, imin, imax)
+    assert ki.tolist() == [1, 2, 4, 5, 6]
+    assert inv.tolist() == [0, 1, 0, 2, 1]
+    assert pairs.tolist() == [[9, 5], [7, 2], [3, 1]]      # (max, min)
+    ki, inv, pairs = host.wireframe_matcher(np.zeros(4, np.float32), np.zeros(4, np.float32), np.zeros(4, np.float32))
+    assert len(ki) == 0 and pairs.shape == (0, 2)
+
+
+def test_normalize_keypoints_integer_half_width():
+    f = np.zeros((259, 2), dtype=np.float32)
+    f[1] = [376.0, 0.0]
+    f[2] = [240.0, 10.0]
+    n = host.normalize_keypoints(f, 753, 481, 0.5)      # 753 / 2 == 376 (integer division, src/point_matcher.cc:45)
+    assert n[1, 0] == 0.0 and n[2, 0] == 0.0
+    l_inv = np.float32(1.0 / 753 * np.float64(np.float32(0.5)))
+    assert n[1, 1] == np.float32(-376.0) * l_inv
+
+
+def test_filter_matches_first_max_and_threshold():
+    s = np.full((3, 4), -10.0, dtype=np.float32)
+    s[0, 1] = s[0, 2] = -0.1          # row tie: first column wins
+    s[1, 1] = -0.05                   # column 1's max is row 1 -> row 0 is not mutual
+    s[2, 3] = np.log(0.1)             # exp == threshold exactly: rejected ('>' 0.1)
+    idx, sc = host.filter_matches(s)
+    assert idx.tolist() == [[1, 1]]
+    assert abs(sc[0] - np.exp(np.float32(-0.05))) < 1e-7
+
+
+def test_superglue_decode_ignores_dustbins_and_thresholds():
+    z = np.full((3, 3), -20.0, dtype=np.float32)
+    z[0, 1] = np.log(0.9)
+    z[1, 0] = np.log(0.15)            # mutual but exp <= 0.2 -> invalid
+    z[2, :] = 5.0                     # dustbin row / col are ignored
+    z[:, 2] = 5.0
+    i0, i1, m0, m1 = host.superglue_decode(z)
+    assert i0.tolist() == [1, -1] and i1.tolist() == [-1, 0]
+    assert abs(m0[0] - 0.9) < 1e-6 and abs(m0[1] - 0.15) < 1e-6 and abs(m1[1] - 0.9) < 1e-6
+
+
+def test_matching_points_empty_side():
+    f = synth.keypoint_set(10, 752, 480, 1)
+    assert host.matching_points(f, np.zeros((259, 0), np.float32), {}, 0, 752, 480) == []
