@@ -54,5 +54,19 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_mock_caller():
+    """g++: the C++ class surfaces (include/*.h + src/frontend/frontend.cc) against the compat shims, linked with libairfe.so."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(root, "tests", "cpp", "mock_caller")
+    srcs = [os.path.join(root, "src", "frontend", "frontend.cc"), os.path.join(root, "tests", "cpp", "mock_caller.cc")]
+    deps = srcs + [os.path.join(root, "include", f) for f in os.listdir(os.path.join(root, "include"))] + [LIB]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(root, "compat"), "-I" + os.path.join(root, "include")] + srcs + [
+        "-o", out, "-L" + HERE, "-lairfe", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../../airslam_b200"]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

@@ -82,7 +82,7 @@ def _declare_match(L):
     L.airfe_detect_match_stereo_batch.argtypes = [vp, i32, i32, i32, vp, vp, i32, i32, i32, i64, vp, i32, vp, vp, i32, vp, vp, i32, vp,
                                                   vp, vp, vp, i32, vp]
     L.airfe_detect_match_stereo_batch.restype = i32
-    L.airfe_superglue_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32]
+    L.airfe_superglue_batch.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i32]
     L.airfe_superglue_batch.restype = i32
     L.airfe_stereo_device.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i64, i32, i32]
     L.airfe_stereo_device.restype = i32
@@ -236,5 +236,5 @@ class Context:
         i0 = np.zeros((p, cap), dtype=np.int32); i1 = np.zeros((p, cap), dtype=np.int32)
         m0 = np.zeros((p, cap), dtype=np.float32); m1 = np.zeros((p, cap), dtype=np.float32)
         q = lambda a: a.ctypes.data_as(vp)
-        check(lib().airfe_superglue_batch(self.h, p, q(f0), q(n0), q(f1), q(n1), cap, q(i0), q(i1), q(m0), q(m1), cap))
+        check(lib().airfe_superglue_batch(self.h, p, q(f0), q(n0), q(f1), q(n1), cap, 0, q(i0), q(i1), q(m0), q(m1), cap))
         return [(i0[i, :n0[i]].copy(), i1[i, :n1[i]].copy(), m0[i, :n0[i]].copy(), m1[i, :n1[i]].copy()) for i in range(p)]

@@ -250,6 +250,19 @@ static int fetch_matches(airfe_ctx* c, int pairs, int* idx0, int* idx1, float* s
   return AIRFE_OK;
 }
 
+static thread_local bool g_prenorm = false;
+
+int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1,
+                      int feat_cap, int* idx0, int* idx1, float* score, int match_cap, int* n_match);
+
+int airfe_match_batch_prenormalized(airfe_ctx* c, int matcher, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1,
+                                    int feat_cap, int* idx0, int* idx1, float* score, int match_cap, int* n_match) {
+  g_prenorm = true;
+  int rc = airfe_match_batch(c, matcher, pairs, feat0, n0, feat1, n1, feat_cap, idx0, idx1, score, match_cap, n_match);
+  g_prenorm = false;
+  return rc;
+}
+
 int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1,
                       int feat_cap, int* idx0, int* idx1, float* score, int match_cap, int* n_match) {
   if (!c || !feat0 || !feat1 || !n0 || !n1 || !idx0 || !idx1 || !score || !n_match) { set_error("null argument"); return AIRFE_ERR_INVALID; }
@@ -273,16 +286,18 @@ int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, 
       cudaMemcpyAsync(c->d_mfeat + (size_t)s * kKpCap * 259, c->h_mfeat + (size_t)s * kKpCap * 259, (size_t)c->h_mn[s] * 259 * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(c->d_mn, c->h_mn, 8 * pairs, cudaMemcpyHostToDevice, st);
   const bool dense = getenv("AIRFE_DEBUG_DENSE") != nullptr;
-  if (sgm ? !c->sg->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st) : !c->lg->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st)) return AIRFE_ERR_CUDA;
+  if (sgm ? !c->sg->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm) : !c->lg->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm)) return AIRFE_ERR_CUDA;
   return fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, zero.data(), matcher);
 }
 
 int airfe_superglue_batch(airfe_ctx* c, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1, int feat_cap,
-                          int* indices0, int* indices1, float* mscores0, float* mscores1, int out_cap) {
+                          int prenormalized, int* indices0, int* indices1, float* mscores0, float* mscores1, int out_cap) {
   if (!c || !c->sg) { set_error("superglue not enabled in this context"); return AIRFE_ERR_INVALID; }
+  g_prenorm = prenormalized != 0;
   std::vector<int> i0((size_t)pairs * 1024), i1((size_t)pairs * 1024), nm(pairs);
   std::vector<float> sc((size_t)pairs * 1024);
   int rc = airfe_match_batch(c, AIRFE_MATCHER_SUPERGLUE, pairs, feat0, n0, feat1, n1, feat_cap, i0.data(), i1.data(), sc.data(), 1024, nm.data());
+  g_prenorm = false;
   if (rc != AIRFE_OK) return rc;
   const SuperGlueOutputs& o = c->sg->out();
   const int cap = c->sg->cap();

@@ -149,14 +149,15 @@ bool LightGlue::build_ops(int P) {
   return true;
 }
 
-bool LightGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bool want_dense, cudaStream_t st) {
+bool LightGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bool want_dense, cudaStream_t st, bool prenorm) {
   if (P < 1 || P > cfg_.max_pairs) { set_error("pairs %d outside [1,%d]", P, cfg_.max_pairs); return false; }
   if (!build_ops(P)) return false;
   const int S = 2 * P, cap = cfg_.cap;
   AIRFE_CUDA_OK(cudaMemcpyAsync(n_, d_n, sizeof(int) * S, cudaMemcpyDeviceToDevice, st));
   // float L_inv = 1.0 / std::max(width, height) * scale;  scale = 0.5 for LightGlue (src/point_matcher.cc:43,58)
   const float l_inv = (float)(1.0 / (double)(cfg_.image_width > cfg_.image_height ? cfg_.image_width : cfg_.image_height) * (double)0.5f);
-  timed("lg_prepare", st, [&] { launch_lg_prepare(d_feat, n_, S, cap, feat_cap, cfg_.image_width, cfg_.image_height, l_inv, wr_, x_, cat16_, rot_, st); });
+  // prenormalised input: (x - 0) * 1 reproduces the value bit for bit
+  timed("lg_prepare", st, [&] { launch_lg_prepare(d_feat, n_, S, cap, feat_cap, prenorm ? 0 : cfg_.image_width, prenorm ? 0 : cfg_.image_height, prenorm ? 1.f : l_inv, wr_, x_, cat16_, rot_, st); });
   if (!ops_[P].run(st)) return false;
   timed("lg_assignment+filter", st, [&] {
     launch_lg_assignment(sim_, x_, wm_, bm_, n_, P, cap, logsig_, lse_, row_arg_, row_val_, col_arg_, 0.1f, out_.idx, out_.score, out_.count,

@@ -22,7 +22,8 @@ class LightGlue {
  public:
   bool init(const MatcherConfig& cfg, const std::string& weights_dir);
   // feat: device [2*pairs][feat_cap][259] (slot = 2*pair + side), n: device [2*pairs].  Asynchronous on st.
-  bool run(const float* d_feat, const int* d_n, int feat_cap, int pairs, bool want_dense, cudaStream_t st);
+  // prenormalised: keypoints in rows 1-2 were already passed through PointMatcher::NormalizeKeypoints by the caller
+  bool run(const float* d_feat, const int* d_n, int feat_cap, int pairs, bool want_dense, cudaStream_t st, bool prenormalised = false);
   const MatchOutputs& out() const { return out_; }
   int cap() const { return cfg_.cap; }
   double tc_flops(int pairs);
@@ -64,7 +65,7 @@ struct SuperGlueOutputs {
 class SuperGlue {
  public:
   bool init(const MatcherConfig& cfg, const std::string& weights_dir, bool outdoor);
-  bool run(const float* d_feat, const int* d_n, int feat_cap, int pairs, bool want_dense, cudaStream_t st);
+  bool run(const float* d_feat, const int* d_n, int feat_cap, int pairs, bool want_dense, cudaStream_t st, bool prenormalised = false);
   const SuperGlueOutputs& out() const { return out_; }
   int cap() const { return cfg_.cap; }
   double tc_flops(int pairs) { return build_ops(pairs) ? ops_[pairs].tc_flops : 0.0; }

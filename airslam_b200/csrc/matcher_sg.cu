@@ -126,14 +126,14 @@ bool SuperGlue::build_ops(int P) {
   return true;
 }
 
-bool SuperGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bool want_dense, cudaStream_t st) {
+bool SuperGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bool want_dense, cudaStream_t st, bool prenorm) {
   if (P < 1 || P > cfg_.max_pairs) { set_error("pairs %d outside [1,%d]", P, cfg_.max_pairs); return false; }
   if (!build_ops(P)) return false;
   const int S = 2 * P, cap = cfg_.cap;
   AIRFE_CUDA_OK(cudaMemcpyAsync(n_, d_n, sizeof(int) * S, cudaMemcpyDeviceToDevice, st));
   // scale = 0.7 for SuperGlue (src/point_matcher.cc:58)
   const float l_inv = (float)(1.0 / (double)(cfg_.image_width > cfg_.image_height ? cfg_.image_width : cfg_.image_height) * (double)0.7f);
-  timed("sg_prepare", st, [&] { launch_sg_prepare(d_feat, n_, S, cap, feat_cap, cfg_.image_width, cfg_.image_height, l_inv, x_, kin16_, st); });
+  timed("sg_prepare", st, [&] { launch_sg_prepare(d_feat, n_, S, cap, feat_cap, prenorm ? 0 : cfg_.image_width, prenorm ? 0 : cfg_.image_height, prenorm ? 1.f : l_inv, x_, kin16_, st); });
   if (!ops_[P].run(st)) return false;
   timed("sg_sinkhorn+decode", st, [&] {
     launch_sg_sinkhorn_decode(sim_, n_, P, cap, bin_score_, 100, Z_, u_, v_, 0.2f, arg0_, val0_, arg1_, out_.idx0, out_.idx1, out_.ms0, out_.ms1,

@@ -92,10 +92,15 @@ int airfe_detect(airfe_ctx* ctx, int net, const uint8_t* gray, int width, int he
 int airfe_match_batch(airfe_ctx* ctx, int matcher, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1,
                       int feat_cap, int* idx0, int* idx1, float* score, int match_cap, int* n_match);
 
+/* Same, for callers that already applied PointMatcher::NormalizeKeypoints (SuperPointLightGlue::infer / SuperGlue::infer take
+ * normalised keypoints, src/point_matcher.cc:59-67). */
+int airfe_match_batch_prenormalized(airfe_ctx* ctx, int matcher, int pairs, const float* feat0, const int* n0, const float* feat1,
+                                    const int* n1, int feat_cap, int* idx0, int* idx1, float* score, int match_cap, int* n_match);
+
 /* SuperGlue::infer surface (src/super_glue.cpp:137-197): per pair p, indices0 / mscores0 have n0[p] entries (at + p*out_cap),
  * indices1 / mscores1 n1[p] entries; -1 = unmatched.  (The class widens the scores to double.) */
 int airfe_superglue_batch(airfe_ctx* ctx, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1, int feat_cap,
-                          int* indices0, int* indices1, float* mscores0, float* mscores1, int out_cap);
+                          int prenormalized, int* indices0, int* indices1, float* mscores0, float* mscores1, int out_cap);
 
 /* The keyframe path of MapBuilder::ExtractFeatureThread (src/map_builder.cc:85-86) for `pairs` stereo pairs at once:
  * Detect(left, right, ...) + MatchingPoints(left, right).  Features never leave the device between detect and match.

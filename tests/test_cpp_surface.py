@@ -1,0 +1,56 @@
+"""The reference-facing C++ class surfaces (include/{feature_detector,plnet,super_point,light_glue,super_glue,point_matcher}.h):
+CPU: they compile and link against libairfe.so with a caller written like src/map_builder.cc / src/map_user.cc.
+GPU: the caller's results equal the C-ABI results bit for bit."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_headers_keep_the_reference_surface():
+    from airslam_b200 import build as b
+    b.build()
+    exe = b.build_mock_caller()
+    assert os.path.exists(exe)
+    hdr = open(os.path.join(ROOT, "include", "feature_detector.h")).read()
+    assert hdr.count("bool Detect(") == 6                        # include/feature_detector.h:12-26 of the reference
+    pm = open(os.path.join(ROOT, "include", "point_matcher.h")).read()
+    assert "int MatchingPoints(" in pm and "void NormalizeKeypoints(" in pm and "bool outlier_rejection=false" in pm
+    for h in ("plnet.h", "super_point.h", "light_glue.h", "super_glue.h"):
+        t = open(os.path.join(ROOT, "include", h)).read()
+        assert "NvInfer" not in t and "bool build();" in t and "bool infer(" in t
+
+
+@pytest.mark.gpu
+def test_mock_caller_equals_c_abi(tmp_path):
+    from airslam_b200 import build as b, capi
+    from oracle import synth
+    exe = b.build_mock_caller()
+    l, r, _ = synth.stereo_pair(752, 480, 77)
+    l.tofile(tmp_path / "l.raw")
+    r.tofile(tmp_path / "r.raw")
+    out = subprocess.run([exe, capi.WEIGHTS_DIR, str(tmp_path / "l.raw"), str(tmp_path / "r.raw"), "752", "480", "0", "1"], cwd=tmp_path,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = open(tmp_path / "mock_caller_out.bin", "rb").read()
+    nl, nr, nll, nrl, nj, nm = struct.unpack_from("6q", raw, 0)
+    off = 48
+    fl = np.frombuffer(raw, np.float32, nl * 259, off).reshape(nl, 259).T; off += nl * 259 * 4
+    fr = np.frombuffer(raw, np.float32, nr * 259, off).reshape(nr, 259).T; off += nr * 259 * 4
+    ll = np.frombuffer(raw, np.float64, nll * 4, off).reshape(nll, 4); off += nll * 32
+    rl = np.frombuffer(raw, np.float64, nrl * 4, off).reshape(nrl, 4); off += nrl * 32
+    jn = np.frombuffer(raw, np.float32, nj * 259, off).reshape(nj, 259).T; off += nj * 259 * 4
+    mt = np.frombuffer(raw, np.dtype([("q", "i4"), ("t", "i4"), ("d", "f4")]), nm, off)
+    ctx = capi.Context(max_batch=1, enable_superpoint=0)
+    ref = ctx.stereo_batch(capi.NET_PLNET, capi.MATCHER_LIGHTGLUE, l[None], r[None], lines=True, junctions=True)[0]
+    ctx.close()
+    assert np.array_equal(fl, ref["feat_l"]) and np.array_equal(fr, ref["feat_r"])
+    assert np.array_equal(ll, ref["lines_l"]) and np.array_equal(rl, ref["lines_r"])
+    assert np.array_equal(jn, ref["junc"])
+    assert np.array_equal(np.stack([mt["q"], mt["t"]], 1), ref["matches"][0])
+    assert np.allclose(mt["d"], 1.0 - ref["matches"][1], atol=1e-6)
+    assert "mono ok 1" in out.stdout and "reloc ok 1" in out.stdout
