@@ -22,7 +22,7 @@ def test_headers_keep_the_reference_surface():
     assert "int MatchingPoints(" in pm and "void NormalizeKeypoints(" in pm and "bool outlier_rejection=false" in pm
     for h in ("plnet.h", "super_point.h", "light_glue.h", "super_glue.h"):
         t = open(os.path.join(ROOT, "include", h)).read()
-        assert "NvInfer" not in t and "bool build();" in t and "bool infer(" in t
+        assert "#include <NvInfer" not in t and "tensorrtbuffer" not in t and "bool build();" in t and "bool infer(" in t
 
 
 @pytest.mark.gpu
