@@ -39,6 +39,8 @@ def _declare(L):
                                    i32, i32, i32, f32p, i32, i32,
                                    vp, i64, i64, i64, i32, i32, i32, i32, vp]
     L.airfe_op_tc_gemm.restype = i32
+    L.airfe_op_conv3x3.argtypes = [vp, i32, i32, i32, i32, i64, vp, f32p, i32, i32, i32, vp, i64, vp, i64, vp]
+    L.airfe_op_conv3x3.restype = i32
 
 
 class Config(C.Structure):

@@ -218,11 +218,6 @@ bool Detector::build_ops(int B) {
   if (trunk_ops_.count(B)) return true;
   OpList t;
   const bool lines = plnet_ && cfg_.enable_lines;
-  auto pool = [&](OpList* ol, const Act& in, const Act& out) {
-    const Act i = in, o = out;
-    ol->push("maxpool2", 0, [=](cudaStream_t st) { launch_maxpool2((const __half*)i.p, i.C, i.H, i.W, B, i.ps, (__half*)o.p, o.ps, st); return true; });
-    ol->launches++;
-  };
   auto up = [&](OpList* ol, const Act& in, const Act& out) {
     const Act i = in, o = out;
     ol->push("upsample2", 0, [=](cudaStream_t st) { launch_upsample2((const __half*)i.p, i.C, i.H, i.W, B, i.ps, (__half*)o.p, o.ps, st); return true; });
@@ -235,14 +230,11 @@ bool Detector::build_ops(int B) {
     t.launches++;
   }
   const Act r3 = cat2_.slice(32, 64), r5 = cat3_.slice(128, 128);
-  if (!add_dense(&t, a1_, w1b_, r1_, B, true)) return false;
-  pool(&t, r1_, p1_);
-  if (!add_dense(&t, p1_, w2a_, a2_, B, true) || !add_dense(&t, a2_, w2b_, r3, B, true)) return false;
-  pool(&t, r3, p2_);
-  if (!add_dense(&t, p2_, w3a_, a3_, B, true) || !add_dense(&t, a3_, w3b_, r5, B, true)) return false;
-  pool(&t, r5, p3_);
-  if (!add_dense(&t, p3_, w4a_, a4_, B, true) || !add_dense(&t, a4_, w4b_, r7_, B, true)) return false;
-  if (!add_dense(&t, r7_, wPD_, pd_, B, true)) return false;
+  if (!add_conv3x3(&t, a1_, w1b_, &r1_, &p1_, B, true)) return false;                         // conv1b (+ fused pool)
+  if (!add_conv3x3(&t, p1_, w2a_, &a2_, nullptr, B, true) || !add_conv3x3(&t, a2_, w2b_, &r3, &p2_, B, true)) return false;
+  if (!add_conv3x3(&t, p2_, w3a_, &a3_, nullptr, B, true) || !add_conv3x3(&t, a3_, w3b_, &r5, &p3_, B, true)) return false;
+  if (!add_conv3x3(&t, p3_, w4a_, &a4_, nullptr, B, true) || !add_conv3x3(&t, a4_, w4b_, &r7_, nullptr, B, true)) return false;
+  if (!add_conv3x3(&t, r7_, wPD_, &pd_, nullptr, B, true)) return false;
   if (!add_dense(&t, pd_.slice(0, 256), wPb_, logits_, B, false, 65, 80)) return false;
   if (!add_dense(&t, pd_.slice(256, 256), wDb_, descraw_, B, false)) return false;
   {
@@ -254,30 +246,34 @@ bool Detector::build_ops(int B) {
 
   if (lines) {
     OpList l;
-    if (!add_dense(&l, r1_, l1a_, l1a_o_, B, true) || !add_dense(&l, l1a_o_, l1b_, l1b_o_, B, true)) return false;
-    pool(&l, l1b_o_, cat2_.slice(0, 32));
-    if (!add_dense(&l, cat2_, l2a_, l2a_o_, B, true) || !add_dense(&l, l2a_o_, l2b_, l2b_o_, B, true)) return false;
-    pool(&l, l2b_o_, cat3_.slice(0, 128));
+    const bool halo = conv3x3_halo_enabled();
+    const Act c2lo = cat2_.slice(0, 32), c3lo = cat3_.slice(0, 128);
+    if (!add_conv3x3(&l, r1_, l1a_, &l1a_o_, nullptr, B, true)) return false;
+    if (!add_conv3x3(&l, l1a_o_, l1b_, halo ? nullptr : &l1b_o_, &c2lo, B, true)) return false;       // only the pooled map is consumed
+    if (!add_conv3x3(&l, cat2_, l2a_, &l2a_o_, nullptr, B, true)) return false;
+    if (!add_conv3x3(&l, l2a_o_, l2b_, halo ? nullptr : &l2b_o_, &c3lo, B, true)) return false;
     Act x = cat3_;
     for (int s = 0; s < 2; ++s) {
       HGBuf& g = hgb_[s];
       Act in = x;
       for (int lv = 0; lv < 5; ++lv) {
-        if (!add_dense(&l, in, hg_[s].c[lv][0], g.a[lv], B, true) || !add_dense(&l, g.a[lv], hg_[s].c[lv][1], g.r[lv], B, true)) return false;
-        if (lv < 4) { pool(&l, g.r[lv], g.pool[lv]); in = g.pool[lv]; }
+        if (!add_conv3x3(&l, in, hg_[s].c[lv][0], &g.a[lv], nullptr, B, true)) return false;
+        if (!add_conv3x3(&l, g.a[lv], hg_[s].c[lv][1], &g.r[lv], lv < 4 ? &g.pool[lv] : nullptr, B, true)) return false;
+        if (lv < 4) in = g.pool[lv];
       }
       Act u = g.r[4];
       for (int k = 0; k < 4; ++k) {      // k = 0: 8 -> 16 (deconv1, skip = level-3 relu), ... k = 3: 64 -> 128 (skip = level-0 relu)
         up(&l, u, g.up[k]);
-        if (!add_dense(&l, g.up[k], hg_[s].dec[k], g.cat[k].slice(0, 64), B, true)) return false;
-        if (!add_dense(&l, g.r[3 - k], hg_[s].aup[k], g.cat[k].slice(64, 64), B, true)) return false;
-        if (!add_dense(&l, g.cat[k], hg_[s].bup[k], g.u[k], B, true)) return false;
+        const Act clo = g.cat[k].slice(0, 64), chi = g.cat[k].slice(64, 64);
+        if (!add_conv3x3(&l, g.up[k], hg_[s].dec[k], &clo, nullptr, B, true)) return false;
+        if (!add_conv3x3(&l, g.r[3 - k], hg_[s].aup[k], &chi, nullptr, B, true)) return false;
+        if (!add_conv3x3(&l, g.cat[k], hg_[s].bup[k], &g.u[k], nullptr, B, true)) return false;
         u = g.u[k];
       }
       x = u;
     }
     if (!add_dense(&l, x, fc2_, fc2_o_, B, false)) return false;                 // no ReLU after fc2 (graph)
-    if (!add_dense(&l, fc2_o_, heads0_, hmid_o_, B, true)) return false;        // 5 x (3x3 256->64) + ReLU
+    if (!add_conv3x3(&l, fc2_o_, heads0_, &hmid_o_, nullptr, B, true)) return false;   // 5 x (3x3 256->64) + ReLU
     if (!add_dense(&l, hmid_o_, heads2_, heads9_o_, B, false, 9, 16)) return false;
     if (!add_dense(&l, fc2_o_, fc1_, loi_o_, B, false)) return false;
     if (!add_dense(&l, fc2_o_, fc34_, thinaux_o_, B, false, 8, 16)) return false;

@@ -130,6 +130,10 @@ bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in
 // Append a tcgen05 conv / GEMM op.
 bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int batch, bool relu, int n_valid = -1, int block_n = 0,
                const int* dyn_rows = nullptr, float scale = 1.f, const float* resid = nullptr, const Act* out2 = nullptr);
+// Append a 3x3 convolution on the halo-reuse tcgen05 kernel (tc_conv3x3.cuh); `out` and/or `pool_out` (fused 2x2 max-pool).
+// Falls back to the generic streaming-tap kernel (+ pool kernel) when AIRFE_CONV_V1 is set or the map is narrower than 8.
+bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu);
+bool conv3x3_halo_enabled();
 // Append a raw tcgen05 GEMM described by `d` (attention products).
 bool add_gemm(OpList* ol, const TcGemmDesc& d, double flops);
 

@@ -1,6 +1,7 @@
 // Low-level operator entry points of the C ABI (device pointers in, device pointers out).  These are what the
 // per-kernel parity tests call; the frame-level entry points live in airfe_capi.cu.
 #include "common.h"
+#include "engine.h"
 #include "../../include/airfe_c.h"
 
 using namespace airfe;
@@ -23,6 +24,19 @@ int airfe_op_tc_gemm(const void* a, int a_C, int W, int H, int B, long long a_sx
   TcGemmPlan plan;
   if (!tc_gemm_plan(d, &plan)) return AIRFE_ERR_INVALID;
   if (!tc_gemm_launch(plan, (cudaStream_t)stream)) return AIRFE_ERR_CUDA;
+  return AIRFE_OK;
+}
+
+int airfe_op_conv3x3(const void* in, int C, int W, int H, int B, long long in_ps, const void* w_packed, const float* bias, int n_rows, int c_in,
+                     int relu, void* out, long long out_ps, void* pool_out, long long pool_ps, void* stream) {
+  Act a; a.p = const_cast<void*>(in); a.C = C; a.W = W; a.H = H; a.ps = in_ps;
+  DenseW w; w.w = (__half*)w_packed; w.bias = const_cast<float*>(bias); w.n_rows = n_rows; w.c_in = c_in; w.c_in_pad = (c_in + 63) / 64 * 64; w.taps = 9;
+  Act o, po;
+  if (out) { o.p = out; o.C = n_rows; o.W = W; o.H = H; o.ps = out_ps; }
+  if (pool_out) { po.p = pool_out; po.C = n_rows; po.W = W / 2; po.H = H / 2; po.ps = pool_ps; }
+  OpList ol;
+  if (!add_conv3x3(&ol, a, w, out ? &o : nullptr, pool_out ? &po : nullptr, B, relu != 0)) return AIRFE_ERR_INVALID;
+  if (!ol.run((cudaStream_t)stream)) return AIRFE_ERR_CUDA;
   return AIRFE_OK;
 }
 

@@ -105,6 +105,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One elected lane of a fully converged warp (the issue loop stays warp-uniform so descriptors live in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// Constant part of a K-major SWIZZLE_128B descriptor (LBO field 1, SBO, version 1, layout 2); add (smem_addr >> 4) to it.
+__device__ __forceinline__ uint64_t smem_desc_base_sw128(uint32_t sbo_bytes) {
+  return (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32) | (static_cast<uint64_t>(1) << 46) |
+         (static_cast<uint64_t>(2) << 61);
+}
+
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) --------------------------------------------
 // Shared-memory matrix descriptor.  layout_type: 0 none, 2 SWIZZLE_128B, 4 SWIZZLE_64B, 6 SWIZZLE_32B.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type,

@@ -1,0 +1,121 @@
+// Host side of the halo-reuse 3x3 convolution kernel: tiling plan, shared-memory budget, launch.
+#include "common.h"
+#include "engine.h"
+#include "tc_conv3x3.cuh"
+
+#include <stdlib.h>
+
+namespace airfe {
+
+struct ConvPlan {
+  ConvParams p;
+  int grid = 0, smem_bytes = 0;
+};
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, tc_conv3x3_kernel);
+    if (cudaFuncSetAttribute(tc_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(tc_conv3x3_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return false;
+    }
+    attr_set = true;
+  }
+  tc_conv3x3_kernel<<<plan.grid, kConvThreads, plan.smem_bytes, st>>>(plan.p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("tc_conv3x3 launch failed: %s", cudaGetErrorString(e)); return false; }
+  return true;
+}
+
+bool conv3x3_halo_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("AIRFE_CONV_V1") ? 0 : 1;
+  return v == 1;
+}
+
+bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu) {
+  if (w.taps != 9 || in.f32 || (out && out->f32) || (pool_out && pool_out->f32)) { set_error("add_conv3x3: unsupported layer"); return false; }
+  if (!conv3x3_halo_enabled() || in.W < 8 || (in.W % 8)) {
+    // generic streaming-tap kernel (+ separate pool kernel)
+    const Act* full = out;
+    if (!full) { set_error("add_conv3x3: v1 path needs a full-resolution output buffer"); return false; }
+    if (!add_dense(ol, in, w, *full, batch, relu)) return false;
+    if (pool_out) {
+      const Act i = *full, o = *pool_out;
+      ol->push("maxpool2", 0, [=](cudaStream_t st) { launch_maxpool2((const __half*)i.p, i.C, i.H, i.W, batch, i.ps, (__half*)o.p, o.ps, st); return true; });
+      ol->launches++;
+    }
+    return true;
+  }
+  ConvPlan plan;
+  ConvParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  const int n_valid = w.n_rows;
+  const int n16 = (n_valid + 15) / 16 * 16;
+  int block_n = n16 <= 256 ? n16 : (n16 % 256 == 0 ? 256 : (n16 % 160 == 0 ? 160 : 128));
+  p.block_n = block_n;
+  p.n_valid = n_valid;
+  p.n_tiles = (n_valid + block_n - 1) / block_n;
+  p.strips = (in.W >= 16 && 4 * conv_acc_stride(block_n) <= 512) ? 2 : 1;
+  p.kblocks = w.c_in_pad / 64;
+  p.c_in_pad = w.c_in_pad;
+  p.W = in.W; p.H = in.H; p.B = batch;
+  p.tiles_x = (in.W + 8 * p.strips - 1) / (8 * p.strips);
+  p.tiles_y = (in.H + kConvTH - 1) / kConvTH;
+  p.bias = w.bias; p.relu = relu;
+  if (out) { p.out = (__half*)out->p; p.out_sx = out->ps; p.out_sy = out->ps * out->W; p.out_sb = out->ps * out->W * out->H; }
+  if (pool_out) { p.pool_out = (__half*)pool_out->p; p.pool_sx = pool_out->ps; p.pool_sy = pool_out->ps * pool_out->W; p.pool_sb = pool_out->ps * pool_out->W * pool_out->H; }
+  const int a_bytes = conv_a_bytes(p.strips), b_bytes = conv_b_bytes(block_n);
+  const int budget = 212 * 1024;
+  const int res_bytes = 9 * p.kblocks * b_bytes;
+  if (p.n_tiles == 1 && res_bytes + 2 * a_bytes <= budget && res_bytes <= 120 * 1024) {
+    p.b_resident = 1;
+    p.stages_a = (budget - res_bytes) / a_bytes;
+    if (p.stages_a > 4) p.stages_a = 4;
+    p.stages_b = 0;
+  } else {
+    p.b_resident = 0;
+    p.stages_a = 2;
+    p.stages_b = (budget - 2 * a_bytes) / b_bytes;
+    if (p.stages_b > 12) p.stages_b = 12;
+    if (p.stages_b < 3) { set_error("add_conv3x3: shared memory budget too small"); return false; }
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)batch};
+    uint64_t str[3] = {(uint64_t)in.ps * 2, (uint64_t)in.ps * in.W * 2, (uint64_t)in.ps * in.W * in.H * 2};
+    uint32_t box[4] = {64, (uint32_t)(8 * p.strips + 2), (uint32_t)(kConvTH + 2), 1};
+    if (!make_tmap_f16(&p.tmA, in.p, 4, dims, str, box)) return false;
+    const uint64_t k_total = (uint64_t)9 * w.c_in_pad;
+    uint64_t bd[4] = {k_total, (uint64_t)w.n_rows, 1, 1};
+    uint64_t bs[3] = {k_total * 2, k_total * 2 * w.n_rows, k_total * 2 * w.n_rows};
+    uint32_t bb[4] = {64, (uint32_t)block_n, 1, 1};
+    if (!make_tmap_f16(&p.tmB, w.w, 4, bd, bs, bb)) return false;
+  }
+  const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
+  plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 4) * 8 + 16;
+  const int total = p.tiles_x * p.tiles_y * batch * p.n_tiles;
+  plan.grid = total < sm_count() ? total : sm_count();
+  if (in.C > w.c_in_pad || in.C < w.c_in) { set_error("add_conv3x3: activation has %d channels, weights expect %d", in.C, w.c_in); return false; }
+  const double fl = 2.0 * (double)in.W * in.H * batch * (double)n_valid * 9 * w.c_in;
+  ol->tc_flops += fl;
+  ol->launches += 1;
+  char nm[160];
+  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d", w.c_in, n_valid, in.W, in.H, batch, p.b_resident ? " Bres" : "", pool_out ? (out ? " +pool" : " pool-only") : "", p.strips);
+  ol->push(nm, fl, [plan](cudaStream_t st) { return conv_launch(plan, st); });
+  return true;
+}
+
+}  // namespace airfe

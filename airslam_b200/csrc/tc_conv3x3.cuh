@@ -1,0 +1,263 @@
+// tcgen05 3x3 convolution with HALO REUSE for sm_100a  (the dominant kernel of the path).
+//
+// The generic kernel (tc_gemm.cuh) streams one shifted 128-pixel A tile per tap: 9x the activation bytes through L2->SMEM,
+// which bounds small-C layers at ~350 TFLOP/s.  Here a CTA loads ONE halo tile of (8S+2) x 18 pixels x 64 channels per K block
+// and the nine taps are nine tcgen05 shared-memory descriptors into that same tile:
+//     start address = halo + ((ky*HW + kx + 8*s) * 128 B),  SBO = HW * 128 B   (HW = 8S + 2 halo pixels per row)
+// i.e. MMA row group g (8 consecutive pixels of image row y0+g) sits 1 halo row further down.  This relies on the measured
+// fact (profiles/r01_umma_descriptor_probe.txt) that SWIZZLE_128B is applied on absolute shared-memory address bits, so
+// a descriptor may start at any 128-byte row and use any SBO.
+//   * S = 1 or 2 strips of 8x16 pixels share the halo tile and each weight tile (S accumulators in TMEM, double-buffered).
+//   * weights: streamed per (K block, tap) through their own ring, or -- when 9*C*N*2 bytes fit -- resident in shared memory
+//     for the whole persistent CTA (64->64, 64->32, 32->32: the 512x512 layers).
+//   * epilogue: +bias, ReLU, fp16 NHWC store and/or fused 2x2 max-pool (warp shuffles: pool partners are lane^1 and lane^8).
+#pragma once
+#include "ptx.cuh"
+
+namespace airfe {
+
+struct ConvParams {
+  CUtensorMap tmA;  // 4-D (C, W, H, B), box (64, 8S+2, 18, 1), SWIZZLE_128B
+  CUtensorMap tmB;  // 4-D (K, N, 1, 1), box (64, block_n, 1, 1)
+  int kblocks, c_in_pad;
+  int strips;
+  int tiles_x, tiles_y, B, W, H;
+  int n_tiles, block_n, n_valid;
+  int b_resident;
+  int stages_a, stages_b;
+  const float* bias;
+  int relu;
+  __half* out;        // full-resolution fp16 NHWC store (nullptr: skip)
+  long long out_sb, out_sy, out_sx;
+  __half* pool_out;   // fused 2x2/2 max-pool store (nullptr: skip)
+  long long pool_sb, pool_sy, pool_sx;
+};
+
+constexpr int kConvThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int kConvTH = 16;
+
+__host__ __device__ inline int conv_a_bytes(int strips) { return ((8 * strips + 2) * (kConvTH + 2) * 128 + 1023) / 1024 * 1024; }
+__host__ __device__ inline int conv_b_bytes(int block_n) { return (block_n * 128 + 1023) / 1024 * 1024; }
+__host__ __device__ inline int conv_acc_stride(int block_n) { return (block_n + 31) / 32 * 32; }
+__host__ __device__ inline int conv_tmem_cols(int block_n, int strips) {
+  int need = 2 * strips * conv_acc_stride(block_n), c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int a_bytes = conv_a_bytes(p.strips);
+  const int b_bytes = conv_b_bytes(p.block_n);
+  const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + p.stages_a * a_bytes;
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem_b + n_b_slots * b_bytes);
+  uint64_t* empty_a = full_a + p.stages_a;
+  uint64_t* full_b = empty_a + p.stages_a;          // [stages_b] (streaming) or [1] (resident: all weights landed)
+  uint64_t* empty_b = full_b + (p.b_resident ? 1 : p.stages_b);
+  uint64_t* tmem_full = empty_b + (p.b_resident ? 1 : p.stages_b);
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = 8 * p.strips + 2;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.B;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const uint32_t acc_stride = conv_acc_stride(p.block_n);
+  const uint32_t tmem_cols = conv_tmem_cols(p.block_n, p.strips);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA);
+    ptx::prefetch_tmap(&p.tmB);
+    for (int s = 0; s < p.stages_a; ++s) { ptx::mbar_init(&full_a[s], 1); ptx::mbar_init(&empty_a[s], 1); }
+    const int nb = p.b_resident ? 1 : p.stages_b;
+    for (int s = 0; s < nb; ++s) { ptx::mbar_init(&full_b[s], 1); ptx::mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, tmem_cols); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  __shared__ float s_bias[512];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;
+  __syncthreads();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      const int n_tile_fixed = (p.n_tiles == 1);
+      if (p.b_resident) {   // weights of this CTA's (single) N tile: load once, keep for every tile
+        ptx::mbar_arrive_expect_tx(&full_b[0], (uint32_t)(9 * p.kblocks * p.block_n * 128));
+        for (int cb = 0; cb < p.kblocks; ++cb)
+          for (int tap = 0; tap < 9; ++tap)
+            ptx::tma_load_4d(smem_b + (cb * 9 + tap) * b_bytes, &p.tmB, &full_b[0], tap * p.c_in_pad + cb * 64, 0, 0, 0);
+      }
+      (void)n_tile_fixed;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tz = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * 8 * p.strips, y0 = ty * kConvTH;
+        for (int cb = 0; cb < p.kblocks; ++cb) {
+          ptx::mbar_wait(&empty_a[sa], pa ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_a[sa], (uint32_t)(HW * (kConvTH + 2) * 128));
+          ptx::tma_load_4d(smem_a + sa * a_bytes, &p.tmA, &full_a[sa], cb * 64, x0 - 1, y0 - 1, tz);
+          if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+          if (!p.b_resident) {
+            for (int tap = 0; tap < 9; ++tap) {
+              ptx::mbar_wait(&empty_b[sb], pb ^ 1);
+              ptx::mbar_arrive_expect_tx(&full_b[sb], (uint32_t)(p.block_n * 128));
+              ptx::tma_load_4d(smem_b + sb * b_bytes, &p.tmB, &full_b[sb], tap * p.c_in_pad + cb * 64, nt * p.block_n, 0, 0);
+              if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues =====
+    const uint32_t idesc = ptx::make_idesc_f16(128, p.block_n, 0);
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pa = 0, pb = 0, acc_phase = 0;
+    if (p.b_resident) { ptx::mbar_wait(&full_b[0], 0); ptx::tc_fence_after(); }
+    const uint64_t da_const = ptx::smem_desc_base_sw128((uint32_t)HW * 128);
+    const uint64_t db_const = ptx::smem_desc_base_sw128(1024);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(acc * p.strips) * acc_stride;
+      for (int cb = 0; cb < p.kblocks; ++cb) {
+        ptx::mbar_wait(&full_a[sa], pa);
+        ptx::tc_fence_after();
+        const uint64_t da_stage = da_const + (ptx::smem_u32(smem_a + sa * a_bytes) >> 4);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          uint64_t db;
+          if (p.b_resident) {
+            db = db_const + (ptx::smem_u32(smem_b + (cb * 9 + tap) * b_bytes) >> 4);
+          } else {
+            ptx::mbar_wait(&full_b[sb], pb);
+            ptx::tc_fence_after();
+            db = db_const + (ptx::smem_u32(smem_b + sb * b_bytes) >> 4);
+          }
+          const int ky = tap / 3, kx = tap % 3;
+          const uint64_t da_tap = da_stage + (uint64_t)((ky * HW + kx) * 8);      // 128-byte rows in 16-byte units
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_f16(d0, da_tap + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
+            if (p.strips == 2) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ptx::umma_f16(d0 + acc_stride, da_tap + 64 + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
+            }
+            if (!p.b_resident) ptx::umma_commit(&empty_b[sb]);
+          }
+          __syncwarp();
+          if (!p.b_resident) { if (++sb == p.stages_b) { sb = 0; pb ^= 1; } }
+        }
+        if (ptx::elect_one()) ptx::umma_commit(&empty_a[sa]);
+        __syncwarp();
+        if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+      }
+      if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===== epilogue: 8 warps; warp (2 + e) owns TMEM lane quarter (warp & 3) and half of the work (strip, or column half) =====
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int lx = lane & 7, ly = quarter * 4 + (lane >> 3);      // pixel of this lane inside an 8 x 16 strip
+    const int chunks = p.block_n / 16;
+    const int s_mine = (p.strips == 2) ? half : 0;
+    const int c_begin = (p.strips == 2) ? 0 : (half ? (chunks + 1) / 2 : 0);
+    const int c_end = (p.strips == 2) ? chunks : (half ? chunks : (chunks + 1) / 2);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tz = mt / (p.tiles_x * p.tiles_y);
+      const int y = ty * kConvTH + ly;
+      const int x = (tx * p.strips + s_mine) * 8 + lx;
+      const bool valid = (x < p.W) && (y < p.H);
+      const int n0 = nt * p.block_n;
+      __half* o_full = p.out ? p.out + (long long)tz * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx : nullptr;
+      __half* o_pool = p.pool_out ? p.pool_out + (long long)tz * p.pool_sb + (long long)(y >> 1) * p.pool_sy + (long long)(x >> 1) * p.pool_sx : nullptr;
+      const bool pool_lane = valid && !(lane & 1) && !(lane & 8);
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * p.strips + s_mine) * acc_stride + (uint32_t(quarter * 32) << 16);
+      uint32_t r[2][16];
+      if (c_begin < c_end) ptx::tmem_ld16(taddr + c_begin * 16, r[0]);
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; c += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int cc = c + u;
+          if (cc >= c_end) break;
+          ptx::tmem_ld_wait();                                              // chunk cc has landed in r[u]
+          if (cc + 1 < c_end) ptx::tmem_ld16(taddr + (cc + 1) * 16, r[u ^ 1]);   // next chunk in flight while this one is processed
+          const int nbase = n0 + cc * 16;
+          uint32_t h[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float f0 = __uint_as_float(r[u][2 * i]) + s_bias[nbase + 2 * i];
+            float f1 = __uint_as_float(r[u][2 * i + 1]) + s_bias[nbase + 2 * i + 1];
+            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+            __half2 h2 = __floats2half2_rn(f0, f1);
+            h[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          if (o_full && valid && nbase < p.n_valid) {
+            __half* o = o_full + nbase;
+            if (nbase + 16 <= p.n_valid) {
+              *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+            } else {
+              const __half* hh = reinterpret_cast<const __half*>(h);
+              for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) o[i] = hh[i];
+            }
+          }
+          if (p.pool_out) {
+            // 2x2 max-pool on the fp16-rounded values (identical to pooling the stored tensor): partners are lane^1 (x) and lane^8 (y)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __half2 a = *reinterpret_cast<__half2*>(&h[i]);
+              uint32_t o1 = __shfl_xor_sync(0xffffffffu, h[i], 1);
+              a = __hmax2(a, *reinterpret_cast<__half2*>(&o1));
+              uint32_t cur = *reinterpret_cast<uint32_t*>(&a);
+              uint32_t o8 = __shfl_xor_sync(0xffffffffu, cur, 8);
+              a = __hmax2(a, *reinterpret_cast<__half2*>(&o8));
+              h[i] = *reinterpret_cast<uint32_t*>(&a);
+            }
+            if (pool_lane && nbase < p.n_valid) {
+              __half* o = o_pool + nbase;
+              if (nbase + 16 <= p.n_valid) {
+                *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+              } else {
+                const __half* hh = reinterpret_cast<const __half*>(h);
+                for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) o[i] = hh[i];
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+}  // namespace airfe

@@ -131,7 +131,9 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
 bool tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, tc_gemm_kernel);
+    if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(tc_gemm_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
       return false;
     }

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 4);
+      ptx::mbar_init(&tmem_empty[s], 8);
     }
     ptx::fence_barrier_init();
   }
@@ -58,6 +58,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  __shared__ float s_bias[1024];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;
+  __syncthreads();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -95,44 +98,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = ptx::make_idesc_f16(kTileM, p.block_n, p.b_mn_major);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        if (p.dyn_w) {
-          const int mt = t / p.n_tiles;
-          if ((mt % tiles_x) * p.tw >= __ldg(p.dyn_w + (mt / (tiles_x * p.tiles_y)) * p.tb * p.dyn_w_stride)) continue;
-        }
-        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * acc_stride;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + kABytes;
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = ptx::make_smem_desc(sa + k * 32, 16, 1024, 2);
-            const uint64_t db = p.b_mn_major ? ptx::make_smem_desc(sb + k * 2048, 8192, 1024, 2)
-                                             : ptx::make_smem_desc(sb + k * 32, 16, 1024, 2);
-            ptx::umma_f16(d_tmem, da, db, idesc, (ks | k) != 0);
-          }
-          ptx::umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
-        ptx::umma_commit(&tmem_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+    // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues =====
+    const uint32_t idesc = ptx::make_idesc_f16(kTileM, p.block_n, p.b_mn_major);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint64_t d_const = ptx::smem_desc_base_sw128(1024);
+    const uint64_t db_mn_const = (static_cast<uint64_t>((8192 >> 4) & 0x3FFF) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                                 (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      if (p.dyn_w) {
+        const int mt = t / p.n_tiles;
+        if ((mt % tiles_x) * p.tw >= __ldg(p.dyn_w + (mt / (tiles_x * p.tiles_y)) * p.tb * p.dyn_w_stride)) continue;
       }
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * acc_stride;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+        const uint64_t da = d_const + (sa >> 4);
+        const uint64_t db = (p.b_mn_major ? db_mn_const : d_const) + ((sa + kABytes) >> 4);
+        const uint32_t bstep = p.b_mn_major ? (2048 >> 4) : 2;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) ptx::umma_f16(d_tmem, da + 2 * k, db + bstep * k, idesc, (ks | k) != 0);
+          ptx::umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ===== epilogue: TMEM -> registers -> (+bias, ReLU) -> global =====
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;
+    const int chunks = p.block_n / 16;
+    const int c_begin = half ? (chunks + 1) / 2 : 0, c_end = half ? chunks : (chunks + 1) / 2;
     const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -153,15 +161,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(quarter * 32) << 16);
       const int n0 = nt * p.block_n;
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld16(taddr + c, r);
+      uint32_t rr[2][16];
+      if (c_begin < c_end) ptx::tmem_ld16(taddr + c_begin * 16, rr[0]);
+#pragma unroll 1
+      for (int cq = c_begin; cq < c_end; cq += 2)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (cq + u >= c_end) break;
+        const int c = (cq + u) * 16;
         ptx::tmem_ld_wait();
+        if (cq + u + 1 < c_end) ptx::tmem_ld16(taddr + c + 16, rr[u ^ 1]);
+        const uint32_t (&r)[16] = rr[u];
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float f = __uint_as_float(r[i]);
-          if (p.bias && n0 + c + i < p.n_valid) f += __ldg(p.bias + n0 + c + i);
+          f += s_bias[(n0 + c + i) & 1023];
           if (n0 + c + i < p.scale_cols) f *= p.scale;
           if (p.relu) f = fmaxf(f, 0.f);
           v[i] = f;

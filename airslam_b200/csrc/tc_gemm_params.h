@@ -34,7 +34,7 @@ struct TcGemmParams {
   const int* dyn_w;  // optional: per-batch-index valid W (rows of a plain GEMM), read from device memory (tb must be 1)
 };
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two per TMEM lane quarter, splitting the columns)
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB

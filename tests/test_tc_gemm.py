@@ -145,3 +145,54 @@ def test_mn_major_b_pv():
     torch.cuda.synchronize()
     ref = torch.einsum("hnm,mhd->nhd", pm[:, :, :n1].float(), v.float().view(n1, 4, 64)).reshape(n0, 256)
     _close(o, ref.half())
+
+
+# ---- halo-reuse 3x3 kernel (csrc/tc_conv3x3.cuh) ---------------------------------------------------------------------
+def run_conv_halo(x_nhwc, w_oihw, bias, relu, want_full=True, want_pool=False, out=None, out_ch_off=0):
+    lib, check = _lib()
+    b, h, w, c = x_nhwc.shape
+    o, i, _, _ = w_oihw.shape
+    wp = pack_conv_weight(w_oihw, (i + 63) // 64 * 64)
+    full = pool = None
+    if want_full:
+        full = out if out is not None else torch.zeros(b, h, w, o, dtype=torch.float16, device="cuda")
+    if want_pool:
+        pool = torch.zeros(b, h // 2, w // 2, o, dtype=torch.float16, device="cuda")
+    fptr = (full.data_ptr() + out_ch_off * 2) if full is not None else None
+    check(lib.airfe_op_conv3x3(x_nhwc.data_ptr(), i, w, h, b, x_nhwc.stride(2), wp.data_ptr(), bias.data_ptr(), o, i, int(relu),
+                               fptr, full.shape[-1] if full is not None else 0, pool.data_ptr() if pool is not None else None, o, None))
+    torch.cuda.synchronize()
+    return full, pool
+
+
+@pytest.mark.parametrize("cfg", [
+    # b, h, w, cin, cout
+    (2, 64, 64, 64, 64),       # weights resident in smem, 2 strips
+    (1, 48, 40, 64, 32),       # N = 32, ragged tiles (h, w not multiples of 16)
+    (2, 32, 32, 32, 32),       # C_in = 32 (channel OOB fill)
+    (1, 64, 64, 96, 128),      # streamed weights, 2 K blocks, C_in = 96
+    (2, 32, 32, 128, 128),     # streamed weights, 2 strips
+    (1, 32, 32, 256, 320),     # N = 320 -> two N tiles of 160, single strip
+    (1, 16, 16, 128, 256),     # N = 256, single strip
+    (3, 8, 8, 128, 128),       # 8x8 maps: half-empty tile
+    (2, 16, 16, 128, 64),
+])
+def test_conv3x3_halo_matches_torch(cfg):
+    b, h, w, cin, cout = cfg
+    x, wt, bias = _mk(b, h, w, cin, cout, 3, seed=(hash(cfg) & 0xFFFF) + 7)
+    full, pool = run_conv_halo(x, wt, bias, True, want_full=True, want_pool=True)
+    ref = ref_conv(x, wt, bias, True).half()
+    _close(full, ref)
+    ref_pool = F.max_pool2d(full.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert torch.equal(pool.float(), ref_pool)     # pooling the fp16-rounded values is exact
+
+
+def test_conv3x3_halo_pool_only_and_channel_offset():
+    x, wt, bias = _mk(1, 64, 64, 64, 32, 3, seed=21)
+    _, pool = run_conv_halo(x, wt, bias, True, want_full=False, want_pool=True)
+    ref = F.max_pool2d(ref_conv(x, wt, bias, True).half().float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    _close(pool, ref.half())
+    buf = torch.zeros(1, 64, 64, 96, dtype=torch.float16, device="cuda")
+    run_conv_halo(x, wt, bias, False, want_full=True, out=buf, out_ch_off=32)
+    _close(buf[..., 32:64], ref_conv(x, wt, bias, False).half())
+    assert float(buf[..., :32].abs().max()) == 0 and float(buf[..., 64:].abs().max()) == 0
