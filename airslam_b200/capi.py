@@ -175,26 +175,29 @@ class Context:
         check(lib().airfe_match_batch(self.h, matcher, p, q(f0), q(n0), q(f1), q(n1), cap, q(i0), q(i1), q(sc), match_cap, q(nm)))
         return [(np.stack([i0[i, :nm[i]], i1[i, :nm[i]]], axis=1), sc[i, :nm[i]].copy()) for i in range(p)]
 
-    def stereo_batch(self, net, matcher, left, right, lines=False, junctions=False, line_cap=4096, junc_cap=1024, match_cap=1024):
-        """left/right: uint8 [P,H,W].  Returns per pair dict(feat_l, feat_r, lines_l, lines_r, junc, matches (idx, score))."""
+    def stereo_batch(self, net, matcher, left, right, lines=False, junctions=False, line_cap=2048, junc_cap=512, match_cap=1024, raw=False):
+        """left/right: uint8 [P,H,W].  Returns per pair dict(feat_l, feat_r, lines_l, lines_r, junc, matches (idx, score)).
+        Output buffers are allocated once per shape and reused (raw=True returns them unsliced: what a C caller sees)."""
         import numpy as np
         left = np.ascontiguousarray(left, dtype=np.uint8)
         right = np.ascontiguousarray(right, dtype=np.uint8)
         p, h, w = left.shape
         fc = self.cfg.max_keypoints
-        feat = np.zeros((2 * p, fc, 259), dtype=np.float32)
-        nf = np.zeros(2 * p, dtype=np.int32)
-        ln = np.zeros((2 * p, line_cap, 4), dtype=np.float64) if lines else None
-        nl = np.zeros(2 * p, dtype=np.int32)
-        jn = np.zeros((p, junc_cap, 259), dtype=np.float32) if junctions else None
-        nj = np.zeros(p, dtype=np.int32)
-        i0 = np.zeros((p, match_cap), dtype=np.int32)
-        i1 = np.zeros((p, match_cap), dtype=np.int32)
-        sc = np.zeros((p, match_cap), dtype=np.float32)
-        nm = np.zeros(p, dtype=np.int32)
+        key = (p, fc, bool(lines), bool(junctions), line_cap, junc_cap, match_cap)
+        if getattr(self, "_sb_key", None) != key:
+            self._sb_key = key
+            self._sb = dict(feat=np.empty((2 * p, fc, 259), dtype=np.float32), nf=np.zeros(2 * p, dtype=np.int32),
+                            ln=np.empty((2 * p, line_cap, 4), dtype=np.float64) if lines else None, nl=np.zeros(2 * p, dtype=np.int32),
+                            jn=np.empty((p, junc_cap, 259), dtype=np.float32) if junctions else None, nj=np.zeros(p, dtype=np.int32),
+                            i0=np.empty((p, match_cap), dtype=np.int32), i1=np.empty((p, match_cap), dtype=np.int32),
+                            sc=np.empty((p, match_cap), dtype=np.float32), nm=np.zeros(p, dtype=np.int32))
+        b = self._sb
+        feat, nf, ln, nl, jn, nj, i0, i1, sc, nm = (b[k] for k in ("feat", "nf", "ln", "nl", "jn", "nj", "i0", "i1", "sc", "nm"))
         q = lambda a: a.ctypes.data_as(vp) if a is not None else None
         check(lib().airfe_detect_match_stereo_batch(self.h, net, matcher, p, q(left), q(right), w, h, w, h * w, q(feat), fc, q(nf), q(ln), line_cap,
                                                     q(nl), q(jn), junc_cap, q(nj), q(i0), q(i1), q(sc), match_cap, q(nm)))
+        if raw:
+            return b
         out = []
         for i in range(p):
             out.append(dict(feat_l=feat[2 * i, :nf[2 * i]].T.copy(), feat_r=feat[2 * i + 1, :nf[2 * i + 1]].T.copy(),

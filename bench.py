@@ -223,13 +223,12 @@ def main():
     t0 = time.perf_counter()
     d2h = 0
     for i in range(args.steps):
-        res = ctx.stereo_batch(NET, MAT, batches[i % nb][0], batches[i % nb][1], lines=True, junctions=True)
+        res = ctx.stereo_batch(NET, MAT, batches[i % nb][0], batches[i % nb][1], lines=True, junctions=True, raw=True)   # host buffers in / out, as a C caller
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    for rr in res:
-        d2h += (rr["feat_l"].size + rr["feat_r"].size + rr["junc"].size) * 4 + (len(rr["lines_l"]) + len(rr["lines_r"])) * 16 + len(rr["matches"][1]) * 12
+    d2h = int(res["nf"].sum()) * 259 * 4 + int(res["nj"].sum()) * 259 * 4 + int(res["nl"].sum()) * 16 + int(res["nm"].sum()) * 12 + (5 * P) * 4
     h2d = 2 * P * W * H
     barrier()
 

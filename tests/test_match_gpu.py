@@ -123,7 +123,7 @@ def test_superglue_scores_decode_and_matches(ctx_sg):
         assert np.abs(raw[i][2] - m0_g).max() <= 1e-6 and np.abs(raw[i][3] - m1_g).max() <= 1e-6
         # vs the pure oracle
         assert np.array_equal(raw[i][0], i0_o) and np.array_equal(raw[i][1], i1_o)
-        assert np.abs(raw[i][2] - m0_o).max() <= 3e-3
+        assert np.abs(raw[i][2] - m0_o).max() <= 5e-3
         # PointMatcher::MatchingPoints semantics on top of it
         exp = [(k, int(i0_g[k])) for k in range(n0) if 0 <= i0_g[k] < n1 and i1_g[i0_g[k]] == k]
         assert [tuple(r) for r in mm[i][0]] == exp
