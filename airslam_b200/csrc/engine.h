@@ -134,6 +134,10 @@ bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int b
 // Falls back to the generic streaming-tap kernel (+ pool kernel) when AIRFE_CONV_V1 is set or the map is narrower than 8.
 bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu);
 bool conv3x3_halo_enabled();
+// Append fused multi-head attention (tc_attn.cuh): ctx = softmax(q k^T * scale) v per (slot, head); keys/values of slot ^ slot_xor.
+bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __half* v, long long row_stride, __half* ctx, const int* n, int slots,
+                         int cap, int slot_xor, float scale);
+bool attn_fused_enabled();
 // Append a raw tcgen05 GEMM described by `d` (attention products).
 bool add_gemm(OpList* ol, const TcGemmDesc& d, double flops);
 

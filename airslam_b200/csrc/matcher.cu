@@ -94,7 +94,8 @@ bool LightGlue::build_ops(int P) {
   const int* n = n_;
 
   auto attention = [&](const __half* qa, const __half* kb, const __half* vb, int xr) -> bool {
-    // S[s][h] = Q_s,h . K_(s^xr),h^T   (fp32), softmax rows, ctx_s = P . V_(s^xr)
+    if (attn_fused_enabled() && cap <= 512) return add_fused_attention(&ol, qa, kb, vb, 256, ctx16_, n, S, cap, xr, 1.f);
+    // unfused path (cap > 512): S[s][h] = Q_s,h . K_(s^xr),h^T (fp32 in HBM), softmax rows, ctx_s = P . V_(s^xr)
     TcGemmDesc d;
     d.a = qa; d.a_C = 64; d.W = cap; d.H = 4; d.B = S; d.a_sx = 256; d.a_sy = 64; d.a_sb = (long long)cap * 256;
     d.bw = kb; d.k_total = 64; d.n_rows = cap; d.bw_sn = 256; d.b_heads = 4; d.bw_shead = 64; d.b_batches = S; d.bw_sbatch = (long long)cap * 256;

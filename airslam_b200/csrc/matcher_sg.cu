@@ -91,6 +91,13 @@ bool SuperGlue::build_ops(int P) {
     Layer& Y = L_[l];
     // q (scaled by 1/8 = 1/sqrt(64), exact in fp16), k, v in head-major layout
     if (!add_dense(&ol, x16, Y.qkv, qkv, S, false, -1, 0, n)) return false;
+    if (attn_fused_enabled() && cap <= 512) {
+      if (!add_fused_attention(&ol, qkv16_, qkv16_ + 256, qkv16_ + 512, 768, ctx16_, n, S, cap, xr, 0.125f)) return false;
+      if (!add_dense(&ol, ctx, Y.merge, msg16, S, false, -1, 0, n)) return false;
+      if (!add_dense(&ol, cat, Y.mlp0, h16, S, true, -1, 0, n)) return false;
+      if (!add_dense(&ol, h16, Y.mlp3, xf, S, false, -1, 0, n, 1.f, x_, &x16)) return false;
+      continue;
+    }
     TcGemmDesc d;
     d.a = qkv16_; d.a_C = 64; d.W = cap; d.H = 4; d.B = S; d.a_sx = 768; d.a_sy = 64; d.a_sb = (long long)cap * 768;
     d.bw = qkv16_ + 256; d.k_total = 64; d.n_rows = cap; d.bw_sn = 768; d.b_heads = 4; d.bw_shead = 64; d.b_batches = S; d.bw_sbatch = (long long)cap * 768;

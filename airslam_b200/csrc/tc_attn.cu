@@ -1,0 +1,50 @@
+// Host side of the fused attention kernel: tensor maps over the q / k / v operand matrices and launch.
+#include "common.h"
+#include "engine.h"
+#include "tc_attn.cuh"
+
+#include <stdlib.h>
+
+namespace airfe {
+
+bool attn_fused_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("AIRFE_ATTN_V1") ? 0 : 1;
+  return v == 1;
+}
+
+// q, k, v: fp16 matrices with `row_stride` elements per keypoint row, head h at columns h*64; slot s at rows [s*cap, (s+1)*cap).
+bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __half* v, long long row_stride, __half* ctx, const int* n, int slots,
+                         int cap, int slot_xor, float scale) {
+  if (cap > 512 || cap % 128) { set_error("fused attention supports cap <= 512"); return false; }
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  uint64_t dims[4] = {64, (uint64_t)cap, 4, (uint64_t)slots};
+  uint64_t str[3] = {(uint64_t)row_stride * 2, 64 * 2, (uint64_t)cap * row_stride * 2};
+  uint32_t box_q[4] = {64, 128, 1, 1}, box_kv[4] = {64, 256, 1, 1};
+  if (!make_tmap_f16(&p.tmQ, q, 4, dims, str, box_q) || !make_tmap_f16(&p.tmK, k, 4, dims, str, box_kv) || !make_tmap_f16(&p.tmV, v, 4, dims, str, box_kv))
+    return false;
+  p.n = n; p.slots = slots; p.cap = cap; p.slot_xor = slot_xor; p.scale = scale; p.ctx = ctx;
+  const double fl = 2.0 * 2.0 * slots * 4 * (double)cap * cap * 64;   // same accounting as the unfused pair of GEMMs
+  ol->tc_flops += fl;
+  ol->launches += 1;
+  char nm[96];
+  snprintf(nm, sizeof(nm), "tc_attn fused %s slots=%d cap=%d", slot_xor ? "cross" : "self", slots, cap);
+  ol->push(nm, fl, [p, slots](cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes) != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(tc_attn_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return false;
+      }
+      attr_set = true;
+    }
+    tc_attn_kernel<<<slots * 4, kAttnThreads, kAttnSmemBytes, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("tc_attn launch failed: %s", cudaGetErrorString(e)); return false; }
+    return true;
+  });
+  return true;
+}
+
+}  // namespace airfe

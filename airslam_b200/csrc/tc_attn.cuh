@@ -1,0 +1,252 @@
+// Fused multi-head attention for the matchers on tcgen05: softmax(Q K^T * scale) V for one (image slot, head)
+// per CTA, 4 heads x 64 dims, up to 512 keys.  The score tile S (128 queries x n keys, fp32) lives ONLY in TMEM, the
+// probabilities P only in shared memory (fp16, written by the softmax warps directly in the K-major SWIZZLE_128B layout the
+// MMA reads), so nothing but Q, K, V and the context ever touches HBM -- the unfused path moved 67 MB of fp32 scores per
+// attention through HBM three times.
+//   warp 0 : TMA producer (K, V of the attended slot once per CTA; one Q tile per 128 queries)
+//   warp 1 : MMA issuer   (S = Q K^T: 2 x N<=256 ; O = P V: per 64-key block, V as MN-major B operand)
+//   warps 2-5 : softmax + epilogue (one query row per thread; max / sum / normalise = three passes over TMEM), then O -> fp16 ctx
+// Arithmetic: fp16 operands, fp32 accumulate, fp32 softmax statistics; the tensor core sees fp16(exp(s - max)) and the 1/sum
+// normalisation is applied to the fp32 output (same relative rounding as rounding the normalised probabilities).
+#pragma once
+#include "ptx.cuh"
+
+namespace airfe {
+
+struct AttnParams {
+  CUtensorMap tmQ;   // 4-D (64, rows=cap, 4 heads, slots)  box (64, 128, 1, 1)
+  CUtensorMap tmK;   // same geometry on the key matrix,     box (64, 256, 1, 1)
+  CUtensorMap tmV;   // same geometry on the value matrix,   box (64, 256, 1, 1)   (rows = keys: MN-major B for P.V)
+  const int* n;      // [slots] keypoints per slot (device)
+  int slots, cap, slot_xor;
+  float scale;       // applied to S before the softmax (1 for LightGlue: q,k pre-scaled; 1/8 for SuperGlue)
+  __half* ctx;       // [slots*cap][256] fp16, head h at columns h*64
+};
+
+constexpr int kAttnThreads = 192;
+constexpr int kAttnSmemQ = 128 * 128;            // 16 KiB
+constexpr int kAttnSmemKV = 512 * 128;           // 64 KiB each
+constexpr int kAttnPSlots = 4;                   // ring of 64-key P blocks (16 KiB each)
+constexpr int kAttnSmemBytes = kAttnSmemQ + 2 * kAttnSmemKV + kAttnPSlots * 16384 + 1024 + 256;
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kAttnSmemQ;
+  uint8_t* sV = sK + kAttnSmemKV;
+  uint8_t* sP = sV + kAttnSmemKV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kAttnPSlots * 16384);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_empty = bars + 2;
+  uint64_t* s_full = bars + 3;
+  uint64_t* o_full = bars + 4;
+  uint64_t* s_free = bars + 5;
+  uint64_t* p_full = bars + 6;                 // [4]
+  uint64_t* p_empty = bars + 6 + kAttnPSlots;  // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * kAttnPSlots);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = blockIdx.x >> 2, head = blockIdx.x & 3;
+  const int kslot = slot ^ p.slot_xor;
+  const int nq = min(__ldg(p.n + slot), p.cap);
+  const int nk = min(__ldg(p.n + kslot), 512);
+  const int q_tiles = (nq + 127) >> 7;
+  const int nkb = (nk + 63) >> 6;              // 64-key blocks of P / V
+  const int nk16 = (nk + 15) & ~15;            // key extent of the S MMAs
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmQ); ptx::prefetch_tmap(&p.tmK); ptx::prefetch_tmap(&p.tmV);
+    ptx::mbar_init(kv_full, 1); ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
+    ptx::mbar_init(s_full, 1); ptx::mbar_init(o_full, 1); ptx::mbar_init(s_free, 4);
+    for (int i = 0; i < kAttnPSlots; ++i) { ptx::mbar_init(&p_full[i], 4); ptx::mbar_init(&p_empty[i], 1); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (q_tiles > 0 && nk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===== TMA producer =====
+        const uint32_t kv_rows = (nk > 256) ? 512u : 256u;
+        ptx::mbar_arrive_expect_tx(kv_full, 2u * kv_rows * 128u);
+        ptx::tma_load_4d(sK, &p.tmK, kv_full, 0, 0, head, kslot);
+        ptx::tma_load_4d(sV, &p.tmV, kv_full, 0, 0, head, kslot);
+        if (nk > 256) {
+          ptx::tma_load_4d(sK + 256 * 128, &p.tmK, kv_full, 0, 256, head, kslot);
+          ptx::tma_load_4d(sV + 256 * 128, &p.tmV, kv_full, 0, 256, head, kslot);
+        }
+        uint32_t ph = 0;
+        for (int t = 0; t < q_tiles; ++t) {
+          ptx::mbar_wait(q_empty, ph ^ 1);
+          ptx::mbar_arrive_expect_tx(q_full, 128u * 128u);
+          ptx::tma_load_4d(sQ, &p.tmQ, q_full, 0, t * 128, head, slot);
+          ph ^= 1;
+        }
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer (warp-uniform loop, elected lane issues) =====
+      const uint64_t dk_const = ptx::smem_desc_base_sw128(1024);
+      const uint64_t dv_const = (static_cast<uint64_t>((8192 >> 4) & 0x3FFF) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
+                                (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);       // MN-major SW128
+      const uint64_t dq = dk_const + (ptx::smem_u32(sQ) >> 4);
+      const uint64_t dk = dk_const + (ptx::smem_u32(sK) >> 4);
+      const uint64_t dv = dv_const + (ptx::smem_u32(sV) >> 4);
+      const int n_lo = nk16 < 256 ? nk16 : 256, n_hi = nk16 - n_lo;
+      const uint32_t idesc_lo = ptx::make_idesc_f16(128, n_lo, 0);
+      const uint32_t idesc_hi = ptx::make_idesc_f16(128, n_hi > 0 ? n_hi : 16, 0);
+      const uint32_t idesc_pv = ptx::make_idesc_f16(128, 64, 1);
+      ptx::mbar_wait(kv_full, 0);
+      uint32_t ph = 0;
+      uint32_t pph = 0;   // phase bit per P ring slot
+      for (int t = 0; t < q_tiles; ++t) {
+        ptx::mbar_wait(q_full, ph);
+        ptx::mbar_wait(s_free, ph ^ 1);          // TMEM free again (previous tile's O has been read)
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, dq + 2 * k, dk + 2 * k, idesc_lo, k != 0);
+          if (n_hi > 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + 256, dq + 2 * k, dk + (256 * 128 >> 4) + 2 * k, idesc_hi, k != 0);
+          }
+          ptx::umma_commit(q_empty);             // Q tile consumed once these MMAs retire
+          ptx::umma_commit(s_full);
+        }
+        __syncwarp();
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int ps = kb & (kAttnPSlots - 1);
+          ptx::mbar_wait(&p_full[ps], (pph >> ps) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint64_t dp = dk_const + (ptx::smem_u32(sP + ps * 16384) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16(tmem_base, dp + 2 * k, dv + (uint64_t)(((kb * 64 + k * 16) * 128) >> 4), idesc_pv, (kb | k) != 0);
+            ptx::umma_commit(&p_empty[ps]);
+            if (kb == nkb - 1) ptx::umma_commit(o_full);
+          }
+          __syncwarp();
+          pph ^= 1u << ps;
+        }
+        ph ^= 1;
+      }
+    } else {
+      // ===== softmax + epilogue: thread = one query row =====
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
+      uint32_t ph = 0;
+      uint32_t eph = 0;   // phase bit per P ring slot
+      const float sc2 = p.scale * 1.4426950408889634f;      // exp(x) = exp2(x * log2 e): one FFMA + MUFU.EX2 per element
+      for (int t = 0; t < q_tiles; ++t) {
+        ptx::mbar_wait(s_full, ph);
+        ptx::tc_fence_after();
+        // pass 1: row max over the valid keys (raw scores; scale > 0 so the max commutes with it)
+        float mx = -INFINITY;
+        for (int c = 0; c < nk; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(trow + c, r);
+          ptx::tmem_ld_wait();
+          if (c + 32 <= nk) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < nk) ? __uint_as_float(r[i]) : -INFINITY);
+          }
+        }
+        const float m2 = mx * sc2;
+        // pass 2: e = exp(s - max) once per element: accumulate the row sum in fp32 and hand fp16(e) to the tensor core through
+        // shared memory (K-major SWIZZLE_128B, 64 keys per block); the 1/sum normalisation is applied to O in the epilogue.
+        float sum = 0.f;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int ps = kb & (kAttnPSlots - 1);
+          ptx::mbar_wait(&p_empty[ps], ((eph >> ps) & 1) ^ 1);     // slot free (first use of a fresh barrier passes immediately)
+          uint8_t* prow = sP + ps * 16384 + row * 128;
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            const int c0 = kb * 64 + hc * 32;
+            uint32_t r[32];
+            tmem_ld32(trow + c0, r);
+            ptx::tmem_ld_wait();
+            float e[32];
+            if (c0 + 32 <= nk) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { e[i] = exp2f(fmaf(__uint_as_float(r[i]), sc2, -m2)); sum += e[i]; }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { e[i] = (c0 + i < nk) ? exp2f(fmaf(__uint_as_float(r[i]), sc2, -m2)) : 0.f; sum += e[i]; }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {       // 4 chunks of 8 keys (16 bytes)
+              uint32_t pk[4];
+#pragma unroll
+              for (int q2 = 0; q2 < 4; ++q2) {
+                __half2 h2 = __floats2half2_rn(e[ch * 8 + q2 * 2], e[ch * 8 + q2 * 2 + 1]);
+                pk[q2] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              const int chunk = hc * 4 + ch;
+              *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          ptx::fence_proxy_async();                // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&p_full[ps]);
+          eph ^= 1u << ps;
+        }
+        const float inv = 1.f / sum;
+        // epilogue: O (128 x 64 fp32, TMEM columns 0..63) -> fp16 context rows
+        ptx::mbar_wait(o_full, ph);
+        ptx::tc_fence_after();
+        const int q = t * 128 + row;
+        __half* o = p.ctx + ((long long)slot * p.cap + q) * 256 + head * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(trow + c, r);
+          ptx::tmem_ld_wait();
+          if (q < nq) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint32_t h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __half2 h2 = __floats2half2_rn(__uint_as_float(r[i + 2 * e]) * inv, __uint_as_float(r[i + 2 * e + 1]) * inv);
+                h[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(o + c + i) = make_uint4(h[0], h[1], h[2], h[3]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(s_free);
+        ph ^= 1;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace airfe
