@@ -56,6 +56,9 @@ WEIGHTS_DIR = os.path.join(os.path.dirname(HERE), "weights")
 
 
 def _declare_frame(L):
+    L.airfe_alloc_pinned.argtypes = [i64]
+    L.airfe_alloc_pinned.restype = vp
+    L.airfe_free_pinned.argtypes = [vp]
     L.airfe_default_config.argtypes = [C.POINTER(Config)]
     L.airfe_create.argtypes = [C.POINTER(Config), i32, C.POINTER(vp)]
     L.airfe_create.restype = i32
@@ -92,6 +95,17 @@ def _declare_match(L):
     L.airfe_profile_stereo.restype = i64
     L.airfe_stereo_cost.argtypes = [vp, i32, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(i32)]
     L.airfe_stereo_cost.restype = i32
+
+
+def pinned_array(shape, dtype):
+    """numpy array backed by page-locked host memory (airfe_alloc_pinned); lives until the process exits."""
+    import numpy as np
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib().airfe_alloc_pinned(max(n, 16))
+    if not ptr:
+        raise AirfeError("pinned allocation failed")
+    buf = (C.c_char * max(n, 16)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 class Context:
@@ -179,16 +193,18 @@ class Context:
         """left/right: uint8 [P,H,W].  Returns per pair dict(feat_l, feat_r, lines_l, lines_r, junc, matches (idx, score)).
         Output buffers are allocated once per shape and reused (raw=True returns them unsliced: what a C caller sees)."""
         import numpy as np
-        left = np.ascontiguousarray(left, dtype=np.uint8)
-        right = np.ascontiguousarray(right, dtype=np.uint8)
+        if not (left.dtype == np.uint8 and left.flags.c_contiguous):
+            left = np.ascontiguousarray(left, dtype=np.uint8)
+        if not (right.dtype == np.uint8 and right.flags.c_contiguous):
+            right = np.ascontiguousarray(right, dtype=np.uint8)
         p, h, w = left.shape
         fc = self.cfg.max_keypoints
         key = (p, fc, bool(lines), bool(junctions), line_cap, junc_cap, match_cap)
         if getattr(self, "_sb_key", None) != key:
             self._sb_key = key
-            self._sb = dict(feat=np.empty((2 * p, fc, 259), dtype=np.float32), nf=np.zeros(2 * p, dtype=np.int32),
+            self._sb = dict(feat=pinned_array((2 * p, fc, 259), np.float32), nf=np.zeros(2 * p, dtype=np.int32),
                             ln=np.empty((2 * p, line_cap, 4), dtype=np.float64) if lines else None, nl=np.zeros(2 * p, dtype=np.int32),
-                            jn=np.empty((p, junc_cap, 259), dtype=np.float32) if junctions else None, nj=np.zeros(p, dtype=np.int32),
+                            jn=pinned_array((p, junc_cap, 259), np.float32) if junctions else None, nj=np.zeros(p, dtype=np.int32),
                             i0=np.empty((p, match_cap), dtype=np.int32), i1=np.empty((p, match_cap), dtype=np.int32),
                             sc=np.empty((p, match_cap), dtype=np.float32), nm=np.zeros(p, dtype=np.int32))
         b = self._sb

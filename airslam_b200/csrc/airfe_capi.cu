@@ -27,7 +27,20 @@ struct airfe_ctx {
   uint8_t* d_img = nullptr; size_t d_img_bytes = 0;
 };
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" {
+
+void* airfe_alloc_pinned(long long bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { set_error("cudaMallocHost(%lld) failed", bytes); return nullptr; }
+  return p;
+}
+void airfe_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 void airfe_default_config(airfe_config* c) {
   memset(c, 0, sizeof(*c));
@@ -374,12 +387,19 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
     if (cudaMallocHost(&c->h_img, need) != cudaSuccess || cudaMalloc(&c->d_img, need) != cudaSuccess) { set_error("staging allocation failed"); return AIRFE_ERR_CUDA; }
     c->h_img_bytes = c->d_img_bytes = need;
   }
-  for (int p = 0; p < pairs; ++p) {
-    memcpy(c->h_img + one * (2 * p), left + (size_t)img_stride * p, one);
-    memcpy(c->h_img + one * (2 * p + 1), right + (size_t)img_stride * p, one);
-  }
   cudaStream_t st = c->stream;
-  cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st);
+  if (is_pinned(left) && is_pinned(right)) {        // caller's frames are in pinned memory: DMA straight from them
+    for (int p = 0; p < pairs; ++p) {
+      cudaMemcpyAsync(c->d_img + one * (2 * p), left + (size_t)img_stride * p, one, cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(c->d_img + one * (2 * p + 1), right + (size_t)img_stride * p, one, cudaMemcpyHostToDevice, st);
+    }
+  } else {
+    for (int p = 0; p < pairs; ++p) {
+      memcpy(c->h_img + one * (2 * p), left + (size_t)img_stride * p, one);
+      memcpy(c->h_img + one * (2 * p + 1), right + (size_t)img_stride * p, one);
+    }
+    cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st);
+  }
   if (!d->run(c->d_img, 2 * pairs, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return AIRFE_ERR_CUDA;
   const DetectOutputs& o = d->out();
   if (!c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, st)) return AIRFE_ERR_CUDA;
@@ -390,14 +410,20 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
   if (lines) cudaMemcpyAsync(hc + B, o.n_lines, 4 * S, cudaMemcpyDeviceToHost, st);
   if (junc) cudaMemcpyAsync(hc + 2 * B, o.n_junc, 4 * S, cudaMemcpyDeviceToHost, st);
   const int kmax = c->cfg.max_keypoints;
+  const bool feat_direct = is_pinned(feat) && feat_cap >= kmax;   // pinned caller buffer: D2H lands in it directly (columns beyond n_feat are scratch)
   for (int i = 0; i < S; ++i)
-    cudaMemcpyAsync(c->h_feat + (size_t)i * kKpCap * 259, o.feat + (size_t)i * kKpCap * 259, (size_t)kmax * 259 * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(feat_direct ? feat + (size_t)i * feat_cap * 259 : c->h_feat + (size_t)i * kKpCap * 259, o.feat + (size_t)i * kKpCap * 259,
+                    (size_t)kmax * 259 * 4, cudaMemcpyDeviceToHost, st);
+  const bool junc_direct = junc && is_pinned(junc) && junc_cap >= kJunc;
+  if (junc_direct)
+    for (int p = 0; p < pairs; ++p)
+      cudaMemcpyAsync(junc + (size_t)p * junc_cap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)kJunc * 259 * 4, cudaMemcpyDeviceToHost, st);
   int rc = fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, nullptr);   // synchronises the stream
   if (rc != AIRFE_OK) return rc;
   for (int i = 0; i < S; ++i) {
     const int n = hc[i] < feat_cap ? hc[i] : feat_cap;
     n_feat[i] = n;
-    memcpy(feat + (size_t)i * feat_cap * 259, c->h_feat + (size_t)i * kKpCap * 259, (size_t)n * 259 * 4);
+    if (!feat_direct) memcpy(feat + (size_t)i * feat_cap * 259, c->h_feat + (size_t)i * kKpCap * 259, (size_t)n * 259 * 4);
   }
   for (int p = 0; p < pairs; ++p)
     if (hc[2 * p] < 1 || hc[2 * p + 1] < 1) n_match[p] = 0;
@@ -412,7 +438,7 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
       for (int p = 0; p < pairs; ++p) {
         const int n = hc[2 * B + 2 * p] < junc_cap ? hc[2 * B + 2 * p] : junc_cap;
         n_junc[p] = n;
-        if (n) cudaMemcpyAsync(c->h_junc + (size_t)p * kKpCap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)n * 259 * 4, cudaMemcpyDeviceToHost, st);
+        if (n && !junc_direct) cudaMemcpyAsync(c->h_junc + (size_t)p * kKpCap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)n * 259 * 4, cudaMemcpyDeviceToHost, st);
       }
     cudaStreamSynchronize(st);
     for (int i = 0; i < S; ++i) {
@@ -423,7 +449,7 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
         dl[k * 4 + 2] = (double)l[k * 4 + 2] * ws; dl[k * 4 + 3] = (double)l[k * 4 + 3] * hs;
       }
     }
-    if (junc)
+    if (junc && !junc_direct)
       for (int p = 0; p < pairs; ++p) memcpy(junc + (size_t)p * junc_cap * 259, c->h_junc + (size_t)p * kKpCap * 259, (size_t)n_junc[p] * 259 * 4);
   }
   return AIRFE_OK;

@@ -115,6 +115,7 @@ bool LightGlue::build_ops(int P) {
     return add_gemm(&ol, e, 2.0 * S * 4 * (double)cap * cap * 64);
   };
   auto ffn = [&](const DenseW& w_out, const DenseW& w0, const DenseW& w3, const float* g, const float* b) -> bool {
+    if (ffn_fused_enabled()) return add_fused_ffn(&ol, ctx16_, cat16_, x_, w_out, w0, w3, g, b, n, S, cap);
     if (!add_dense(&ol, ctx, w_out, msg16, S, false, -1, 0, n)) return false;                     // msg -> [x | msg] operand buffer
     if (!add_dense(&ol, cat, w0, hf, S, false, -1, 0, n)) return false;
     {

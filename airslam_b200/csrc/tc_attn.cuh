@@ -29,17 +29,6 @@ constexpr int kAttnSmemKV = 512 * 128;           // 64 KiB each
 constexpr int kAttnPSlots = 4;                   // ring of 64-key P blocks (16 KiB each)
 constexpr int kAttnSmemBytes = kAttnSmemQ + 2 * kAttnSmemKV + kAttnPSlots * 16384 + 1024 + 256;
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-
 __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -162,7 +151,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
         float mx = -INFINITY;
         for (int c = 0; c < nk; c += 32) {
           uint32_t r[32];
-          tmem_ld32(trow + c, r);
+          ptx::tmem_ld32(trow + c, r);
           ptx::tmem_ld_wait();
           if (c + 32 <= nk) {
 #pragma unroll
@@ -184,7 +173,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
           for (int hc = 0; hc < 2; ++hc) {
             const int c0 = kb * 64 + hc * 32;
             uint32_t r[32];
-            tmem_ld32(trow + c0, r);
+            ptx::tmem_ld32(trow + c0, r);
             ptx::tmem_ld_wait();
             float e[32];
             if (c0 + 32 <= nk) {
@@ -221,7 +210,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
 #pragma unroll
         for (int c = 0; c < 64; c += 32) {
           uint32_t r[32];
-          tmem_ld32(trow + c, r);
+          ptx::tmem_ld32(trow + c, r);
           ptx::tmem_ld_wait();
           if (q < nq) {
 #pragma unroll

@@ -1,0 +1,73 @@
+// Host side of the fused LightGlue transformer-block kernel.
+#include "common.h"
+#include "engine.h"
+#include "tc_ffn.cuh"
+
+#include <stdlib.h>
+
+namespace airfe {
+
+bool ffn_fused_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("AIRFE_FFN_V1") ? 0 : 1;
+  return v == 1;
+}
+
+static int ffn_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, const DenseW& w_out, const DenseW& w0, const DenseW& w3, const float* ln_g,
+                   const float* ln_b, const int* n, int slots, int cap) {
+  if (w_out.n_rows != 256 || w_out.c_in_pad != 256 || w0.n_rows != 512 || w0.c_in_pad != 512 || w3.n_rows != 256 || w3.c_in_pad != 512) {
+    set_error("add_fused_ffn: unexpected layer shapes");
+    return false;
+  }
+  FfnParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    uint64_t dims[4] = {256, (uint64_t)cap, 1, (uint64_t)slots};
+    uint32_t box[4] = {64, 128, 1, 1};
+    uint64_t s_ctx[3] = {256 * 2, (uint64_t)cap * 256 * 2, (uint64_t)cap * 256 * 2};
+    uint64_t s_x[3] = {512 * 2, (uint64_t)cap * 512 * 2, (uint64_t)cap * 512 * 2};
+    if (!make_tmap_f16(&p.tmCtx, ctx16, 4, dims, s_ctx, box) || !make_tmap_f16(&p.tmX16, cat16, 4, dims, s_x, box)) return false;
+  }
+  auto wmap = [&](CUtensorMap* tm, const DenseW& w) {
+    uint64_t dims[4] = {(uint64_t)w.c_in_pad, (uint64_t)w.n_rows, 1, 1};
+    uint64_t str[3] = {(uint64_t)w.c_in_pad * 2, (uint64_t)w.c_in_pad * 2 * w.n_rows, (uint64_t)w.c_in_pad * 2 * w.n_rows};
+    uint32_t box[4] = {64, 128, 1, 1};
+    return make_tmap_f16(tm, w.w, 4, dims, str, box);
+  };
+  if (!wmap(&p.tmWo, w_out) || !wmap(&p.tmW0, w0) || !wmap(&p.tmW3, w3)) return false;
+  p.b_out = w_out.bias; p.b0 = w0.bias; p.b3 = w3.bias; p.ln_g = ln_g; p.ln_b = ln_b;
+  p.x = x; p.x16 = cat16; p.n = n; p.slots = slots; p.cap = cap;
+  const int tiles = slots * (cap / 128);
+  const int grid = tiles < ffn_sm_count() ? tiles : ffn_sm_count();
+  const double fl = 2.0 * (double)slots * cap * (256.0 * 256 + 512.0 * 512 + 512.0 * 256);
+  ol->tc_flops += fl;
+  ol->launches += 1;
+  ol->push("tc_ffn fused block (out_proj+ffn0+LN+GELU+ffn3+residual)", fl, [p, grid](cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(tc_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmemBytes) != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(tc_ffn_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return false;
+      }
+      attr_set = true;
+    }
+    tc_ffn_kernel<<<grid, kFfnThreads, kFfnSmemBytes, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("tc_ffn launch failed: %s", cudaGetErrorString(e)); return false; }
+    return true;
+  });
+  return true;
+}
+
+}  // namespace airfe

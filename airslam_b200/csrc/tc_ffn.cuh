@@ -1,0 +1,269 @@
+// Fused LightGlue transformer-block tail on tcgen05 (G4: out_proj / to_out -> ffn.0 -> LayerNorm -> GELU -> ffn.3 -> residual).
+// Per 128-keypoint tile a CTA chains three GEMMs whose intermediates never leave the SM:
+//   phase 1  msg = ctx . Wout^T + b           (K = 256, N = 256)   TMEM -> fp16 -> shared memory (A operand, K-major SWIZZLE_128B)
+//   phase 2  h   = [x | msg] . W0^T + b0      (K = 512, N = 512)   accumulators fill all 512 TMEM columns
+//            LayerNorm(512, eps 1e-5) + exact GELU over TMEM rows -> fp16 -> shared memory (overwrites [x | msg])
+//   phase 3  y   = gelu . W3^T + b3           (K = 512, N = 256)   x += y  (fp32 residual stream + fp16 operand copy to HBM)
+// Weights (896 KB per tile) stream from L2 through a 4-stage TMA ring of [128 x 64] tiles.  The unfused path needed four GEMM
+// launches + one LayerNorm launch per block and moved msg / h / gelu(h) through HBM.
+//   warp 0: TMA producer   warp 1: MMA issuer   warps 2-5: epilogues / LayerNorm (thread = one keypoint row)
+#pragma once
+#include "ptx.cuh"
+
+namespace airfe {
+
+struct FfnParams {
+  CUtensorMap tmCtx;   // 4-D (256, cap, 1, slots)  box (64, 128, 1, 1)   attention context (fp16)
+  CUtensorMap tmX16;   // 4-D (256, cap, 1, slots)  box (64, 128, 1, 1)   fp16 operand copy of x (row stride 512)
+  CUtensorMap tmWo;    // 4-D (256, 256, 1, 1)      box (64, 128, 1, 1)
+  CUtensorMap tmW0;    // 4-D (512, 512, 1, 1)
+  CUtensorMap tmW3;    // 4-D (512, 256, 1, 1)
+  const float *b_out, *b0, *b3, *ln_g, *ln_b;
+  float* x;            // [slots*cap][256] fp32 residual stream (in/out)
+  __half* x16;         // fp16 copy (row stride 512 elements)
+  const int* n;        // [slots]
+  int slots, cap;
+};
+
+constexpr int kFfnThreads = 192;
+constexpr int kFfnBStages = 4;
+constexpr int kFfnSmemBytes = 8 * 16384 + kFfnBStages * 16384 + 2048 * 4 + 1024 + 256;
+
+__global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_constant__ FfnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                   // 8 K blocks of [128 rows x 64] fp16
+  uint8_t* sB = sA + 8 * 16384;                         // weight ring
+  float* sPar = reinterpret_cast<float*>(sB + kFfnBStages * 16384);   // b_out[256] b0[512] b3[256] g[512] beta[512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 2048);
+  uint64_t* b_full = bars;                              // [4]
+  uint64_t* b_empty = bars + kFfnBStages;               // [4]
+  uint64_t* ctx_full = bars + 2 * kFfnBStages;
+  uint64_t* x_full = ctx_full + 1;
+  uint64_t* a_free = ctx_full + 2;                      // all MMAs of the tile retired: A blocks may be reloaded
+  uint64_t* acc_full = ctx_full + 3;                    // a GEMM phase finished: accumulators valid
+  uint64_t* epi_done = ctx_full + 4;                    // (count 4) epilogue finished with TMEM and with its smem writes
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctx_full + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_slot = p.cap >> 7;
+  const int total_tiles = p.slots * tiles_per_slot;
+
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+    float v;
+    if (i < 256) v = p.b_out[i];
+    else if (i < 768) v = p.b0[i - 256];
+    else if (i < 1024) v = p.b3[i - 768];
+    else if (i < 1536) v = p.ln_g[i - 1024];
+    else v = p.ln_b[i - 1536];
+    sPar[i] = v;
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmCtx); ptx::prefetch_tmap(&p.tmX16); ptx::prefetch_tmap(&p.tmWo); ptx::prefetch_tmap(&p.tmW0); ptx::prefetch_tmap(&p.tmW3);
+    for (int i = 0; i < kFfnBStages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+    ptx::mbar_init(ctx_full, 1); ptx::mbar_init(x_full, 1); ptx::mbar_init(a_free, 1); ptx::mbar_init(acc_full, 1); ptx::mbar_init(epi_done, 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const float* s_bout = sPar; const float* s_b0 = sPar + 256; const float* s_b3 = sPar + 768; const float* s_g = sPar + 1024; const float* s_be = sPar + 1536;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int sb = 0; uint32_t pb = 0, pt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int slot = t / tiles_per_slot, r0 = (t % tiles_per_slot) * 128;
+        if (r0 >= __ldg(p.n + slot)) continue;
+        ptx::mbar_wait(a_free, pt ^ 1);
+        ptx::mbar_arrive_expect_tx(ctx_full, 4u * 16384u);
+        for (int kb = 0; kb < 4; ++kb) ptx::tma_load_4d(sA + (4 + kb) * 16384, &p.tmCtx, ctx_full, kb * 64, r0, 0, slot);
+        ptx::mbar_arrive_expect_tx(x_full, 4u * 16384u);
+        for (int kb = 0; kb < 4; ++kb) ptx::tma_load_4d(sA + kb * 16384, &p.tmX16, x_full, kb * 64, r0, 0, slot);
+        pt ^= 1;
+        // weight tiles in the order the MMA warp consumes them: phase 1 (Wout: 2 n x 4 k), phase 2 (W0: 4 n x 8 k), phase 3 (W3: 2 n x 8 k)
+        for (int ph = 0; ph < 3; ++ph) {
+          const CUtensorMap* tm = ph == 0 ? &p.tmWo : (ph == 1 ? &p.tmW0 : &p.tmW3);
+          const int nn = ph == 1 ? 4 : 2, nk = ph == 0 ? 4 : 8;
+          for (int nt = 0; nt < nn; ++nt)
+            for (int kb = 0; kb < nk; ++kb) {
+              ptx::mbar_wait(&b_empty[sb], pb ^ 1);
+              ptx::mbar_arrive_expect_tx(&b_full[sb], 16384u);
+              ptx::tma_load_4d(sB + sb * 16384, tm, &b_full[sb], kb * 64, nt * 128, 0, 0);
+              if (++sb == kFfnBStages) { sb = 0; pb ^= 1; }
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint64_t d_const = ptx::smem_desc_base_sw128(1024);
+    const uint32_t idesc = ptx::make_idesc_f16(128, 128, 0);
+    const uint64_t da0 = d_const + (ptx::smem_u32(sA) >> 4);
+    int sb = 0; uint32_t pb = 0, pt = 0, pepi = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int slot = t / tiles_per_slot, r0 = (t % tiles_per_slot) * 128;
+      if (r0 >= __ldg(p.n + slot)) continue;
+      for (int ph = 0; ph < 3; ++ph) {
+        // operands ready?  phase 1: ctx tile landed and the previous tile's last epilogue released TMEM; phase 2: msg written + x tile
+        // landed; phase 3: gelu(h) written.  epi_done completes once per phase (three times per tile).
+        if (ph == 0) { ptx::mbar_wait(ctx_full, pt); ptx::mbar_wait(epi_done, pepi ^ 1); }
+        else { ptx::mbar_wait(epi_done, pepi ^ 1); if (ph == 1) ptx::mbar_wait(x_full, pt); }
+        pepi ^= 1;
+        ptx::tc_fence_after();
+        const int nn = ph == 1 ? 4 : 2, nk = ph == 0 ? 4 : 8, a_first = ph == 0 ? 4 : 0;
+        for (int nt = 0; nt < nn; ++nt)
+          for (int kb = 0; kb < nk; ++kb) {
+            ptx::mbar_wait(&b_full[sb], pb);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint64_t da = da0 + (uint64_t)((a_first + kb) * (16384 >> 4));
+              const uint64_t db = d_const + (ptx::smem_u32(sB + sb * 16384) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + nt * 128, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              ptx::umma_commit(&b_empty[sb]);
+            }
+            __syncwarp();
+            if (++sb == kFfnBStages) { sb = 0; pb ^= 1; }
+          }
+        if (ptx::elect_one()) {
+          ptx::umma_commit(acc_full);
+          if (ph == 2) ptx::umma_commit(a_free);
+        }
+        __syncwarp();
+      }
+      pt ^= 1;
+    }
+  } else {
+    // ===== epilogues: thread = one keypoint row =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
+    uint32_t pacc = 0;
+    // TMEM is free at kernel start: complete phase 0 of epi_done so the MMA warp's first wait (parity 1... ) -- see below
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int slot = t / tiles_per_slot, r0 = (t % tiles_per_slot) * 128;
+      const int ns = __ldg(p.n + slot);
+      if (r0 >= ns) continue;
+      const bool valid = (r0 + row) < ns;
+      const long long grow = (long long)slot * p.cap + r0 + row;
+      // ---- phase 1 epilogue: msg = acc + b_out -> fp16 -> A blocks 4..7 ----
+      ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 256; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(trow + c, r);
+        ptx::tmem_ld_wait();
+        uint8_t* dst = sA + (4 + (c >> 6)) * 16384 + row * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = ch * 8 + e * 2;
+            __half2 h2 = __floats2half2_rn(__uint_as_float(r[j]) + s_bout[c + j], __uint_as_float(r[j + 1]) + s_bout[c + j + 1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          const int chunk = ((c & 63) >> 3) + ch;
+          *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(epi_done);
+      // ---- phase 2 epilogue: LayerNorm + GELU over 512 columns -> fp16 -> A blocks 0..7 ----
+      ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
+      ptx::tc_fence_after();
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 512; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(trow + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += __uint_as_float(r[j]) + s_b0[c + j];
+      }
+      const float mean = sum * (1.f / 512.f);
+      float var = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 512; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(trow + c, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(r[j]) + s_b0[c + j] - mean; var = fmaf(d, d, var); }
+      }
+      const float rstd = 1.f / sqrtf(var * (1.f / 512.f) + 1e-5f);
+#pragma unroll 1
+      for (int c = 0; c < 512; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(trow + c, r);
+        ptx::tmem_ld_wait();
+        uint8_t* dst = sA + (c >> 6) * 16384 + row * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float g2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int j = ch * 8 + e * 2 + u;
+              const float y = (__uint_as_float(r[j]) + s_b0[c + j] - mean) * rstd * s_g[c + j] + s_be[c + j];
+              g2[u] = 0.5f * y * (1.f + erff(y * 0.70710678118654752440f));
+            }
+            __half2 h2 = __floats2half2_rn(g2[0], g2[1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          const int chunk = ((c & 63) >> 3) + ch;
+          *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(epi_done);
+      // ---- phase 3 epilogue: x += acc + b3 ; fp32 residual + fp16 operand copy ----
+      ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
+      ptx::tc_fence_after();
+      float* xr = p.x + grow * 256;
+      __half* x16r = p.x16 + grow * 512;
+#pragma unroll 1
+      for (int c = 0; c < 256; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(trow + c, r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const float4 a = *reinterpret_cast<const float4*>(xr + c + j);
+            const float4 b = *reinterpret_cast<const float4*>(xr + c + j + 4);
+            float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(r[j + e]) + s_b3[c + j + e];
+            *reinterpret_cast<float4*>(xr + c + j) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(xr + c + j + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            uint32_t h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]); h[e] = *reinterpret_cast<uint32_t*>(&h2); }
+            *reinterpret_cast<uint4*>(x16r + c + j) = make_uint4(h[0], h[1], h[2], h[3]);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(epi_done);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace airfe

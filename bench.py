@@ -185,7 +185,13 @@ def main():
     NET, MAT = capi.NET_PLNET, capi.MATCHER_LIGHTGLUE
     # 4 distinct synthetic batches per rank, rotated; each step's activations (~0.3 GB / image) exceed the 126 MB L2
     nb = 4
-    batches = [make_pairs(P, 0xA1750002 + 1000 * rank + 100 * b) for b in range(nb)]
+    batches = []
+    for b in range(nb):      # frames live in pinned host memory, as the e2e contract asks (the C ABI then DMAs straight from them)
+        l, r = make_pairs(P, 0xA1750002 + 1000 * rank + 100 * b)
+        lp, rp = capi.pinned_array(l.shape, np.uint8), capi.pinned_array(r.shape, np.uint8)
+        lp[...] = l
+        rp[...] = r
+        batches.append((lp, rp))
     d_imgs = []
     for l, r in batches:
         inter = np.empty((2 * P, H, W), dtype=np.uint8)

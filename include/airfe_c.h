@@ -71,6 +71,11 @@ typedef struct airfe_config {
 #define AIRFE_MATCHER_SUPERGLUE 1
 #define AIRFE_FEAT_DIM 259
 
+/* Page-locked host buffers.  Frame / feature buffers allocated here (or otherwise pinned) are DMA'd directly, skipping the
+ * internal staging copy; pageable buffers work too. */
+void* airfe_alloc_pinned(long long bytes);
+void airfe_free_pinned(void* p);
+
 void airfe_default_config(airfe_config* cfg);
 int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out);
 void airfe_destroy(airfe_ctx* ctx);
