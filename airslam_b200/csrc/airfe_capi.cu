@@ -332,12 +332,13 @@ int airfe_stereo_device(airfe_ctx* c, int net, int matcher, int pairs, const voi
                         int lines, int junctions) {
   Detector* d = pick(c, net);
   if (!d) return AIRFE_ERR_INVALID;
-  if (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
+  const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
+  if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
   if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return AIRFE_ERR_INVALID; }
   cudaSetDevice(c->device);
   if (!d->run((const uint8_t*)d_images, 2 * pairs, w, h, stride, img_stride, lines != 0, junctions != 0, c->stream)) return AIRFE_ERR_CUDA;
   const DetectOutputs& o = d->out();
-  if (!c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream)) return AIRFE_ERR_CUDA;
+  if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream)) return AIRFE_ERR_CUDA;
   return AIRFE_OK;
 }
 
@@ -362,9 +363,10 @@ long long airfe_profile_stereo(airfe_ctx* c, int net, int matcher, int pairs, co
 
 int airfe_stereo_cost(airfe_ctx* c, int net, int matcher, int pairs, int lines, double* tc_flops, int* launches) {
   Detector* d = pick(c, net);
-  if (!d || !c->lg) { set_error("networks not enabled"); return AIRFE_ERR_INVALID; }
-  if (tc_flops) *tc_flops = d->tc_flops(2 * pairs, lines != 0) + c->lg->tc_flops(pairs);
-  if (launches) *launches = d->launches(2 * pairs, lines != 0) + c->lg->launches(pairs) + 12;
+  const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
+  if (!d || (sgm ? !c->sg : !c->lg)) { set_error("networks not enabled"); return AIRFE_ERR_INVALID; }
+  if (tc_flops) *tc_flops = d->tc_flops(2 * pairs, lines != 0) + (sgm ? c->sg->tc_flops(pairs) : c->lg->tc_flops(pairs));
+  if (launches) *launches = d->launches(2 * pairs, lines != 0) + (sgm ? c->sg->launches(pairs) : c->lg->launches(pairs)) + 12;
   return AIRFE_OK;
 }
 
@@ -376,7 +378,8 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
   if (w <= 1 || h <= 1 || stride < w) { set_error("empty image"); return AIRFE_ERR_INVALID; }
   Detector* d = pick(c, net);
   if (!d) return AIRFE_ERR_INVALID;
-  if (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
+  const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
+  if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
   if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return AIRFE_ERR_INVALID; }
   if ((lines || junc) && net != AIRFE_NET_PLNET) { set_error("lines / junctions need the PLNet network"); return AIRFE_ERR_INVALID; }
   cudaSetDevice(c->device);
@@ -402,7 +405,7 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
   }
   if (!d->run(c->d_img, 2 * pairs, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return AIRFE_ERR_CUDA;
   const DetectOutputs& o = d->out();
-  if (!c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, st)) return AIRFE_ERR_CUDA;
+  if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, st) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, st)) return AIRFE_ERR_CUDA;
   // results: features of 2*pairs images, lines, left junctions, matches
   const int B = 2 * c->cfg.max_batch, S = 2 * pairs;
   int* hc = c->h_counts;
@@ -418,7 +421,7 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
   if (junc_direct)
     for (int p = 0; p < pairs; ++p)
       cudaMemcpyAsync(junc + (size_t)p * junc_cap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)kJunc * 259 * 4, cudaMemcpyDeviceToHost, st);
-  int rc = fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, nullptr);   // synchronises the stream
+  int rc = fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, nullptr, matcher);   // synchronises the stream
   if (rc != AIRFE_OK) return rc;
   for (int i = 0; i < S; ++i) {
     const int n = hc[i] < feat_cap ? hc[i] : feat_cap;

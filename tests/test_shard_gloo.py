@@ -52,3 +52,42 @@ def test_two_rank_sharding_and_reduction():
     assert mx0 == mx1 == 2.0
     assert abs(thr0 - 9 / 2.0) < 1e-12 and thr0 == thr1          # all units / slowest rank
     assert shp0 == (10, 4, 259) and c0 == c1 == [1] * 5 + [2] * 4 + [0]
+
+
+def _reloc_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from airslam_b200 import reloc
+    n_kf, q_total = 10, 5
+    qb, qe = D.shard_range(q_total, rank, world)
+    # query i has (10 + i) keypoints whose score row encodes the query id
+    qf = []
+    for i in range(qb, qe):
+        f = np.zeros((259, 10 + i), dtype=np.float32)
+        f[0] = i
+        qf.append(f)
+    cand = np.array([[(3 * q + c) % n_kf for c in range(3)] for q in range(q_total)])
+    # mock matcher: "number of matches" = 100*query + keyframe id, computed only by the owner of the keyframe
+    seen = {}
+
+    def fake(jobs):
+        for q, c, kf in jobs:
+            seen[(q, kf)] = True
+        return [100 * q + kf for q, c, kf in jobs]
+    best, cnt, table = reloc.relocalize(None, 0, qf, None, cand, n_kf, rank, world, match_fn=fake)
+    out[rank] = (best.tolist(), cnt.tolist(), table.tolist(), sorted(seen))
+    dist.destroy_process_group()
+
+
+def test_relocalization_exchange_two_ranks():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_reloc_worker, args=(2, port, out), nprocs=2, join=True)
+    b0, c0, t0, s0 = out[0]
+    b1, c1, t1, s1 = out[1]
+    assert (b0, c0, t0) == (b1, c1, t1)                           # every rank ends with the same decision
+    exp = [[100 * q + (3 * q + c) % 10 for c in range(3)] for q in range(5)]
+    assert t0 == exp
+    assert not (set(map(tuple, s0)) & set(map(tuple, s1)))       # each (query, keyframe) job ran on exactly one rank
+    assert all(kf < 5 for _, kf in s0) and all(kf >= 5 for _, kf in s1)
