@@ -253,7 +253,14 @@ def main():
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12
     cv = [x for x in tc if x[0].startswith("tc_conv3x3")]
     cv_ms = sum(x[2] for x in cv)
-    cv_tf = sum(x[1] for x in cv) / (cv_ms * 1e-3) / 1e12 if cv_ms > 0 else 0.0
+    cv_fl = sum(x[1] for x in cv)
+    cv_tf = cv_fl / (cv_ms * 1e-3) / 1e12 if cv_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, "profiles", "r01_conv3x3_traffic.json")
+    if os.path.exists(tj):
+        tjd = json.load(open(tj))
+        if tjd.get("pairs_per_step") == P:      # dram__bytes_read+write per launch from the committed ncu capture of the same command
+            traffic, traffic_src = tjd["dram_bytes_per_launch"], tjd["source"]
     if args.profile_out and rank == 0:
         with open(args.profile_out, "w") as fh:
             fh.write("# per-op CUDA-event profile of one step (P=%d pairs); tc share of step %.1f%%\n" % (P, 100 * tc_ms / all_ms))
@@ -272,10 +279,13 @@ def main():
             "clocks": sampler.summary(),
             "e2e": {"value": world * P * args.steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches * args.steps),
-            "roofline": {"bound": "tensor", "kernel": "tc_conv3x3_kernel + tc_gemm_kernel (all %d tcgen05 launches of a step; conv3x3 alone: %.0f TFLOP/s over %.2f ms)" % (len(tc), cv_tf, cv_ms),
-                         "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": None,
+            "roofline": {"bound": "tensor", "kernel": "tc_conv3x3_kernel (dominant: %d launches = %.0f%% of the step's kernel time)" % (len(cv), 100 * cv_ms / all_ms),
+                         "achieved": cv_tf, "peak": sustained, "unit": "TFLOP/s", "frac": cv_tf / sustained, "traffic": traffic,
                          "peak_source": "%s bf16_tflops_sustained (fp16 runs on the same kind::f16 pipe)" % how,
-                         "flops_per_step": tc_flops, "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / all_ms},
+                         "flops_per_launch": cv_fl / max(1, len(cv)), "ms_per_launch": cv_ms / max(1, len(cv)),
+                         "traffic_source": traffic_src,
+                         "all_tcgen05": {"launches": len(tc), "achieved": achieved, "frac": achieved / sustained, "ms_per_step": tc_ms,
+                                         "share_of_step": tc_ms / all_ms}},
         }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import weights
