@@ -63,7 +63,8 @@ struct TcGemmPlan {
   int smem_bytes = 0;
   double flops = 0;
 };
-bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                   int swizzle_bytes = 128);
 bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan);
 bool tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream);
 }  // namespace airfe

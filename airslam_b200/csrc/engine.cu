@@ -70,7 +70,7 @@ void* Arena::alloc(size_t bytes, size_t align) {
 
 // ---- packing --------------------------------------------------------------------------------------------------------------
 bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in_total, Arena* arena, DenseW* out,
-                const std::vector<int>* in_perm, const std::vector<int>* out_perm) {
+                const std::vector<int>* in_perm, const std::vector<int>* out_perm, int k_align) {
   int n_rows = 0, taps = 0;
   for (auto& s : srcs) {
     const WTensor* t = wf.find(s.weight);
@@ -80,7 +80,7 @@ bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in
     taps = tp;
     n_rows += t->dims[0];
   }
-  const int c_pad = (c_in_total + 63) / 64 * 64;
+  const int c_pad = (c_in_total + k_align - 1) / k_align * k_align;
   const size_t k_total = (size_t)taps * c_pad;
   std::vector<uint16_t> hw((size_t)n_rows * k_total, 0);
   std::vector<float> hb((size_t)n_rows, 0.f);

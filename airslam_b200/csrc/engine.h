@@ -125,7 +125,8 @@ struct PackSrc {
   int in_offset = 0;         // place this source's input channels at [in_offset, in_offset + c_in) of the packed K (block-diagonal / concat remap)
 };
 bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in_total, Arena* arena, DenseW* out,
-                const std::vector<int>* in_perm = nullptr, const std::vector<int>* out_perm = nullptr /* old row -> new row */);
+                const std::vector<int>* in_perm = nullptr, const std::vector<int>* out_perm = nullptr /* old row -> new row */,
+                int k_align = 64 /* K padding per tap: 64, or 32 for the SWIZZLE_64B conv path */);
 
 // Append a tcgen05 conv / GEMM op.
 bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int batch, bool relu, int n_valid = -1, int block_n = 0,

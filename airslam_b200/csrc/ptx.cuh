@@ -132,6 +132,12 @@ __device__ __forceinline__ uint64_t smem_desc_base_sw128(uint32_t sbo_bytes) {
          (static_cast<uint64_t>(2) << 61);
 }
 
+// Same for K-major SWIZZLE_64B (64-byte rows, layout type 4).
+__device__ __forceinline__ uint64_t smem_desc_base_sw64(uint32_t sbo_bytes) {
+  return (static_cast<uint64_t>(1) << 16) | (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32) | (static_cast<uint64_t>(1) << 46) |
+         (static_cast<uint64_t>(4) << 61);
+}
+
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) --------------------------------------------
 // Shared-memory matrix descriptor.  layout_type: 0 none, 2 SWIZZLE_128B, 4 SWIZZLE_64B, 6 SWIZZLE_32B.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type,

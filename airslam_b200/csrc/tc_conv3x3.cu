@@ -70,7 +70,8 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   p.n_valid = n_valid;
   p.n_tiles = (n_valid + block_n - 1) / block_n;
   p.strips = (in.W >= 16 && 4 * conv_acc_stride(block_n) <= 512) ? 2 : 1;
-  p.kblocks = w.c_in_pad / 64;
+  p.kw = (w.c_in_pad % 64) ? 32 : 64;
+  p.kblocks = w.c_in_pad / p.kw;
   p.c_in_pad = w.c_in_pad;
   p.W = in.W; p.H = in.H; p.B = batch;
   p.tiles_x = (in.W + 8 * p.strips - 1) / (8 * p.strips);
@@ -78,7 +79,7 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   p.bias = w.bias; p.relu = relu;
   if (out) { p.out = (__half*)out->p; p.out_sx = out->ps; p.out_sy = out->ps * out->W; p.out_sb = out->ps * out->W * out->H; }
   if (pool_out) { p.pool_out = (__half*)pool_out->p; p.pool_sx = pool_out->ps; p.pool_sy = pool_out->ps * pool_out->W; p.pool_sb = pool_out->ps * pool_out->W * pool_out->H; }
-  const int a_bytes = conv_a_bytes(p.strips), b_bytes = conv_b_bytes(block_n);
+  const int a_bytes = conv_a_bytes(p.strips, p.kw), b_bytes = conv_b_bytes(block_n, p.kw);
   const int budget = 212 * 1024;
   const int res_bytes = 9 * p.kblocks * b_bytes;
   if (p.n_tiles == 1 && res_bytes + 2 * a_bytes <= budget && res_bytes <= 120 * 1024) {
@@ -96,13 +97,13 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   {
     uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)batch};
     uint64_t str[3] = {(uint64_t)in.ps * 2, (uint64_t)in.ps * in.W * 2, (uint64_t)in.ps * in.W * in.H * 2};
-    uint32_t box[4] = {64, (uint32_t)(8 * p.strips + 2), (uint32_t)(kConvTH + 2), 1};
-    if (!make_tmap_f16(&p.tmA, in.p, 4, dims, str, box)) return false;
+    uint32_t box[4] = {(uint32_t)p.kw, (uint32_t)(8 * p.strips + 2), (uint32_t)(kConvTH + 2), 1};
+    if (!make_tmap_f16(&p.tmA, in.p, 4, dims, str, box, p.kw * 2)) return false;
     const uint64_t k_total = (uint64_t)9 * w.c_in_pad;
     uint64_t bd[4] = {k_total, (uint64_t)w.n_rows, 1, 1};
     uint64_t bs[3] = {k_total * 2, k_total * 2 * w.n_rows, k_total * 2 * w.n_rows};
-    uint32_t bb[4] = {64, (uint32_t)block_n, 1, 1};
-    if (!make_tmap_f16(&p.tmB, w.w, 4, bd, bs, bb)) return false;
+    uint32_t bb[4] = {(uint32_t)p.kw, (uint32_t)block_n, 1, 1};
+    if (!make_tmap_f16(&p.tmB, w.w, 4, bd, bs, bb, p.kw * 2)) return false;
   }
   const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
   plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 4) * 8 + 16;
@@ -113,7 +114,7 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   ol->tc_flops += fl;
   ol->launches += 1;
   char nm[160];
-  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d", w.c_in, n_valid, in.W, in.H, batch, p.b_resident ? " Bres" : "", pool_out ? (out ? " +pool" : " pool-only") : "", p.strips);
+  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d%s", w.c_in, n_valid, in.W, in.H, batch, p.b_resident ? " Bres" : "", pool_out ? (out ? " +pool" : " pool-only") : "", p.strips, p.kw == 32 ? " K32" : "");
   ol->push(nm, fl, [plan](cudaStream_t st) { return conv_launch(plan, st); });
   return true;
 }

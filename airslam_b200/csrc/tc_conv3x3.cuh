@@ -20,6 +20,7 @@ struct ConvParams {
   CUtensorMap tmA;  // 4-D (C, W, H, B), box (64, 8S+2, 18, 1), SWIZZLE_128B
   CUtensorMap tmB;  // 4-D (K, N, 1, 1), box (64, block_n, 1, 1)
   int kblocks, c_in_pad;
+  int kw;           // channels per K block: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, for C_in = 32 layers)
   int strips;
   int tiles_x, tiles_y, B, W, H;
   int n_tiles, block_n, n_valid;
@@ -36,8 +37,8 @@ struct ConvParams {
 constexpr int kConvThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kConvTH = 16;
 
-__host__ __device__ inline int conv_a_bytes(int strips) { return ((8 * strips + 2) * (kConvTH + 2) * 128 + 1023) / 1024 * 1024; }
-__host__ __device__ inline int conv_b_bytes(int block_n) { return (block_n * 128 + 1023) / 1024 * 1024; }
+__host__ __device__ inline int conv_a_bytes(int strips, int kw = 64) { return ((8 * strips + 2) * (kConvTH + 2) * kw * 2 + 1023) / 1024 * 1024; }
+__host__ __device__ inline int conv_b_bytes(int block_n, int kw = 64) { return (block_n * kw * 2 + 1023) / 1024 * 1024; }
 __host__ __device__ inline int conv_acc_stride(int block_n) { return (block_n + 31) / 32 * 32; }
 __host__ __device__ inline int conv_tmem_cols(int block_n, int strips) {
   int need = 2 * strips * conv_acc_stride(block_n), c = 32;
@@ -48,8 +49,9 @@ __host__ __device__ inline int conv_tmem_cols(int block_n, int strips) {
 __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_bytes = conv_a_bytes(p.strips);
-  const int b_bytes = conv_b_bytes(p.block_n);
+  const int a_bytes = conv_a_bytes(p.strips, p.kw);
+  const int b_bytes = conv_b_bytes(p.block_n, p.kw);
+  const int rowb = p.kw * 2;                      // bytes per pixel row of a K block
   const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.stages_a * a_bytes;
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  __shared__ float s_bias[512];
+  __shared__ __align__(16) float s_bias[512];
   for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;
   __syncthreads();
 
@@ -91,10 +93,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
       // ===== TMA producer =====
       const int n_tile_fixed = (p.n_tiles == 1);
       if (p.b_resident) {   // weights of this CTA's (single) N tile: load once, keep for every tile
-        ptx::mbar_arrive_expect_tx(&full_b[0], (uint32_t)(9 * p.kblocks * p.block_n * 128));
+        ptx::mbar_arrive_expect_tx(&full_b[0], (uint32_t)(9 * p.kblocks * p.block_n * rowb));
         for (int cb = 0; cb < p.kblocks; ++cb)
           for (int tap = 0; tap < 9; ++tap)
-            ptx::tma_load_4d(smem_b + (cb * 9 + tap) * b_bytes, &p.tmB, &full_b[0], tap * p.c_in_pad + cb * 64, 0, 0, 0);
+            ptx::tma_load_4d(smem_b + (cb * 9 + tap) * b_bytes, &p.tmB, &full_b[0], tap * p.c_in_pad + cb * p.kw, 0, 0, 0);
       }
       (void)n_tile_fixed;
       int sa = 0, sb = 0;
@@ -105,14 +107,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
         const int x0 = tx * 8 * p.strips, y0 = ty * kConvTH;
         for (int cb = 0; cb < p.kblocks; ++cb) {
           ptx::mbar_wait(&empty_a[sa], pa ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_a[sa], (uint32_t)(HW * (kConvTH + 2) * 128));
-          ptx::tma_load_4d(smem_a + sa * a_bytes, &p.tmA, &full_a[sa], cb * 64, x0 - 1, y0 - 1, tz);
+          ptx::mbar_arrive_expect_tx(&full_a[sa], (uint32_t)(HW * (kConvTH + 2) * rowb));
+          ptx::tma_load_4d(smem_a + sa * a_bytes, &p.tmA, &full_a[sa], cb * p.kw, x0 - 1, y0 - 1, tz);
           if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
           if (!p.b_resident) {
             for (int tap = 0; tap < 9; ++tap) {
               ptx::mbar_wait(&empty_b[sb], pb ^ 1);
-              ptx::mbar_arrive_expect_tx(&full_b[sb], (uint32_t)(p.block_n * 128));
-              ptx::tma_load_4d(smem_b + sb * b_bytes, &p.tmB, &full_b[sb], tap * p.c_in_pad + cb * 64, nt * p.block_n, 0, 0);
+              ptx::mbar_arrive_expect_tx(&full_b[sb], (uint32_t)(p.block_n * rowb));
+              ptx::tma_load_4d(smem_b + sb * b_bytes, &p.tmB, &full_b[sb], tap * p.c_in_pad + cb * p.kw, nt * p.block_n, 0, 0);
               if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
             }
           }
@@ -125,8 +127,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
     int sa = 0, sb = 0, acc = 0;
     uint32_t pa = 0, pb = 0, acc_phase = 0;
     if (p.b_resident) { ptx::mbar_wait(&full_b[0], 0); ptx::tc_fence_after(); }
-    const uint64_t da_const = ptx::smem_desc_base_sw128((uint32_t)HW * 128);
-    const uint64_t db_const = ptx::smem_desc_base_sw128(1024);
+    const uint64_t da_const = p.kw == 64 ? ptx::smem_desc_base_sw128((uint32_t)HW * 128) : ptx::smem_desc_base_sw64((uint32_t)HW * 64);
+    const uint64_t db_const = p.kw == 64 ? ptx::smem_desc_base_sw128(1024) : ptx::smem_desc_base_sw64(512);
+    const int row16 = rowb >> 4;                    // pixel-row pitch in 16-byte units (8 or 4)
+    const int ksteps = p.kw >> 4;                   // tcgen05.mma K = 16 steps per block (4 or 2)
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
@@ -146,13 +150,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
             db = db_const + (ptx::smem_u32(smem_b + sb * b_bytes) >> 4);
           }
           const int ky = tap / 3, kx = tap % 3;
-          const uint64_t da_tap = da_stage + (uint64_t)((ky * HW + kx) * 8);      // 128-byte rows in 16-byte units
+          const uint64_t da_tap = da_stage + (uint64_t)((ky * HW + kx) * row16);
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ptx::umma_f16(d0, da_tap + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
+            for (int k = 0; k < 4; ++k)
+              if (k < ksteps) ptx::umma_f16(d0, da_tap + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
             if (p.strips == 2) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) ptx::umma_f16(d0 + acc_stride, da_tap + 64 + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
+              for (int k = 0; k < 4; ++k)
+                if (k < ksteps) ptx::umma_f16(d0 + acc_stride, da_tap + 8 * row16 + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
             }
             if (!p.b_resident) ptx::umma_commit(&empty_b[sb]);
           }
@@ -204,13 +210,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
           if (cc + 1 < c_end) ptx::tmem_ld16(taddr + (cc + 1) * 16, r[u ^ 1]);   // next chunk in flight while this one is processed
           const int nbase = n0 + cc * 16;
           uint32_t h[8];
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + nbase);     // 4 x LDS.128 instead of 16 scalar loads
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float f0 = __uint_as_float(r[u][2 * i]) + s_bias[nbase + 2 * i];
-            float f1 = __uint_as_float(r[u][2 * i + 1]) + s_bias[nbase + 2 * i + 1];
-            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-            __half2 h2 = __floats2half2_rn(f0, f1);
-            h[i] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = b4[i];
+            float f0 = __uint_as_float(r[u][4 * i]) + bb.x, f1 = __uint_as_float(r[u][4 * i + 1]) + bb.y;
+            float f2 = __uint_as_float(r[u][4 * i + 2]) + bb.z, f3 = __uint_as_float(r[u][4 * i + 3]) + bb.w;
+            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+            __half2 ha = __floats2half2_rn(f0, f1), hb = __floats2half2_rn(f2, f3);
+            h[2 * i] = *reinterpret_cast<uint32_t*>(&ha);
+            h[2 * i + 1] = *reinterpret_cast<uint32_t*>(&hb);
           }
           if (o_full && valid && nbase < p.n_valid) {
             __half* o = o_full + nbase;

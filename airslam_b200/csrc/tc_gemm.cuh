@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  __shared__ float s_bias[1024];
+  __shared__ __align__(16) float s_bias[1024];
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;
   __syncthreads();
 
@@ -173,10 +173,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
         if (cq + u + 1 < c_end) ptx::tmem_ld16(taddr + c + 16, rr[u ^ 1]);
         const uint32_t (&r)[16] = rr[u];
         float v[16];
+        float bsm[16];
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + ((n0 + c) & 1023));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float4 bb = b4[i]; bsm[4 * i] = bb.x; bsm[4 * i + 1] = bb.y; bsm[4 * i + 2] = bb.z; bsm[4 * i + 3] = bb.w; }
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float f = __uint_as_float(r[i]);
-          f += s_bias[(n0 + c + i) & 1023];
+          f += bsm[i];
           if (n0 + c + i < p.scale_cols) f *= p.scale;
           if (p.relu) f = fmaxf(f, 0.f);
           v[i] = f;

@@ -152,7 +152,7 @@ def run_conv_halo(x_nhwc, w_oihw, bias, relu, want_full=True, want_pool=False, o
     lib, check = _lib()
     b, h, w, c = x_nhwc.shape
     o, i, _, _ = w_oihw.shape
-    wp = pack_conv_weight(w_oihw, (i + 63) // 64 * 64)
+    wp = pack_conv_weight(w_oihw, 32 if i == 32 else (i + 63) // 64 * 64)   # C_in = 32 runs the SWIZZLE_64B (K = 32) variant
     full = pool = None
     if want_full:
         full = out if out is not None else torch.zeros(b, h, w, o, dtype=torch.float16, device="cuda")

@@ -16,7 +16,7 @@ def pack(w, c_pad):
 
 def conv(b, h, w, cin, cout, pool, reps=3):
     x = torch.randn(b, h, w, cin, device="cuda").half()
-    wt = pack(torch.randn(cout, cin, 3, 3, device="cuda") * 0.05, (cin + 63) // 64 * 64)
+    wt = pack(torch.randn(cout, cin, 3, 3, device="cuda") * 0.05, 32 if cin == 32 else (cin + 63) // 64 * 64)
     bias = torch.randn(cout, device="cuda")
     out = torch.zeros(b, h, w, cout, dtype=torch.float16, device="cuda")
     po = torch.zeros(b, h // 2, w // 2, cout, dtype=torch.float16, device="cuda") if pool else None
