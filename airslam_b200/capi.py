@@ -63,6 +63,8 @@ def _declare_frame(L):
     L.airfe_create.argtypes = [C.POINTER(Config), i32, C.POINTER(vp)]
     L.airfe_create.restype = i32
     L.airfe_destroy.argtypes = [vp]
+    L.airfe_debug_conv_trace.argtypes = [vp]
+    L.airfe_debug_conv_trace.restype = None
     L.airfe_stream.argtypes = [vp]
     L.airfe_stream.restype = vp
     L.airfe_detect_batch.argtypes = [vp, i32, i32, vp, i32, i32, i32, i64, vp, i32, vp, vp, i32, vp, vp, i32, vp]

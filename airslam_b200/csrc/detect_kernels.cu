@@ -79,13 +79,6 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const __half* __restrict__ 
   const int yy = (int)((grp / gpr) % H);
   const long long img = grp / ((long long)gpr * H);
   const __half* xi = x + img * (long long)W * H;
-  float wr[8][9], br[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    br[j] = sb[cg * 8 + j];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) wr[j][k] = sw[(cg * 8 + j) * 9 + k];
-  }
   float in[3][kC1Px + 2];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
@@ -96,27 +89,33 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const __half* __restrict__ 
       in[ky][c] = (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? __half2float(xi[(long long)y2 * W + x2]) : 0.f;
     }
   }
+  // channel-outer / pixel-inner: the 9 weights of one output channel sit in registers while 8 pixels reuse them (72 LDS per
+  // thread instead of 576); the 8x8 results are packed to fp16 pairs as they are produced
+  uint32_t packed[kC1Px][4];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    float w0[9], w1[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { w0[k] = sw[(cg * 8 + j) * 9 + k]; w1[k] = sw[(cg * 8 + j + 1) * 9 + k]; }
+    const float b0 = sb[cg * 8 + j], b1 = sb[cg * 8 + j + 1];
+#pragma unroll
+    for (int px = 0; px < kC1Px; ++px) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          a0 = fmaf(in[ky][px + kx], w0[ky * 3 + kx], a0);
+          a1 = fmaf(in[ky][px + kx], w1[ky * 3 + kx], a1);
+        }
+      __half2 h2 = __floats2half2_rn(fmaxf(a0 + b0, 0.f), fmaxf(a1 + b1, 0.f));
+      packed[px][j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+  }
   __half* o = out + ((img * H + yy) * (long long)W + x0) * 64 + cg * 8;
 #pragma unroll
-  for (int px = 0; px < kC1Px; ++px) {
-    uint32_t packed[4];
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-      float acc[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float a = 0.f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) a = fmaf(in[ky][px + kx], wr[j + u][ky * 3 + kx], a);
-        acc[u] = fmaxf(a + br[j + u], 0.f);
-      }
-      __half2 h2 = __floats2half2_rn(acc[0], acc[1]);
-      packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
-    }
-    *reinterpret_cast<uint4*>(o + (long long)px * 64) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-  }
+  for (int px = 0; px < kC1Px; ++px)
+    *reinterpret_cast<uint4*>(o + (long long)px * 64) = make_uint4(packed[px][0], packed[px][1], packed[px][2], packed[px][3]);
 }
 
 void launch_conv1a(const __half* x, const __half* w, const float* bias, __half* out, int batch, int H, int W, cudaStream_t st) {

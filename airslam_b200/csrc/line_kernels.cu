@@ -349,8 +349,17 @@ __global__ void __launch_bounds__(512) junction_scan_kernel(const uint8_t* __res
   const uint8_t* jm = junc_map + (long long)b * 262144 + y * 512;
   const bool row_ok = (y >= border) && (y < 512 - border);
   int cnt = 0;
-  if (row_ok)
-    for (int x = border; x < 512 - border; ++x) cnt += jm[x] ? 1 : 0;
+  if (row_ok) {   // 16 bytes at a time; the border columns are masked out afterwards
+    const uint4* jv = reinterpret_cast<const uint4*>(jm);
+    for (int q = 0; q < 32; ++q) {
+      const uint4 v = jv[q];
+      if ((v.x | v.y | v.z | v.w) == 0) continue;
+      for (int e = 0; e < 16; ++e) {
+        const int x = q * 16 + e;
+        if (x >= border && x < 512 - border && jm[x]) ++cnt;
+      }
+    }
+  }
   // exclusive scan over 512 rows
   __shared__ int ws[16];
   const int lane = y & 31, warp = y >> 5;
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(512) junction_scan_kernel(const uint8_t* __res
   if (y == 0) kp_count[b] = min(ws[15], kp_cap);
   if (row_ok && cnt)
     for (int x = border; x < 512 - border; ++x)
-      if (jm[x]) {
+      if (jm[x]) {   // rows with junctions are rare (<= 300 per image): this scalar pass runs on a handful of rows only
         if (pos < kp_cap) {
           float* o = kp + ((long long)b * kp_cap + pos) * 3;
           o[0] = scores[(long long)b * 262144 + y * 512 + x];

@@ -23,18 +23,45 @@ static int sm_count() {
   return n;
 }
 
+static long long* g_conv_trace = nullptr;
+void conv3x3_set_trace(long long* dev_buf) { g_conv_trace = dev_buf; }
+
+using ConvKernel = void (*)(const ConvParams);
+
+static ConvKernel conv_kernel_for(const ConvParams& p) {
+  const int key = (p.kw == 32 ? 4 : 0) | (p.strips == 2 ? 2 : 0) | (p.b_resident ? 1 : 0);
+  switch (key) {
+    case 0: return tc_conv3x3_kernel<64, 1, false>;
+    case 1: return tc_conv3x3_kernel<64, 1, true>;
+    case 2: return tc_conv3x3_kernel<64, 2, false>;
+    case 3: return tc_conv3x3_kernel<64, 2, true>;
+    case 4: return tc_conv3x3_kernel<32, 1, false>;
+    case 5: return tc_conv3x3_kernel<32, 1, true>;
+    case 6: return tc_conv3x3_kernel<32, 2, false>;
+    default: return tc_conv3x3_kernel<32, 2, true>;
+  }
+}
+
 static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[8] = {};
+  const int key = (plan.p.kw == 32 ? 4 : 0) | (plan.p.strips == 2 ? 2 : 0) | (plan.p.b_resident ? 1 : 0);
+  ConvKernel kern = conv_kernel_for(plan.p);
+  if (!attr_set[key]) {
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, tc_conv3x3_kernel);
-    if (cudaFuncSetAttribute(tc_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes) != cudaSuccess) {
+    cudaFuncGetAttributes(&fa, kern);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(tc_conv3x3_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
       return false;
     }
-    attr_set = true;
+    attr_set[key] = true;
   }
-  tc_conv3x3_kernel<<<plan.grid, kConvThreads, plan.smem_bytes, st>>>(plan.p);
+  if (g_conv_trace) {
+    ConvPlan traced = plan;
+    traced.p.trace = g_conv_trace;
+    kern<<<traced.grid, kConvThreads, traced.smem_bytes, st>>>(traced.p);
+  } else {
+    kern<<<plan.grid, kConvThreads, plan.smem_bytes, st>>>(plan.p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("tc_conv3x3 launch failed: %s", cudaGetErrorString(e)); return false; }
   return true;
@@ -70,6 +97,7 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   p.n_valid = n_valid;
   p.n_tiles = (n_valid + block_n - 1) / block_n;
   p.strips = (in.W >= 16 && 4 * conv_acc_stride(block_n) <= 512) ? 2 : 1;
+  p.nacc = conv_nacc(block_n, p.strips);
   p.kw = (w.c_in_pad % 64) ? 32 : 64;
   p.kblocks = w.c_in_pad / p.kw;
   p.c_in_pad = w.c_in_pad;
@@ -106,7 +134,7 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
     if (!make_tmap_f16(&p.tmB, w.w, 4, bd, bs, bb, p.kw * 2)) return false;
   }
   const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
-  plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 4) * 8 + 16;
+  plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 8) * 8 + 16;
   const int total = p.tiles_x * p.tiles_y * batch * p.n_tiles;
   plan.grid = total < sm_count() ? total : sm_count();
   if (in.C > w.c_in_pad || in.C < w.c_in) { set_error("add_conv3x3: activation has %d channels, weights expect %d", in.C, w.c_in); return false; }

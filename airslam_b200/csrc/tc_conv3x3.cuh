@@ -26,57 +26,68 @@ struct ConvParams {
   int n_tiles, block_n, n_valid;
   int b_resident;
   int stages_a, stages_b;
+  int nacc;         // TMEM accumulator buffers (2..4): deeper than 2 hides the MMA -> epilogue -> MMA hand-shake latency on small-N layers
   const float* bias;
   int relu;
   __half* out;        // full-resolution fp16 NHWC store (nullptr: skip)
   long long out_sb, out_sy, out_sx;
   __half* pool_out;   // fused 2x2/2 max-pool store (nullptr: skip)
   long long pool_sb, pool_sy, pool_sx;
+  long long* trace;   // authoring aid (airfe_debug_conv_trace): CTA 0 writes clock64 stamps of its first 64 tiles, 8 slots per tile
 };
 
 constexpr int kConvThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kConvTH = 16;
 
-__host__ __device__ inline int conv_a_bytes(int strips, int kw = 64) { return ((8 * strips + 2) * (kConvTH + 2) * kw * 2 + 1023) / 1024 * 1024; }
+__host__ __device__ constexpr int conv_a_bytes(int strips, int kw = 64) { return ((8 * strips + 2) * (kConvTH + 2) * kw * 2 + 1023) / 1024 * 1024; }
 __host__ __device__ inline int conv_b_bytes(int block_n, int kw = 64) { return (block_n * kw * 2 + 1023) / 1024 * 1024; }
 __host__ __device__ inline int conv_acc_stride(int block_n) { return (block_n + 31) / 32 * 32; }
+__host__ __device__ inline int conv_nacc(int block_n, int strips) {
+  int n = 512 / (strips * conv_acc_stride(block_n));
+  return n > 4 ? 4 : (n < 2 ? 2 : n);
+}
 __host__ __device__ inline int conv_tmem_cols(int block_n, int strips) {
-  int need = 2 * strips * conv_acc_stride(block_n), c = 32;
+  int need = conv_nacc(block_n, strips) * strips * conv_acc_stride(block_n), c = 32;
   while (c < need) c <<= 1;
   return c;
 }
 
+// Template parameters fix everything the MMA issue loop would otherwise branch on: measured with the clock64 trace
+// (tools/trace_conv.py, profiles/r01_conv_trace.txt) the runtime-generic loop spent ~550 cycles of uniform-datapath
+// instructions per tap, i.e. the single issuing warp -- not the tensor pipe (48 cycles per 128x64x16 MMA in SS mode,
+// tools/probe_mma_rate.cu) -- bounded every small-N layer.
+template <int KW, int STRIPS, bool BRES>
 __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_bytes = conv_a_bytes(p.strips, p.kw);
-  const int b_bytes = conv_b_bytes(p.block_n, p.kw);
-  const int rowb = p.kw * 2;                      // bytes per pixel row of a K block
-  const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
+  constexpr int a_bytes = conv_a_bytes(STRIPS, KW);
+  const int b_bytes = conv_b_bytes(p.block_n, KW);
+  constexpr int rowb = KW * 2;                    // bytes per pixel row of a K block
+  const int n_b_slots = BRES ? 9 * p.kblocks : p.stages_b;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.stages_a * a_bytes;
   uint64_t* full_a = reinterpret_cast<uint64_t*>(smem_b + n_b_slots * b_bytes);
   uint64_t* empty_a = full_a + p.stages_a;
   uint64_t* full_b = empty_a + p.stages_a;          // [stages_b] (streaming) or [1] (resident: all weights landed)
-  uint64_t* empty_b = full_b + (p.b_resident ? 1 : p.stages_b);
-  uint64_t* tmem_full = empty_b + (p.b_resident ? 1 : p.stages_b);
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* empty_b = full_b + (BRES ? 1 : p.stages_b);
+  uint64_t* tmem_full = empty_b + (BRES ? 1 : p.stages_b);
+  uint64_t* tmem_empty = tmem_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int HW = 8 * p.strips + 2;
+  constexpr int HW = 8 * STRIPS + 2;
   const int m_tiles = p.tiles_x * p.tiles_y * p.B;
   const int total_tiles = m_tiles * p.n_tiles;
   const uint32_t acc_stride = conv_acc_stride(p.block_n);
-  const uint32_t tmem_cols = conv_tmem_cols(p.block_n, p.strips);
+  const uint32_t tmem_cols = conv_tmem_cols(p.block_n, STRIPS);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB);
     for (int s = 0; s < p.stages_a; ++s) { ptx::mbar_init(&full_a[s], 1); ptx::mbar_init(&empty_a[s], 1); }
-    const int nb = p.b_resident ? 1 : p.stages_b;
+    const int nb = BRES ? 1 : p.stages_b;
     for (int s = 0; s < nb; ++s) { ptx::mbar_init(&full_b[s], 1); ptx::mbar_init(&empty_b[s], 1); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < 4; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) { ptx::tmem_alloc(tmem_slot, tmem_cols); ptx::tmem_relinquish(); }
@@ -91,30 +102,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      const int n_tile_fixed = (p.n_tiles == 1);
-      if (p.b_resident) {   // weights of this CTA's (single) N tile: load once, keep for every tile
+      if (BRES) {   // weights of this CTA's (single) N tile: load once, keep for every tile
         ptx::mbar_arrive_expect_tx(&full_b[0], (uint32_t)(9 * p.kblocks * p.block_n * rowb));
         for (int cb = 0; cb < p.kblocks; ++cb)
           for (int tap = 0; tap < 9; ++tap)
-            ptx::tma_load_4d(smem_b + (cb * 9 + tap) * b_bytes, &p.tmB, &full_b[0], tap * p.c_in_pad + cb * p.kw, 0, 0, 0);
+            ptx::tma_load_4d(smem_b + (cb * 9 + tap) * b_bytes, &p.tmB, &full_b[0], tap * p.c_in_pad + cb * KW, 0, 0, 0);
       }
-      (void)n_tile_fixed;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % p.n_tiles, mt = t / p.n_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tz = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * 8 * p.strips, y0 = ty * kConvTH;
+        const int x0 = tx * 8 * STRIPS, y0 = ty * kConvTH;
         for (int cb = 0; cb < p.kblocks; ++cb) {
           ptx::mbar_wait(&empty_a[sa], pa ^ 1);
+          if (p.trace && blockIdx.x == 0 && cb == 0 && t / (int)gridDim.x < 64) p.trace[(t / gridDim.x) * 8 + 0] = clock64();
           ptx::mbar_arrive_expect_tx(&full_a[sa], (uint32_t)(HW * (kConvTH + 2) * rowb));
-          ptx::tma_load_4d(smem_a + sa * a_bytes, &p.tmA, &full_a[sa], cb * p.kw, x0 - 1, y0 - 1, tz);
+          ptx::tma_load_4d(smem_a + sa * a_bytes, &p.tmA, &full_a[sa], cb * KW, x0 - 1, y0 - 1, tz);
           if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
-          if (!p.b_resident) {
+          if (!BRES) {
             for (int tap = 0; tap < 9; ++tap) {
               ptx::mbar_wait(&empty_b[sb], pb ^ 1);
               ptx::mbar_arrive_expect_tx(&full_b[sb], (uint32_t)(p.block_n * rowb));
-              ptx::tma_load_4d(smem_b + sb * b_bytes, &p.tmB, &full_b[sb], tap * p.c_in_pad + cb * p.kw, nt * p.block_n, 0, 0);
+              ptx::tma_load_4d(smem_b + sb * b_bytes, &p.tmB, &full_b[sb], tap * p.c_in_pad + cb * KW, nt * p.block_n, 0, 0);
               if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
             }
           }
@@ -126,53 +136,72 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
     const uint32_t idesc = ptx::make_idesc_f16(128, p.block_n, 0);
     int sa = 0, sb = 0, acc = 0;
     uint32_t pa = 0, pb = 0, acc_phase = 0;
-    if (p.b_resident) { ptx::mbar_wait(&full_b[0], 0); ptx::tc_fence_after(); }
-    const uint64_t da_const = p.kw == 64 ? ptx::smem_desc_base_sw128((uint32_t)HW * 128) : ptx::smem_desc_base_sw64((uint32_t)HW * 64);
-    const uint64_t db_const = p.kw == 64 ? ptx::smem_desc_base_sw128(1024) : ptx::smem_desc_base_sw64(512);
-    const int row16 = rowb >> 4;                    // pixel-row pitch in 16-byte units (8 or 4)
-    const int ksteps = p.kw >> 4;                   // tcgen05.mma K = 16 steps per block (4 or 2)
+    if (BRES) { ptx::mbar_wait(&full_b[0], 0); ptx::tc_fence_after(); }
+    constexpr int row16 = rowb >> 4;                // pixel-row pitch in 16-byte units (8 or 4)
+    constexpr int ksteps = KW >> 4;                 // tcgen05.mma K = 16 steps per block (4 or 2)
+    const uint64_t da_const = KW == 64 ? ptx::smem_desc_base_sw128((uint32_t)HW * 128) : ptx::smem_desc_base_sw64((uint32_t)HW * 64);
+    const uint64_t db_const = KW == 64 ? ptx::smem_desc_base_sw128(1024) : ptx::smem_desc_base_sw64(512);
+    const uint64_t da_base = da_const + (ptx::smem_u32(smem_a) >> 4);
+    const uint64_t db_base = db_const + (ptx::smem_u32(smem_b) >> 4);
+    const uint32_t b16 = (uint32_t)b_bytes >> 4;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && t / (int)gridDim.x < 64;
+      long long* trp = tr ? p.trace + (t / gridDim.x) * 8 : nullptr;
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d0 = tmem_base + (uint32_t)(acc * p.strips) * acc_stride;
+      if (tr) trp[1] = clock64();
+      const uint32_t d0 = tmem_base + (uint32_t)(acc * STRIPS) * acc_stride;
       for (int cb = 0; cb < p.kblocks; ++cb) {
         ptx::mbar_wait(&full_a[sa], pa);
         ptx::tc_fence_after();
-        const uint64_t da_stage = da_const + (ptx::smem_u32(smem_a + sa * a_bytes) >> 4);
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          uint64_t db;
-          if (p.b_resident) {
-            db = db_const + (ptx::smem_u32(smem_b + (cb * 9 + tap) * b_bytes) >> 4);
-          } else {
-            ptx::mbar_wait(&full_b[sb], pb);
-            ptx::tc_fence_after();
-            db = db_const + (ptx::smem_u32(smem_b + sb * b_bytes) >> 4);
-          }
-          const int ky = tap / 3, kx = tap % 3;
-          const uint64_t da_tap = da_stage + (uint64_t)((ky * HW + kx) * row16);
+        if (tr && cb == 0) trp[2] = clock64();
+        const uint64_t da_stage = da_base + (uint64_t)((uint32_t)(sa * a_bytes) >> 4);
+        const uint32_t first = cb != 0;   // accumulate flag of the very first MMA of a tile
+        if (BRES) {
+          // resident weights: 9 taps x ksteps x STRIPS MMAs as one straight-line issue block under a single election
+          const uint64_t db_cb = db_base + (uint64_t)((uint32_t)(cb * 9) * b16);
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < ksteps) ptx::umma_f16(d0, da_tap + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
-            if (p.strips == 2) {
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t da_tap = da_stage + (uint64_t)(((tap / 3) * HW + tap % 3) * row16);
+              const uint64_t db = db_cb + (uint64_t)((uint32_t)tap * b16);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (k < ksteps) ptx::umma_f16(d0 + acc_stride, da_tap + 8 * row16 + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0);
+              for (int k = 0; k < ksteps; ++k) ptx::umma_f16(d0, da_tap + 2 * k, db + 2 * k, idesc, (tap | k) ? 1u : first);
+              if (STRIPS == 2) {
+#pragma unroll
+                for (int k = 0; k < ksteps; ++k) ptx::umma_f16(d0 + acc_stride, da_tap + 8 * row16 + 2 * k, db + 2 * k, idesc, (tap | k) ? 1u : first);
+              }
             }
-            if (!p.b_resident) ptx::umma_commit(&empty_b[sb]);
+            ptx::umma_commit(&empty_a[sa]);
           }
           __syncwarp();
-          if (!p.b_resident) { if (++sb == p.stages_b) { sb = 0; pb ^= 1; } }
+        } else {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            ptx::mbar_wait(&full_b[sb], pb);
+            ptx::tc_fence_after();
+            const uint64_t db = db_base + (uint64_t)((uint32_t)sb * b16);
+            const uint64_t da_tap = da_stage + (uint64_t)(((tap / 3) * HW + tap % 3) * row16);
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < ksteps; ++k) ptx::umma_f16(d0, da_tap + 2 * k, db + 2 * k, idesc, (tap | k) ? 1u : first);
+              if (STRIPS == 2) {
+#pragma unroll
+                for (int k = 0; k < ksteps; ++k) ptx::umma_f16(d0 + acc_stride, da_tap + 8 * row16 + 2 * k, db + 2 * k, idesc, (tap | k) ? 1u : first);
+              }
+              ptx::umma_commit(&empty_b[sb]);
+              if (tap == 8) ptx::umma_commit(&empty_a[sa]);
+            }
+            __syncwarp();
+            if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
+          }
         }
-        if (ptx::elect_one()) ptx::umma_commit(&empty_a[sa]);
-        __syncwarp();
         if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
       }
       if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
       __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (tr) trp[3] = clock64();
+      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===== epilogue: 8 warps; warp (2 + e) owns TMEM lane quarter (warp & 3) and half of the work (strip, or column half) =====
@@ -180,24 +209,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
     const int half = (warp - 2) >> 2;
     const int lx = lane & 7, ly = quarter * 4 + (lane >> 3);      // pixel of this lane inside an 8 x 16 strip
     const int chunks = p.block_n / 16;
-    const int s_mine = (p.strips == 2) ? half : 0;
-    const int c_begin = (p.strips == 2) ? 0 : (half ? (chunks + 1) / 2 : 0);
-    const int c_end = (p.strips == 2) ? chunks : (half ? chunks : (chunks + 1) / 2);
+    const int s_mine = (STRIPS == 2) ? half : 0;
+    const int c_begin = (STRIPS == 2) ? 0 : (half ? (chunks + 1) / 2 : 0);
+    const int c_end = (STRIPS == 2) ? chunks : (half ? chunks : (chunks + 1) / 2);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tz = mt / (p.tiles_x * p.tiles_y);
       const int y = ty * kConvTH + ly;
-      const int x = (tx * p.strips + s_mine) * 8 + lx;
+      const int x = (tx * STRIPS + s_mine) * 8 + lx;
       const bool valid = (x < p.W) && (y < p.H);
       const int n0 = nt * p.block_n;
       __half* o_full = p.out ? p.out + (long long)tz * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx : nullptr;
       __half* o_pool = p.pool_out ? p.pool_out + (long long)tz * p.pool_sb + (long long)(y >> 1) * p.pool_sy + (long long)(x >> 1) * p.pool_sx : nullptr;
       const bool pool_lane = valid && !(lane & 1) && !(lane & 8);
+      const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9) && t / (int)gridDim.x < 64;
+      long long* trp = tr ? p.trace + (t / gridDim.x) * 8 + (warp == 2 ? 4 : 6) : nullptr;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * p.strips + s_mine) * acc_stride + (uint32_t(quarter * 32) << 16);
+      if (tr) trp[0] = clock64();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * STRIPS + s_mine) * acc_stride + (uint32_t(quarter * 32) << 16);
       uint32_t r[2][16];
       if (c_begin < c_end) ptx::tmem_ld16(taddr + c_begin * 16, r[0]);
 #pragma unroll 1
@@ -259,8 +291,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (tr) trp[1] = clock64();
+      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   }
 

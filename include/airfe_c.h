@@ -137,6 +137,11 @@ int airfe_stereo_cost(airfe_ctx* ctx, int net, int matcher, int pairs, int lines
 /* Parity taps: copy a named intermediate of the last detect call (image `index`) to `dst`; returns bytes, <0 on error. */
 long long airfe_debug_read(airfe_ctx* ctx, int net, const char* name, int index, void* dst, long long dst_bytes);
 
+/* Authoring aid: when `dev_buf` (device memory, >= 64*8 int64) is non-NULL, CTA 0 of every following tc_conv3x3 launch writes
+ * clock64 stamps of its first 64 tiles there (8 slots per tile: producer issue, MMA start / operands landed / issued,
+ * epilogue start / end of the first and last epilogue warp).  NULL switches tracing off.  See tools/trace_conv.py. */
+void airfe_debug_conv_trace(long long* dev_buf);
+
 /* The CUDA stream all work of this context is issued on (cudaStream_t), for event timing by the caller. */
 void* airfe_stream(airfe_ctx* ctx);
 
