@@ -259,8 +259,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
               *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
               *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
             } else {
-              const __half* hh = reinterpret_cast<const __half*>(h);
-              for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) o[i] = hh[i];
+              unsigned short* os = reinterpret_cast<unsigned short*>(o);   // static indices only: h[] must stay in registers
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (nbase + 2 * i < p.n_valid) os[2 * i] = (unsigned short)(h[i] & 0xffffu);
+                if (nbase + 2 * i + 1 < p.n_valid) os[2 * i + 1] = (unsigned short)(h[i] >> 16);
+              }
             }
           }
           if (p.pool_out) {
@@ -281,8 +285,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
                 *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
               } else {
-                const __half* hh = reinterpret_cast<const __half*>(h);
-                for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) o[i] = hh[i];
+                unsigned short* os = reinterpret_cast<unsigned short*>(o);   // static indices only: h[] must stay in registers
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (nbase + 2 * i < p.n_valid) os[2 * i] = (unsigned short)(h[i] & 0xffffu);
+                  if (nbase + 2 * i + 1 < p.n_valid) os[2 * i + 1] = (unsigned short)(h[i] >> 16);
+                }
               }
             }
           }

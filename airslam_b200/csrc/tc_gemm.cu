@@ -5,6 +5,7 @@
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace airfe {
 
@@ -116,31 +117,47 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   p.n_valid = d.n_valid;
   p.dyn_w = d.dyn_w;
   p.dyn_w_stride = d.dyn_w_stride;
-  const int stage_bytes = kABytes + tc_b_bytes(d.block_n, d.b_mn_major);
-  int stages = (200 * 1024) / stage_bytes;
+  const int b_bytes = tc_b_bytes(d.block_n, d.b_mn_major);
+  const int budget = 200 * 1024;
+  const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
+  const int panel = p.taps * p.kblocks * b_bytes;
+  static const bool bres_off = getenv("AIRFE_GEMM_NO_BRES") != nullptr;
+  // weights-resident: not for per-head / per-image B operands, and only when >= 3 A stages still fit and every CTA can keep one N tile
+  p.b_resident = (!bres_off && !p.b_batched && panel + 3 * kABytes <= budget && p.n_tiles <= num_sms() && total > p.n_tiles) ? 1 : 0;
+  int stages;
+  if (p.b_resident) {
+    stages = (budget - panel) / kABytes;
+  } else {
+    stages = budget / (kABytes + b_bytes);
+  }
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  plan->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 16;
-  const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
-  plan->grid = total < num_sms() ? total : num_sms();
+  plan->smem_bytes = stages * (p.b_resident ? kABytes : kABytes + b_bytes) + (p.b_resident ? panel : 0) + 1024 /*align slack*/ + (2 * stages + 5) * 8 + 16;
+  int grid = total < num_sms() ? total : num_sms();
+  if (p.b_resident) grid = grid / p.n_tiles * p.n_tiles;   // a CTA's N tile (blockIdx % n_tiles) must never change
+  plan->grid = grid;
   plan->flops = 2.0 * (double)d.W * d.H * d.B * (double)d.n_valid * (double)d.taps * (double)d.a_C;
   return true;
 }
 
+using TcKernel = void (*)(const TcGemmParams);
+
 bool tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[4] = {};
+  const int key = (plan.p.b_mn_major ? 2 : 0) | (plan.p.b_resident ? 1 : 0);
+  TcKernel kern = key == 0 ? tc_gemm_kernel<false, false> : key == 1 ? tc_gemm_kernel<false, true> : key == 2 ? tc_gemm_kernel<true, false> : tc_gemm_kernel<true, true>;
+  if (!attr_set[key]) {
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, tc_gemm_kernel);
-    if (cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes) != cudaSuccess) {
+    cudaFuncGetAttributes(&fa, kern);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(tc_gemm_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
       return false;
     }
-    attr_set = true;
+    attr_set[key] = true;
   }
   if (plan.grid <= 0) return true;
-  tc_gemm_kernel<<<plan.grid, kTcThreads, plan.smem_bytes, stream>>>(plan.p);
+  kern<<<plan.grid, kTcThreads, plan.smem_bytes, stream>>>(plan.p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("tc_gemm launch failed: %s", cudaGetErrorString(e));

@@ -10,30 +10,38 @@
 //  * Accumulators live in TMEM (double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1).
 //  * Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+ TMEM owner), warps 2-5 = epilogue.
 //  * Persistent: grid = min(#tiles, #SMs); tiles are strided over CTAs.
+//  * BRES (weights-resident) mode: when the [block_n x K] weight panel fits, every CTA loads the panel of its own N tile once
+//    (the grid is a multiple of n_tiles, so a CTA's N tile never changes) and the ring carries A tiles only.  Without it all
+//    148 CTAs re-stream the same few KiB of weights from L2 for every 128-row tile, which bounded the 1x1 convolutions and the
+//    matcher projections at 2-3 TB/s of L2 traffic (tools/prof_gemm.py).
+//  * MN_MAJOR / BRES are template parameters so the single-warp MMA issue loop carries no runtime branches (see tc_conv3x3.cuh).
 #pragma once
 #include "ptx.cuh"
 #include "tc_gemm_params.h"
 
 namespace airfe {
 
+template <bool MN_MAJOR, bool BRES>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A | B)] | barriers | tmem slot
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_bytes = tc_b_bytes(p.block_n, p.b_mn_major);
-  const int stage_bytes = kABytes + b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  const int b_bytes = tc_b_bytes(p.block_n, MN_MAJOR);
+  const int stage_bytes = BRES ? kABytes : kABytes + b_bytes;
+  const int ksteps = p.taps * p.kblocks;
+  uint8_t* smem_bres = smem + p.stages * stage_bytes;                       // BRES: ksteps panels of b_bytes behind the A ring
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_bres + (BRES ? ksteps * b_bytes : 0));
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* bres_bar = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_x = p.tiles_x;
   const int m_tiles = tiles_x * p.tiles_y * p.tiles_b;
   const int total_tiles = m_tiles * p.n_tiles;
-  const int ksteps = p.taps * p.kblocks;
   const uint32_t tmem_cols = tc_tmem_cols(p.block_n);
   const uint32_t acc_stride = tc_acc_stride(p.block_n);
 
@@ -48,6 +56,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       ptx::mbar_init(&tmem_full[s], 1);
       ptx::mbar_init(&tmem_empty[s], 8);
     }
+    ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -67,7 +76,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kABytes + (p.b_mn_major ? 64 * 128 : p.block_n * 128);
+      const uint32_t b_tx = MN_MAJOR ? 64 * 128 : p.block_n * 128;
+      const uint32_t tx_bytes = BRES ? kABytes : kABytes + b_tx;
+      if (BRES) {   // this CTA's N tile is fixed (grid % n_tiles == 0): load its weight panel once
+        const int nt = blockIdx.x % p.n_tiles;
+        ptx::mbar_arrive_expect_tx(bres_bar, (uint32_t)ksteps * b_tx);
+        for (int tap = 0; tap < p.taps; ++tap)
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            const int koff = tap * p.c_in_pad + kb * kBlockK;
+            uint8_t* sb = smem_bres + (tap * p.kblocks + kb) * b_bytes;
+            if (MN_MAJOR) ptx::tma_load_4d(sb, &p.tmB, bres_bar, nt * p.block_n, koff, 0, 0);
+            else ptx::tma_load_4d(sb, &p.tmB, bres_bar, koff, nt * p.block_n, 0, 0);
+          }
+      }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % p.n_tiles;
         const int mt = t / p.n_tiles;
@@ -87,11 +108,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
             uint8_t* sb = sa + kABytes;
             ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
             ptx::tma_load_4d(sa, &p.tmA, &full_bar[stage], kb * kBlockK, x0 + dx, y0 + dy, b0);
-            const int koff = tap * p.c_in_pad + kb * kBlockK;
-            if (p.b_mn_major)
-              ptx::tma_load_4d(sb, &p.tmB, &full_bar[stage], nt * p.block_n, koff, hb, bb);
-            else
-              ptx::tma_load_4d(sb, &p.tmB, &full_bar[stage], koff, nt * p.block_n, hb, bb);
+            if (!BRES) {
+              const int koff = tap * p.c_in_pad + kb * kBlockK;
+              if (MN_MAJOR) ptx::tma_load_4d(sb, &p.tmB, &full_bar[stage], nt * p.block_n, koff, hb, bb);
+              else ptx::tma_load_4d(sb, &p.tmB, &full_bar[stage], koff, nt * p.block_n, hb, bb);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -99,7 +120,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues =====
-    const uint32_t idesc = ptx::make_idesc_f16(kTileM, p.block_n, p.b_mn_major);
+    const uint32_t idesc = ptx::make_idesc_f16(kTileM, p.block_n, MN_MAJOR ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -107,6 +128,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     const uint64_t d_const = ptx::smem_desc_base_sw128(1024);
     const uint64_t db_mn_const = (static_cast<uint64_t>((8192 >> 4) & 0x3FFF) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) |
                                  (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+    const uint64_t da_base = d_const + (ptx::smem_u32(smem) >> 4);
+    const uint64_t db_base = (MN_MAJOR ? db_mn_const : d_const) + (ptx::smem_u32(BRES ? smem_bres : smem + kABytes) >> 4);
+    constexpr uint32_t bstep = MN_MAJOR ? (2048 >> 4) : 2;
+    const uint32_t stage16 = (uint32_t)stage_bytes >> 4, b16 = (uint32_t)b_bytes >> 4;
+    if (BRES) { ptx::mbar_wait(bres_bar, 0); ptx::tc_fence_after(); }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       if (p.dyn_w) {
         const int mt = t / p.n_tiles;
@@ -118,13 +144,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       for (int ks = 0; ks < ksteps; ++ks) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
-        const uint64_t da = d_const + (sa >> 4);
-        const uint64_t db = (p.b_mn_major ? db_mn_const : d_const) + ((sa + kABytes) >> 4);
-        const uint32_t bstep = p.b_mn_major ? (2048 >> 4) : 2;
+        const uint64_t da = da_base + (uint64_t)((uint32_t)stage * stage16);
+        const uint64_t db = db_base + (uint64_t)(BRES ? (uint32_t)ks * b16 : (uint32_t)stage * stage16);
+        const uint32_t first = ks != 0;
         if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) ptx::umma_f16(d_tmem, da + 2 * k, db + bstep * k, idesc, (ks | k) != 0);
+          for (int k = 0; k < kBlockK / 16; ++k) ptx::umma_f16(d_tmem, da + 2 * k, db + bstep * k, idesc, k ? 1u : first);
           ptx::umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
@@ -198,7 +223,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
                 v[i] += q.x; v[i + 1] += q.y; v[i + 2] += q.z; v[i + 3] += q.w;
               }
             } else {
-              for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) v[i] += __ldg(rs + i);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) if (nbase + i < p.n_valid) v[i] += __ldg(rs + i);   // static indices: v[] must stay in registers
             }
           }
           if (p.out2) {
@@ -213,7 +239,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
               *reinterpret_cast<uint4*>(o2) = make_uint4(h[0], h[1], h[2], h[3]);
               *reinterpret_cast<uint4*>(o2 + 8) = make_uint4(h[4], h[5], h[6], h[7]);
             } else {
-              for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) o2[i] = __float2half_rn(v[i]);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) if (nbase + i < p.n_valid) o2[i] = __float2half_rn(v[i]);
             }
           }
           if (p.out_f32) {
@@ -222,7 +249,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
               for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             } else {
-              for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) o[i] = v[i];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) if (nbase + i < p.n_valid) o[i] = v[i];
             }
           } else {
             __half* o = reinterpret_cast<__half*>(p.out) + off + nbase;
@@ -236,7 +264,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
               *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
               *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
             } else {
-              for (int i = 0; i < 16 && nbase + i < p.n_valid; ++i) o[i] = __float2half_rn(v[i]);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) if (nbase + i < p.n_valid) o[i] = __float2half_rn(v[i]);
             }
           }
         }
