@@ -14,6 +14,8 @@ struct airfe_ctx {
   int device = 0;
   airfe_config cfg;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;                 // D2H of the detector results overlaps the matcher (stereo entry point)
+  cudaEvent_t ev_det = nullptr, ev_copy = nullptr;
   std::unique_ptr<Detector> sp, pl;
   std::unique_ptr<LightGlue> lg;
   std::unique_ptr<SuperGlue> sg;
@@ -70,7 +72,11 @@ int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out) {
   std::unique_ptr<airfe_ctx> c(new airfe_ctx);
   c->device = device;
   c->cfg = *cfg;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return AIRFE_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_det, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("stream creation failed");
+    return AIRFE_ERR_CUDA;
+  }
   DetectorConfig dc;
   dc.max_batch = 2 * cfg->max_batch;   // a stereo batch of max_batch pairs = 2*max_batch images
   dc.max_keypoints = cfg->max_keypoints;
@@ -155,6 +161,9 @@ void airfe_destroy(airfe_ctx* c) {
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->d_img) cudaFree(c->d_img);
   cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev_det) cudaEventDestroy(c->ev_det);
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   delete c;
 }
 
@@ -405,45 +414,50 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
   }
   if (!d->run(c->d_img, 2 * pairs, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return AIRFE_ERR_CUDA;
   const DetectOutputs& o = d->out();
-  if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, st) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, st)) return AIRFE_ERR_CUDA;
-  // results: features of 2*pairs images, lines, left junctions, matches
+  // detector results go home on a second stream while the matcher runs on the first (13 MB of descriptors per 16 pairs)
+  cudaStream_t cs = c->copy_stream;
+  cudaEventRecord(c->ev_det, st);
+  cudaStreamWaitEvent(cs, c->ev_det, 0);
   const int B = 2 * c->cfg.max_batch, S = 2 * pairs;
   int* hc = c->h_counts;
-  cudaMemcpyAsync(hc, o.n_feat, 4 * S, cudaMemcpyDeviceToHost, st);
-  if (lines) cudaMemcpyAsync(hc + B, o.n_lines, 4 * S, cudaMemcpyDeviceToHost, st);
-  if (junc) cudaMemcpyAsync(hc + 2 * B, o.n_junc, 4 * S, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hc, o.n_feat, 4 * S, cudaMemcpyDeviceToHost, cs);
+  if (lines) cudaMemcpyAsync(hc + B, o.n_lines, 4 * S, cudaMemcpyDeviceToHost, cs);
+  if (junc) cudaMemcpyAsync(hc + 2 * B, o.n_junc, 4 * S, cudaMemcpyDeviceToHost, cs);
   const int kmax = c->cfg.max_keypoints;
   const bool feat_direct = is_pinned(feat) && feat_cap >= kmax;   // pinned caller buffer: D2H lands in it directly (columns beyond n_feat are scratch)
   for (int i = 0; i < S; ++i)
     cudaMemcpyAsync(feat_direct ? feat + (size_t)i * feat_cap * 259 : c->h_feat + (size_t)i * kKpCap * 259, o.feat + (size_t)i * kKpCap * 259,
-                    (size_t)kmax * 259 * 4, cudaMemcpyDeviceToHost, st);
+                    (size_t)kmax * 259 * 4, cudaMemcpyDeviceToHost, cs);
   const bool junc_direct = junc && is_pinned(junc) && junc_cap >= kJunc;
   if (junc_direct)
     for (int p = 0; p < pairs; ++p)
-      cudaMemcpyAsync(junc + (size_t)p * junc_cap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)kJunc * 259 * 4, cudaMemcpyDeviceToHost, st);
-  int rc = fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, nullptr, matcher);   // synchronises the stream
-  if (rc != AIRFE_OK) return rc;
+      cudaMemcpyAsync(junc + (size_t)p * junc_cap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)kJunc * 259 * 4, cudaMemcpyDeviceToHost, cs);
+  cudaEventRecord(c->ev_copy, cs);
+  if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, st) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, st)) {
+    cudaStreamSynchronize(cs);
+    return AIRFE_ERR_CUDA;
+  }
+  // the detector results land while the matcher is still running: size the line / junction copies from the counts and queue them too
+  if (cudaEventSynchronize(c->ev_copy) != cudaSuccess) { set_error("detector readback failed: %s", cudaGetErrorString(cudaGetLastError())); return AIRFE_ERR_CUDA; }
   for (int i = 0; i < S; ++i) {
     const int n = hc[i] < feat_cap ? hc[i] : feat_cap;
     n_feat[i] = n;
     if (!feat_direct) memcpy(feat + (size_t)i * feat_cap * 259, c->h_feat + (size_t)i * kKpCap * 259, (size_t)n * 259 * 4);
   }
-  for (int p = 0; p < pairs; ++p)
-    if (hc[2 * p] < 1 || hc[2 * p + 1] < 1) n_match[p] = 0;
   if (lines) {
-    const double ws = (double)((float)w / 512.f), hs = (double)((float)h / 512.f);
     for (int i = 0; i < S; ++i) {
       const int n = hc[B + i] < line_cap ? hc[B + i] : line_cap;
       n_lines[i] = n;
-      if (n) cudaMemcpyAsync(c->h_lines + (size_t)i * kLineCap * 4, o.lines + (size_t)i * kLineCap * 4, (size_t)n * 16, cudaMemcpyDeviceToHost, st);
+      if (n) cudaMemcpyAsync(c->h_lines + (size_t)i * kLineCap * 4, o.lines + (size_t)i * kLineCap * 4, (size_t)n * 16, cudaMemcpyDeviceToHost, cs);
     }
     if (junc)
       for (int p = 0; p < pairs; ++p) {
         const int n = hc[2 * B + 2 * p] < junc_cap ? hc[2 * B + 2 * p] : junc_cap;
         n_junc[p] = n;
-        if (n && !junc_direct) cudaMemcpyAsync(c->h_junc + (size_t)p * kKpCap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)n * 259 * 4, cudaMemcpyDeviceToHost, st);
+        if (n && !junc_direct) cudaMemcpyAsync(c->h_junc + (size_t)p * kKpCap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)n * 259 * 4, cudaMemcpyDeviceToHost, cs);
       }
-    cudaStreamSynchronize(st);
+    if (cudaStreamSynchronize(cs) != cudaSuccess) { set_error("line readback failed: %s", cudaGetErrorString(cudaGetLastError())); return AIRFE_ERR_CUDA; }
+    const double ws = (double)((float)w / 512.f), hs = (double)((float)h / 512.f);
     for (int i = 0; i < S; ++i) {
       const float* l = c->h_lines + (size_t)i * kLineCap * 4;
       double* dl = lines + (size_t)i * line_cap * 4;
@@ -455,6 +469,10 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
     if (junc && !junc_direct)
       for (int p = 0; p < pairs; ++p) memcpy(junc + (size_t)p * junc_cap * 259, c->h_junc + (size_t)p * kKpCap * 259, (size_t)n_junc[p] * 259 * 4);
   }
+  int rc = fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, nullptr, matcher);   // synchronises the compute stream
+  if (rc != AIRFE_OK) return rc;
+  for (int p = 0; p < pairs; ++p)
+    if (hc[2 * p] < 1 || hc[2 * p + 1] < 1) n_match[p] = 0;
   return AIRFE_OK;
 }
 

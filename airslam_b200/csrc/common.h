@@ -24,6 +24,22 @@ const char* get_error();
 
 struct TcGemmParams;
 
+// Launch with programmatic dependent launch (PDL) allowed: the kernel may become resident while its predecessor in the stream is
+// still draining (it called griddepcontrol.launch_dependents), runs its prologue (barrier init, TMEM allocation, tensor-map
+// prefetch, bias staging) and then blocks in griddepcontrol.wait until the predecessor's results are visible.  Every kernel
+// launched through here MUST execute ptx::pdl_wait() before it touches data produced by earlier kernels.  AIRFE_NO_PDL=1 disables.
+bool pdl_enabled();
+template <typename P>
+inline cudaError_t launch_pdl(void (*kern)(const P), int grid, int block, size_t smem, cudaStream_t st, const P& params) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, params);
+}
+
 // Description of one dense contraction for tc_gemm_plan().
 struct TcGemmDesc {
   // A: NHWC fp16 view (element strides), a_C valid channels

@@ -1,3 +1,4 @@
+#include <stdlib.h>
 #include "common.h"
 #include <stdarg.h>
 namespace airfe {
@@ -9,4 +10,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+bool pdl_enabled() {
+  static const bool on = getenv("AIRFE_NO_PDL") == nullptr;
+  return on;
+}
+
 }  // namespace airfe

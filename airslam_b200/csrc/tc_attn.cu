@@ -39,8 +39,7 @@ bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __h
       }
       attr_set = true;
     }
-    tc_attn_kernel<<<slots * 4, kAttnThreads, kAttnSmemBytes, st>>>(p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(tc_attn_kernel, slots * 4, kAttnThreads, kAttnSmemBytes, st, p);
     if (e != cudaSuccess) { set_error("tc_attn launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
   });

@@ -50,11 +50,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x >> 2, head = blockIdx.x & 3;
   const int kslot = slot ^ p.slot_xor;
-  const int nq = min(__ldg(p.n + slot), p.cap);
-  const int nk = min(__ldg(p.n + kslot), 512);
-  const int q_tiles = (nq + 127) >> 7;
-  const int nkb = (nk + 63) >> 6;              // 64-key blocks of P / V
-  const int nk16 = (nk + 15) & ~15;            // key extent of the S MMAs
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmQ); ptx::prefetch_tmap(&p.tmK); ptx::prefetch_tmap(&p.tmV);
@@ -68,6 +63,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_launch_dependents();   // programmatic dependent launch: see launch_pdl (common.h)
+  ptx::pdl_wait();                // the keypoint counts and Q / K / V are produced by earlier kernels: read them only from here on
+  const int nq = min(__ldg(p.n + slot), p.cap);
+  const int nk = min(__ldg(p.n + kslot), 512);
+  const int q_tiles = (nq + 127) >> 7;
+  const int nkb = (nk + 63) >> 6;              // 64-key blocks of P / V
+  const int nk16 = (nk + 15) & ~15;            // key extent of the S MMAs
 
   if (q_tiles > 0 && nk > 0) {
     if (warp == 0) {

@@ -55,14 +55,14 @@ static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
     }
     attr_set[key] = true;
   }
+  cudaError_t e;
   if (g_conv_trace) {
     ConvPlan traced = plan;
     traced.p.trace = g_conv_trace;
-    kern<<<traced.grid, kConvThreads, traced.smem_bytes, st>>>(traced.p);
+    e = launch_pdl(kern, traced.grid, kConvThreads, traced.smem_bytes, st, traced.p);
   } else {
-    kern<<<plan.grid, kConvThreads, plan.smem_bytes, st>>>(plan.p);
+    e = launch_pdl(kern, plan.grid, kConvThreads, plan.smem_bytes, st, plan.p);
   }
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("tc_conv3x3 launch failed: %s", cudaGetErrorString(e)); return false; }
   return true;
 }
@@ -93,6 +93,14 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   const int n_valid = w.n_rows;
   const int n16 = (n_valid + 15) / 16 * 16;
   int block_n = n16 <= 256 ? n16 : (n16 % 256 == 0 ? 256 : (n16 % 160 == 0 ? 160 : 128));
+  {
+    // small maps (hourglass bottom: 8x8 .. 32x32 x batch) give fewer M tiles than SMs: split N further so more CTAs share the
+    // layer (each then streams only its slice of the weights).  AIRFE_CONV_SPLIT_N=0 switches this off for A/B timing.
+    static const int split_n = getenv("AIRFE_CONV_SPLIT_N") ? atoi(getenv("AIRFE_CONV_SPLIT_N")) : 1;
+    const int strips0 = (in.W >= 16 && 4 * conv_acc_stride(block_n) <= 512) ? 2 : 1;
+    const int m_tiles = ((in.W + 8 * strips0 - 1) / (8 * strips0)) * ((in.H + kConvTH - 1) / kConvTH) * batch;
+    while (split_n && block_n >= 64 && block_n % 32 == 0 && m_tiles * ((n_valid + block_n - 1) / block_n) * 2 <= sm_count()) block_n /= 2;
+  }
   p.block_n = block_n;
   p.n_valid = n_valid;
   p.n_tiles = (n_valid + block_n - 1) / block_n;

@@ -96,8 +96,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   __shared__ __align__(16) float s_bias[512];
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;   // weights: not produced by a kernel
   __syncthreads();
+  ptx::pdl_launch_dependents();   // the next kernel may start its own prologue on SMs this grid has left
+  ptx::pdl_wait();                // everything above overlapped the predecessor's tail; activations are touched only below
 
   if (warp == 0) {
     if (lane == 0) {

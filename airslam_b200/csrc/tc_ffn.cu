@@ -62,8 +62,7 @@ bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, con
       }
       attr_set = true;
     }
-    tc_ffn_kernel<<<grid, kFfnThreads, kFfnSmemBytes, st>>>(p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(tc_ffn_kernel, grid, kFfnThreads, kFfnSmemBytes, st, p);
     if (e != cudaSuccess) { set_error("tc_ffn launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
   });

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_slot = p.cap >> 7;
+  const int rot_n = blockIdx.x & 3, rot_k = (blockIdx.x >> 2) & 7;   // per-CTA rotation of the weight-tile order (masked to the phase's extent)
   const int total_tiles = p.slots * tiles_per_slot;
 
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
@@ -69,6 +70,8 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_launch_dependents();   // programmatic dependent launch: see launch_pdl (common.h); only weights / biases were read so far
+  ptx::pdl_wait();
   const float* s_bout = sPar; const float* s_b0 = sPar + 256; const float* s_b3 = sPar + 768; const float* s_g = sPar + 1024; const float* s_be = sPar + 1536;
 
   if (warp == 0) {
@@ -90,9 +93,12 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
           const int nn = ph == 1 ? 4 : 2, nk = ph == 0 ? 4 : 8;
           for (int nt = 0; nt < nn; ++nt)
             for (int kb = 0; kb < nk; ++kb) {
+              // every CTA streams the same 896 KB of weights: rotate the (n tile, k block) order per CTA so that the CTAs do not all
+              // hit the same few L2 lines in lock-step (the MMA warp applies the same rotation)
+              const int ntr = (nt + rot_n) & (nn - 1), kbr = (kb + rot_k) & (nk - 1);
               ptx::mbar_wait(&b_empty[sb], pb ^ 1);
               ptx::mbar_arrive_expect_tx(&b_full[sb], 16384u);
-              ptx::tma_load_4d(sB + sb * 16384, tm, &b_full[sb], kb * 64, nt * 128, 0, 0);
+              ptx::tma_load_4d(sB + sb * 16384, tm, &b_full[sb], kbr * 64, ntr * 128, 0, 0);
               if (++sb == kFfnBStages) { sb = 0; pb ^= 1; }
             }
         }
@@ -119,11 +125,12 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
           for (int kb = 0; kb < nk; ++kb) {
             ptx::mbar_wait(&b_full[sb], pb);
             ptx::tc_fence_after();
+            const int ntr = (nt + rot_n) & (nn - 1), kbr = (kb + rot_k) & (nk - 1);
             if (ptx::elect_one()) {
-              const uint64_t da = da0 + (uint64_t)((a_first + kb) * (16384 >> 4));
+              const uint64_t da = da0 + (uint64_t)((a_first + kbr) * (16384 >> 4));
               const uint64_t db = d_const + (ptx::smem_u32(sB + sb * 16384) >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + nt * 128, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + ntr * 128, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
               ptx::umma_commit(&b_empty[sb]);
             }
             __syncwarp();

@@ -157,8 +157,7 @@ bool tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream) {
     attr_set[key] = true;
   }
   if (plan.grid <= 0) return true;
-  kern<<<plan.grid, kTcThreads, plan.smem_bytes, stream>>>(plan.p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, plan.grid, kTcThreads, plan.smem_bytes, stream, plan.p);
   if (e != cudaSuccess) {
     set_error("tc_gemm launch failed: %s", cudaGetErrorString(e));
     return false;

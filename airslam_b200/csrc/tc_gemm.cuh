@@ -68,8 +68,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   __shared__ __align__(16) float s_bias[1024];
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;   // weights: not produced by a kernel
   __syncthreads();
+  ptx::pdl_launch_dependents();   // programmatic dependent launch: see launch_pdl (common.h)
+  ptx::pdl_wait();                // activations, device-side counts and residuals are read only below this line
 
   if (warp == 0) {
     if (lane == 0) {
