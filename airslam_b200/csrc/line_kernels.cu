@@ -109,31 +109,76 @@ __global__ void junc_topk_kernel(const float* __restrict__ jloc, const float* __
 }
 
 // ---- K10a: association: nearest junction (first index on ties) of both endpoints of every proposal ----------------------
-__global__ void assoc_kernel(const float* __restrict__ lines, const float* __restrict__ juncs, int* __restrict__ imin_o,
-                             int* __restrict__ imax_o, uint8_t* __restrict__ keep_o, int* __restrict__ pair_table) {
+// Only proposals whose two endpoints both lie within sqrt(10) px of a junction survive (keep), and nothing downstream reads
+// imin / imax of the others, so the 300-junction scan is pruned with a 32x32 grid of 4x4-px cells built per CTA in shared memory:
+// a junction closer than sqrt(10) must sit in the 3x3 cells around the endpoint.  Candidates are compared on (distance, index) so
+// the result is the sequential first-minimum of the reference.  A cell with more than kCellCap junctions (TopK padding with
+// non-peak cells makes runs of adjacent junctions possible) sends the whole CTA down the exact full scan.
+constexpr int kCellCap = 8;
+constexpr int kAssocPer = 4;     // proposals per thread
+__global__ void __launch_bounds__(256) assoc_kernel(const float* __restrict__ lines, const float* __restrict__ juncs, int* __restrict__ imin_o,
+                                                    int* __restrict__ imax_o, uint8_t* __restrict__ keep_o, int* __restrict__ pair_table) {
   __shared__ float2 sj[kJunctions];
+  __shared__ int s_cnt[1024];
+  __shared__ unsigned short s_list[1024 * kCellCap];
+  __shared__ int s_overflow;
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < kJunctions; i += blockDim.x) sj[i] = reinterpret_cast<const float2*>(juncs)[(long long)b * kJunctions + i];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_cnt[i] = 0;
+  if (threadIdx.x == 0) s_overflow = 0;
   __syncthreads();
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= kProposals) return;
-  const float4 l = *reinterpret_cast<const float4*>(lines + ((long long)b * kProposals + k) * 4);
-  float m1 = INFINITY, m2 = INFINITY;
-  int i1 = 0, i2 = 0;
-  for (int q = 0; q < kJunctions; ++q) {
-    const float2 p = sj[q];
-    const float dx1 = __fsub_rn(l.x, p.x), dy1 = __fsub_rn(l.y, p.y);
-    const float dx2 = __fsub_rn(l.z, p.x), dy2 = __fsub_rn(l.w, p.y);
-    const float d1 = __fadd_rn(__fmul_rn(dx1, dx1), __fmul_rn(dy1, dy1));
-    const float d2 = __fadd_rn(__fmul_rn(dx2, dx2), __fmul_rn(dy2, dy2));
-    if (d1 < m1) { m1 = d1; i1 = q; }
-    if (d2 < m2) { m2 = d2; i2 = q; }
+  for (int i = threadIdx.x; i < kJunctions; i += blockDim.x) {
+    const float2 p = sj[i];
+    const int cx = min(31, max(0, (int)(p.x * 0.25f))), cy = min(31, max(0, (int)(p.y * 0.25f)));
+    const int slot = atomicAdd(&s_cnt[cy * 32 + cx], 1);
+    if (slot < kCellCap) s_list[(cy * 32 + cx) * kCellCap + slot] = (unsigned short)i;
+    else s_overflow = 1;
   }
-  const int lo = min(i1, i2), hi = max(i1, i2);
-  const bool keep = (lo < hi) && (m1 < 10.f) && (m2 < 10.f);
-  const long long o = (long long)b * kProposals + k;
-  imin_o[o] = lo; imax_o[o] = hi; keep_o[o] = keep;
-  if (keep) atomicMin(pair_table + (long long)b * kJunctions * kJunctions + lo * kJunctions + hi, k);
+  __syncthreads();
+  const bool full_scan = s_overflow != 0;
+#pragma unroll 1
+  for (int r = 0; r < kAssocPer; ++r) {
+    const int k = (blockIdx.x * kAssocPer + r) * blockDim.x + threadIdx.x;
+    if (k >= kProposals) break;
+    const float4 l = *reinterpret_cast<const float4*>(lines + ((long long)b * kProposals + k) * 4);
+    float m1 = INFINITY, m2 = INFINITY;
+    int i1 = 0, i2 = 0;
+    if (full_scan) {
+      for (int q = 0; q < kJunctions; ++q) {
+        const float2 p = sj[q];
+        const float dx1 = __fsub_rn(l.x, p.x), dy1 = __fsub_rn(l.y, p.y);
+        const float dx2 = __fsub_rn(l.z, p.x), dy2 = __fsub_rn(l.w, p.y);
+        const float d1 = __fadd_rn(__fmul_rn(dx1, dx1), __fmul_rn(dy1, dy1));
+        const float d2 = __fadd_rn(__fmul_rn(dx2, dx2), __fmul_rn(dy2, dy2));
+        if (d1 < m1) { m1 = d1; i1 = q; }
+        if (d2 < m2) { m2 = d2; i2 = q; }
+      }
+    } else {
+      auto nearest = [&](float ex, float ey, float& m, int& im) {
+        const int cx0 = max(0, (int)floorf((ex - 3.17f) * 0.25f)), cx1 = min(31, (int)floorf((ex + 3.17f) * 0.25f));
+        const int cy0 = max(0, (int)floorf((ey - 3.17f) * 0.25f)), cy1 = min(31, (int)floorf((ey + 3.17f) * 0.25f));
+        for (int cy = cy0; cy <= cy1; ++cy)
+          for (int cx = cx0; cx <= cx1; ++cx) {
+            const int c = cy * 32 + cx, n = s_cnt[c];
+            for (int e = 0; e < n; ++e) {
+              const int q = s_list[c * kCellCap + e];
+              const float2 p = sj[q];
+              const float dx = __fsub_rn(ex, p.x), dy = __fsub_rn(ey, p.y);
+              const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+              if (d < m || (d == m && q < im)) { m = d; im = q; }
+            }
+          }
+      };
+      nearest(l.x, l.y, m1, i1);
+      nearest(l.z, l.w, m2, i2);
+      if (!(m1 < 10.f) || !(m2 < 10.f)) { i1 = 0; i2 = 0; }   // not kept: indices are never read
+    }
+    const int lo = min(i1, i2), hi = max(i1, i2);
+    const bool keep = (lo < hi) && (m1 < 10.f) && (m2 < 10.f);
+    const long long o = (long long)b * kProposals + k;
+    imin_o[o] = lo; imax_o[o] = hi; keep_o[o] = keep;
+    if (keep) atomicMin(pair_table + (long long)b * kJunctions * kJunctions + lo * kJunctions + hi, k);
+  }
 }
 
 // ---- block-wide exclusive scan helper (1024 threads) --------------------------------------------------------------------
@@ -403,7 +448,7 @@ void launch_junctions(const float* jloc, const float* heads, int ld, int* peaks,
 void launch_association(const float* lines, const float* juncs, int* imin, int* imax, uint8_t* keep, int* pair_table, int* uid_pairs,
                         int* uid_first, int* n_unique, int line_cap, int batch, cudaStream_t st) {
   cudaMemsetAsync(pair_table, 0x7f, sizeof(int) * (size_t)batch * kJunctions * kJunctions, st);
-  assoc_kernel<<<dim3(kProposals / 256, batch), 256, 0, st>>>(lines, juncs, imin, imax, keep, pair_table);
+  assoc_kernel<<<dim3((kProposals + 256 * kAssocPer - 1) / (256 * kAssocPer), batch), 256, 0, st>>>(lines, juncs, imin, imax, keep, pair_table);
   unique_pairs_kernel<<<batch, 1024, 0, st>>>(imin, imax, keep, pair_table, uid_pairs, uid_first, n_unique, line_cap);
 }
 void launch_loi_gather(const float* loi, int loi_ld, const float* thinaux, int ta_ld, const float* juncs, const float* lines,

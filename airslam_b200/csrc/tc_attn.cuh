@@ -5,7 +5,8 @@
 // attention through HBM three times.
 //   warp 0 : TMA producer (K, V of the attended slot once per CTA; one Q tile per 128 queries)
 //   warp 1 : MMA issuer   (S = Q K^T: 2 x N<=256 ; O = P V: per 64-key block, V as MN-major B operand)
-//   warps 2-5 : softmax + epilogue (one query row per thread; max / sum / normalise = three passes over TMEM), then O -> fp16 ctx
+//   warps 2-9 : softmax + epilogue: two warps per TMEM lane quarter; a thread owns one query row and every second 64-key block
+//               (row max and row sum of the two halves meet in shared memory, named barrier 1), then half of the O columns -> fp16 ctx
 // Arithmetic: fp16 operands, fp32 accumulate, fp32 softmax statistics; the tensor core sees fp16(exp(s - max)) and the 1/sum
 // normalisation is applied to the fp32 output (same relative rounding as rounding the normalised probabilities).
 #pragma once
@@ -23,11 +24,11 @@ struct AttnParams {
   __half* ctx;       // [slots*cap][256] fp16, head h at columns h*64
 };
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;
 constexpr int kAttnSmemQ = 128 * 128;            // 16 KiB
 constexpr int kAttnSmemKV = 512 * 128;           // 64 KiB each
 constexpr int kAttnPSlots = 4;                   // ring of 64-key P blocks (16 KiB each)
-constexpr int kAttnSmemBytes = kAttnSmemQ + 2 * kAttnSmemKV + kAttnPSlots * 16384 + 1024 + 256;
+constexpr int kAttnSmemBytes = kAttnSmemQ + 2 * kAttnSmemKV + kAttnPSlots * 16384 + 2048 + 1024 + 256;
 
 __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -36,7 +37,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
   uint8_t* sK = sQ + kAttnSmemQ;
   uint8_t* sV = sK + kAttnSmemKV;
   uint8_t* sP = sV + kAttnSmemKV;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kAttnPSlots * 16384);
+  float* sRed = reinterpret_cast<float*>(sP + kAttnPSlots * 16384);   // row max [2][128], row sum [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 512);
   uint64_t* kv_full = bars + 0;
   uint64_t* q_full = bars + 1;
   uint64_t* q_empty = bars + 2;
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmQ); ptx::prefetch_tmap(&p.tmK); ptx::prefetch_tmap(&p.tmV);
     ptx::mbar_init(kv_full, 1); ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
-    ptx::mbar_init(s_full, 1); ptx::mbar_init(o_full, 1); ptx::mbar_init(s_free, 4);
+    ptx::mbar_init(s_full, 1); ptx::mbar_init(o_full, 1); ptx::mbar_init(s_free, 8);
     for (int i = 0; i < kAttnPSlots; ++i) { ptx::mbar_init(&p_full[i], 4); ptx::mbar_init(&p_empty[i], 1); }
     ptx::fence_barrier_init();
   }
@@ -139,35 +141,43 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
         ph ^= 1;
       }
     } else {
-      // ===== softmax + epilogue: thread = one query row =====
+      // ===== softmax + epilogue: thread = one query row x every second 64-key block =====
       const int quarter = warp & 3;
+      const int half = (warp - 2) >> 2;
       const int row = quarter * 32 + lane;
       const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
       uint32_t ph = 0;
-      uint32_t eph = 0;   // phase bit per P ring slot
+      uint32_t eph = 0;   // phase bit per P ring slot (a slot always belongs to the same half: slot parity == block parity)
       const float sc2 = p.scale * 1.4426950408889634f;      // exp(x) = exp2(x * log2 e): one FFMA + MUFU.EX2 per element
       for (int t = 0; t < q_tiles; ++t) {
         ptx::mbar_wait(s_full, ph);
         ptx::tc_fence_after();
-        // pass 1: row max over the valid keys (raw scores; scale > 0 so the max commutes with it)
+        // pass 1: row max over this half's key blocks (raw scores; scale > 0 so the max commutes with it)
         float mx = -INFINITY;
-        for (int c = 0; c < nk; c += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld32(trow + c, r);
-          ptx::tmem_ld_wait();
-          if (c + 32 <= nk) {
+        for (int kb = half; kb < nkb; kb += 2) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-          } else {
+          for (int hc = 0; hc < 2; ++hc) {
+            const int c = kb * 64 + hc * 32;
+            if (c >= nk) break;
+            uint32_t r[32];
+            ptx::tmem_ld32(trow + c, r);
+            ptx::tmem_ld_wait();
+            if (c + 32 <= nk) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < nk) ? __uint_as_float(r[i]) : -INFINITY);
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < nk) ? __uint_as_float(r[i]) : -INFINITY);
+            }
           }
         }
-        const float m2 = mx * sc2;
+        sRed[half * 128 + row] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float m2 = fmaxf(sRed[row], sRed[128 + row]) * sc2;
         // pass 2: e = exp(s - max) once per element: accumulate the row sum in fp32 and hand fp16(e) to the tensor core through
         // shared memory (K-major SWIZZLE_128B, 64 keys per block); the 1/sum normalisation is applied to O in the epilogue.
         float sum = 0.f;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = half; kb < nkb; kb += 2) {
           const int ps = kb & (kAttnPSlots - 1);
           ptx::mbar_wait(&p_empty[ps], ((eph >> ps) & 1) ^ 1);     // slot free (first use of a fresh barrier passes immediately)
           uint8_t* prow = sP + ps * 16384 + row * 128;
@@ -203,14 +213,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
           if (lane == 0) ptx::mbar_arrive(&p_full[ps]);
           eph ^= 1u << ps;
         }
-        const float inv = 1.f / sum;
-        // epilogue: O (128 x 64 fp32, TMEM columns 0..63) -> fp16 context rows
+        sRed[256 + half * 128 + row] = sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float inv = 1.f / (sRed[256 + row] + sRed[384 + row]);
+        // epilogue: O (128 x 64 fp32, TMEM columns 0..63) -> fp16 context rows; this warp writes columns half*32 .. +32
         ptx::mbar_wait(o_full, ph);
         ptx::tc_fence_after();
         const int q = t * 128 + row;
         __half* o = p.ctx + ((long long)slot * p.cap + q) * 256 + head * 64;
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
+        {
+          const int c = half * 32;
           uint32_t r[32];
           ptx::tmem_ld32(trow + c, r);
           ptx::tmem_ld_wait();

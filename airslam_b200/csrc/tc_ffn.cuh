@@ -6,7 +6,8 @@
 //   phase 3  y   = gelu . W3^T + b3           (K = 512, N = 256)   x += y  (fp32 residual stream + fp16 operand copy to HBM)
 // Weights (896 KB per tile) stream from L2 through a 4-stage TMA ring of [128 x 64] tiles.  The unfused path needed four GEMM
 // launches + one LayerNorm launch per block and moved msg / h / gelu(h) through HBM.
-//   warp 0: TMA producer   warp 1: MMA issuer   warps 2-5: epilogues / LayerNorm (thread = one keypoint row)
+//   warp 0: TMA producer   warp 1: MMA issuer   warps 2-9: epilogues / LayerNorm: two warps per TMEM lane quarter, each thread owns one
+//   keypoint row and one half of the columns; the LayerNorm statistics of the two halves meet in shared memory (named barrier 1)
 #pragma once
 #include "ptx.cuh"
 
@@ -25,9 +26,9 @@ struct FfnParams {
   int slots, cap;
 };
 
-constexpr int kFfnThreads = 192;
+constexpr int kFfnThreads = 320;
 constexpr int kFfnBStages = 4;
-constexpr int kFfnSmemBytes = 8 * 16384 + kFfnBStages * 16384 + 2048 * 4 + 1024 + 256;
+constexpr int kFfnSmemBytes = 8 * 16384 + kFfnBStages * 16384 + (2048 + 512) * 4 + 1024 + 256;
 
 __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_constant__ FfnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -35,14 +36,15 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
   uint8_t* sA = smem;                                   // 8 K blocks of [128 rows x 64] fp16
   uint8_t* sB = sA + 8 * 16384;                         // weight ring
   float* sPar = reinterpret_cast<float*>(sB + kFfnBStages * 16384);   // b_out[256] b0[512] b3[256] g[512] beta[512]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPar + 2048);
+  float* sRed = sPar + 2048;                             // LayerNorm partials: sum[2][128], var[2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 512);
   uint64_t* b_full = bars;                              // [4]
   uint64_t* b_empty = bars + kFfnBStages;               // [4]
   uint64_t* ctx_full = bars + 2 * kFfnBStages;
   uint64_t* x_full = ctx_full + 1;
   uint64_t* a_free = ctx_full + 2;                      // all MMAs of the tile retired: A blocks may be reloaded
   uint64_t* acc_full = ctx_full + 3;                    // a GEMM phase finished: accumulators valid
-  uint64_t* epi_done = ctx_full + 4;                    // (count 4) epilogue finished with TMEM and with its smem writes
+  uint64_t* epi_done = ctx_full + 4;                    // (count 8) epilogue finished with TMEM and with its smem writes
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctx_full + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmCtx); ptx::prefetch_tmap(&p.tmX16); ptx::prefetch_tmap(&p.tmWo); ptx::prefetch_tmap(&p.tmW0); ptx::prefetch_tmap(&p.tmW3);
     for (int i = 0; i < kFfnBStages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    ptx::mbar_init(ctx_full, 1); ptx::mbar_init(x_full, 1); ptx::mbar_init(a_free, 1); ptx::mbar_init(acc_full, 1); ptx::mbar_init(epi_done, 4);
+    ptx::mbar_init(ctx_full, 1); ptx::mbar_init(x_full, 1); ptx::mbar_init(a_free, 1); ptx::mbar_init(acc_full, 1); ptx::mbar_init(epi_done, 8);
     ptx::fence_barrier_init();
   }
   if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
@@ -145,23 +147,23 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       pt ^= 1;
     }
   } else {
-    // ===== epilogues: thread = one keypoint row =====
+    // ===== epilogues: thread = one keypoint row x one half of the columns =====
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
     uint32_t pacc = 0;
-    // TMEM is free at kernel start: complete phase 0 of epi_done so the MMA warp's first wait (parity 1... ) -- see below
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int slot = t / tiles_per_slot, r0 = (t % tiles_per_slot) * 128;
       const int ns = __ldg(p.n + slot);
       if (r0 >= ns) continue;
       const bool valid = (r0 + row) < ns;
       const long long grow = (long long)slot * p.cap + r0 + row;
-      // ---- phase 1 epilogue: msg = acc + b_out -> fp16 -> A blocks 4..7 ----
+      // ---- phase 1 epilogue: msg = acc + b_out -> fp16 -> A blocks 4..7 (this warp: columns half*128 .. +128) ----
       ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 256; c += 32) {
+      for (int c = half * 128; c < half * 128 + 128; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld32(trow + c, r);
         ptx::tmem_ld_wait();
@@ -183,31 +185,36 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(epi_done);
-      // ---- phase 2 epilogue: LayerNorm + GELU over 512 columns -> fp16 -> A blocks 0..7 ----
+      // ---- phase 2 epilogue: LayerNorm + GELU over 512 columns (this warp: columns half*256 .. +256) -> fp16 -> A blocks 0..7 ----
       ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
       ptx::tc_fence_after();
+      const int c_lo = half * 256, c_hi = c_lo + 256;
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 512; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld32(trow + c, r);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) sum += __uint_as_float(r[j]) + s_b0[c + j];
       }
-      const float mean = sum * (1.f / 512.f);
+      sRed[half * 128 + row] = sum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mean = (sRed[row] + sRed[128 + row]) * (1.f / 512.f);      // low half + high half: the same order in both warps
       float var = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 512; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld32(trow + c, r);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(r[j]) + s_b0[c + j] - mean; var = fmaf(d, d, var); }
       }
-      const float rstd = 1.f / sqrtf(var * (1.f / 512.f) + 1e-5f);
+      sRed[256 + half * 128 + row] = var;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float rstd = 1.f / sqrtf((sRed[256 + row] + sRed[384 + row]) * (1.f / 512.f) + 1e-5f);
 #pragma unroll 1
-      for (int c = 0; c < 512; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld32(trow + c, r);
         ptx::tmem_ld_wait();
@@ -235,13 +242,13 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(epi_done);
-      // ---- phase 3 epilogue: x += acc + b3 ; fp32 residual + fp16 operand copy ----
+      // ---- phase 3 epilogue: x += acc + b3 ; fp32 residual + fp16 operand copy (this warp: columns half*128 .. +128) ----
       ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
       ptx::tc_fence_after();
       float* xr = p.x + grow * 256;
       __half* x16r = p.x16 + grow * 512;
 #pragma unroll 1
-      for (int c = 0; c < 256; c += 32) {
+      for (int c = half * 128; c < half * 128 + 128; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld32(trow + c, r);
         ptx::tmem_ld_wait();
