@@ -57,6 +57,8 @@ struct TcGemmDesc {
   int block_n = 64;
   const float* bias = nullptr;
   float scale = 1.f; int scale_cols = 0;
+  const float* rot = nullptr; int rot_cols = 0;          // fused rotary embedding (see TcGemmParams)
+  int out_split = 0; long long out_split_stride = 0;     // column sections stored to separate matrices
   const float* resid = nullptr;
   void* out2 = nullptr; long long out2_sb = 0, out2_sy = 0, out2_sx = 0;
   int relu = 0, out_f32 = 0;

@@ -152,7 +152,7 @@ bool add_gemm(OpList* ol, const TcGemmDesc& d, double flops) {
 }
 
 bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int batch, bool relu, int n_valid, int block_n,
-               const int* dyn_rows, float scale, const float* resid, const Act* out2) {
+               const int* dyn_rows, float scale, const float* resid, const Act* out2, const DenseExtra* ex) {
   TcGemmDesc d;
   d.a = in.p; d.a_C = in.C; d.W = in.W; d.H = in.H; d.B = batch;
   d.a_sx = in.ps; d.a_sy = in.ps * in.W; d.a_sb = in.ps * in.W * in.H;
@@ -176,7 +176,8 @@ bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int b
   else if (in.W >= 16) { d.tw = 16; d.th = 8; d.tb = 1; }
   else { d.tw = 8; d.th = 8; d.tb = 2; }
   d.dyn_w = dyn_rows;
-  if (scale != 1.f) { d.scale = scale; d.scale_cols = n_valid; }
+  if (scale != 1.f) { d.scale = scale; d.scale_cols = (ex && ex->scale_cols) ? ex->scale_cols : n_valid; }
+  if (ex) { d.rot = ex->rot; d.rot_cols = ex->rot_cols; d.out_split = ex->out_split; d.out_split_stride = ex->out_split_stride; }
   d.resid = resid;
   if (out2) { d.out2 = out2->p; d.out2_sx = out2->ps; d.out2_sy = out2->ps * out2->W; d.out2_sb = out2->ps * out2->W * out2->H; }
   if (in.C > w.c_in_pad || in.C < w.c_in) { set_error("add_dense: activation has %d channels, weights expect %d", in.C, w.c_in); return false; }

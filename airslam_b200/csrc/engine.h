@@ -128,9 +128,16 @@ bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in
                 const std::vector<int>* in_perm = nullptr, const std::vector<int>* out_perm = nullptr /* old row -> new row */,
                 int k_align = 64 /* K padding per tap: 64, or 32 for the SWIZZLE_64B conv path */);
 
+// Optional epilogue extras of add_dense (the LightGlue projections): scale only the first scale_cols columns, rotary embedding on the
+// first rot_cols columns, column sections of out_split stored out_split_stride elements apart.
+struct DenseExtra {
+  int scale_cols = 0;
+  const float* rot = nullptr; int rot_cols = 0;
+  int out_split = 0; long long out_split_stride = 0;
+};
 // Append a tcgen05 conv / GEMM op.
 bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int batch, bool relu, int n_valid = -1, int block_n = 0,
-               const int* dyn_rows = nullptr, float scale = 1.f, const float* resid = nullptr, const Act* out2 = nullptr);
+               const int* dyn_rows = nullptr, float scale = 1.f, const float* resid = nullptr, const Act* out2 = nullptr, const DenseExtra* ex = nullptr);
 // Append a 3x3 convolution on the halo-reuse tcgen05 kernel (tc_conv3x3.cuh); `out` and/or `pool_out` (fused 2x2 max-pool).
 // Falls back to the generic streaming-tap kernel (+ pool kernel) when AIRFE_CONV_V1 is set or the map is narrower than 8.
 bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu);

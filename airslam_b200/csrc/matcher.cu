@@ -1,4 +1,5 @@
 #include "matcher.h"
+#include <stdlib.h>
 #include "match_kernels.h"
 
 #include <math.h>
@@ -39,6 +40,17 @@ bool LightGlue::init(const MatcherConfig& cfg, const std::string& wdir) {
         !pk("self_attn.ffn.3", 512, &Y.ffn3) || !pk("cross_attn.to_qk", 256, &Y.c_qk) || !pk("cross_attn.to_v", 256, &Y.c_v) ||
         !pk("cross_attn.to_out", 256, &Y.c_out) || !pk("cross_attn.ffn.0", 512, &Y.c_ffn0) || !pk("cross_attn.ffn.3", 512, &Y.c_ffn3))
       return false;
+    {   // cross attention: to_qk and to_v read the same input -> one [512 x 256] GEMM whose two column sections go to q16_ / v16_
+      Y.c_qv = Y.c_qk;
+      Y.c_qv.n_rows = 512;
+      Y.c_qv.w = ar->alloc_n<__half>(512 * 256);
+      Y.c_qv.bias = ar->alloc_n<float>(512);
+      if (!ar->ok()) return false;
+      AIRFE_CUDA_OK(cudaMemcpy(Y.c_qv.w, Y.c_qk.w, 256 * 256 * 2, cudaMemcpyDeviceToDevice));
+      AIRFE_CUDA_OK(cudaMemcpy(Y.c_qv.w + 256 * 256, Y.c_v.w, 256 * 256 * 2, cudaMemcpyDeviceToDevice));
+      AIRFE_CUDA_OK(cudaMemcpy(Y.c_qv.bias, Y.c_qk.bias, 256 * 4, cudaMemcpyDeviceToDevice));
+      AIRFE_CUDA_OK(cudaMemcpy(Y.c_qv.bias + 256, Y.c_v.bias, 256 * 4, cudaMemcpyDeviceToDevice));
+    }
     if (!up_f32(ar, wf, T + "self_attn.ffn.1.weight", &Y.ln_g) || !up_f32(ar, wf, T + "self_attn.ffn.1.bias", &Y.ln_b) ||
         !up_f32(ar, wf, T + "cross_attn.ffn.1.weight", &Y.c_ln_g) || !up_f32(ar, wf, T + "cross_attn.ffn.1.bias", &Y.c_ln_b))
       return false;
@@ -58,9 +70,9 @@ bool LightGlue::init(const MatcherConfig& cfg, const std::string& wdir) {
   x_ = ar->alloc_n<float>(R * 256);
   cat16_ = ar->alloc_n<__half>(R * 512);
   qkv_ = ar->alloc_n<float>(R * 768);
-  q16_ = ar->alloc_n<__half>(R * 256);
-  k16_ = ar->alloc_n<__half>(R * 256);
-  v16_ = ar->alloc_n<__half>(R * 256);
+  q16_ = ar->alloc_n<__half>(R * 768);        // q | k | v as three [R][256] matrices, R*256 elements apart (split-column GEMM stores)
+  k16_ = q16_ + R * 256;
+  v16_ = q16_ + 2 * R * 256;
   ctx16_ = ar->alloc_n<__half>(R * 256);
   md16_ = ar->alloc_n<__half>(R * 256);
   h_ = ar->alloc_n<float>(R * 512);
@@ -92,6 +104,8 @@ bool LightGlue::build_ops(int P) {
   const Act ctx = rows(ctx16_, 256, 256, false), hf = rows(h_, 512, 512, true), h16 = rows(h16_, 512, 512, false), md = rows(md16_, 256, 256, false);
   const float sc = 0.35355339059327379f;   // 64^-1/4
   const int* n = n_;
+  const size_t Rall = (size_t)2 * cfg_.max_pairs * cap;             // rows of the q / k / v matrices as allocated
+  static const bool fused_proj = getenv("AIRFE_LG_UNFUSED_PROJ") == nullptr;
 
   auto attention = [&](const __half* qa, const __half* kb, const __half* vb, int xr) -> bool {
     if (attn_fused_enabled() && cap <= 512) return add_fused_attention(&ol, qa, kb, vb, 256, ctx16_, n, S, cap, xr, 1.f);
@@ -127,15 +141,27 @@ bool LightGlue::build_ops(int P) {
   };
   for (int l = 0; l < 9; ++l) {
     Layer& Y = L_[l];
-    if (!add_dense(&ol, x16, Y.qkv, qkv, S, false, -1, 0, n)) return false;
-    {
+    if (fused_proj) {
+      // Wqkv with the rotary embedding, the 64^-1/4 scaling of q,k and the fp16 rounding in the GEMM epilogue; q | k | v land in their
+      // own matrices.  (The unfused path wrote 50 MB of fp32 qkv and re-read it in a separate rotary kernel.)
+      DenseExtra ex;
+      ex.scale_cols = 512; ex.rot = rot_; ex.rot_cols = 512; ex.out_split = 256; ex.out_split_stride = (long long)Rall * 256;
+      if (!add_dense(&ol, x16, Y.qkv, rows(q16_, 768, 256, false), S, false, -1, 0, n, sc, nullptr, nullptr, &ex)) return false;
+    } else {
+      if (!add_dense(&ol, x16, Y.qkv, qkv, S, false, -1, 0, n)) return false;
       const float* qp = qkv_; const float* rp = rot_; __half* q = q16_; __half* k = k16_; __half* v = v16_;
       ol.push("rotary", 0, [=](cudaStream_t st) { launch_lg_rotary(qp, rp, n, S, cap, q, k, v, st); return true; });
       ol.launches++;
     }
     if (!attention(q16_, k16_, v16_, 0) || !ffn(Y.out, Y.ffn0, Y.ffn3, Y.ln_g, Y.ln_b)) return false;
-    if (!add_dense(&ol, x16, Y.c_qk, q16, S, false, -1, 0, n, sc)) return false;
-    if (!add_dense(&ol, x16, Y.c_v, v16, S, false, -1, 0, n)) return false;
+    if (fused_proj) {
+      DenseExtra ex;
+      ex.scale_cols = 256; ex.out_split = 256; ex.out_split_stride = (long long)Rall * 512;   // section 0 -> q16_, section 1 -> v16_
+      if (!add_dense(&ol, x16, Y.c_qv, rows(q16_, 512, 256, false), S, false, -1, 0, n, sc, nullptr, nullptr, &ex)) return false;
+    } else {
+      if (!add_dense(&ol, x16, Y.c_qk, q16, S, false, -1, 0, n, sc)) return false;
+      if (!add_dense(&ol, x16, Y.c_v, v16, S, false, -1, 0, n)) return false;
+    }
     if (!attention(q16_, q16_, v16_, 1) || !ffn(Y.c_out, Y.c_ffn0, Y.c_ffn3, Y.c_ln_g, Y.c_ln_b)) return false;
   }
   if (!add_dense(&ol, x16, final_, md, S, false, -1, 0, n, 0.25f)) return false;                 // / 256^(1/4)

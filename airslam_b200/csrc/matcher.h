@@ -35,7 +35,7 @@ class LightGlue {
   MatcherConfig cfg_;
   Arena arena_;
   std::map<int, OpList> ops_;
-  struct Layer { DenseW qkv, out, ffn0, ffn3, c_qk, c_v, c_out, c_ffn0, c_ffn3; float *ln_g, *ln_b, *c_ln_g, *c_ln_b; } L_[9];
+  struct Layer { DenseW qkv, out, ffn0, ffn3, c_qk, c_v, c_qv /* [to_qk ; to_v] rows concatenated: one launch */, c_out, c_ffn0, c_ffn3; float *ln_g, *ln_b, *c_ln_g, *c_ln_b; } L_[9];
   DenseW final_;
   __half* wr_ = nullptr; __half* wm_ = nullptr; float bm_ = 0.f;
   float *x_ = nullptr, *qkv_ = nullptr, *S_ = nullptr, *h_ = nullptr, *rot_ = nullptr, *sim_ = nullptr, *logsig_ = nullptr, *lse_ = nullptr, *row_val_ = nullptr;

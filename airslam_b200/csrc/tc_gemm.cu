@@ -106,6 +106,10 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   p.b_batched = d.b_batches > 1 || d.b_heads > 1;
   p.b_batch_xor = d.b_batch_xor;
   p.scale = d.scale; p.scale_cols = d.scale_cols;
+  p.rot = d.rot; p.rot_cols = d.rot_cols;
+  p.out_split = d.out_split; p.out_split_stride = d.out_split_stride;
+  if (d.out_split && (d.out_split % d.block_n)) { set_error("tc_gemm: out_split %d must be a multiple of block_n %d", d.out_split, d.block_n); return false; }
+  if (d.rot && d.H != 1) { set_error("tc_gemm: fused rotary needs a row GEMM (H == 1)"); return false; }
   p.resid = d.resid;
   p.out2 = d.out2; p.out2_sb = d.out2_sb; p.out2_sy = d.out2_sy; p.out2_sx = d.out2_sx;
   p.b_mn_major = d.b_mn_major;

@@ -215,6 +215,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
           v[i] = f;
         }
         const int nbase = n0 + c;
+        if (p.rot && nbase < p.rot_cols && valid) {
+          // fused rotary embedding: adjacent columns (2j, 2j+1) of a 64-wide head rotate by the keypoint's angle j;
+          // rot[row][2j] = cos, rot[row][2j+1] = sin  (lg_prepare_kernel), rows are (b, x) of the H == 1 layout
+          const float4* r4 = reinterpret_cast<const float4*>(p.rot + ((long long)b * p.W + x) * 64 + (nbase & 63));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 cs = __ldg(r4 + i);
+            const float a0 = v[4 * i], a1 = v[4 * i + 1], a2 = v[4 * i + 2], a3 = v[4 * i + 3];
+            v[4 * i] = a0 * cs.x - a1 * cs.y;     v[4 * i + 1] = a1 * cs.x + a0 * cs.y;
+            v[4 * i + 2] = a2 * cs.z - a3 * cs.w; v[4 * i + 3] = a3 * cs.z + a2 * cs.w;
+          }
+        }
+        // column -> address: plain, or split into sections that live in separate matrices
+        const long long ncol = p.out_split ? (long long)(nbase / p.out_split) * p.out_split_stride + (nbase % p.out_split) : (long long)nbase;
         if (valid && nbase < p.n_valid) {
           if (p.resid) {
             const float* rs = p.resid + off + nbase;
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
             }
           }
           if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + off + nbase;
+            float* o = reinterpret_cast<float*>(p.out) + off + ncol;
             if (nbase + 16 <= p.n_valid) {
 #pragma unroll
               for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
               for (int i = 0; i < 16; ++i) if (nbase + i < p.n_valid) o[i] = v[i];
             }
           } else {
-            __half* o = reinterpret_cast<__half*>(p.out) + off + nbase;
+            __half* o = reinterpret_cast<__half*>(p.out) + off + ncol;
             if (nbase + 16 <= p.n_valid) {
               uint32_t h[8];
 #pragma unroll

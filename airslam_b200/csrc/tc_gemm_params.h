@@ -21,6 +21,10 @@ struct TcGemmParams {
   const float* bias;
   float scale;      // (acc + bias) * scale for columns < scale_cols (the 64^-1/4 / 256^-1/4 factors of the matchers)
   int scale_cols;
+  const float* rot;    // optional rotary table [B*W rows][64] = (cos, sin) per pair: columns < rot_cols are rotated pairwise (LightGlue q, k; H == 1 only)
+  int rot_cols;
+  int out_split;       // > 0: column n is stored at out[(n / out_split) * out_split_stride + row offset + n % out_split]  (q | k | v go to separate matrices)
+  long long out_split_stride;
   const float* resid;  // optional fp32 residual, same indexing as `out` (which must be fp32): out = resid + acc + bias
   void* out2;       // optional second store of the same values as fp16 (operand copy for the next GEMM)
   long long out2_sb, out2_sy, out2_sx;
