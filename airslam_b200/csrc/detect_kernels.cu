@@ -59,57 +59,78 @@ void launch_resize_u8_to_f16(const uint8_t* src, int src_w, int src_h, int src_s
 }
 
 // =====================================================================================================================
-// First layer: 3x3, 1 -> 64 channels.  K = 9 is no tensor-core shape; the layer is bound by its 32 MiB/frame NHWC store.
-// Thread = (pixel, group of 8 output channels): consecutive threads write consecutive 16-byte vectors.
+// First layer: 3x3, 1 -> 64 channels.  K = 9 is no tensor-core shape and the layer is FP32-FMA bound (4.8 GFMA per 32 frames), so the
+// inner product runs on Blackwell's packed FFMA2 (fma.rn.f32x2): one instruction = the same input pixel times the weights of two
+// adjacent output channels.  That halves the issue slots and leaves the kernel bound by the FMA pipe rather than by instruction issue.
+// Thread = (8 pixels along x, group of 8 output channels): consecutive threads write consecutive 16-byte vectors of one pixel.
 // =====================================================================================================================
-constexpr int kC1Px = 8;   // pixels along x per thread: the 72 weights of a thread's 8 channels live in registers
+constexpr int kC1Px = 8;
+__device__ __forceinline__ unsigned long long ffma2_(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2_(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
 __global__ void __launch_bounds__(256) conv1a_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
                                                      __half* __restrict__ out, int H, int W, long long total) {
-  __shared__ float sw[64 * 9];
-  __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 576; i += blockDim.x) sw[i] = __half2float(w[i]);
-  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __shared__ float2 sw2[8 * 4 * 9];   // [channel group][channel pair][tap] = (w of channel 2p, w of channel 2p+1)
+  __shared__ float2 sb2[32];
+  for (int i = threadIdx.x; i < 288; i += blockDim.x) {
+    const int k = i % 9, cp = i / 9;              // cp = channel pair 0..31
+    sw2[i] = make_float2(__half2float(w[(2 * cp) * 9 + k]), __half2float(w[(2 * cp + 1) * 9 + k]));
+  }
+  if (threadIdx.x < 32) sb2[threadIdx.x] = make_float2(bias[2 * threadIdx.x], bias[2 * threadIdx.x + 1]);
   __syncthreads();
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int cg = (int)(gid & 7);
-  const long long grp = gid >> 3;                 // group of kC1Px pixels
-  const int gpr = W / kC1Px;                      // groups per row
-  const int x0 = (int)(grp % gpr) * kC1Px;
-  const int yy = (int)((grp / gpr) % H);
-  const long long img = grp / ((long long)gpr * H);
+  // grid = (threads along a row / 256, H, batch): no integer divisions on the index path
+  const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tix >= W) return;                            // W / 8 pixel groups x 8 channel groups = W threads per row
+  const int cg = tix & 7;
+  const int x0 = (tix >> 3) * kC1Px;
+  const int yy = blockIdx.y;
+  const long long img = blockIdx.z;
   const __half* xi = x + img * (long long)W * H;
-  float in[3][kC1Px + 2];
+  // inputs: per row one aligned 16-byte vector (x0 is a multiple of 8) plus the two halo pixels; each value duplicated into a float2
+  unsigned long long in2[3][kC1Px + 2];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int y2 = yy + ky - 1;
+    const bool rv = (y2 >= 0) && (y2 < H);
+    const __half* rp = xi + (long long)(rv ? y2 : yy) * W + x0;
+    uint4 v = *reinterpret_cast<const uint4*>(rp);
+    const __half hl = (x0 > 0) ? rp[-1] : __float2half(0.f);
+    const __half hr = (x0 + kC1Px < W) ? rp[kC1Px] : __float2half(0.f);
+    if (!rv) v = make_uint4(0, 0, 0, 0);
+    const __half2* v2 = reinterpret_cast<const __half2*>(&v);
+    const float fl = rv ? __half2float(hl) : 0.f, fr = rv ? __half2float(hr) : 0.f;
+    in2[ky][0] = pack2_(fl, fl);
+    in2[ky][kC1Px + 1] = pack2_(fr, fr);
 #pragma unroll
-    for (int c = 0; c < kC1Px + 2; ++c) {
-      const int x2 = x0 + c - 1;
-      in[ky][c] = (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? __half2float(xi[(long long)y2 * W + x2]) : 0.f;
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = __half22float2(v2[q]);
+      in2[ky][1 + 2 * q] = pack2_(f.x, f.x);
+      in2[ky][2 + 2 * q] = pack2_(f.y, f.y);
     }
   }
-  // channel-outer / pixel-inner: the 9 weights of one output channel sit in registers while 8 pixels reuse them (72 LDS per
-  // thread instead of 576); the 8x8 results are packed to fp16 pairs as they are produced
   uint32_t packed[kC1Px][4];
 #pragma unroll
-  for (int j = 0; j < 8; j += 2) {
-    float w0[9], w1[9];
+  for (int jp = 0; jp < 4; ++jp) {
+    unsigned long long wp[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { w0[k] = sw[(cg * 8 + j) * 9 + k]; w1[k] = sw[(cg * 8 + j + 1) * 9 + k]; }
-    const float b0 = sb[cg * 8 + j], b1 = sb[cg * 8 + j + 1];
+    for (int k = 0; k < 9; ++k) { const float2 t = sw2[(cg * 4 + jp) * 9 + k]; wp[k] = pack2_(t.x, t.y); }
+    const float2 bb = sb2[cg * 4 + jp];
+    const unsigned long long b2 = pack2_(bb.x, bb.y);
 #pragma unroll
     for (int px = 0; px < kC1Px; ++px) {
-      float a0 = 0.f, a1 = 0.f;
+      unsigned long long acc = b2;                 // bias folded into the accumulator
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          a0 = fmaf(in[ky][px + kx], w0[ky * 3 + kx], a0);
-          a1 = fmaf(in[ky][px + kx], w1[ky * 3 + kx], a1);
-        }
-      __half2 h2 = __floats2half2_rn(fmaxf(a0 + b0, 0.f), fmaxf(a1 + b1, 0.f));
-      packed[px][j >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+        for (int kx = 0; kx < 3; ++kx) acc = ffma2_(in2[ky][px + kx], wp[ky * 3 + kx], acc);
+      const float a0 = fmaxf(__uint_as_float((unsigned)(acc & 0xffffffffu)), 0.f), a1 = fmaxf(__uint_as_float((unsigned)(acc >> 32)), 0.f);
+      __half2 h2 = __floats2half2_rn(a0, a1);
+      packed[px][jp] = *reinterpret_cast<uint32_t*>(&h2);
     }
   }
   __half* o = out + ((img * H + yy) * (long long)W + x0) * 64 + cg * 8;
@@ -119,8 +140,7 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const __half* __restrict__ 
 }
 
 void launch_conv1a(const __half* x, const __half* w, const float* bias, __half* out, int batch, int H, int W, cudaStream_t st) {
-  const long long total = (long long)batch * H * (W / kC1Px) * 8;
-  conv1a_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, w, bias, out, H, W, total);
+  conv1a_kernel<<<dim3((W + 255) / 256, H, batch), 256, 0, st>>>(x, w, bias, out, H, W, 0);
 }
 
 // =====================================================================================================================

@@ -225,13 +225,21 @@ bool Detector::build_ops(int B) {
     ol->launches++;
   };
   // SuperPoint trunk + heads (G1; G2 /backbone/point_detector/*)
-  {
+  const Act r3 = cat2_.slice(32, 64), r5 = cat3_.slice(128, 128);
+  // Experimental (AIRFE_FUSE1A=1, off by default): conv1a computed inside conv1b's producer warps so that its 32 MiB/frame output never
+  // goes to HBM.  Parity-green, but measured SLOWER on B200 (1.38 ms vs 0.37 + 0.69 ms per 32 frames, profiles/r01_fused_conv1a_trace.txt):
+  // the FFMA2 producer needs ~3300 issue cycles per tile per SM sub-partition and starves the epilogue warps.  The tensor-core
+  // (im2col K=16 + TMEM round trip) variant is the follow-up.
+  static const bool fuse1a = conv3x3_halo_enabled() && getenv("AIRFE_FUSE1A") != nullptr;
+  if (fuse1a) {
+    const Conv1aFuse f{x16_, w_conv1a_, b_conv1a_};
+    if (!add_conv3x3(&t, a1_, w1b_, &r1_, &p1_, B, true, &f)) return false;                   // conv1a + conv1b (+ fused pool)
+  } else {
     const __half* x = x16_; const __half* w = w_conv1a_; const float* bb = b_conv1a_; __half* o = (__half*)a1_.p;
     t.push("conv1a 1->64", 0, [=](cudaStream_t st) { launch_conv1a(x, w, bb, o, B, 512, 512, st); return true; });
     t.launches++;
+    if (!add_conv3x3(&t, a1_, w1b_, &r1_, &p1_, B, true)) return false;                       // conv1b (+ fused pool)
   }
-  const Act r3 = cat2_.slice(32, 64), r5 = cat3_.slice(128, 128);
-  if (!add_conv3x3(&t, a1_, w1b_, &r1_, &p1_, B, true)) return false;                         // conv1b (+ fused pool)
   if (!add_conv3x3(&t, p1_, w2a_, &a2_, nullptr, B, true) || !add_conv3x3(&t, a2_, w2b_, &r3, &p2_, B, true)) return false;
   if (!add_conv3x3(&t, p2_, w3a_, &a3_, nullptr, B, true) || !add_conv3x3(&t, a3_, w3b_, &r5, &p3_, B, true)) return false;
   if (!add_conv3x3(&t, p3_, w4a_, &a4_, nullptr, B, true) || !add_conv3x3(&t, a4_, w4b_, &r7_, nullptr, B, true)) return false;

@@ -33,10 +33,15 @@ struct ConvParams {
   long long out_sb, out_sy, out_sx;
   __half* pool_out;   // fused 2x2/2 max-pool store (nullptr: skip)
   long long pool_sb, pool_sy, pool_sx;
+  // FUSE1A (SuperPoint conv1a fused into conv1b): the 64-channel input never exists in HBM; producer warps compute the halo tile from
+  // the 1-channel image with packed FFMA2 straight into the swizzled A stage.  img1 = fp16 [B][H][W], w1a = fp16 [64][9], b1a = fp32 [64].
+  const __half* img1; const __half* w1a; const float* b1a;
   long long* trace;   // authoring aid (airfe_debug_conv_trace): CTA 0 writes clock64 stamps of its first 64 tiles, 8 slots per tile
 };
 
 constexpr int kConvThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int kConvFuseProducers = 8;                                    // FUSE1A: warps 10-17 compute the conv1a halo tile
+constexpr int kConvThreadsFused = kConvThreads + 32 * kConvFuseProducers;
 constexpr int kConvTH = 16;
 
 __host__ __device__ constexpr int conv_a_bytes(int strips, int kw = 64) { return ((8 * strips + 2) * (kConvTH + 2) * kw * 2 + 1023) / 1024 * 1024; }
@@ -56,8 +61,18 @@ __host__ __device__ inline int conv_tmem_cols(int block_n, int strips) {
 // (tools/trace_conv.py, profiles/r01_conv_trace.txt) the runtime-generic loop spent ~550 cycles of uniform-datapath
 // instructions per tap, i.e. the single issuing warp -- not the tensor pipe (48 cycles per 128x64x16 MMA in SS mode,
 // tools/probe_mma_rate.cu) -- bounded every small-N layer.
-template <int KW, int STRIPS, bool BRES>
-__global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __grid_constant__ ConvParams p) {
+__device__ __forceinline__ unsigned long long conv_ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long conv_pack2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+
+template <int KW, int STRIPS, bool BRES, bool FUSE1A = false>
+__global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) tc_conv3x3_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(!FUSE1A || (KW == 64 && STRIPS == 2 && BRES), "conv1a fusion is specialised for the 64->64 resident-weights layer");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int a_bytes = conv_a_bytes(STRIPS, KW);
@@ -82,9 +97,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
   const uint32_t tmem_cols = conv_tmem_cols(p.block_n, STRIPS);
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&p.tmA);
+    if (!FUSE1A) ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB);
-    for (int s = 0; s < p.stages_a; ++s) { ptx::mbar_init(&full_a[s], 1); ptx::mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < p.stages_a; ++s) { ptx::mbar_init(&full_a[s], FUSE1A ? kConvFuseProducers : 1); ptx::mbar_init(&empty_a[s], 1); }
     const int nb = BRES ? 1 : p.stages_b;
     for (int s = 0; s < nb; ++s) { ptx::mbar_init(&full_b[s], 1); ptx::mbar_init(&empty_b[s], 1); }
     for (int s = 0; s < 4; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
@@ -97,6 +112,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
   const uint32_t tmem_base = *tmem_slot;
   __shared__ __align__(16) float s_bias[512];
   for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;   // weights: not produced by a kernel
+  __shared__ float2 s_w1a[FUSE1A ? 288 : 1];     // conv1a: [channel pair][tap] = (w[2p][tap], w[2p+1][tap])
+  __shared__ float2 s_b1a[FUSE1A ? 32 : 1];
+  if (FUSE1A) {
+    for (int i = threadIdx.x; i < 288; i += blockDim.x) {
+      const int k = i % 9, cp = i / 9;
+      s_w1a[i] = make_float2(__half2float(p.w1a[(2 * cp) * 9 + k]), __half2float(p.w1a[(2 * cp + 1) * 9 + k]));
+    }
+    if (threadIdx.x < 32) s_b1a[threadIdx.x] = make_float2(p.b1a[2 * threadIdx.x], p.b1a[2 * threadIdx.x + 1]);
+  }
   __syncthreads();
   ptx::pdl_launch_dependents();   // the next kernel may start its own prologue on SMs this grid has left
   ptx::pdl_wait();                // everything above overlapped the predecessor's tail; activations are touched only below
@@ -112,7 +136,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; !FUSE1A && t < total_tiles; t += gridDim.x) {
         const int nt = t % p.n_tiles, mt = t / p.n_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tz = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * 8 * STRIPS, y0 = ty * kConvTH;
@@ -205,7 +229,73 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
       if (tr) trp[3] = clock64();
       if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if (FUSE1A && warp >= 10) {
+    // ===== conv1a producers (8 warps): halo tile of 18 x 18 pixels x 64 channels = relu(conv3x3(image) + b), written as the
+    // K-major SWIZZLE_128B A operand the nine tap descriptors read.  Halo pixels outside the image are conv1b's zero padding.
+    // task = (halo row hy, group of 6 pixels gx, group of 8 channels cg): 18 * 3 * 8 = 432 tasks over 256 threads.
+    const int ptid = threadIdx.x - kConvThreads;
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int mt = t / p.n_tiles;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tz = mt / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * 8 * STRIPS, y0 = ty * kConvTH;
+      const __half* img = p.img1 + (long long)tz * p.W * p.H;
+      ptx::mbar_wait(&empty_a[sa], pa ^ 1);
+      const bool trp_on = p.trace && blockIdx.x == 0 && ptid == 0 && t / (int)gridDim.x < 64;
+      if (trp_on) p.trace[(t / gridDim.x) * 8 + 0] = clock64();
+      uint8_t* stage = smem_a + sa * a_bytes;
+#pragma unroll 1
+      for (int task = ptid; task < 18 * 3 * 8; task += 32 * kConvFuseProducers) {
+        const int cg = task & 7, gx = (task >> 3) % 3, hy = task / 24;
+        const int oy = y0 - 1 + hy;                 // conv1a output row of this task
+        const int ox0 = x0 - 1 + gx * 6;            // first of its 6 output columns; inputs span columns ox0-1 .. ox0+6 (even start: pairs)
+        unsigned long long in2[3][8];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int iy = oy + ky - 1;
+          const bool rv = (iy >= 0) && (iy < p.H);
+          const __half* rp = img + (long long)(rv ? iy : 0) * p.W;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int ix = ox0 - 1 + 2 * q;          // even: a pair never straddles the image border (W is even)
+            float2 f = make_float2(0.f, 0.f);
+            if (rv && ix >= 0 && ix < p.W) f = __half22float2(*reinterpret_cast<const __half2*>(rp + ix));
+            in2[ky][2 * q] = conv_pack2(f.x, f.x);
+            in2[ky][2 * q + 1] = conv_pack2(f.y, f.y);
+          }
+        }
+        const bool row_in = (oy >= 0) && (oy < p.H);
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          unsigned long long wp[9];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) { const float2 w2 = s_w1a[(cg * 4 + jp) * 9 + k]; wp[k] = conv_pack2(w2.x, w2.y); }
+          const float2 bb = s_b1a[cg * 4 + jp];
+          const unsigned long long b2 = conv_pack2(bb.x, bb.y);
+#pragma unroll
+          for (int px = 0; px < 6; ++px) {
+            unsigned long long acc = b2;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) acc = conv_ffma2(in2[ky][px + kx], wp[ky * 3 + kx], acc);
+            const float a0 = fmaxf(__uint_as_float((unsigned)(acc & 0xffffffffu)), 0.f), a1 = fmaxf(__uint_as_float((unsigned)(acc >> 32)), 0.f);
+            __half2 h2 = __floats2half2_rn(a0, a1);
+            const int ox = ox0 + px;
+            const bool in_img = row_in && ox >= 0 && ox < p.W;
+            const int r = hy * HW + gx * 6 + px;       // halo pixel = 128-byte row of the A stage; channel pair jp = 4 bytes of chunk cg
+            *reinterpret_cast<uint32_t*>(stage + r * 128 + ((cg ^ (r & 7)) << 4) + jp * 4) = in_img ? *reinterpret_cast<uint32_t*>(&h2) : 0u;
+          }
+        }
+      }
+      ptx::fence_proxy_async();                      // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+      __syncwarp();
+      if (trp_on) p.trace[(t / gridDim.x) * 8 + 6] = clock64();   // (fused mode: slot 6 = producer done, warp 9 does not stamp)
+      if (lane == 0) ptx::mbar_arrive(&full_a[sa]);
+      if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+    }
+  } else if (!FUSE1A || warp < 10) {
     // ===== epilogue: 8 warps; warp (2 + e) owns TMEM lane quarter (warp & 3) and half of the work (strip, or column half) =====
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -226,7 +316,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
       __half* o_full = p.out ? p.out + (long long)tz * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx : nullptr;
       __half* o_pool = p.pool_out ? p.pool_out + (long long)tz * p.pool_sb + (long long)(y >> 1) * p.pool_sy + (long long)(x >> 1) * p.pool_sx : nullptr;
       const bool pool_lane = valid && !(lane & 1) && !(lane & 8);
-      const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9) && t / (int)gridDim.x < 64;
+      const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && (warp == 2 || (warp == 9 && !FUSE1A)) && t / (int)gridDim.x < 64;
       long long* trp = tr ? p.trace + (t / gridDim.x) * 8 + (warp == 2 ? 4 : 6) : nullptr;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
