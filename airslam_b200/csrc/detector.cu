@@ -80,7 +80,7 @@ bool Detector::init(const DetectorConfig& cfg, const std::string& wdir, bool use
   if (lines) {
     const std::string L = "plnet.";
     auto pl = [&](const std::string& name, int cin, DenseW* out) { return pack_dense(wf, {{L + name + ".weight", L + name + ".bias", 0}}, cin, ar, out); };
-    if (!pl("conv1a", 64, &l1a_) || !pack_dense(wf, {{L + "conv1b.weight", L + "conv1b.bias", 0}}, 32, ar, &l1b_, nullptr, nullptr, (conv3x3_halo_enabled() && !getenv("AIRFE_CONV_K64")) ? 32 : 64) || !pl("conv2a", 96, &l2a_) || !pl("conv2b", 128, &l2b_) ||
+    if (!pl("conv1a", 64, &l1a_) || !pack_dense(wf, {{L + "conv1b.weight", L + "conv1b.bias", 0}}, 32, ar, &l1b_, nullptr, nullptr, (conv3x3_halo_enabled() && !getenv("AIRFE_CONV_K64")) ? 32 : 64) || !pack_dense(wf, {{L + "conv2a.weight", L + "conv2a.bias", 0}}, 96, ar, &l2a_, nullptr, nullptr, (conv3x3_halo_enabled() && !getenv("AIRFE_CONV_K64")) ? 32 : 64 /* 96 = 3 x 32: no K padding on the SWIZZLE_64B path */) || !pl("conv2b", 128, &l2b_) ||
         !pl("fc2", 128, &fc2_) || !pl("fc1", 256, &fc1_))
       return false;
     for (int s = 0; s < 2; ++s) {

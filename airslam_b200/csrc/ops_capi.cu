@@ -30,7 +30,7 @@ int airfe_op_tc_gemm(const void* a, int a_C, int W, int H, int B, long long a_sx
 int airfe_op_conv3x3(const void* in, int C, int W, int H, int B, long long in_ps, const void* w_packed, const float* bias, int n_rows, int c_in,
                      int relu, void* out, long long out_ps, void* pool_out, long long pool_ps, void* stream) {
   Act a; a.p = const_cast<void*>(in); a.C = C; a.W = W; a.H = H; a.ps = in_ps;
-  DenseW w; w.w = (__half*)w_packed; w.bias = const_cast<float*>(bias); w.n_rows = n_rows; w.c_in = c_in; w.c_in_pad = (c_in == 32) ? 32 : (c_in + 63) / 64 * 64; w.taps = 9;
+  DenseW w; w.w = (__half*)w_packed; w.bias = const_cast<float*>(bias); w.n_rows = n_rows; w.c_in = c_in; w.c_in_pad = (c_in % 32 == 0) ? c_in : (c_in + 63) / 64 * 64;   /* multiples of 32 that are not multiples of 64 run on the K=32 (SWIZZLE_64B) path */ w.taps = 9;
   Act o, po;
   if (out) { o.p = out; o.C = n_rows; o.W = W; o.H = H; o.ps = out_ps; }
   if (pool_out) { po.p = pool_out; po.C = n_rows; po.W = W / 2; po.H = H / 2; po.ps = pool_ps; }

@@ -39,7 +39,8 @@ int airfe_op_tc_gemm(const void* a, int a_C, int W, int H, int B, long long a_sx
                      int tw, int th, int tb, void* stream);
 
 /* 3x3 convolution (+bias, ReLU, optional fused 2x2 max-pool) on the halo-reuse tcgen05 kernel; see csrc/tc_conv3x3.cuh.
- * in: fp16 NHWC [B,H,W,in_ps]; w_packed: fp16 [n_rows][9 * round_up(c_in,64)] (tap-major, zero padded); out / pool_out may be NULL. */
+ * in: fp16 NHWC [B,H,W,in_ps]; w_packed: fp16 [n_rows][9 * c_pad] (tap-major, zero padded) with c_pad = c_in when c_in is a multiple of 32,
+ * else round_up(c_in,64); out / pool_out may be NULL. */
 int airfe_op_conv3x3(const void* in, int C, int W, int H, int B, long long in_ps, const void* w_packed, const float* bias, int n_rows, int c_in,
                      int relu, void* out, long long out_ps, void* pool_out, long long pool_ps, void* stream);
 

@@ -152,7 +152,7 @@ def run_conv_halo(x_nhwc, w_oihw, bias, relu, want_full=True, want_pool=False, o
     lib, check = _lib()
     b, h, w, c = x_nhwc.shape
     o, i, _, _ = w_oihw.shape
-    wp = pack_conv_weight(w_oihw, 32 if i == 32 else (i + 63) // 64 * 64)   # C_in = 32 runs the SWIZZLE_64B (K = 32) variant
+    wp = pack_conv_weight(w_oihw, i if i % 32 == 0 else (i + 63) // 64 * 64)   # C_in = 32 / 96: the SWIZZLE_64B (K = 32 blocks) variant
     full = pool = None
     if want_full:
         full = out if out is not None else torch.zeros(b, h, w, o, dtype=torch.float16, device="cuda")
@@ -170,7 +170,8 @@ def run_conv_halo(x_nhwc, w_oihw, bias, relu, want_full=True, want_pool=False, o
     (2, 64, 64, 64, 64),       # weights resident in smem, 2 strips
     (1, 48, 40, 64, 32),       # N = 32, ragged tiles (h, w not multiples of 16)
     (2, 32, 32, 32, 32),       # C_in = 32 (channel OOB fill)
-    (1, 64, 64, 96, 128),      # streamed weights, 2 K blocks, C_in = 96
+    (1, 64, 64, 96, 128),      # streamed weights, C_in = 96 = 3 K blocks of 32 (SWIZZLE_64B, no K padding)
+    (1, 32, 32, 72, 128),      # streamed weights, C_in = 72 -> padded to 128: 2 K blocks of 64
     (2, 32, 32, 128, 128),     # streamed weights, 2 strips
     (1, 32, 32, 256, 320),     # N = 320 -> two N tiles of 160, single strip
     (1, 16, 16, 128, 256),     # N = 256, single strip

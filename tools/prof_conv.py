@@ -17,7 +17,7 @@ def pack(w, c_pad):
 
 def conv(tag, b, h, w, cin, cout, full=True, pool=False, reps=5):
     x = torch.randn(b, h, w, cin, device="cuda").half()
-    wt = pack(torch.randn(cout, cin, 3, 3, device="cuda") * 0.05, 32 if cin == 32 else (cin + 63) // 64 * 64)
+    wt = pack(torch.randn(cout, cin, 3, 3, device="cuda") * 0.05, cin if cin % 32 == 0 else (cin + 63) // 64 * 64)
     bias = torch.randn(cout, device="cuda")
     out = torch.zeros(b, h, w, cout, dtype=torch.float16, device="cuda") if full else None
     po = torch.zeros(b, h // 2, w // 2, cout, dtype=torch.float16, device="cuda") if pool else None
@@ -44,3 +44,4 @@ for t in which:
     if t == "c128": conv(t, B, 256, 256, 128, 128, True, False)
     if t == "c128po": conv(t, B, 256, 256, 128, 128, False, True)
     if t == "c256": conv(t, B, 128, 128, 256, 320, True, False)
+    if t == "c96": conv(t, B, 256, 256, 96, 128, True, False)
