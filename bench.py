@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--pairs", type=int, default=16, help="stereo pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per step per GPU")
     ap.add_argument("--impl", default="airfe", choices=["airfe", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--device-only", action="store_true", help="only the device-resident loop (for ncu launch lists): no e2e, no per-op profile, no CPU baseline")
