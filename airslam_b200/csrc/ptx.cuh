@@ -51,6 +51,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// 32 bytes per thread in one instruction (STG.256, sm_100): an epilogue thread owns 16 consecutive fp16 channels of one pixel, and the
+// L1 charges a store instruction per distinct 128-byte line it touches -- one 256-bit store instead of two 128-bit ones halves that.
+// `p` must be 32-byte aligned (callers check and fall back to two 16-byte stores).
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&h)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]),
+               "r"(h[6]), "r"(h[7])
+               : "memory");
+}
+
 // ---- programmatic dependent launch (see launch_pdl in common.h) -----------------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -348,8 +348,12 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
           if (o_full && valid && nbase < p.n_valid) {
             __half* o = o_full + nbase;
             if (nbase + 16 <= p.n_valid) {
-              *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+              if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+                ptx::st_global_256(o, h);
+              } else {
+                *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+              }
             } else {
               unsigned short* os = reinterpret_cast<unsigned short*>(o);   // static indices only: h[] must stay in registers
 #pragma unroll
@@ -374,8 +378,12 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
             if (pool_lane && nbase < p.n_valid) {
               __half* o = o_pool + nbase;
               if (nbase + 16 <= p.n_valid) {
-                *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+                if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+                  ptx::st_global_256(o, h);
+                } else {
+                  *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+                }
               } else {
                 unsigned short* os = reinterpret_cast<unsigned short*>(o);   // static indices only: h[] must stay in registers
 #pragma unroll

@@ -277,8 +277,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
                 __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
                 h[i] = *reinterpret_cast<uint32_t*>(&h2);
               }
-              *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+              if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+                ptx::st_global_256(o, h);
+              } else {
+                *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) if (nbase + i < p.n_valid) o[i] = __float2half_rn(v[i]);
