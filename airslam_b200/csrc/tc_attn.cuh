@@ -228,14 +228,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
           ptx::tmem_ld_wait();
           if (q < nq) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint32_t h[4];
+            for (int i = 0; i < 32; i += 16) {
+              uint32_t h[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
+              for (int e = 0; e < 8; ++e) {
                 __half2 h2 = __floats2half2_rn(__uint_as_float(r[i + 2 * e]) * inv, __uint_as_float(r[i + 2 * e + 1]) * inv);
                 h[e] = *reinterpret_cast<uint32_t*>(&h2);
               }
-              *reinterpret_cast<uint4*>(o + c + i) = make_uint4(h[0], h[1], h[2], h[3]);
+              ptx::st_global_256(o + c + i, h);       // ctx rows are 512 B, head * 64 + c + i a multiple of 16 halves: 32-byte aligned
             }
           }
         }

@@ -255,13 +255,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            const float4 a = *reinterpret_cast<const float4*>(xr + c + j);
-            const float4 b = *reinterpret_cast<const float4*>(xr + c + j + 4);
-            float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            float v[8];
+            ptx::ld_global_256f(xr + c + j, v);      // rows are 1 KiB, c + j a multiple of 8 floats: 32-byte aligned
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(r[j + e]) + s_b3[c + j + e];
-            *reinterpret_cast<float4*>(xr + c + j) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(xr + c + j + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            ptx::st_global_256f(xr + c + j, v);
             uint32_t h[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) { __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]); h[e] = *reinterpret_cast<uint32_t*>(&h2); }

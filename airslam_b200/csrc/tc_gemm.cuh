@@ -262,8 +262,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
           if (p.out_f32) {
             float* o = reinterpret_cast<float*>(p.out) + off + ncol;
             if (nbase + 16 <= p.n_valid) {
+              if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+                const float lo[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]}, hi[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+                ptx::st_global_256f(o, lo);
+                ptx::st_global_256f(o + 8, hi);
+              } else {
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) if (nbase + i < p.n_valid) o[i] = v[i];
