@@ -93,3 +93,77 @@ def test_superglue_decode_ignores_dustbins_and_thresholds():
 def test_matching_points_empty_side():
     f = synth.keypoint_set(10, 752, 480, 1)
     assert host.matching_points(f, np.zeros((259, 0), np.float32), {}, 0, 752, 480) == []
+
+
+def _assoc_full(lines, juncs):
+    """The graph's association (G2, plnet.cpp:453-462 outputs): first-minimum ArgMin over all junctions, fp32 arithmetic."""
+    def nearest(ex, ey):
+        dx = (ex[:, None] - juncs[None, :, 0]).astype(np.float32)
+        dy = (ey[:, None] - juncs[None, :, 1]).astype(np.float32)
+        d = (dx * dx).astype(np.float32) + (dy * dy).astype(np.float32)
+        return d.min(1), d.argmin(1)
+    m1, i1 = nearest(lines[:, 0], lines[:, 1])
+    m2, i2 = nearest(lines[:, 2], lines[:, 3])
+    lo, hi = np.minimum(i1, i2), np.maximum(i1, i2)
+    return lo, hi, (lo < hi) & (m1 < 10.0) & (m2 < 10.0)
+
+
+def _assoc_grid(lines, juncs, cell_cap=8):
+    """What assoc_kernel (csrc/line_kernels.cu) does: 32x32 grid of 4x4-px cells, 3x3 neighbourhood around each endpoint,
+    candidates ordered by (distance, index); returns None when a cell overflows (the kernel then runs the full scan)."""
+    cells = {}
+    for q, (x, y) in enumerate(juncs):
+        c = (min(31, max(0, int(np.float32(y) * np.float32(0.25)))), min(31, max(0, int(np.float32(x) * np.float32(0.25)))))
+        cells.setdefault(c, []).append(q)
+    if max(len(v) for v in cells.values()) > cell_cap:
+        return None
+    n = len(lines)
+    lo, hi, keep = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, bool)
+
+    def nearest(ex, ey):
+        best, bi = np.float32(np.inf), 0
+        cx0, cx1 = max(0, int(np.floor((ex - 3.17) * 0.25))), min(31, int(np.floor((ex + 3.17) * 0.25)))
+        cy0, cy1 = max(0, int(np.floor((ey - 3.17) * 0.25))), min(31, int(np.floor((ey + 3.17) * 0.25)))
+        for cy in range(cy0, cy1 + 1):
+            for cx in range(cx0, cx1 + 1):
+                for q in cells.get((cy, cx), ()):
+                    dx, dy = np.float32(ex - juncs[q, 0]), np.float32(ey - juncs[q, 1])
+                    d = np.float32(dx * dx) + np.float32(dy * dy)
+                    if d < best or (d == best and q < bi):
+                        best, bi = d, q
+        return best, bi
+    for k in range(n):
+        m1, i1 = nearest(lines[k, 0], lines[k, 1])
+        m2, i2 = nearest(lines[k, 2], lines[k, 3])
+        if not (m1 < 10.0 and m2 < 10.0):
+            continue
+        lo[k], hi[k] = min(i1, i2), max(i1, i2)
+        keep[k] = lo[k] < hi[k]
+    return lo, hi, keep
+
+
+def test_association_grid_pruning_equals_full_scan_on_kept_rows():
+    """The device prunes the 300-junction scan to the sqrt(10)-px neighbourhood: the keep mask must be identical for every proposal and
+    (imin, imax) identical wherever keep is set -- the only rows wireframe_matcher reads (plnet.cpp:272-307)."""
+    rng = np.random.RandomState(5)
+    for trial in range(3):
+        # junctions: distinct integer cells + sub-pixel offsets, like TopK over a 3x3-NMS'd map (plus exact-tie bait: duplicated coordinates)
+        cellsel = rng.choice(128 * 128, 300, replace=False)
+        juncs = np.stack([(cellsel % 128) + 0.5 + rng.uniform(-0.49, 0.49, 300), (cellsel // 128) + 0.5 + rng.uniform(-0.49, 0.49, 300)], 1).astype(np.float32)
+        juncs[7] = juncs[3]                      # an exact tie: the first index must win
+        # proposals: half of them start / end near junctions so that many are kept
+        n = 1500
+        a, b = rng.randint(0, 300, n), rng.randint(0, 300, n)
+        lines = np.concatenate([juncs[a] + rng.normal(0, 1.5, (n, 2)), juncs[b] + rng.normal(0, 1.5, (n, 2))], 1)
+        lines[n // 2:] = rng.uniform(0, 127, (n - n // 2, 4))
+        lines = np.clip(lines, 0, 127).astype(np.float32)
+        lo_f, hi_f, keep_f = _assoc_full(lines, juncs)
+        got = _assoc_grid(lines, juncs)
+        assert got is not None
+        lo_g, hi_g, keep_g = got
+        assert np.array_equal(keep_f, keep_g)
+        assert keep_f.sum() > 100
+        assert np.array_equal(lo_f[keep_f], lo_g[keep_f]) and np.array_equal(hi_f[keep_f], hi_g[keep_f])
+    # TopK padding with non-peak cells produces runs of adjacent junctions: the grid must refuse (the kernel falls back to the full scan)
+    dense = np.stack([np.arange(300) % 128 + 0.5, np.arange(300) // 128 + 0.5], 1).astype(np.float32)
+    assert _assoc_grid(lines, dense) is None
