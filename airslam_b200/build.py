@@ -1,5 +1,6 @@
 """Build libairfe.so (hand-written sm_100a CUDA + C ABI) in-tree with nvcc.  No torch extension machinery:
 the product is a plain C-ABI shared library (include/airfe_c.h)."""
+import hashlib
 import os
 import subprocess
 import sys
@@ -11,6 +12,25 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unused-function"]
 FLAGS.remove("--use_fast_math=false")
+
+
+STAMP = LIB + ".srchash"
+
+
+def source_hash():
+    """sha256 over every file the library is built from: a stamp next to the .so lets the loader detect a stale build
+    independently of file times (which a snapshot copy does not preserve)."""
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cc", ".cuh", ".h")))
+    files.append(os.path.join(os.path.dirname(HERE), "include", "airfe_c.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+def is_current():
+    return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == source_hash()
 
 
 def sources():
@@ -29,7 +49,7 @@ def _stale(objs_srcs):
 def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     pairs = [(os.path.join(HERE, "build", os.path.basename(s) + ".o"), s) for s in sources()]
-    if not force and not _stale(pairs):
+    if not force and not _stale(pairs) and is_current():
         return LIB
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "airfe_c.h"))
@@ -51,6 +71,8 @@ def build(force=False, verbose=False):
             print(out.decode())
     cmd = [NVCC, "-shared", "-o", LIB] + [o for o, _ in pairs] + ["-lcudart"]
     subprocess.check_call(cmd)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

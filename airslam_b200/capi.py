@@ -19,6 +19,14 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise AirfeError("libairfe.so not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                              "there is no CPU fallback")
+        from . import build as _build
+        if not _build.is_current():
+            # sources changed after the last build (or the stamp is missing): rebuild when a compiler is here, else refuse -- never run a
+            # library that does not correspond to the sources next to it
+            if os.path.exists(_build.NVCC):
+                _build.build()
+            else:
+                raise AirfeError("libairfe.so is stale with respect to airslam_b200/csrc (no nvcc here to rebuild it)")
         _lib = C.CDLL(LIB_PATH)
         _lib.airfe_last_error.restype = C.c_char_p
         _declare(_lib)
