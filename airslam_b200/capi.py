@@ -24,7 +24,11 @@ def lib():
             # sources changed after the last build (or the stamp is missing): rebuild when a compiler is here, else refuse -- never run a
             # library that does not correspond to the sources next to it
             if os.path.exists(_build.NVCC):
-                _build.build()
+                import fcntl
+                with open(LIB_PATH + ".lock", "w") as lk:      # several ranks may get here at once: one builds, the others wait and re-check
+                    fcntl.flock(lk, fcntl.LOCK_EX)
+                    if not _build.is_current():
+                        _build.build()
             else:
                 raise AirfeError("libairfe.so is stale with respect to airslam_b200/csrc (no nvcc here to rebuild it)")
         _lib = C.CDLL(LIB_PATH)
