@@ -126,6 +126,8 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
     p.b_resident = 1;
     p.stages_a = (budget - res_bytes) / a_bytes;
     if (p.stages_a > 4) p.stages_a = 4;
+    static const int cap_a = getenv("AIRFE_CONV_STAGES_A") ? atoi(getenv("AIRFE_CONV_STAGES_A")) : 0;   // experiments: cap the halo-tile ring depth
+    if (cap_a >= 2 && p.stages_a > cap_a) p.stages_a = cap_a;
     p.stages_b = 0;
   } else {
     p.b_resident = 0;
