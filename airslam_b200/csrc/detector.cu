@@ -226,10 +226,10 @@ bool Detector::build_ops(int B) {
   };
   // SuperPoint trunk + heads (G1; G2 /backbone/point_detector/*)
   const Act r3 = cat2_.slice(32, 64), r5 = cat3_.slice(128, 128);
-  // Experimental (AIRFE_FUSE1A=1, off by default): conv1a computed inside conv1b's producer warps so that its 32 MiB/frame output never
-  // goes to HBM.  Parity-green, but measured SLOWER on B200 (1.38 ms vs 0.37 + 0.69 ms per 32 frames, profiles/r01_fused_conv1a_trace.txt):
-  // the FFMA2 producer needs ~3300 issue cycles per tile per SM sub-partition and starves the epilogue warps.  The tensor-core
-  // (im2col K=16 + TMEM round trip) variant is the follow-up.
+  // Experimental (AIRFE_FUSE1A=1, off by default): conv1a computed inside the conv1b kernel so that its 32 MiB/frame output never goes to
+  // HBM.  Round 1 measured a CUDA-core (FFMA2) producer: parity-green but slower (1.38 ms vs 0.37 + 0.69 ms per 32 frames,
+  // profiles/r01_fused_conv1a_trace.txt).  The code now holds the tensor-core producer (im2col K = 16 -> three MMAs -> TMEM -> A stage),
+  // written at the end of round 1 WITHOUT a GPU: compile-checked only, to be validated (tools/probe_k16.cu first) before it is enabled.
   static const bool fuse1a = conv3x3_halo_enabled() && getenv("AIRFE_FUSE1A") != nullptr;
   if (fuse1a) {
     const Conv1aFuse f{x16_, w_conv1a_, b_conv1a_};

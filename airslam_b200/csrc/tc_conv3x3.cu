@@ -150,9 +150,12 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   if (fuse) {
     if (!p.b_resident || p.strips != 2 || p.kw != 64 || p.kblocks != 1) { set_error("add_conv3x3: conv1a fusion: unexpected plan"); return false; }
     p.img1 = fuse->img; p.w1a = fuse->w; p.b1a = fuse->bias;
+    p.nacc = 2;                        // TMEM: 2 x 2 x 64 conv1b columns + 3 x 64 conv1a columns
+    p.stages_a = 2;                    // the A stages are written on chip: no load latency to cover, and the im2col tiles need the room
   }
   const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
-  plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 8) * 8 + 16;
+  plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 8) * 8 + 16 +
+                    (fuse ? 1024 + 2048 + 2 * 12288 : 0);   // fused conv1a: W1 + two im2col tiles behind the barriers
   const int total = p.tiles_x * p.tiles_y * batch * p.n_tiles;
   plan.grid = total < sm_count() ? total : sm_count();
   if (in.C > w.c_in_pad || in.C < w.c_in) { set_error("add_conv3x3: activation has %d channels, weights expect %d", in.C, w.c_in); return false; }

@@ -33,8 +33,9 @@ struct ConvParams {
   long long out_sb, out_sy, out_sx;
   __half* pool_out;   // fused 2x2/2 max-pool store (nullptr: skip)
   long long pool_sb, pool_sy, pool_sx;
-  // FUSE1A (SuperPoint conv1a fused into conv1b): the 64-channel input never exists in HBM; producer warps compute the halo tile from
-  // the 1-channel image with packed FFMA2 straight into the swizzled A stage.  img1 = fp16 [B][H][W], w1a = fp16 [64][9], b1a = fp32 [64].
+  // FUSE1A (SuperPoint conv1a fused into conv1b, experimental): the 64-channel input never exists in HBM.  Producer warps build the im2col
+  // tile of the 1-channel image (K = 9 -> 16), the MMA warp runs conv1a as three 128x64x16 MMAs into spare TMEM columns, and the producers
+  // move the result (+bias, ReLU, fp16) from TMEM into the swizzled A stage.  img1 = fp16 [B][H][W], w1a = fp16 [64][9], b1a = fp32 [64].
   const __half* img1; const __half* w1a; const float* b1a;
   long long* trace;   // authoring aid (airfe_debug_conv_trace): CTA 0 writes clock64 stamps of its first 64 tiles, 8 slots per tile
 };
@@ -70,6 +71,29 @@ __device__ __forceinline__ unsigned long long conv_pack2(float lo, float hi) {
   return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
 
+// ---- FUSE1A helpers (only instantiated by the conv1a-fused kernel) ---------------------------------------------------------
+constexpr uint32_t kC1aCol = 256;                // conv1a accumulators: TMEM columns 256 .. 447 (conv1b uses 2 x 2 x 64 = 256)
+__device__ __forceinline__ uint8_t* conv_c1a_smem(uint32_t* tmem_slot) {   // W1 [64 x 16] (2 KiB) + two im2col tiles (12 KiB each) behind the TMEM slot
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023));
+}
+// conv1a of the k-th tile of this CTA: three 128x64x16 MMAs on im2col buffer k & 1 into the spare TMEM columns
+__device__ __forceinline__ void conv_issue_conv1a(int k, uint64_t* fbar, uint8_t* c1a, uint32_t tmem_base) {
+  const int b = k & 1;
+  ptx::mbar_wait(&fbar[b], (uint32_t)(k >> 1) & 1);            // im2col tile landed
+  ptx::tc_fence_after();
+  if (ptx::elect_one()) {
+    const uint32_t idesc1 = ptx::make_idesc_f16(128, 64, 0);
+    const uint64_t d1_const = ptx::make_smem_desc(0, 128, 256, 0);   // K-major INTERLEAVE: LBO = 128 B, SBO = 256 B
+    const uint64_t d1_w = d1_const + (ptx::smem_u32(c1a) >> 4);
+    const uint64_t d1_a = d1_const + (ptx::smem_u32(c1a + 2048 + b * 12288) >> 4);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ptx::umma_f16(tmem_base + kC1aCol + i * 64, d1_a + (uint64_t)(i * (4096 >> 4)), d1_w, idesc1, 0);
+    ptx::umma_commit(&fbar[2 + b]);                             // im2col buffer free again
+    ptx::umma_commit(&fbar[4]);                                 // conv1a accumulators valid
+  }
+  __syncwarp();
+}
+
 template <int KW, int STRIPS, bool BRES, bool FUSE1A = false>
 __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) tc_conv3x3_kernel(const __grid_constant__ ConvParams p) {
   static_assert(!FUSE1A || (KW == 64 && STRIPS == 2 && BRES), "conv1a fusion is specialised for the 64->64 resident-weights layer");
@@ -94,7 +118,7 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
   const int m_tiles = p.tiles_x * p.tiles_y * p.B;
   const int total_tiles = m_tiles * p.n_tiles;
   const uint32_t acc_stride = conv_acc_stride(p.block_n);
-  const uint32_t tmem_cols = conv_tmem_cols(p.block_n, STRIPS);
+  const uint32_t tmem_cols = FUSE1A ? 512u : conv_tmem_cols(p.block_n, STRIPS);
 
   if (warp == 0 && lane == 0) {
     if (!FUSE1A) ptx::prefetch_tmap(&p.tmA);
@@ -112,14 +136,24 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
   const uint32_t tmem_base = *tmem_slot;
   __shared__ __align__(16) float s_bias[512];
   for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;   // weights: not produced by a kernel
-  __shared__ float2 s_w1a[FUSE1A ? 288 : 1];     // conv1a: [channel pair][tap] = (w[2p][tap], w[2p+1][tap])
-  __shared__ float2 s_b1a[FUSE1A ? 32 : 1];
-  if (FUSE1A) {
-    for (int i = threadIdx.x; i < 288; i += blockDim.x) {
-      const int k = i % 9, cp = i / 9;
-      s_w1a[i] = make_float2(__half2float(p.w1a[(2 * cp) * 9 + k]), __half2float(p.w1a[(2 * cp + 1) * 9 + k]));
+  // FUSE1A: conv1a bias, six extra barriers, and (in dynamic smem behind the TMEM slot) W1 [64 x 16] + two im2col tiles [384 x 16] in the
+  // K-major INTERLEAVE (no swizzle) layout: element (r, k) at (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2   (LBO = 128 B, SBO = 256 B)
+  __shared__ float s_b1a[FUSE1A ? 64 : 1];
+  __shared__ uint64_t s_fbar[FUSE1A ? 6 : 1];      // im2col full[2], im2col empty[2], conv1a acc full, conv1a acc empty
+  if constexpr (FUSE1A) {
+    uint8_t* c1a_w = conv_c1a_smem(tmem_slot);
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+      const int n = i >> 4, k = i & 15;
+      *reinterpret_cast<__half*>(c1a_w + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = k < 9 ? p.w1a[n * 9 + k] : __float2half(0.f);
     }
-    if (threadIdx.x < 32) s_b1a[threadIdx.x] = make_float2(p.b1a[2 * threadIdx.x], p.b1a[2 * threadIdx.x + 1]);
+    if (threadIdx.x < 64) s_b1a[threadIdx.x] = p.b1a[threadIdx.x];
+    if (threadIdx.x == 0) {
+      ptx::mbar_init(&s_fbar[0], kConvFuseProducers); ptx::mbar_init(&s_fbar[1], kConvFuseProducers);
+      ptx::mbar_init(&s_fbar[2], 1); ptx::mbar_init(&s_fbar[3], 1);
+      ptx::mbar_init(&s_fbar[4], 1); ptx::mbar_init(&s_fbar[5], kConvFuseProducers);
+      ptx::fence_barrier_init();
+    }
+    ptx::fence_proxy_async();                      // W1 was written with generic stores, tcgen05.mma reads it through the async proxy
   }
   __syncthreads();
   ptx::pdl_launch_dependents();   // the next kernel may start its own prologue on SMs this grid has left
@@ -170,9 +204,23 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
     const uint64_t da_base = da_const + (ptx::smem_u32(smem_a) >> 4);
     const uint64_t db_base = db_const + (ptx::smem_u32(smem_b) >> 4);
     const uint32_t b16 = (uint32_t)b_bytes >> 4;
+    // FUSE1A: conv1a of tile k+1 is issued ahead of the 72 conv1b MMAs of tile k, so the producers' TMEM -> A-stage pass for tile k+1 runs
+    // while the tensor pipe works on tile k
+    int kseq = 0;
+    if constexpr (FUSE1A) {
+      if ((int)blockIdx.x < total_tiles) conv_issue_conv1a(0, s_fbar, conv_c1a_smem(tmem_slot), tmem_base);
+    }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && t / (int)gridDim.x < 64;
       long long* trp = tr ? p.trace + (t / gridDim.x) * 8 : nullptr;
+      if constexpr (FUSE1A) {
+        if (t + (int)gridDim.x < total_tiles) {
+          ptx::mbar_wait(&s_fbar[5], (uint32_t)kseq & 1);           // producers have read tile k's conv1a accumulators out of TMEM
+          ptx::tc_fence_after();
+          conv_issue_conv1a(kseq + 1, s_fbar, conv_c1a_smem(tmem_slot), tmem_base);
+        }
+        ++kseq;
+      }
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       if (tr) trp[1] = clock64();
@@ -230,70 +278,87 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
       if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   } else if (FUSE1A && warp >= 10) {
-    // ===== conv1a producers (8 warps): halo tile of 18 x 18 pixels x 64 channels = relu(conv3x3(image) + b), written as the
-    // K-major SWIZZLE_128B A operand the nine tap descriptors read.  Halo pixels outside the image are conv1b's zero padding.
-    // task = (halo row hy, group of 6 pixels gx, group of 8 channels cg): 18 * 3 * 8 = 432 tasks over 256 threads.
+    // ===== conv1a producers (8 warps) =====
+    //  (1) im2col of tile k+1: row r = halo pixel (hy, hx) of the 18 x 18 tile, 9 taps of the 1-channel image (zero outside) -> 16 fp16
+    //  (2) after the MMA warp's three conv1a MMAs of tile k: TMEM -> +bias, ReLU, fp16 -> A stage (K-major SWIZZLE_128B row r), zero for
+    //      halo pixels outside the image (conv1b's padding)
     const int ptid = threadIdx.x - kConvThreads;
+    uint8_t* c1a_im = conv_c1a_smem(tmem_slot) + 2048;
+    const int quarter = warp & 3, halfc = (warp - 10) >> 2;     // TMEM lane quarter (= warp % 4) and column half of this warp
     int sa = 0;
     uint32_t pa = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    auto build_im2col = [&](int t, int k) {
+      const int b = k & 1;
       const int mt = t / p.n_tiles;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tz = mt / (p.tiles_x * p.tiles_y);
       const int x0 = tx * 8 * STRIPS, y0 = ty * kConvTH;
       const __half* img = p.img1 + (long long)tz * p.W * p.H;
-      ptx::mbar_wait(&empty_a[sa], pa ^ 1);
-      const bool trp_on = p.trace && blockIdx.x == 0 && ptid == 0 && t / (int)gridDim.x < 64;
-      if (trp_on) p.trace[(t / gridDim.x) * 8 + 0] = clock64();
-      uint8_t* stage = smem_a + sa * a_bytes;
-#pragma unroll 1
-      for (int task = ptid; task < 18 * 3 * 8; task += 32 * kConvFuseProducers) {
-        const int cg = task & 7, gx = (task >> 3) % 3, hy = task / 24;
-        const int oy = y0 - 1 + hy;                 // conv1a output row of this task
-        const int ox0 = x0 - 1 + gx * 6;            // first of its 6 output columns; inputs span columns ox0-1 .. ox0+6 (even start: pairs)
-        unsigned long long in2[3][8];
+      ptx::mbar_wait(&s_fbar[2 + b], ((uint32_t)(k >> 1) & 1) ^ 1);   // buffer released by the conv1a MMAs two tiles ago (first use passes)
+      uint8_t* im = c1a_im + b * 12288;
+      for (int r = ptid; r < 384; r += 32 * kConvFuseProducers) {
+        uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (r < HW * (kConvTH + 2)) {
+          const int hy = r / HW, hx = r - hy * HW;
+          const int cy = y0 - 1 + hy, cx = x0 - 1 + hx;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int iy = oy + ky - 1;
-          const bool rv = (iy >= 0) && (iy < p.H);
-          const __half* rp = img + (long long)(rv ? iy : 0) * p.W;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int ix = ox0 - 1 + 2 * q;          // even: a pair never straddles the image border (W is even)
-            float2 f = make_float2(0.f, 0.f);
-            if (rv && ix >= 0 && ix < p.W) f = __half22float2(*reinterpret_cast<const __half2*>(rp + ix));
-            in2[ky][2 * q] = conv_pack2(f.x, f.x);
-            in2[ky][2 * q + 1] = conv_pack2(f.y, f.y);
+          for (int k9 = 0; k9 < 9; ++k9) {
+            const int iy = cy + k9 / 3 - 1, ix = cx + k9 % 3 - 1;
+            unsigned short bits = 0;
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) bits = reinterpret_cast<const unsigned short*>(img)[(long long)iy * p.W + ix];
+            v[k9 >> 1] |= (uint32_t)bits << ((k9 & 1) * 16);
           }
         }
-        const bool row_in = (oy >= 0) && (oy < p.H);
+        uint8_t* dst = im + (r >> 3) * 256 + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);          // k = 0..7
+        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(v[4], v[5], v[6], v[7]);    // k = 8..15 (only k = 8 is non-zero)
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_fbar[b]);
+    };
+    int kseq = 0;
+    if ((int)blockIdx.x < total_tiles) build_im2col(blockIdx.x, 0);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      if (t + (int)gridDim.x < total_tiles) build_im2col(t + gridDim.x, kseq + 1);
+      const int mt = t / p.n_tiles;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y;
+      const int x0 = tx * 8 * STRIPS, y0 = ty * kConvTH;
+      ptx::mbar_wait(&s_fbar[4], (uint32_t)kseq & 1);             // conv1a accumulators of this tile are in TMEM
+      ptx::mbar_wait(&empty_a[sa], pa ^ 1);                       // the A stage is free
+      ptx::tc_fence_after();
+      uint8_t* stage = smem_a + sa * a_bytes;
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) {
+        const int r = i * 128 + quarter * 32 + lane;
+        uint32_t acc32[32];
+        ptx::tmem_ld32(tmem_base + kC1aCol + i * 64 + halfc * 32 + ((uint32_t)(quarter * 32) << 16), acc32);
+        ptx::tmem_ld_wait();
+        if (r < HW * (kConvTH + 2)) {
+          const int hy = r / HW, hx = r - hy * HW;
+          const int oy = y0 - 1 + hy, ox = x0 - 1 + hx;
+          const bool in_img = oy >= 0 && oy < p.H && ox >= 0 && ox < p.W;
 #pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {
-          unsigned long long wp[9];
+          for (int c4 = 0; c4 < 4; ++c4) {                        // four 16-byte chunks = this warp's 32 channels
+            uint32_t h[4];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) { const float2 w2 = s_w1a[(cg * 4 + jp) * 9 + k]; wp[k] = conv_pack2(w2.x, w2.y); }
-          const float2 bb = s_b1a[cg * 4 + jp];
-          const unsigned long long b2 = conv_pack2(bb.x, bb.y);
-#pragma unroll
-          for (int px = 0; px < 6; ++px) {
-            unsigned long long acc = b2;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) acc = conv_ffma2(in2[ky][px + kx], wp[ky * 3 + kx], acc);
-            const float a0 = fmaxf(__uint_as_float((unsigned)(acc & 0xffffffffu)), 0.f), a1 = fmaxf(__uint_as_float((unsigned)(acc >> 32)), 0.f);
-            __half2 h2 = __floats2half2_rn(a0, a1);
-            const int ox = ox0 + px;
-            const bool in_img = row_in && ox >= 0 && ox < p.W;
-            const int r = hy * HW + gx * 6 + px;       // halo pixel = 128-byte row of the A stage; channel pair jp = 4 bytes of chunk cg
-            *reinterpret_cast<uint32_t*>(stage + r * 128 + ((cg ^ (r & 7)) << 4) + jp * 4) = in_img ? *reinterpret_cast<uint32_t*>(&h2) : 0u;
+            for (int e = 0; e < 4; ++e) {
+              const int j = c4 * 8 + e * 2;
+              const float a0 = fmaxf(__uint_as_float(acc32[j]) + s_b1a[halfc * 32 + j], 0.f);
+              const float a1 = fmaxf(__uint_as_float(acc32[j + 1]) + s_b1a[halfc * 32 + j + 1], 0.f);
+              __half2 h2 = __floats2half2_rn(a0, a1);
+              h[e] = in_img ? *reinterpret_cast<uint32_t*>(&h2) : 0u;
+            }
+            const int chunk = halfc * 4 + c4;
+            *reinterpret_cast<uint4*>(stage + r * 128 + ((chunk ^ (r & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
           }
         }
       }
-      ptx::fence_proxy_async();                      // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async();                                    // generic-proxy stores -> visible to tcgen05.mma (async proxy)
       __syncwarp();
-      if (trp_on) p.trace[(t / gridDim.x) * 8 + 6] = clock64();   // (fused mode: slot 6 = producer done, warp 9 does not stamp)
-      if (lane == 0) ptx::mbar_arrive(&full_a[sa]);
+      if (lane == 0) { ptx::mbar_arrive(&full_a[sa]); ptx::mbar_arrive(&s_fbar[5]); }
       if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+      ++kseq;
     }
   } else if (!FUSE1A || warp < 10) {
     // ===== epilogue: 8 warps; warp (2 + e) owns TMEM lane quarter (warp & 3) and half of the work (strip, or column half) =====
