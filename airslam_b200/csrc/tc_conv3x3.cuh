@@ -326,6 +326,8 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
       ptx::mbar_wait(&s_fbar[4], (uint32_t)kseq & 1);             // conv1a accumulators of this tile are in TMEM
       ptx::mbar_wait(&empty_a[sa], pa ^ 1);                       // the A stage is free
       ptx::tc_fence_after();
+      const bool trp_on = p.trace && blockIdx.x == 0 && ptid == 0 && kseq < 64;
+      if (trp_on) p.trace[kseq * 8 + 0] = clock64();              // trace slot 0: TMEM -> A-stage pass starts
       uint8_t* stage = smem_a + sa * a_bytes;
 #pragma unroll 1
       for (int i = 0; i < 3; ++i) {
@@ -357,6 +359,7 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
       ptx::fence_proxy_async();                                    // generic-proxy stores -> visible to tcgen05.mma (async proxy)
       __syncwarp();
       if (lane == 0) { ptx::mbar_arrive(&full_a[sa]); ptx::mbar_arrive(&s_fbar[5]); }
+      if (trp_on) p.trace[kseq * 8 + 6] = clock64();              // trace slot 6: A stage handed to the MMA warp
       if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
       ++kseq;
     }
