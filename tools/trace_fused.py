@@ -1,8 +1,10 @@
 """clock64 trace of the conv1a-fused conv1b launch inside a detector run (authoring aid).  AIRFE_TRACE_FUSED=1 is set here so that only
-that launch stamps the buffer.  Slots: 0 producer got a free stage, 1 MMA start, 2 A landed, 3 MMAs issued, 4/5 epilogue warp 2 start/end,
-6 producer finished the tile."""
+that launch stamps the buffer.  Slots: 0 producers start the TMEM -> A-stage pass of the tile (conv1a accumulators ready, stage free),
+1 MMA warp start, 2 A stage landed, 3 conv1b MMAs issued, 4/5 epilogue warp 2 start/end, 6 A stage handed to the MMA warp.
+Needs AIRFE_FUSE1A=1 in the environment (the fusion is experimental and off by default)."""
 import os, sys
 os.environ["AIRFE_TRACE_FUSED"] = "1"
+os.environ.setdefault("AIRFE_FUSE1A", "1")
 import numpy as np
 import torch
 sys.path.insert(0, ".")
