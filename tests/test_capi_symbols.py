@@ -43,3 +43,12 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_library_matches_sources():
+    """The in-tree libairfe.so must have been built from the sources next to it (sha256 stamp written by build()); the loader refuses or
+    rebuilds a stale library, this test makes a stale one visible in the CPU suite already."""
+    from airslam_b200 import build
+    build.build()
+    assert build.is_current()
+    assert open(build.STAMP).read().strip() == build.source_hash()
