@@ -69,11 +69,20 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on " + src)
         if verbose and out:
             print(out.decode())
-    cmd = [NVCC, "-shared", "-o", LIB] + [o for o, _ in pairs] + ["-lcudart"]
+    # link to a temporary name and rename over the library: a process that already dlopen'ed the old file keeps its (now unlinked)
+    # image instead of having its mapped pages rewritten under it
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [NVCC, "-shared", "-o", tmp] + [o for o, _ in pairs] + ["-lcudart"]
     subprocess.check_call(cmd)
-    with open(STAMP, "w") as f:
+    os.replace(tmp, LIB)
+    with open(STAMP + ".tmp", "w") as f:
         f.write(source_hash() + "\n")
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
+
+
+def have_nvcc():
+    return os.path.exists(NVCC)
 
 
 def build_mock_caller():
@@ -81,6 +90,20 @@ def build_mock_caller():
     root = os.path.dirname(HERE)
     out = os.path.join(root, "tests", "cpp", "mock_caller")
     srcs = [os.path.join(root, "src", "frontend", "frontend.cc"), os.path.join(root, "tests", "cpp", "mock_caller.cc")]
+    deps = srcs + [os.path.join(root, "include", f) for f in os.listdir(os.path.join(root, "include"))] + [LIB]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(root, "compat"), "-I" + os.path.join(root, "include")] + srcs + [
+        "-o", out, "-L" + HERE, "-lairfe", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../../airslam_b200"]
+    subprocess.check_call(cmd)
+    return out
+
+
+def build_class_bench():
+    """g++: tests/cpp/class_bench.cc (bench.py --mode class) against the same class surfaces."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(root, "tests", "cpp", "class_bench")
+    srcs = [os.path.join(root, "src", "frontend", "frontend.cc"), os.path.join(root, "tests", "cpp", "class_bench.cc")]
     deps = srcs + [os.path.join(root, "include", f) for f in os.listdir(os.path.join(root, "include"))] + [LIB]
     if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
         return out

@@ -33,13 +33,14 @@ def lib():
                 raise AirfeError("libairfe.so is stale with respect to airslam_b200/csrc (no nvcc here to rebuild it)")
         _lib = C.CDLL(LIB_PATH)
         _lib.airfe_last_error.restype = C.c_char_p
+        _lib.airfe_last_error.argtypes = [C.c_void_p]
         _declare(_lib)
     return _lib
 
 
-def check(rc):
+def check(rc, ctx=None):
     if rc != 0:
-        raise AirfeError("airfe error %d: %s" % (rc, lib().airfe_last_error().decode()))
+        raise AirfeError("airfe error %d: %s" % (rc, lib().airfe_last_error(ctx).decode()))
 
 
 vp, i32, i64, f32p = C.c_void_p, C.c_int, C.c_longlong, C.c_void_p
@@ -109,6 +110,16 @@ def _declare_match(L):
     L.airfe_profile_stereo.restype = i64
     L.airfe_stereo_cost.argtypes = [vp, i32, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(i32)]
     L.airfe_stereo_cost.restype = i32
+    L.airfe_kf_reserve.argtypes = [vp, i32, i32]
+    L.airfe_kf_reserve.restype = i32
+    L.airfe_kf_put.argtypes = [vp, i32, vp, i32]
+    L.airfe_kf_put.restype = i32
+    L.airfe_kf_size.argtypes = [vp]
+    L.airfe_kf_size.restype = i32
+    L.airfe_reloc_match.argtypes = [vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32]
+    L.airfe_reloc_match.restype = i32
+    L.airfe_reloc_pick.argtypes = [i32, i32, vp, vp, vp]
+    L.airfe_reloc_pick.restype = None
 
 
 def pinned_array(shape, dtype):
@@ -139,6 +150,9 @@ class Context:
         self.h = vp()
         check(L.airfe_create(C.byref(self.cfg), device, C.byref(self.h)))
 
+    def _check(self, rc):
+        check(rc, self.h)
+
     def close(self):
         if self.h:
             lib().airfe_destroy(self.h)
@@ -167,7 +181,7 @@ class Context:
         jn = np.zeros((b, junc_cap, 259), dtype=np.float32) if junctions else None
         n_jn = np.zeros(b, dtype=np.int32)
         p = lambda a: a.ctypes.data_as(vp) if a is not None else None
-        check(lib().airfe_detect_batch(self.h, net, b, p(images), w, h, w, h * w, p(feat), feat_cap, p(n_feat), p(ln), line_cap,
+        self._check(lib().airfe_detect_batch(self.h, net, b, p(images), w, h, w, h * w, p(feat), feat_cap, p(n_feat), p(ln), line_cap,
                                        p(n_ln), p(jn), junc_cap, p(n_jn)))
         out = []
         for i in range(b):
@@ -180,7 +194,7 @@ class Context:
         out = np.zeros(shape, dtype=dtype)
         n = lib().airfe_debug_read(self.h, net, name.encode(), index, out.ctypes.data_as(vp), out.nbytes)
         if n < 0:
-            check(int(n))
+            self._check(int(n))
         return out
 
     def match_batch(self, matcher, feats0, feats1, match_cap=1024):
@@ -200,7 +214,7 @@ class Context:
         sc = np.zeros((p, match_cap), dtype=np.float32)
         nm = np.zeros(p, dtype=np.int32)
         q = lambda a: a.ctypes.data_as(vp)
-        check(lib().airfe_match_batch(self.h, matcher, p, q(f0), q(n0), q(f1), q(n1), cap, q(i0), q(i1), q(sc), match_cap, q(nm)))
+        self._check(lib().airfe_match_batch(self.h, matcher, p, q(f0), q(n0), q(f1), q(n1), cap, q(i0), q(i1), q(sc), match_cap, q(nm)))
         return [(np.stack([i0[i, :nm[i]], i1[i, :nm[i]]], axis=1), sc[i, :nm[i]].copy()) for i in range(p)]
 
     def stereo_batch(self, net, matcher, left, right, lines=False, junctions=False, line_cap=2048, junc_cap=512, match_cap=1024, raw=False):
@@ -224,7 +238,7 @@ class Context:
         b = self._sb
         feat, nf, ln, nl, jn, nj, i0, i1, sc, nm = (b[k] for k in ("feat", "nf", "ln", "nl", "jn", "nj", "i0", "i1", "sc", "nm"))
         q = lambda a: a.ctypes.data_as(vp) if a is not None else None
-        check(lib().airfe_detect_match_stereo_batch(self.h, net, matcher, p, q(left), q(right), w, h, w, h * w, q(feat), fc, q(nf), q(ln), line_cap,
+        self._check(lib().airfe_detect_match_stereo_batch(self.h, net, matcher, p, q(left), q(right), w, h, w, h * w, q(feat), fc, q(nf), q(ln), line_cap,
                                                     q(nl), q(jn), junc_cap, q(nj), q(i0), q(i1), q(sc), match_cap, q(nm)))
         if raw:
             return b
@@ -237,11 +251,11 @@ class Context:
         return out
 
     def stereo_device(self, net, matcher, pairs, d_images_ptr, w, h, stride, img_stride, lines=True, junctions=True):
-        check(lib().airfe_stereo_device(self.h, net, matcher, pairs, d_images_ptr, w, h, stride, img_stride, int(lines), int(junctions)))
+        self._check(lib().airfe_stereo_device(self.h, net, matcher, pairs, d_images_ptr, w, h, stride, img_stride, int(lines), int(junctions)))
 
     def stereo_cost(self, net, matcher, pairs, lines=True):
         fl, ln = C.c_double(0), i32(0)
-        check(lib().airfe_stereo_cost(self.h, net, matcher, pairs, int(lines), C.byref(fl), C.byref(ln)))
+        self._check(lib().airfe_stereo_cost(self.h, net, matcher, pairs, int(lines), C.byref(fl), C.byref(ln)))
         return fl.value, ln.value
 
     def profile_stereo(self, net, matcher, pairs, d_images_ptr, w, h, stride, img_stride, lines=True, junctions=True):
@@ -249,12 +263,43 @@ class Context:
         buf = C.create_string_buffer(1 << 18)
         n = lib().airfe_profile_stereo(self.h, net, matcher, pairs, d_images_ptr, w, h, stride, img_stride, int(lines), int(junctions), buf, len(buf))
         if n < 0:
-            check(int(n))
+            self._check(int(n))
         out = []
         for line in buf.value.decode().splitlines():
             nm, fl, ms = line.split("\t")
             out.append((nm, float(fl), float(ms)))
         return out
+
+    # ---- device-resident keyframe features + batched candidate matching (config 5) ----
+    def kf_reserve(self, n_keyframes, feat_cap):
+        self._check(lib().airfe_kf_reserve(self.h, n_keyframes, feat_cap))
+
+    def kf_put(self, slot, feat):
+        """feat: [259, N] float32 (the class-surface layout) on the host."""
+        import numpy as np
+        a = np.ascontiguousarray(feat.T, dtype=np.float32)        # column-major 259 x N == row-major [N][259]
+        self._check(lib().airfe_kf_put(self.h, slot, a.ctypes.data_as(vp), a.shape[0]))
+
+    def kf_put_ptr(self, slot, ptr, n):
+        """Raw pointer (host or device) to [n][259] float32."""
+        self._check(lib().airfe_kf_put(self.h, slot, ptr, n))
+
+    def reloc_match(self, matcher, query_feat_ptr, query_n, feat_cap, job_query, job_kf, want_matches=False, match_cap=1024):
+        """query_feat_ptr: pointer (host or device) to [Q][feat_cap][259] float32; query_n: int32 [Q] (host).  Returns counts [J]
+        (and per-job (idx [K,2], score [K]) when want_matches)."""
+        import numpy as np
+        qn = np.ascontiguousarray(query_n, dtype=np.int32)
+        jq = np.ascontiguousarray(job_query, dtype=np.int32)
+        jk = np.ascontiguousarray(job_kf, dtype=np.int32)
+        J = len(jq)
+        nm = np.zeros(max(J, 1), dtype=np.int32)
+        q = lambda a: a.ctypes.data_as(vp)
+        if want_matches:
+            i0 = np.zeros((max(J, 1), match_cap), np.int32); i1 = np.zeros((max(J, 1), match_cap), np.int32); sc = np.zeros((max(J, 1), match_cap), np.float32)
+            self._check(lib().airfe_reloc_match(self.h, matcher, query_feat_ptr, q(qn), len(qn), feat_cap, J, q(jq), q(jk), q(nm), q(i0), q(i1), q(sc), match_cap))
+            return nm[:J], [(np.stack([i0[j, :nm[j]], i1[j, :nm[j]]], 1), sc[j, :nm[j]].copy()) for j in range(J)]
+        self._check(lib().airfe_reloc_match(self.h, matcher, query_feat_ptr, q(qn), len(qn), feat_cap, J, q(jq), q(jk), q(nm), None, None, None, 0))
+        return nm[:J]
 
     def superglue_batch(self, feats0, feats1):
         """Raw SuperGlue::infer outputs per pair: (indices0, indices1, mscores0, mscores1)."""
@@ -271,5 +316,15 @@ class Context:
         i0 = np.zeros((p, cap), dtype=np.int32); i1 = np.zeros((p, cap), dtype=np.int32)
         m0 = np.zeros((p, cap), dtype=np.float32); m1 = np.zeros((p, cap), dtype=np.float32)
         q = lambda a: a.ctypes.data_as(vp)
-        check(lib().airfe_superglue_batch(self.h, p, q(f0), q(n0), q(f1), q(n1), cap, 0, q(i0), q(i1), q(m0), q(m1), cap))
+        self._check(lib().airfe_superglue_batch(self.h, p, q(f0), q(n0), q(f1), q(n1), cap, 0, q(i0), q(i1), q(m0), q(m1), cap))
         return [(i0[i, :n0[i]].copy(), i1[i, :n1[i]].copy(), m0[i, :n0[i]].copy(), m1[i, :n1[i]].copy()) for i in range(p)]
+
+
+def reloc_pick(counts):
+    """airfe_reloc_pick: winner per query under the rule of src/map_user.cc:370-373.  counts int32 [Q, C] (negative = absent)."""
+    import numpy as np
+    c = np.ascontiguousarray(counts, dtype=np.int32)
+    best = np.zeros(c.shape[0], np.int32)
+    cnt = np.zeros(c.shape[0], np.int32)
+    lib().airfe_reloc_pick(c.shape[0], c.shape[1], c.ctypes.data_as(vp), best.ctypes.data_as(vp), cnt.ctypes.data_as(vp))
+    return best, cnt

@@ -12,6 +12,7 @@ using namespace airfe;
 
 struct airfe_ctx {
   int device = 0;
+  char err[1024] = "";                                // message of the last failing call on THIS context (airfe_last_error(ctx))
   airfe_config cfg;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;                 // D2H of the detector results overlaps the matcher (stereo entry point)
@@ -19,6 +20,13 @@ struct airfe_ctx {
   std::unique_ptr<Detector> sp, pl;
   std::unique_ptr<LightGlue> lg;
   std::unique_ptr<SuperGlue> sg;
+  // Contexts sized for the reference's 1024-keypoint TRT profile (max_keypoints > 512: the C++ PointMatcher surface) also hold a 512-row
+  // instance: calls whose feature sets fit run on it, i.e. on the FUSED attention kernel (tc_attn.cuh covers <= 512 keys); only genuinely
+  // larger sets take the unfused 1024-row path.  lg_use / sg_use = the instance the current call runs on.
+  std::unique_ptr<LightGlue> lg_small;
+  std::unique_ptr<SuperGlue> sg_small;
+  LightGlue* lg_use = nullptr;
+  SuperGlue* sg_use = nullptr;
   int* h_sgidx = nullptr; float* h_sgms = nullptr;   // [2][max_batch][1024] each
   float* d_mfeat = nullptr; int* d_mn = nullptr;   // staging for host-provided features [2*max_batch][kKpCap][259]
   float* h_mfeat = nullptr; int* h_mn = nullptr; int* h_midx = nullptr; float* h_mscore = nullptr; int* h_mcount = nullptr;
@@ -27,7 +35,40 @@ struct airfe_ctx {
   float* h_feat = nullptr; float* h_junc = nullptr; float* h_lines = nullptr;
   int* h_counts = nullptr;   // [3][max_batch]
   uint8_t* d_img = nullptr; size_t d_img_bytes = 0;
+  // device-resident keyframe features (airfe_kf_*) and the job tables of airfe_reloc_match
+  float* kf_feat = nullptr; int* kf_n = nullptr;       // [kf_slots][kf_cap][259] on the device; counts on the host
+  int kf_slots = 0, kf_cap = 0;
+  int rj_cap = 0;                                      // jobs the tables below are sized for
+  const float** h_rptr = nullptr; const float** d_rptr = nullptr;   // [2*rj_cap] per-slot feature pointers
+  int* h_rn = nullptr; int* d_rn = nullptr;            // [2*rj_cap] per-slot counts
+  int* d_rcount = nullptr; int* d_ridx = nullptr; float* d_rscore = nullptr;   // per job: match count, [cap][2] indices, [cap] scores
+  int* h_rcount = nullptr; int* h_ridx = nullptr; float* h_rscore = nullptr;
+  float* d_qfeat = nullptr; size_t d_qfeat_bytes = 0;  // staging for host-resident query features
 };
+
+// Every failing frame-level call leaves its message in the context it was made on (contexts are per thread / per device; a
+// process-global string would let one thread's error overwrite another's).  Failures without a context (airfe_create, the operator
+// entry points) are readable through airfe_last_error(NULL) on the calling thread.
+static int fail(airfe_ctx* c, int code) {
+  if (c) { strncpy(c->err, get_error(), sizeof(c->err) - 1); c->err[sizeof(c->err) - 1] = 0; }
+  return code;
+}
+
+// (Re)allocate the pinned + device frame staging.  On failure the context holds NO staging (pointers null, sizes zero), so that neither
+// the next call nor airfe_destroy touches freed memory.
+static bool grow_image_staging(airfe_ctx* c, size_t need) {
+  if (c->h_img) cudaFreeHost(c->h_img);
+  if (c->d_img) cudaFree(c->d_img);
+  c->h_img = nullptr; c->d_img = nullptr; c->h_img_bytes = c->d_img_bytes = 0;
+  if (cudaMallocHost(&c->h_img, need) != cudaSuccess) { c->h_img = nullptr; cudaGetLastError(); set_error("pinned staging allocation (%zu bytes) failed", need); return false; }
+  if (cudaMalloc(&c->d_img, need) != cudaSuccess) {
+    cudaGetLastError(); cudaFreeHost(c->h_img); c->h_img = nullptr; c->d_img = nullptr;
+    set_error("device staging allocation (%zu bytes) failed", need);
+    return false;
+  }
+  c->h_img_bytes = c->d_img_bytes = need;
+  return true;
+}
 
 static bool is_pinned(const void* p) {
   cudaPointerAttributes a;
@@ -36,6 +77,8 @@ static bool is_pinned(const void* p) {
 }
 
 extern "C" {
+
+const char* airfe_last_error(const airfe_ctx* ctx) { return ctx ? ctx->err : get_error(); }
 
 void* airfe_alloc_pinned(long long bytes) {
   void* p = nullptr;
@@ -103,6 +146,12 @@ int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out) {
     mc.image_height = cfg->image_height;
     c->sg.reset(new SuperGlue);
     if (!c->sg->init(mc, wdir, cfg->enable_superglue == 2)) return AIRFE_ERR_IO;
+    c->sg_use = c->sg.get();
+    if (mc.cap > 512) {
+      mc.cap = 512;
+      c->sg_small.reset(new SuperGlue);
+      if (!c->sg_small->init(mc, wdir, cfg->enable_superglue == 2)) return AIRFE_ERR_IO;
+    }
     if (cudaMallocHost(&c->h_sgidx, (size_t)2 * cfg->max_batch * 1024 * 4) != cudaSuccess || cudaMallocHost(&c->h_sgms, (size_t)2 * cfg->max_batch * 1024 * 4) != cudaSuccess) {
       set_error("superglue staging allocation failed");
       return AIRFE_ERR_CUDA;
@@ -126,6 +175,12 @@ int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out) {
     mc.image_height = cfg->image_height;
     c->lg.reset(new LightGlue);
     if (!c->lg->init(mc, wdir)) return AIRFE_ERR_IO;
+    c->lg_use = c->lg.get();
+    if (mc.cap > 512) {
+      mc.cap = 512;
+      c->lg_small.reset(new LightGlue);
+      if (!c->lg_small->init(mc, wdir)) return AIRFE_ERR_IO;
+    }
   }
   const int B = cfg->max_batch;
   if (cudaMallocHost(&c->h_feat, (size_t)2 * B * kKpCap * 259 * 4) != cudaSuccess || cudaMallocHost(&c->h_junc, (size_t)2 * B * kKpCap * 259 * 4) != cudaSuccess ||
@@ -145,6 +200,8 @@ void airfe_destroy(airfe_ctx* c) {
   c->pl.reset();
   c->lg.reset();
   c->sg.reset();
+  c->lg_small.reset();
+  c->sg_small.reset();
   if (c->h_sgidx) cudaFreeHost(c->h_sgidx);
   if (c->h_sgms) cudaFreeHost(c->h_sgms);
   if (c->d_mfeat) cudaFree(c->d_mfeat);
@@ -160,6 +217,19 @@ void airfe_destroy(airfe_ctx* c) {
   if (c->h_lines) cudaFreeHost(c->h_lines);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->d_img) cudaFree(c->d_img);
+  if (c->kf_feat) cudaFree(c->kf_feat);
+  delete[] c->kf_n;
+  if (c->h_rptr) cudaFreeHost(c->h_rptr);
+  if (c->d_rptr) cudaFree(c->d_rptr);
+  if (c->h_rn) cudaFreeHost(c->h_rn);
+  if (c->d_rn) cudaFree(c->d_rn);
+  if (c->d_rcount) cudaFree(c->d_rcount);
+  if (c->d_ridx) cudaFree(c->d_ridx);
+  if (c->d_rscore) cudaFree(c->d_rscore);
+  if (c->h_rcount) cudaFreeHost(c->h_rcount);
+  if (c->h_ridx) cudaFreeHost(c->h_ridx);
+  if (c->h_rscore) cudaFreeHost(c->h_rscore);
+  if (c->d_qfeat) cudaFree(c->d_qfeat);
   cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev_det) cudaEventDestroy(c->ev_det);
@@ -178,26 +248,24 @@ static Detector* pick(airfe_ctx* c, int net) {
 int airfe_detect_batch(airfe_ctx* c, int net, int batch, const uint8_t* gray, int w, int h, int stride, long long img_stride,
                        float* feat, int feat_cap, int* n_feat, double* lines, int line_cap, int* n_lines, float* junc, int junc_cap,
                        int* n_junc) {
-  if (!c || !gray || !feat || !n_feat) { set_error("null argument"); return AIRFE_ERR_INVALID; }
-  if (w <= 1 || h <= 1 || stride < w) { set_error("empty image"); return AIRFE_ERR_INVALID; }   // image.empty() -> false (plnet.cpp:247)
+  if (!c || !gray || !feat || !n_feat) { set_error("null argument"); return fail(c, AIRFE_ERR_INVALID); }
+  if (w <= 1 || h <= 1 || stride < w) { set_error("empty image"); return fail(c, AIRFE_ERR_INVALID); }   // image.empty() -> false (plnet.cpp:247)
   Detector* d = pick(c, net);
-  if (!d) return AIRFE_ERR_INVALID;
-  if (batch < 1 || batch > 2 * c->cfg.max_batch) { set_error("batch %d outside [1,%d]", batch, 2 * c->cfg.max_batch); return AIRFE_ERR_INVALID; }
-  if ((lines || junc) && net != AIRFE_NET_PLNET) { set_error("lines / junctions need the PLNet network"); return AIRFE_ERR_INVALID; }
-  if (junc && !lines) { set_error("junction detection needs line detection"); return AIRFE_ERR_INVALID; }
+  if (!d) return fail(c, AIRFE_ERR_INVALID);
+  if (batch < 1 || batch > 2 * c->cfg.max_batch) { set_error("batch %d outside [1,%d]", batch, 2 * c->cfg.max_batch); return fail(c, AIRFE_ERR_INVALID); }
+  if ((lines || junc) && net != AIRFE_NET_PLNET) { set_error("lines / junctions need the PLNet network"); return fail(c, AIRFE_ERR_INVALID); }
+  if (junc && !lines) { set_error("junction detection needs line detection"); return fail(c, AIRFE_ERR_INVALID); }
+  if ((lines && !n_lines) || (junc && !n_junc)) { set_error("n_lines / n_junc must be given with their buffers"); return fail(c, AIRFE_ERR_INVALID); }
   cudaSetDevice(c->device);
   const size_t one = (size_t)h * stride;
   const size_t need = one * batch;
   if (need > c->h_img_bytes) {
-    if (c->h_img) cudaFreeHost(c->h_img);
-    if (c->d_img) cudaFree(c->d_img);
-    if (cudaMallocHost(&c->h_img, need) != cudaSuccess || cudaMalloc(&c->d_img, need) != cudaSuccess) { set_error("staging allocation failed"); return AIRFE_ERR_CUDA; }
-    c->h_img_bytes = c->d_img_bytes = need;
+    if (!grow_image_staging(c, need)) return fail(c, AIRFE_ERR_CUDA);
   }
   for (int i = 0; i < batch; ++i) memcpy(c->h_img + one * i, gray + (size_t)img_stride * i, one);
   cudaStream_t st = c->stream;
-  if (cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return AIRFE_ERR_CUDA; }
-  if (!d->run(c->d_img, batch, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return AIRFE_ERR_CUDA;
+  if (cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return fail(c, AIRFE_ERR_CUDA); }
+  if (!d->run(c->d_img, batch, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return fail(c, AIRFE_ERR_CUDA);
   const DetectOutputs& o = d->out();
   const int B = 2 * c->cfg.max_batch;
   int* hc = c->h_counts;
@@ -208,7 +276,7 @@ int airfe_detect_batch(airfe_ctx* c, int net, int batch, const uint8_t* gray, in
   const int kmax = c->cfg.max_keypoints;
   for (int i = 0; i < batch; ++i)
     cudaMemcpyAsync(c->h_feat + (size_t)i * kKpCap * 259, o.feat + (size_t)i * kKpCap * 259, (size_t)kmax * 259 * 4, cudaMemcpyDeviceToHost, st);
-  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("detect failed: %s", cudaGetErrorString(cudaGetLastError())); return AIRFE_ERR_CUDA; }
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("detect failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(c, AIRFE_ERR_CUDA); }
   for (int i = 0; i < batch; ++i) {
     const int n = hc[i] < feat_cap ? hc[i] : feat_cap;
     n_feat[i] = n;
@@ -249,15 +317,15 @@ int airfe_detect(airfe_ctx* c, int net, const uint8_t* gray, int w, int h, int s
 static int fetch_matches(airfe_ctx* c, int pairs, int* idx0, int* idx1, float* score, int match_cap, int* n_match, const int* zero_mask,
                          int matcher = AIRFE_MATCHER_LIGHTGLUE) {
   const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
-  const int cap = sgm ? c->sg->cap() : c->lg->cap();
-  const int* d_count = sgm ? c->sg->out().m_count : c->lg->out().count;
-  const int* d_idx = sgm ? c->sg->out().m_idx : c->lg->out().idx;
-  const float* d_score = sgm ? c->sg->out().m_score : c->lg->out().score;
+  const int cap = sgm ? c->sg_use->cap() : c->lg_use->cap();
+  const int* d_count = sgm ? c->sg_use->out().m_count : c->lg_use->out().count;
+  const int* d_idx = sgm ? c->sg_use->out().m_idx : c->lg_use->out().idx;
+  const float* d_score = sgm ? c->sg_use->out().m_score : c->lg_use->out().score;
   cudaStream_t st = c->stream;
   cudaMemcpyAsync(c->h_mcount, d_count, 4 * pairs, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(c->h_midx, d_idx, (size_t)pairs * cap * 8, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(c->h_mscore, d_score, (size_t)pairs * cap * 4, cudaMemcpyDeviceToHost, st);
-  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("match failed: %s", cudaGetErrorString(cudaGetLastError())); return AIRFE_ERR_CUDA; }
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("match failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(c, AIRFE_ERR_CUDA); }
   for (int p = 0; p < pairs; ++p) {
     int n = c->h_mcount[p];
     if (zero_mask && zero_mask[p]) n = 0;      // features0.cols() < 1 || features1.cols() < 1 -> return 0 (point_matcher.cc:53-55)
@@ -287,15 +355,21 @@ int airfe_match_batch_prenormalized(airfe_ctx* c, int matcher, int pairs, const 
 
 int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1,
                       int feat_cap, int* idx0, int* idx1, float* score, int match_cap, int* n_match) {
-  if (!c || !feat0 || !feat1 || !n0 || !n1 || !idx0 || !idx1 || !score || !n_match) { set_error("null argument"); return AIRFE_ERR_INVALID; }
+  if (!c || !feat0 || !feat1 || !n0 || !n1 || !idx0 || !idx1 || !score || !n_match) { set_error("null argument"); return fail(c, AIRFE_ERR_INVALID); }
   const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
-  if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
-  if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return AIRFE_ERR_INVALID; }
+  if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return fail(c, AIRFE_ERR_INVALID); }
+  if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return fail(c, AIRFE_ERR_INVALID); }
   cudaSetDevice(c->device);
-  const int cap = sgm ? c->sg->cap() : c->lg->cap();
+  {
+    int nmax = 0;
+    for (int p = 0; p < pairs; ++p) { nmax = n0[p] > nmax ? n0[p] : nmax; nmax = n1[p] > nmax ? n1[p] : nmax; }
+    if (sgm) c->sg_use = (c->sg_small && nmax <= 512) ? c->sg_small.get() : c->sg.get();
+    else c->lg_use = (c->lg_small && nmax <= 512) ? c->lg_small.get() : c->lg.get();
+  }
+  const int cap = sgm ? c->sg_use->cap() : c->lg_use->cap();
   std::vector<int> zero(pairs, 0);
   for (int p = 0; p < pairs; ++p) {
-    if (n0[p] > cap || n1[p] > cap || n0[p] > feat_cap || n1[p] > feat_cap) { set_error("pair %d: %d/%d keypoints exceed capacity %d", p, n0[p], n1[p], cap); return AIRFE_ERR_CAPACITY; }
+    if (n0[p] > cap || n1[p] > cap || n0[p] > feat_cap || n1[p] > feat_cap) { set_error("pair %d: %d/%d keypoints exceed capacity %d", p, n0[p], n1[p], cap); return fail(c, AIRFE_ERR_CAPACITY); }
     zero[p] = (n0[p] < 1 || n1[p] < 1);
     c->h_mn[2 * p] = n0[p];
     c->h_mn[2 * p + 1] = n1[p];
@@ -308,29 +382,29 @@ int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, 
       cudaMemcpyAsync(c->d_mfeat + (size_t)s * kKpCap * 259, c->h_mfeat + (size_t)s * kKpCap * 259, (size_t)c->h_mn[s] * 259 * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(c->d_mn, c->h_mn, 8 * pairs, cudaMemcpyHostToDevice, st);
   const bool dense = getenv("AIRFE_DEBUG_DENSE") != nullptr;
-  if (sgm ? !c->sg->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm) : !c->lg->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm)) return AIRFE_ERR_CUDA;
+  if (sgm ? !c->sg_use->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm) : !c->lg_use->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm)) return fail(c, AIRFE_ERR_CUDA);
   return fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, zero.data(), matcher);
 }
 
 int airfe_superglue_batch(airfe_ctx* c, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1, int feat_cap,
                           int prenormalized, int* indices0, int* indices1, float* mscores0, float* mscores1, int out_cap) {
-  if (!c || !c->sg) { set_error("superglue not enabled in this context"); return AIRFE_ERR_INVALID; }
+  if (!c || !c->sg) { set_error("superglue not enabled in this context"); return fail(c, AIRFE_ERR_INVALID); }
   g_prenorm = prenormalized != 0;
   std::vector<int> i0((size_t)pairs * 1024), i1((size_t)pairs * 1024), nm(pairs);
   std::vector<float> sc((size_t)pairs * 1024);
   int rc = airfe_match_batch(c, AIRFE_MATCHER_SUPERGLUE, pairs, feat0, n0, feat1, n1, feat_cap, i0.data(), i1.data(), sc.data(), 1024, nm.data());
   g_prenorm = false;
-  if (rc != AIRFE_OK) return rc;
-  const SuperGlueOutputs& o = c->sg->out();
-  const int cap = c->sg->cap();
+  if (rc != AIRFE_OK) return fail(c, rc);
+  const SuperGlueOutputs& o = c->sg_use->out();
+  const int cap = c->sg_use->cap();
   const size_t PC = (size_t)pairs * cap;
   cudaMemcpyAsync(c->h_sgidx, o.idx0, PC * 4, cudaMemcpyDeviceToHost, c->stream);
   cudaMemcpyAsync(c->h_sgidx + PC, o.idx1, PC * 4, cudaMemcpyDeviceToHost, c->stream);
   cudaMemcpyAsync(c->h_sgms, o.ms0, PC * 4, cudaMemcpyDeviceToHost, c->stream);
   cudaMemcpyAsync(c->h_sgms + PC, o.ms1, PC * 4, cudaMemcpyDeviceToHost, c->stream);
-  if (cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("superglue readback failed"); return AIRFE_ERR_CUDA; }
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("superglue readback failed"); return fail(c, AIRFE_ERR_CUDA); }
   for (int p = 0; p < pairs; ++p) {
-    if (n0[p] > out_cap || n1[p] > out_cap) { set_error("output capacity %d too small", out_cap); return AIRFE_ERR_CAPACITY; }
+    if (n0[p] > out_cap || n1[p] > out_cap) { set_error("output capacity %d too small", out_cap); return fail(c, AIRFE_ERR_CAPACITY); }
     for (int k = 0; k < n0[p]; ++k) { indices0[(size_t)p * out_cap + k] = c->h_sgidx[(size_t)p * cap + k]; mscores0[(size_t)p * out_cap + k] = c->h_sgms[(size_t)p * cap + k]; }
     for (int k = 0; k < n1[p]; ++k) { indices1[(size_t)p * out_cap + k] = c->h_sgidx[PC + (size_t)p * cap + k]; mscores1[(size_t)p * out_cap + k] = c->h_sgms[PC + (size_t)p * cap + k]; }
   }
@@ -340,14 +414,14 @@ int airfe_superglue_batch(airfe_ctx* c, int pairs, const float* feat0, const int
 int airfe_stereo_device(airfe_ctx* c, int net, int matcher, int pairs, const void* d_images, int w, int h, int stride, long long img_stride,
                         int lines, int junctions) {
   Detector* d = pick(c, net);
-  if (!d) return AIRFE_ERR_INVALID;
+  if (!d) return fail(c, AIRFE_ERR_INVALID);
   const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
-  if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
-  if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return AIRFE_ERR_INVALID; }
+  if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return fail(c, AIRFE_ERR_INVALID); }
+  if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return fail(c, AIRFE_ERR_INVALID); }
   cudaSetDevice(c->device);
-  if (!d->run((const uint8_t*)d_images, 2 * pairs, w, h, stride, img_stride, lines != 0, junctions != 0, c->stream)) return AIRFE_ERR_CUDA;
+  if (!d->run((const uint8_t*)d_images, 2 * pairs, w, h, stride, img_stride, lines != 0, junctions != 0, c->stream)) return fail(c, AIRFE_ERR_CUDA);
   const DetectOutputs& o = d->out();
-  if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream)) return AIRFE_ERR_CUDA;
+  if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream)) return fail(c, AIRFE_ERR_CUDA);
   return AIRFE_OK;
 }
 
@@ -357,11 +431,27 @@ long long airfe_profile_stereo(airfe_ctx* c, int net, int matcher, int pairs, co
   profiler().begin();
   int rc = airfe_stereo_device(c, net, matcher, pairs, d_images, w, h, stride, img_stride, lines, junctions);
   profiler().finish();
-  if (rc != AIRFE_OK) return rc;
+  if (rc != AIRFE_OK) return fail(c, rc);
+  // FLOPs of the ops whose row counts live on the device were accumulated at slot capacity; scale them to the rows actually processed
+  Detector* d = pick(c, net);
+  const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
+  const int S = 2 * pairs, mcap = sgm ? c->sg->cap() : c->lg->cap();
+  std::vector<int> hn(S, 0), hu(S, 0);
+  cudaMemcpy(hn.data(), sgm ? c->sg->counts() : c->lg->counts(), 4 * S, cudaMemcpyDeviceToHost);
+  if (lines && d->n_unique()) cudaMemcpy(hu.data(), d->n_unique(), 4 * S, cudaMemcpyDeviceToHost);
+  double f_rows = 0, f_self = 0, f_cross = 0, f_sim = 0, f_lines = 0;
+  for (int s2 = 0; s2 < S; ++s2) {
+    const double n = hn[s2] < mcap ? hn[s2] : mcap, m = hn[s2 ^ 1] < mcap ? hn[s2 ^ 1] : mcap;
+    f_rows += n; f_self += n * n; f_cross += n * m; f_lines += hu[s2] < kLineCap ? hu[s2] : kLineCap;
+    if (!(s2 & 1)) f_sim += n * m;
+  }
+  f_rows /= (double)S * mcap; f_self /= (double)S * mcap * mcap; f_cross /= (double)S * mcap * mcap; f_sim /= (double)pairs * mcap * mcap;
+  f_lines /= (double)S * kLineCap;
+  const double factor[6] = {1.0, f_rows, f_self, f_cross, f_sim, f_lines};
   long long off = 0;
   for (auto& r : profiler().recs) {
     char line[256];
-    int n = snprintf(line, sizeof(line), "%s\t%.0f\t%.6f\n", r.name.c_str(), r.flops, r.ms);
+    int n = snprintf(line, sizeof(line), "%s\t%.0f\t%.6f\n", r.name.c_str(), r.flops * factor[r.kind >= 0 && r.kind < 6 ? r.kind : 0], r.ms);
     if (off + n >= cap) break;
     memcpy(out + off, line, n);
     off += n;
@@ -373,7 +463,7 @@ long long airfe_profile_stereo(airfe_ctx* c, int net, int matcher, int pairs, co
 int airfe_stereo_cost(airfe_ctx* c, int net, int matcher, int pairs, int lines, double* tc_flops, int* launches) {
   Detector* d = pick(c, net);
   const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
-  if (!d || (sgm ? !c->sg : !c->lg)) { set_error("networks not enabled"); return AIRFE_ERR_INVALID; }
+  if (!d || (sgm ? !c->sg : !c->lg)) { set_error("networks not enabled"); return fail(c, AIRFE_ERR_INVALID); }
   if (tc_flops) *tc_flops = d->tc_flops(2 * pairs, lines != 0) + (sgm ? c->sg->tc_flops(pairs) : c->lg->tc_flops(pairs));
   if (launches) *launches = d->launches(2 * pairs, lines != 0) + (sgm ? c->sg->launches(pairs) : c->lg->launches(pairs)) + 12;
   return AIRFE_OK;
@@ -383,21 +473,20 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
                                     int stride, long long img_stride, float* feat, int feat_cap, int* n_feat, double* lines, int line_cap,
                                     int* n_lines, float* junc, int junc_cap, int* n_junc, int* idx0, int* idx1, float* score, int match_cap,
                                     int* n_match) {
-  if (!c || !left || !right || !feat || !n_feat || !idx0 || !idx1 || !score || !n_match) { set_error("null argument"); return AIRFE_ERR_INVALID; }
-  if (w <= 1 || h <= 1 || stride < w) { set_error("empty image"); return AIRFE_ERR_INVALID; }
+  if (!c || !left || !right || !feat || !n_feat || !idx0 || !idx1 || !score || !n_match) { set_error("null argument"); return fail(c, AIRFE_ERR_INVALID); }
+  if (w <= 1 || h <= 1 || stride < w) { set_error("empty image"); return fail(c, AIRFE_ERR_INVALID); }
   Detector* d = pick(c, net);
-  if (!d) return AIRFE_ERR_INVALID;
+  if (!d) return fail(c, AIRFE_ERR_INVALID);
   const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
-  if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return AIRFE_ERR_INVALID; }
-  if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return AIRFE_ERR_INVALID; }
-  if ((lines || junc) && net != AIRFE_NET_PLNET) { set_error("lines / junctions need the PLNet network"); return AIRFE_ERR_INVALID; }
+  if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return fail(c, AIRFE_ERR_INVALID); }
+  if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return fail(c, AIRFE_ERR_INVALID); }
+  if ((lines || junc) && net != AIRFE_NET_PLNET) { set_error("lines / junctions need the PLNet network"); return fail(c, AIRFE_ERR_INVALID); }
+  if (junc && !lines) { set_error("junction detection needs line detection"); return fail(c, AIRFE_ERR_INVALID); }
+  if ((lines && !n_lines) || (junc && !n_junc)) { set_error("n_lines / n_junc must be given with their buffers"); return fail(c, AIRFE_ERR_INVALID); }
   cudaSetDevice(c->device);
   const size_t one = (size_t)h * stride, need = one * 2 * pairs;
   if (need > c->h_img_bytes) {
-    if (c->h_img) cudaFreeHost(c->h_img);
-    if (c->d_img) cudaFree(c->d_img);
-    if (cudaMallocHost(&c->h_img, need) != cudaSuccess || cudaMalloc(&c->d_img, need) != cudaSuccess) { set_error("staging allocation failed"); return AIRFE_ERR_CUDA; }
-    c->h_img_bytes = c->d_img_bytes = need;
+    if (!grow_image_staging(c, need)) return fail(c, AIRFE_ERR_CUDA);
   }
   cudaStream_t st = c->stream;
   if (is_pinned(left) && is_pinned(right)) {        // caller's frames are in pinned memory: DMA straight from them
@@ -412,7 +501,7 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
     }
     cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st);
   }
-  if (!d->run(c->d_img, 2 * pairs, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return AIRFE_ERR_CUDA;
+  if (!d->run(c->d_img, 2 * pairs, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return fail(c, AIRFE_ERR_CUDA);
   const DetectOutputs& o = d->out();
   // detector results go home on a second stream while the matcher runs on the first (13 MB of descriptors per 16 pairs)
   cudaStream_t cs = c->copy_stream;
@@ -433,12 +522,13 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
     for (int p = 0; p < pairs; ++p)
       cudaMemcpyAsync(junc + (size_t)p * junc_cap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)kJunc * 259 * 4, cudaMemcpyDeviceToHost, cs);
   cudaEventRecord(c->ev_copy, cs);
+  if (sgm) c->sg_use = c->sg.get(); else c->lg_use = c->lg.get();     // the detector's feature sets are bounded by max_keypoints = this instance's sizing
   if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, st) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, st)) {
     cudaStreamSynchronize(cs);
-    return AIRFE_ERR_CUDA;
+    return fail(c, AIRFE_ERR_CUDA);
   }
   // the detector results land while the matcher is still running: size the line / junction copies from the counts and queue them too
-  if (cudaEventSynchronize(c->ev_copy) != cudaSuccess) { set_error("detector readback failed: %s", cudaGetErrorString(cudaGetLastError())); return AIRFE_ERR_CUDA; }
+  if (cudaEventSynchronize(c->ev_copy) != cudaSuccess) { set_error("detector readback failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(c, AIRFE_ERR_CUDA); }
   for (int i = 0; i < S; ++i) {
     const int n = hc[i] < feat_cap ? hc[i] : feat_cap;
     n_feat[i] = n;
@@ -456,7 +546,7 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
         n_junc[p] = n;
         if (n && !junc_direct) cudaMemcpyAsync(c->h_junc + (size_t)p * kKpCap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)n * 259 * 4, cudaMemcpyDeviceToHost, cs);
       }
-    if (cudaStreamSynchronize(cs) != cudaSuccess) { set_error("line readback failed: %s", cudaGetErrorString(cudaGetLastError())); return AIRFE_ERR_CUDA; }
+    if (cudaStreamSynchronize(cs) != cudaSuccess) { set_error("line readback failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(c, AIRFE_ERR_CUDA); }
     const double ws = (double)((float)w / 512.f), hs = (double)((float)h / 512.f);
     for (int i = 0; i < S; ++i) {
       const float* l = c->h_lines + (size_t)i * kLineCap * 4;
@@ -470,41 +560,187 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
       for (int p = 0; p < pairs; ++p) memcpy(junc + (size_t)p * junc_cap * 259, c->h_junc + (size_t)p * kKpCap * 259, (size_t)n_junc[p] * 259 * 4);
   }
   int rc = fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, nullptr, matcher);   // synchronises the compute stream
-  if (rc != AIRFE_OK) return rc;
+  if (rc != AIRFE_OK) return fail(c, rc);
   for (int p = 0; p < pairs; ++p)
     if (hc[2 * p] < 1 || hc[2 * p + 1] < 1) n_match[p] = 0;
   return AIRFE_OK;
 }
 
+// ---- device-resident keyframe cache + batched candidate matching -----------------------------------------------------------------
+int airfe_kf_reserve(airfe_ctx* c, int n_keyframes, int feat_cap) {
+  if (!c || n_keyframes < 1 || feat_cap < 1 || feat_cap > kKpCap) { set_error("kf_reserve: bad arguments"); return fail(c, AIRFE_ERR_INVALID); }
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->kf_feat) cudaFree(c->kf_feat);
+  delete[] c->kf_n;
+  c->kf_feat = nullptr; c->kf_n = nullptr; c->kf_slots = c->kf_cap = 0;
+  const size_t bytes = (size_t)n_keyframes * feat_cap * 259 * 4;
+  if (cudaMalloc(&c->kf_feat, bytes) != cudaSuccess) { cudaGetLastError(); c->kf_feat = nullptr; set_error("keyframe cache allocation (%zu bytes) failed", bytes); return fail(c, AIRFE_ERR_CUDA); }
+  c->kf_n = new int[n_keyframes]();
+  c->kf_slots = n_keyframes; c->kf_cap = feat_cap;
+  return AIRFE_OK;
+}
+int airfe_kf_size(const airfe_ctx* c) { return c ? c->kf_slots : 0; }
+int airfe_kf_put(airfe_ctx* c, int slot, const float* feat, int n) {
+  if (!c || !c->kf_feat || slot < 0 || slot >= c->kf_slots || n < 0 || n > c->kf_cap || (!feat && n)) { set_error("kf_put: bad slot / count"); return fail(c, AIRFE_ERR_INVALID); }
+  cudaSetDevice(c->device);
+  // cudaMemcpyDefault: the source may be host (map load) or device memory (features that were just detected)
+  if (n && cudaMemcpyAsync(c->kf_feat + (size_t)slot * c->kf_cap * 259, feat, (size_t)n * 259 * 4, cudaMemcpyDefault, c->stream) != cudaSuccess) {
+    set_error("kf_put: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(c, AIRFE_ERR_CUDA);
+  }
+  if (!is_pinned(feat) && n) cudaStreamSynchronize(c->stream);   // pageable / device sources may be reused by the caller right away
+  c->kf_n[slot] = n;
+  return AIRFE_OK;
+}
+
+static bool grow_reloc_tables(airfe_ctx* c, int n_jobs, int cap) {
+  if (n_jobs <= c->rj_cap) return true;
+  cudaStreamSynchronize(c->stream);
+  if (c->h_rptr) cudaFreeHost(c->h_rptr);
+  if (c->d_rptr) cudaFree(c->d_rptr);
+  if (c->h_rn) cudaFreeHost(c->h_rn);
+  if (c->d_rn) cudaFree(c->d_rn);
+  if (c->d_rcount) cudaFree(c->d_rcount);
+  if (c->d_ridx) cudaFree(c->d_ridx);
+  if (c->d_rscore) cudaFree(c->d_rscore);
+  if (c->h_rcount) cudaFreeHost(c->h_rcount);
+  if (c->h_ridx) cudaFreeHost(c->h_ridx);
+  if (c->h_rscore) cudaFreeHost(c->h_rscore);
+  c->h_rptr = nullptr; c->d_rptr = nullptr; c->h_rn = nullptr; c->d_rn = nullptr; c->d_rcount = nullptr; c->d_ridx = nullptr; c->d_rscore = nullptr;
+  c->h_rcount = nullptr; c->h_ridx = nullptr; c->h_rscore = nullptr; c->rj_cap = 0;
+  const size_t J = (size_t)n_jobs;
+  if (cudaMallocHost(&c->h_rptr, 2 * J * sizeof(float*)) != cudaSuccess || cudaMalloc(&c->d_rptr, 2 * J * sizeof(float*)) != cudaSuccess ||
+      cudaMallocHost(&c->h_rn, 2 * J * 4) != cudaSuccess || cudaMalloc(&c->d_rn, 2 * J * 4) != cudaSuccess || cudaMalloc(&c->d_rcount, J * 4) != cudaSuccess ||
+      cudaMalloc(&c->d_ridx, J * cap * 8) != cudaSuccess || cudaMalloc(&c->d_rscore, J * cap * 4) != cudaSuccess || cudaMallocHost(&c->h_rcount, J * 4) != cudaSuccess ||
+      cudaMallocHost(&c->h_ridx, J * cap * 8) != cudaSuccess || cudaMallocHost(&c->h_rscore, J * cap * 4) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("reloc job tables (%d jobs) allocation failed", n_jobs);
+    return false;
+  }
+  c->rj_cap = n_jobs;
+  return true;
+}
+
+int airfe_reloc_match(airfe_ctx* c, int matcher, const float* query_feat, const int* query_n, int n_queries, int feat_cap, int n_jobs,
+                      const int* job_query, const int* job_kf, int* n_match, int* idx0, int* idx1, float* score, int match_cap) {
+  if (!c || !query_feat || !query_n || !job_query || !job_kf || !n_match || n_queries < 1 || n_jobs < 0) { set_error("null argument"); return fail(c, AIRFE_ERR_INVALID); }
+  if (idx0 && (!idx1 || !score || match_cap < 1)) { set_error("idx0 needs idx1, score and match_cap"); return fail(c, AIRFE_ERR_INVALID); }
+  if (!c->kf_feat) { set_error("no keyframe cache: call airfe_kf_reserve / airfe_kf_put first"); return fail(c, AIRFE_ERR_INVALID); }
+  const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
+  if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return fail(c, AIRFE_ERR_INVALID); }
+  if (n_jobs == 0) return AIRFE_OK;
+  cudaSetDevice(c->device);
+  const int cap = sgm ? c->sg->cap() : c->lg->cap();
+  for (int q = 0; q < n_queries; ++q)
+    if (query_n[q] < 0 || query_n[q] > cap || query_n[q] > feat_cap) { set_error("query %d: %d keypoints exceed capacity %d", q, query_n[q], cap < feat_cap ? cap : feat_cap); return fail(c, AIRFE_ERR_CAPACITY); }
+  if (!grow_reloc_tables(c, n_jobs, cap)) return fail(c, AIRFE_ERR_CUDA);
+  cudaStream_t st = c->stream;
+  // queries: used in place when they are already on the device (NCCL all-gather output), else staged once
+  cudaPointerAttributes pa;
+  bool on_device = cudaPointerGetAttributes(&pa, query_feat) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  const float* dq = query_feat;
+  if (!on_device) {
+    const size_t need = (size_t)n_queries * feat_cap * 259 * 4;
+    if (need > c->d_qfeat_bytes) {
+      cudaStreamSynchronize(st);
+      if (c->d_qfeat) cudaFree(c->d_qfeat);
+      c->d_qfeat = nullptr; c->d_qfeat_bytes = 0;
+      if (cudaMalloc(&c->d_qfeat, need) != cudaSuccess) { cudaGetLastError(); c->d_qfeat = nullptr; set_error("query staging allocation failed"); return fail(c, AIRFE_ERR_CUDA); }
+      c->d_qfeat_bytes = need;
+    }
+    for (int q = 0; q < n_queries; ++q)
+      if (query_n[q]) cudaMemcpyAsync(c->d_qfeat + (size_t)q * feat_cap * 259, query_feat + (size_t)q * feat_cap * 259, (size_t)query_n[q] * 259 * 4, cudaMemcpyHostToDevice, st);
+    if (!is_pinned(query_feat)) cudaStreamSynchronize(st);
+    dq = c->d_qfeat;
+  }
+  for (int j = 0; j < n_jobs; ++j) {
+    const int q = job_query[j], k = job_kf[j];
+    if (q < 0 || q >= n_queries || k < 0 || k >= c->kf_slots) { set_error("job %d: query %d / keyframe %d out of range", j, q, k); return fail(c, AIRFE_ERR_INVALID); }
+    if (c->kf_n[k] > cap) { set_error("keyframe %d: %d keypoints exceed capacity %d", k, c->kf_n[k], cap); return fail(c, AIRFE_ERR_CAPACITY); }
+    c->h_rptr[2 * j] = dq + (size_t)q * feat_cap * 259;
+    c->h_rptr[2 * j + 1] = c->kf_feat + (size_t)k * c->kf_cap * 259;
+    c->h_rn[2 * j] = query_n[q];
+    c->h_rn[2 * j + 1] = c->kf_n[k];
+  }
+  cudaMemcpyAsync(c->d_rptr, c->h_rptr, (size_t)2 * n_jobs * sizeof(float*), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(c->d_rn, c->h_rn, (size_t)2 * n_jobs * 4, cudaMemcpyHostToDevice, st);
+  const int B = c->cfg.max_batch;
+  for (int j0 = 0; j0 < n_jobs; j0 += B) {
+    const int P = n_jobs - j0 < B ? n_jobs - j0 : B;
+    if (sgm ? !c->sg->run(nullptr, c->d_rn + 2 * j0, 0, P, false, st, false, c->d_rptr + 2 * j0)
+            : !c->lg->run(nullptr, c->d_rn + 2 * j0, 0, P, false, st, false, c->d_rptr + 2 * j0))
+      return fail(c, AIRFE_ERR_CUDA);
+    const int* d_count = sgm ? c->sg->out().m_count : c->lg->out().count;
+    cudaMemcpyAsync(c->d_rcount + j0, d_count, (size_t)P * 4, cudaMemcpyDeviceToDevice, st);
+    if (idx0) {
+      cudaMemcpyAsync(c->d_ridx + (size_t)j0 * cap * 2, sgm ? c->sg->out().m_idx : c->lg->out().idx, (size_t)P * cap * 8, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(c->d_rscore + (size_t)j0 * cap, sgm ? c->sg->out().m_score : c->lg->out().score, (size_t)P * cap * 4, cudaMemcpyDeviceToDevice, st);
+    }
+  }
+  cudaMemcpyAsync(c->h_rcount, c->d_rcount, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, st);
+  if (idx0) {
+    cudaMemcpyAsync(c->h_ridx, c->d_ridx, (size_t)n_jobs * cap * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(c->h_rscore, c->d_rscore, (size_t)n_jobs * cap * 4, cudaMemcpyDeviceToHost, st);
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("reloc match failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(c, AIRFE_ERR_CUDA); }
+  for (int j = 0; j < n_jobs; ++j) {
+    int n = c->h_rcount[j];
+    if (c->h_rn[2 * j] < 1 || c->h_rn[2 * j + 1] < 1) n = 0;     // features0.cols() < 1 || features1.cols() < 1 -> 0 (point_matcher.cc:53-55)
+    if (idx0 && n > match_cap) n = match_cap;
+    n_match[j] = n;
+    if (idx0)
+      for (int k = 0; k < n; ++k) {
+        idx0[(size_t)j * match_cap + k] = c->h_ridx[((size_t)j * cap + k) * 2];
+        idx1[(size_t)j * match_cap + k] = c->h_ridx[((size_t)j * cap + k) * 2 + 1];
+        score[(size_t)j * match_cap + k] = c->h_rscore[(size_t)j * cap + k];
+      }
+  }
+  return AIRFE_OK;
+}
+
+void airfe_reloc_pick(int n_queries, int n_cand, const int* counts, int* best_cand, int* best_count) {
+  for (int q = 0; q < n_queries; ++q) {
+    int best = -1, bc = 0;                       // relocalization_matches starts empty: a candidate must have > 0 matches to win
+    for (int k = 0; k < n_cand; ++k) {
+      const int v = counts[(size_t)q * n_cand + k];
+      if (v > bc) { bc = v; best = k; }          // strictly more than every earlier candidate (map_user.cc:370)
+    }
+    if (best_cand) best_cand[q] = best;
+    if (best_count) best_count[q] = bc;
+  }
+}
+
 long long airfe_debug_read(airfe_ctx* c, int net, const char* name, int index, void* dst, long long dst_bytes) {
   if (net == 101) {   // SuperGlue tap: "sg_scores" = final [cap+1][cap+1] score matrix of pair `index` (needs AIRFE_DEBUG_DENSE=1)
-    if (!c->sg) { set_error("superglue not enabled"); return AIRFE_ERR_INVALID; }
-    const long long ld = c->sg->cap() + 1, nb = ld * ld * 4;
-    if (nb > dst_bytes) { set_error("tap needs %lld bytes", nb); return AIRFE_ERR_CAPACITY; }
+    if (!c->sg) { set_error("superglue not enabled"); return fail(c, AIRFE_ERR_INVALID); }
+    const long long ld = c->sg_use->cap() + 1, nb = ld * ld * 4;
+    if (nb > dst_bytes) { set_error("tap needs %lld bytes", nb); return fail(c, AIRFE_ERR_CAPACITY); }
     cudaStreamSynchronize(c->stream);
-    if (cudaMemcpy(dst, c->sg->out().dense + (size_t)index * ld * ld, (size_t)nb, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("debug read failed"); return AIRFE_ERR_CUDA; }
+    if (cudaMemcpy(dst, c->sg_use->out().dense + (size_t)index * ld * ld, (size_t)nb, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("debug read failed"); return fail(c, AIRFE_ERR_CUDA); }
     return nb;
   }
   if (net == 100) {   // LightGlue taps: "lg_scores" = dense log-assignment [cap][cap] of pair `index` (needs AIRFE_DEBUG_DENSE=1)
-    if (!c->lg) { set_error("lightglue not enabled"); return AIRFE_ERR_INVALID; }
-    const long long cap = c->lg->cap(), nb = cap * cap * 4;
-    if (nb > dst_bytes) { set_error("tap needs %lld bytes", nb); return AIRFE_ERR_CAPACITY; }
+    if (!c->lg) { set_error("lightglue not enabled"); return fail(c, AIRFE_ERR_INVALID); }
+    const long long cap = c->lg_use->cap(), nb = cap * cap * 4;
+    if (nb > dst_bytes) { set_error("tap needs %lld bytes", nb); return fail(c, AIRFE_ERR_CAPACITY); }
     cudaStreamSynchronize(c->stream);
-    const float* src = !strcmp(name, "lg_scores") ? c->lg->out().dense + (size_t)index * cap * cap : nullptr;
-    if (!src) { set_error("unknown tap %s", name); return AIRFE_ERR_INVALID; }
-    if (cudaMemcpy(dst, src, (size_t)nb, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("debug read failed"); return AIRFE_ERR_CUDA; }
+    const float* src = !strcmp(name, "lg_scores") ? c->lg_use->out().dense + (size_t)index * cap * cap : nullptr;
+    if (!src) { set_error("unknown tap %s", name); return fail(c, AIRFE_ERR_INVALID); }
+    if (cudaMemcpy(dst, src, (size_t)nb, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("debug read failed"); return fail(c, AIRFE_ERR_CUDA); }
     return nb;
   }
   Detector* d = pick(c, net);
-  if (!d) return AIRFE_ERR_INVALID;
+  if (!d) return fail(c, AIRFE_ERR_INVALID);
   auto it = d->taps.find(name);
-  if (it == d->taps.end()) { set_error("unknown tap %s", name); return AIRFE_ERR_INVALID; }
+  if (it == d->taps.end()) { set_error("unknown tap %s", name); return fail(c, AIRFE_ERR_INVALID); }
   const long long nb = (long long)it->second.second;
-  if (nb > dst_bytes) { set_error("tap %s needs %lld bytes", name, nb); return AIRFE_ERR_CAPACITY; }
+  if (nb > dst_bytes) { set_error("tap %s needs %lld bytes", name, nb); return fail(c, AIRFE_ERR_CAPACITY); }
   cudaStreamSynchronize(c->stream);
   if (cudaMemcpy(dst, (const uint8_t*)it->second.first + (size_t)index * nb, (size_t)nb, cudaMemcpyDeviceToHost) != cudaSuccess) {
     set_error("debug read failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return AIRFE_ERR_CUDA;
+    return fail(c, AIRFE_ERR_CUDA);
   }
   return nb;
 }

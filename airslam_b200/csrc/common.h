@@ -24,6 +24,12 @@ const char* get_error();
 
 struct TcGemmParams;
 
+// Per-device one-time state (cudaFuncSetAttribute opt-ins, SM counts): the function attribute and the SM count belong to a device, and a
+// process may hold contexts on several devices (airfe_create takes a device ordinal), so nothing here may be cached process-wide.
+constexpr int kMaxDevices = 64;
+inline int current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < kMaxDevices) ? d : 0; }
+int device_sm_count();   // multiprocessors of the CURRENT device (cached per device)
+
 // Launch with programmatic dependent launch (PDL) allowed: the kernel may become resident while its predecessor in the stream is
 // still draining (it called griddepcontrol.launch_dependents), runs its prologue (barrier init, TMEM allocation, tensor-map
 // prefetch, bias staging) and then blocks in griddepcontrol.wait until the predecessor's results are visible.  Every kernel

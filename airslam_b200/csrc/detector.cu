@@ -288,6 +288,7 @@ bool Detector::build_ops(int B) {
     if (!add_dense(&l, fc2_o_, fc34_, thinaux_o_, B, false, 8, 16)) return false;
     line_ops_[B] = std::move(l);
     OpList m;
+    m.dyn_kind = kDynLines;
     if (!add_dense(&m, feat496_.slice(0, 496), s1_fc0_, mlp_a_, B, true, -1, 0, n_unique_)) return false;
     if (!add_dense(&m, mlp_a_, s1_fc2_, mlp_b_, B, true, -1, 0, n_unique_)) return false;
     if (!add_dense(&m, mlp_b_, s1_fc4_, mlp_c_, B, false, -1, 0, n_unique_)) return false;

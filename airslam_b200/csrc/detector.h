@@ -45,6 +45,7 @@ class Detector {
   float* scores() { return scores_; }
   float* desc_raw() { return desc_raw_; }
   __half* x16() { return x16_; }
+  const int* n_unique() const { return n_unique_; }   // [B] unique junction pairs = rows of the stage-1 MLP
   struct Taps;  // stage outputs for stage-wise parity tests
   std::map<std::string, std::pair<void*, size_t>> taps;   // name -> (device ptr, bytes per image)
 

@@ -17,6 +17,9 @@ bool WeightFile::load(const std::string& path) {
   if (rd != (size_t)sz || sz < 16 || memcmp(blob_.data(), "AIRFEW01", 8) != 0) { set_error("bad weight file %s", path.c_str()); return false; }
   uint32_t count;
   memcpy(&count, blob_.data() + 8, 4);
+  const size_t size = blob_.size();
+  if ((size - 16) / 160 < (size_t)count) { set_error("weight file %s: entry table (%u entries) exceeds the file", path.c_str(), count); return false; }
+  static const size_t esz[3] = {4, 2, 4};   // f32, f16, i32
   for (uint32_t i = 0; i < count; ++i) {
     const uint8_t* e = blob_.data() + 16 + (size_t)160 * i;
     char name[121];
@@ -26,9 +29,17 @@ bool WeightFile::load(const std::string& path) {
     uint32_t dt, nd, dims[4];
     uint64_t off, nb;
     memcpy(&dt, e + 120, 4); memcpy(&nd, e + 124, 4); memcpy(dims, e + 128, 16); memcpy(&off, e + 144, 8); memcpy(&nb, e + 152, 8);
+    if (dt > 2 || nd > 4) { set_error("weight file %s: tensor %s has dtype %u / rank %u", path.c_str(), name, dt, nd); return false; }
     t.dtype = (int)dt; t.ndim = (int)nd;
-    for (int k = 0; k < 4; ++k) t.dims[k] = k < (int)nd ? (int)dims[k] : 1;
-    if (off + nb > blob_.size()) { set_error("weight file %s truncated", path.c_str()); return false; }
+    uint64_t numel = 1;
+    for (int k = 0; k < 4; ++k) {
+      t.dims[k] = k < (int)nd ? (int)dims[k] : 1;
+      if (k < (int)nd && (dims[k] == 0 || dims[k] > (1u << 28))) { set_error("weight file %s: tensor %s has a bad extent", path.c_str(), name); return false; }
+      numel *= (uint64_t)t.dims[k];
+      if (numel > ((uint64_t)1 << 40)) { set_error("weight file %s: tensor %s is too large", path.c_str(), name); return false; }
+    }
+    if (off > size || nb > size - off) { set_error("weight file %s truncated (tensor %s)", path.c_str(), name); return false; }   // no off + nb overflow
+    if (numel * esz[dt] != nb) { set_error("weight file %s: tensor %s: %llu elements do not fill %llu bytes", path.c_str(), name, (unsigned long long)numel, (unsigned long long)nb); return false; }
     t.data = blob_.data() + off;
     t.nbytes = nb;
     index_[name] = t;
@@ -116,7 +127,7 @@ bool pack_dense(const WeightFile& wf, const std::vector<PackSrc>& srcs, int c_in
 
 // ---- profiler ---------------------------------------------------------------------------------------------------------------
 Profiler& profiler() { static Profiler p; return p; }
-void Profiler::record(const std::string& name, double fl, cudaStream_t st, const std::function<bool(cudaStream_t)>& fn, bool* ok) {
+void Profiler::record(const std::string& name, double fl, cudaStream_t st, const std::function<bool(cudaStream_t)>& fn, bool* ok, int kind) {
   cudaEvent_t a, b;
   cudaEventCreate(&a);
   cudaEventCreate(&b);
@@ -124,7 +135,7 @@ void Profiler::record(const std::string& name, double fl, cudaStream_t st, const
   *ok = fn(st);
   cudaEventRecord(b, st);
   OpProfile r;
-  r.name = name; r.flops = fl;
+  r.name = name; r.flops = fl; r.kind = kind;
   recs.push_back(r);
   evs.push_back({a, b});
 }
@@ -140,14 +151,14 @@ void Profiler::finish() {
 }
 
 // ---- op construction -----------------------------------------------------------------------------------------------------
-bool add_gemm(OpList* ol, const TcGemmDesc& d, double flops) {
+bool add_gemm(OpList* ol, const TcGemmDesc& d, double flops, int kind) {
   TcGemmPlan plan;
   if (!tc_gemm_plan(d, &plan)) return false;
   ol->tc_flops += flops;
   ol->launches += 1;
   char nm[160];
   snprintf(nm, sizeof(nm), "tc_gemm attn M=%dx%dx%d K=%d N=%d%s", d.W, d.H, d.B, d.c_in_pad, d.n_valid, d.b_mn_major ? " (P.V)" : "");
-  ol->push(nm, flops, [plan](cudaStream_t st) { return tc_gemm_launch(plan, st); });
+  ol->push(nm, flops, [plan](cudaStream_t st) { return tc_gemm_launch(plan, st); }, kind);
   return true;
 }
 
@@ -188,7 +199,7 @@ bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int b
   ol->launches += 1;
   char nm[160];
   snprintf(nm, sizeof(nm), "tc_gemm %s %d->%d @%dx%dx%d", w.taps == 9 ? "conv3x3" : (in.H == 1 ? "linear" : "conv1x1"), w.c_in, n_valid, in.W, in.H, batch);
-  ol->push(nm, fl, [plan](cudaStream_t st) { return tc_gemm_launch(plan, st); });
+  ol->push(nm, fl, [plan](cudaStream_t st) { return tc_gemm_launch(plan, st); }, dyn_rows ? ol->dyn_kind : kDynNone);
   return true;
 }
 

@@ -70,9 +70,15 @@ struct Act {
 };
 
 using Op = std::function<bool(cudaStream_t)>;
+// How an op's algorithmic work depends on the device-side counts (keypoints per slot, verified lines per image): the op lists are built for
+// the CAPACITY of a slot (cap rows), but rows beyond the counts are skipped on the device, so roofline accounting must scale the FLOPs to the
+// rows actually processed (airfe_profile_stereo reads the counts back once and applies the factor).
+enum DynKind { kDynNone = 0, kDynRows = 1 /* ~ sum n_s */, kDynAttSelf = 2 /* ~ sum n_s^2 */, kDynAttCross = 3 /* ~ sum n_s n_(s^1) */,
+               kDynSim = 4 /* ~ sum n_2p n_2p+1 */, kDynLines = 5 /* ~ sum unique lines */ };
 struct OpProfile {            // filled when profiling is on (airfe_profile_begin): one record per executed op
   std::string name;
-  double flops = 0;           // algorithmic tensor-core FLOPs (0 for non-GEMM ops)
+  double flops = 0;           // algorithmic tensor-core FLOPs at slot capacity (0 for non-GEMM ops)
+  int kind = kDynNone;
   float ms = 0;
 };
 struct Profiler {
@@ -80,7 +86,7 @@ struct Profiler {
   std::vector<OpProfile> recs;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs;
   void begin() { on = true; recs.clear(); }
-  void record(const std::string& name, double flops, cudaStream_t st, const std::function<bool(cudaStream_t)>& fn, bool* ok);
+  void record(const std::string& name, double flops, cudaStream_t st, const std::function<bool(cudaStream_t)>& fn, bool* ok, int kind = kDynNone);
   void finish();              // synchronises and converts events to milliseconds
 };
 Profiler& profiler();
@@ -89,15 +95,17 @@ struct OpList {
   std::vector<Op> ops;
   std::vector<std::string> names;   // parallel to ops (tensor-core ops carry their shape in the name)
   std::vector<double> flops;        // parallel to ops
-  double tc_flops = 0;   // algorithmic FLOPs of the tensor-core ops in this list
+  std::vector<int> kinds;           // parallel to ops (DynKind)
+  double tc_flops = 0;   // algorithmic FLOPs of the tensor-core ops in this list (at slot capacity)
   int launches = 0;
-  void push(const std::string& name, double fl, Op op) { ops.push_back(std::move(op)); names.push_back(name); flops.push_back(fl); }
+  int dyn_kind = kDynRows;          // what a dyn_rows GEMM of this list scales with (the detector's stage-1 MLP list sets kDynLines)
+  void push(const std::string& name, double fl, Op op, int kind = kDynNone) { ops.push_back(std::move(op)); names.push_back(name); flops.push_back(fl); kinds.push_back(kind); }
   bool run(cudaStream_t st) const {
     Profiler& pr = profiler();
     for (size_t i = 0; i < ops.size(); ++i) {
       if (pr.on) {
         bool ok = true;
-        pr.record(i < names.size() ? names[i] : "op", i < flops.size() ? flops[i] : 0.0, st, ops[i], &ok);
+        pr.record(i < names.size() ? names[i] : "op", i < flops.size() ? flops[i] : 0.0, st, ops[i], &ok, i < kinds.size() ? kinds[i] : 0);
         if (!ok) return false;
       } else if (!ops[i](st)) {
         return false;
@@ -155,6 +163,6 @@ bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, con
                    const float* ln_b, const int* n, int slots, int cap);
 bool ffn_fused_enabled();
 // Append a raw tcgen05 GEMM described by `d` (attention products).
-bool add_gemm(OpList* ol, const TcGemmDesc& d, double flops);
+bool add_gemm(OpList* ol, const TcGemmDesc& d, double flops, int kind = kDynNone);
 
 }  // namespace airfe

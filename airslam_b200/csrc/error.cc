@@ -10,6 +10,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+int device_sm_count() {
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
+  }
+  return n[dev];
+}
 bool pdl_enabled() {
   static const bool on = getenv("AIRFE_NO_PDL") == nullptr;
   return on;

@@ -19,14 +19,16 @@ __device__ __forceinline__ float warp_max_(float v) {
 
 // ---- K13: unpack 259xN host features -> normalised keypoints, fp32 state x, fp16 operand copy, rotary table ---------------
 // NormalizeKeypoints (src/point_matcher.cc:39-48): (x - width/2) * L_inv with integer width/2; L_inv = float(1.0/max(w,h)*scale).
-__global__ void lg_prepare_kernel(const float* __restrict__ feat, const int* __restrict__ n, int cap, int feat_cap, int width, int height,
+// `feat_ptrs` (optional): per-slot base pointers instead of the dense [slot][feat_cap][259] array -- relocalization jobs pair a query
+// with a keyframe of the device-resident cache without copying either (airfe_reloc_match).
+__global__ void lg_prepare_kernel(const float* __restrict__ feat, const float* const* __restrict__ feat_ptrs, const int* __restrict__ n, int cap, int feat_cap, int width, int height,
                                   float l_inv, const __half* __restrict__ wr /*[32][2]*/, float* __restrict__ x, __half* __restrict__ cat16,
                                   float* __restrict__ rot /*[slots][cap][64] cos | sin interleaved as (cos,sin) per freq*/) {
   const int s = blockIdx.y;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= n[s]) return;
-  const float* f = feat + ((long long)s * feat_cap + r) * 259;
+  const float* f = feat_ptrs ? feat_ptrs[s] + (long long)r * 259 : feat + ((long long)s * feat_cap + r) * 259;
   const float kx = __fmul_rn(__fsub_rn(f[1], (float)(width / 2)), l_inv);
   const float ky = __fmul_rn(__fsub_rn(f[2], (float)(height / 2)), l_inv);
   const long long row = (long long)s * cap + r;
@@ -290,9 +292,9 @@ __global__ void __launch_bounds__(1024) lg_filter_kernel(const int* __restrict__
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------------------------------
-void launch_lg_prepare(const float* feat, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, const __half* wr,
+void launch_lg_prepare(const float* feat, const float* const* feat_ptrs, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, const __half* wr,
                        float* x, __half* cat16, float* rot, cudaStream_t st) {
-  lg_prepare_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(feat, n, cap, feat_cap, width, height, l_inv, wr, x, cat16, rot);
+  lg_prepare_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(feat, feat_ptrs, n, cap, feat_cap, width, height, l_inv, wr, x, cat16, rot);
 }
 void launch_lg_rotary(const float* qkv, const float* rot, const int* n, int slots, int cap, __half* q16, __half* k16, __half* v16, cudaStream_t st) {
   lg_rotary_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(qkv, rot, n, cap, q16, k16, v16, 0.35355339059327379f /* 64^-1/4 */);
@@ -323,13 +325,13 @@ void launch_lg_assignment(const float* sim, const float* x, const __half* wm, fl
 namespace airfe {
 
 // kenc input rows [x', y', score, 0...] (fp16, K padded to 64) and residual stream x = descriptors (fp32)
-__global__ void sg_prepare_kernel(const float* __restrict__ feat, const int* __restrict__ n, int cap, int feat_cap, int width, int height,
+__global__ void sg_prepare_kernel(const float* __restrict__ feat, const float* const* __restrict__ feat_ptrs, const int* __restrict__ n, int cap, int feat_cap, int width, int height,
                                   float l_inv, float* __restrict__ x, __half* __restrict__ kin16) {
   const int s = blockIdx.y;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= n[s]) return;
-  const float* f = feat + ((long long)s * feat_cap + r) * 259;
+  const float* f = feat_ptrs ? feat_ptrs[s] + (long long)r * 259 : feat + ((long long)s * feat_cap + r) * 259;
   const long long row = (long long)s * cap + r;
 #pragma unroll
   for (int e = 0; e < 8; ++e) x[row * 256 + lane * 8 + e] = f[3 + lane * 8 + e];
@@ -339,9 +341,9 @@ __global__ void sg_prepare_kernel(const float* __restrict__ feat, const int* __r
   *reinterpret_cast<__half2*>(kin16 + row * 64 + lane * 2) = o;
 }
 
-void launch_sg_prepare(const float* feat, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, float* x,
+void launch_sg_prepare(const float* feat, const float* const* feat_ptrs, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, float* x,
                        __half* kin16, cudaStream_t st) {
-  sg_prepare_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(feat, n, cap, feat_cap, width, height, l_inv, x, kin16);
+  sg_prepare_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(feat, feat_ptrs, n, cap, feat_cap, width, height, l_inv, x, kin16);
 }
 
 // Z = [[S, bin],[bin, bin]] with leading dimension ld = cap + 1; u = v = 0

@@ -4,7 +4,7 @@
 
 namespace airfe {
 
-void launch_lg_prepare(const float* feat, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, const __half* wr,
+void launch_lg_prepare(const float* feat, const float* const* feat_ptrs /* optional per-slot bases */, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, const __half* wr,
                        float* x, __half* cat16, float* rot, cudaStream_t st);
 void launch_lg_rotary(const float* qkv, const float* rot, const int* n, int slots, int cap, __half* q16, __half* k16, __half* v16, cudaStream_t st);
 void launch_softmax_rows(const float* S, __half* P, const int* n, int slots, int cap, int col_xor, cudaStream_t st);
@@ -17,7 +17,7 @@ void launch_lg_assignment(const float* sim, const float* x, const __half* wm, fl
 
 namespace airfe {
 // ---- SuperGlue (G5) ------------------------------------------------------------------------------------------------------------
-void launch_sg_prepare(const float* feat, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, float* x,
+void launch_sg_prepare(const float* feat, const float* const* feat_ptrs, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, float* x,
                        __half* kin16, cudaStream_t st);
 // couplings Z [pair][cap+1][cap+1] from sim (already divided by 16) + bin score; 100 log-Sinkhorn iterations; decode
 void launch_sg_sinkhorn_decode(const float* sim, const int* n, int pairs, int cap, float bin_score, int iters, float* Z, float* u, float* v,

@@ -115,7 +115,7 @@ bool LightGlue::build_ops(int P) {
     d.bw = kb; d.k_total = 64; d.n_rows = cap; d.bw_sn = 256; d.b_heads = 4; d.bw_shead = 64; d.b_batches = S; d.bw_sbatch = (long long)cap * 256;
     d.b_batch_xor = xr; d.taps = 1; d.c_in_pad = 64; d.block_n = 128; d.out_f32 = 1; d.out = S_;
     d.out_sb = 4ll * cap * cap; d.out_sy = (long long)cap * cap; d.out_sx = cap; d.n_valid = cap; d.tw = 128; d.th = 1; d.tb = 1; d.dyn_w = n;
-    if (!add_gemm(&ol, d, 2.0 * S * 4 * (double)cap * cap * 64)) return false;
+    if (!add_gemm(&ol, d, 2.0 * S * 4 * (double)cap * cap * 64, xr ? kDynAttCross : kDynAttSelf)) return false;
     {
       const float* Sp = S_; __half* Pp = P_;
       ol.push("softmax_rows", 0, [=](cudaStream_t st) { launch_softmax_rows(Sp, Pp, n, S, cap, xr, st); return true; });
@@ -126,7 +126,7 @@ bool LightGlue::build_ops(int P) {
     e.bw = vb; e.k_total = cap; e.n_rows = 64; e.bw_sn = 256; e.b_heads = 4; e.bw_shead = 64; e.b_batches = S; e.bw_sbatch = (long long)cap * 256;
     e.b_batch_xor = xr; e.b_mn_major = 1; e.taps = 1; e.c_in_pad = cap; e.block_n = 64; e.out_f32 = 0; e.out = ctx16_;
     e.out_sb = (long long)cap * 256; e.out_sy = 64; e.out_sx = 256; e.n_valid = 64; e.tw = 128; e.th = 1; e.tb = 1; e.dyn_w = n;
-    return add_gemm(&ol, e, 2.0 * S * 4 * (double)cap * cap * 64);
+    return add_gemm(&ol, e, 2.0 * S * 4 * (double)cap * cap * 64, xr ? kDynAttCross : kDynAttSelf);
   };
   auto ffn = [&](const DenseW& w_out, const DenseW& w0, const DenseW& w3, const float* g, const float* b) -> bool {
     if (ffn_fused_enabled()) return add_fused_ffn(&ol, ctx16_, cat16_, x_, w_out, w0, w3, g, b, n, S, cap);
@@ -171,13 +171,13 @@ bool LightGlue::build_ops(int P) {
     d.bw = md16_ + (size_t)cap * 256; d.k_total = 256; d.n_rows = cap; d.bw_sn = 256; d.b_batches = P > 1 ? P : 0; d.bw_sbatch = 2ll * cap * 256;
     d.taps = 1; d.c_in_pad = 256; d.block_n = 128; d.out_f32 = 1; d.out = sim_; d.out_sb = (long long)cap * cap; d.out_sy = 0; d.out_sx = cap;
     d.n_valid = cap; d.tw = 128; d.th = 1; d.tb = 1; d.dyn_w = n; d.dyn_w_stride = 2;
-    if (!add_gemm(&ol, d, 2.0 * P * (double)cap * cap * 256)) return false;
+    if (!add_gemm(&ol, d, 2.0 * P * (double)cap * cap * 256, kDynSim)) return false;
   }
   ops_[P] = std::move(ol);
   return true;
 }
 
-bool LightGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bool want_dense, cudaStream_t st, bool prenorm) {
+bool LightGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bool want_dense, cudaStream_t st, bool prenorm, const float* const* d_feat_ptrs) {
   if (P < 1 || P > cfg_.max_pairs) { set_error("pairs %d outside [1,%d]", P, cfg_.max_pairs); return false; }
   if (!build_ops(P)) return false;
   const int S = 2 * P, cap = cfg_.cap;
@@ -185,7 +185,7 @@ bool LightGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bo
   // float L_inv = 1.0 / std::max(width, height) * scale;  scale = 0.5 for LightGlue (src/point_matcher.cc:43,58)
   const float l_inv = (float)(1.0 / (double)(cfg_.image_width > cfg_.image_height ? cfg_.image_width : cfg_.image_height) * (double)0.5f);
   // prenormalised input: (x - 0) * 1 reproduces the value bit for bit
-  timed("lg_prepare", st, [&] { launch_lg_prepare(d_feat, n_, S, cap, feat_cap, prenorm ? 0 : cfg_.image_width, prenorm ? 0 : cfg_.image_height, prenorm ? 1.f : l_inv, wr_, x_, cat16_, rot_, st); });
+  timed("lg_prepare", st, [&] { launch_lg_prepare(d_feat, d_feat_ptrs, n_, S, cap, feat_cap, prenorm ? 0 : cfg_.image_width, prenorm ? 0 : cfg_.image_height, prenorm ? 1.f : l_inv, wr_, x_, cat16_, rot_, st); });
   if (!ops_[P].run(st)) return false;
   timed("lg_assignment+filter", st, [&] {
     launch_lg_assignment(sim_, x_, wm_, bm_, n_, P, cap, logsig_, lse_, row_arg_, row_val_, col_arg_, 0.1f, out_.idx, out_.score, out_.count,

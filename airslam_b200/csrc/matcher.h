@@ -23,12 +23,15 @@ class LightGlue {
   bool init(const MatcherConfig& cfg, const std::string& weights_dir);
   // feat: device [2*pairs][feat_cap][259] (slot = 2*pair + side), n: device [2*pairs].  Asynchronous on st.
   // prenormalised: keypoints in rows 1-2 were already passed through PointMatcher::NormalizeKeypoints by the caller
-  bool run(const float* d_feat, const int* d_n, int feat_cap, int pairs, bool want_dense, cudaStream_t st, bool prenormalised = false);
+  // d_feat_ptrs (optional, device array of 2*pairs pointers): slot s reads its [n][259] rows from d_feat_ptrs[s] instead of d_feat
+  bool run(const float* d_feat, const int* d_n, int feat_cap, int pairs, bool want_dense, cudaStream_t st, bool prenormalised = false,
+           const float* const* d_feat_ptrs = nullptr);
   const MatchOutputs& out() const { return out_; }
   int cap() const { return cfg_.cap; }
   double tc_flops(int pairs);
   int launches(int pairs);
   float* x_state() { return x_; }
+  const int* counts() const { return n_; }   // [2*pairs] keypoints per slot of the last run (device)
 
  private:
   bool build_ops(int pairs);
@@ -65,11 +68,13 @@ struct SuperGlueOutputs {
 class SuperGlue {
  public:
   bool init(const MatcherConfig& cfg, const std::string& weights_dir, bool outdoor);
-  bool run(const float* d_feat, const int* d_n, int feat_cap, int pairs, bool want_dense, cudaStream_t st, bool prenormalised = false);
+  bool run(const float* d_feat, const int* d_n, int feat_cap, int pairs, bool want_dense, cudaStream_t st, bool prenormalised = false,
+           const float* const* d_feat_ptrs = nullptr);
   const SuperGlueOutputs& out() const { return out_; }
   int cap() const { return cfg_.cap; }
   double tc_flops(int pairs) { return build_ops(pairs) ? ops_[pairs].tc_flops : 0.0; }
   int launches(int pairs) { return build_ops(pairs) ? ops_[pairs].launches + 210 : 0; }
+  const int* counts() const { return n_; }
 
  private:
   bool build_ops(int pairs);

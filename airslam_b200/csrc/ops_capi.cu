@@ -8,8 +8,6 @@ using namespace airfe;
 
 extern "C" {
 
-const char* airfe_last_error(void) { return get_error(); }
-
 int airfe_op_tc_gemm(const void* a, int a_C, int W, int H, int B, long long a_sx, long long a_sy, long long a_sb,
                      const void* bw, int k_total, int n_rows, long long bw_sn, long long bw_sbatch, int b_batches, int b_mn_major,
                      int taps, int c_in_pad, int block_n, const float* bias, int relu, int out_f32,

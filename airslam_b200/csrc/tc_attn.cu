@@ -31,18 +31,19 @@ bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __h
   char nm[96];
   snprintf(nm, sizeof(nm), "tc_attn fused %s slots=%d cap=%d", slot_xor ? "cross" : "self", slots, cap);
   ol->push(nm, fl, [p, slots](cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!attr_set[dev]) {
       if (cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes) != cudaSuccess) {
         set_error("cudaFuncSetAttribute(tc_attn_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
         return false;
       }
-      attr_set = true;
+      attr_set[dev] = true;
     }
     cudaError_t e = launch_pdl(tc_attn_kernel, slots * 4, kAttnThreads, kAttnSmemBytes, st, p);
     if (e != cudaSuccess) { set_error("tc_attn launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
-  });
+  }, slot_xor ? kDynAttCross : kDynAttSelf);
   return true;
 }
 

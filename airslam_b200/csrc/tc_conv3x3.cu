@@ -12,16 +12,7 @@ struct ConvPlan {
   int grid = 0, smem_bytes = 0;
 };
 
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int sm_count() { return device_sm_count(); }
 
 static long long* g_conv_trace = nullptr;
 void conv3x3_set_trace(long long* dev_buf) { g_conv_trace = dev_buf; }
@@ -44,18 +35,19 @@ static ConvKernel conv_kernel_for(const ConvParams& p) {
 }
 
 static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[9] = {};
+  static bool attr_set[kMaxDevices][9] = {};
+  const int dev = current_device();
   const int key = plan.p.img1 ? 8 : ((plan.p.kw == 32 ? 4 : 0) | (plan.p.strips == 2 ? 2 : 0) | (plan.p.b_resident ? 1 : 0));
   const int threads = plan.p.img1 ? kConvThreadsFused : kConvThreads;
   ConvKernel kern = conv_kernel_for(plan.p);
-  if (!attr_set[key]) {
+  if (!attr_set[dev][key]) {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, kern);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(tc_conv3x3_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
       return false;
     }
-    attr_set[key] = true;
+    attr_set[dev][key] = true;
   }
   cudaError_t e;
   static const bool trace_fused_only = getenv("AIRFE_TRACE_FUSED") != nullptr;   // authoring aid: stamp only the conv1a-fused launch of a detector run

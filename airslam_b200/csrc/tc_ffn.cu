@@ -13,16 +13,7 @@ bool ffn_fused_enabled() {
   return v == 1;
 }
 
-static int ffn_sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int ffn_sm_count() { return device_sm_count(); }
 
 bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, const DenseW& w_out, const DenseW& w0, const DenseW& w3, const float* ln_g,
                    const float* ln_b, const int* n, int slots, int cap) {
@@ -54,18 +45,19 @@ bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, con
   ol->tc_flops += fl;
   ol->launches += 1;
   ol->push("tc_ffn fused block (out_proj+ffn0+LN+GELU+ffn3+residual)", fl, [p, grid](cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!attr_set[dev]) {
       if (cudaFuncSetAttribute(tc_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmemBytes) != cudaSuccess) {
         set_error("cudaFuncSetAttribute(tc_ffn_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
         return false;
       }
-      attr_set = true;
+      attr_set[dev] = true;
     }
     cudaError_t e = launch_pdl(tc_ffn_kernel, grid, kFfnThreads, kFfnSmemBytes, st, p);
     if (e != cudaSuccess) { set_error("tc_ffn launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
-  });
+  }, kDynRows);
   return true;
 }
 

