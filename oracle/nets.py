@@ -24,6 +24,19 @@ def _r(x, emul):
     return x.to(torch.float16).to(torch.float32) if emul else x
 
 
+def _attend(scores, v_of, emul):
+    """softmax(scores) . V for one attention, `v_of(p)` = the P.V product for a probability operand p (already fp16-rounded when emul).
+    emul == "fused" models WHERE the fused attention kernel (csrc/tc_attn.cuh) rounds: it hands fp16(exp(s - max)) to the tensor core and
+    applies 1/sum to the fp32 product, whereas plain emul (and a framework executing the graph node by node) rounds the NORMALISED
+    probabilities.  Both are fp16-operand realisations with the same relative rounding (2^-11), but the rounding errors are uncorrelated,
+    and 18 stacked attentions amplify that into ~1e-2 on the match probability of ambiguous keypoints -- the same class of drift as
+    fp32 vs emul (tools/experiments/r02_attention_rounding_drift.py has the numbers)."""
+    if emul == "fused":
+        e = torch.exp(scores - scores.amax(dim=-1, keepdim=True))
+        return v_of(_r(e, True)) / e.sum(dim=-1, keepdim=True)
+    return v_of(_r(torch.softmax(scores, dim=-1), emul))
+
+
 def _t(a):
     return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
 
@@ -337,8 +350,7 @@ def lightglue_forward(kpts0, kpts1, desc0, desc1, weights, emul=False, keep=None
                 q, k, v = qkv[..., 0].permute(1, 0, 2), qkv[..., 1].permute(1, 0, 2), qkv[..., 2].permute(1, 0, 2)
                 q = q * c + _rot_half(q) * s
                 k = k * c + _rot_half(k) * s
-                att = torch.softmax(mm(q * sc, (k * sc).transpose(-1, -2)), dim=-1)
-                ctx = mm(att, v).permute(1, 0, 2).reshape(-1, 256)
+                ctx = _attend(mm(q * sc, (k * sc).transpose(-1, -2)), lambda pr, v=v: torch.matmul(pr, _r(v, emul)), emul).permute(1, 0, 2).reshape(-1, 256)
                 msg = lin(ctx, p + "out_proj")
                 new.append(ffn(x, msg, p))
             x0, x1 = new
@@ -347,8 +359,8 @@ def lightglue_forward(kpts0, kpts1, desc0, desc1, weights, emul=False, keep=None
             v0, v1 = heads(lin(x0, p + "to_v")), heads(lin(x1, p + "to_v"))
             s01 = mm(qk0 * sc, (qk1 * sc).transpose(-1, -2))                    # [4,N0,N1]
             s10 = mm(qk1 * sc, (qk0 * sc).transpose(-1, -2))
-            m0 = mm(torch.softmax(s01, dim=-1), v1).permute(1, 0, 2).reshape(-1, 256)
-            m1 = mm(torch.softmax(s10, dim=-1), v0).permute(1, 0, 2).reshape(-1, 256)
+            m0 = _attend(s01, lambda pr: torch.matmul(pr, _r(v1, emul)), emul).permute(1, 0, 2).reshape(-1, 256)
+            m1 = _attend(s10, lambda pr: torch.matmul(pr, _r(v0, emul)), emul).permute(1, 0, 2).reshape(-1, 256)
             m0, m1 = lin(m0, p + "to_out"), lin(m1, p + "to_out")
             x0, x1 = ffn(x0, m0, p), ffn(x1, m1, p)
             if keep is not None:
@@ -406,8 +418,7 @@ def superglue_forward(kpts0, scores0, desc0, kpts1, scores1, desc1, weights, emu
             n, m = q.shape[1], k.shape[1]
             q, k, v = q.view(64, 4, n), k.view(64, 4, m), v.view(64, 4, m)     # channel c -> (d=c//4, h=c%4)
             sc = torch.einsum("dhn,dhm->hnm", _r(q, emul), _r(k, emul)) / 8.0
-            pr = torch.softmax(sc, dim=-1)
-            o = torch.einsum("hnm,dhm->dhn", _r(pr, emul), _r(v, emul)).reshape(256, n)
+            o = _attend(sc, lambda pr: torch.einsum("hnm,dhm->hnd", pr, _r(v, emul)), emul).permute(2, 0, 1).reshape(256, n)
             return c1(o, p + "merge")
 
         for l in range(18):
