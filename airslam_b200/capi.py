@@ -110,6 +110,12 @@ def _declare_match(L):
     L.airfe_profile_stereo.restype = i64
     L.airfe_stereo_cost.argtypes = [vp, i32, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(i32)]
     L.airfe_stereo_cost.restype = i32
+    L.airfe_set_rectify_maps.argtypes = [vp, i32, vp, vp, i32, i32]
+    L.airfe_set_rectify_maps.restype = i32
+    L.airfe_set_rectify.argtypes = [vp, i32]
+    L.airfe_set_rectify.restype = i32
+    L.airfe_undistort.argtypes = [vp, i32, vp, i32, i32, i32, vp, i32]
+    L.airfe_undistort.restype = i32
     L.airfe_kf_reserve.argtypes = [vp, i32, i32]
     L.airfe_kf_reserve.restype = i32
     L.airfe_kf_put.argtypes = [vp, i32, vp, i32]
@@ -268,6 +274,23 @@ class Context:
         for line in buf.value.decode().splitlines():
             nm, fl, ms = line.split("\t")
             out.append((nm, float(fl), float(ms)))
+        return out
+
+    # ---- rectification (Camera::UndistortImage) fused into the first kernel ----
+    def set_rectify_maps(self, side, map_x, map_y):
+        import numpy as np
+        mx = np.ascontiguousarray(map_x, dtype=np.float32)
+        my = np.ascontiguousarray(map_y, dtype=np.float32)
+        self._check(lib().airfe_set_rectify_maps(self.h, side, mx.ctypes.data_as(vp), my.ctypes.data_as(vp), mx.shape[1], mx.shape[0]))
+
+    def set_rectify(self, mode):
+        self._check(lib().airfe_set_rectify(self.h, mode))
+
+    def undistort(self, side, raw):
+        import numpy as np
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        out = np.empty_like(raw)
+        self._check(lib().airfe_undistort(self.h, side, raw.ctypes.data_as(vp), raw.shape[1], raw.shape[0], raw.shape[1], out.ctypes.data_as(vp), raw.shape[1]))
         return out
 
     # ---- device-resident keyframe features + batched candidate matching (config 5) ----

@@ -44,7 +44,23 @@ struct airfe_ctx {
   int* d_rcount = nullptr; int* d_ridx = nullptr; float* d_rscore = nullptr;   // per job: match count, [cap][2] indices, [cap] scores
   int* h_rcount = nullptr; int* h_ridx = nullptr; float* h_rscore = nullptr;
   float* d_qfeat = nullptr; size_t d_qfeat_bytes = 0;  // staging for host-resident query features
+  // rectification maps (airfe_set_rectify_maps): fixed-point form of cv::remap, per camera side
+  RemapMaps remap = {};
+  short* d_rxy[2] = {nullptr, nullptr}; unsigned short* d_ra[2] = {nullptr, nullptr};
+  int remap_w = 0, remap_h = 0;
+  uint8_t* d_rect = nullptr; size_t d_rect_bytes = 0;
 };
+
+// The maps to hand to the detector for a call on w x h frames, or nullptr (rectification off).  `stereo`: the call interleaves left / right.
+static const RemapMaps* remap_for(airfe_ctx* c, int w, int h, bool stereo, RemapMaps* tmp, bool* size_error) {
+  *size_error = false;
+  if (!c->remap.mode) return nullptr;
+  if (w != c->remap_w || h != c->remap_h) { *size_error = true; set_error("rectification maps are %dx%d, frames %dx%d", c->remap_w, c->remap_h, w, h); return nullptr; }
+  *tmp = c->remap;
+  if (stereo) tmp->mode = c->d_rxy[1] ? 2 : 1;
+  if (tmp->mode == 2 && !c->d_rxy[1]) { *size_error = true; set_error("rectification mode 2 needs the right-camera map"); return nullptr; }
+  return tmp;
+}
 
 // Every failing frame-level call leaves its message in the context it was made on (contexts are per thread / per device; a
 // process-global string would let one thread's error overwrite another's).  Failures without a context (airfe_create, the operator
@@ -230,6 +246,8 @@ void airfe_destroy(airfe_ctx* c) {
   if (c->h_ridx) cudaFreeHost(c->h_ridx);
   if (c->h_rscore) cudaFreeHost(c->h_rscore);
   if (c->d_qfeat) cudaFree(c->d_qfeat);
+  for (int k = 0; k < 2; ++k) { if (c->d_rxy[k]) cudaFree(c->d_rxy[k]); if (c->d_ra[k]) cudaFree(c->d_ra[k]); }
+  if (c->d_rect) cudaFree(c->d_rect);
   cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev_det) cudaEventDestroy(c->ev_det);
@@ -265,7 +283,10 @@ int airfe_detect_batch(airfe_ctx* c, int net, int batch, const uint8_t* gray, in
   for (int i = 0; i < batch; ++i) memcpy(c->h_img + one * i, gray + (size_t)img_stride * i, one);
   cudaStream_t st = c->stream;
   if (cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return fail(c, AIRFE_ERR_CUDA); }
-  if (!d->run(c->d_img, batch, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return fail(c, AIRFE_ERR_CUDA);
+  RemapMaps rm; bool rm_err;
+  const RemapMaps* rmp = remap_for(c, w, h, false, &rm, &rm_err);
+  if (rm_err) return fail(c, AIRFE_ERR_INVALID);
+  if (!d->run(c->d_img, batch, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st, rmp)) return fail(c, AIRFE_ERR_CUDA);
   const DetectOutputs& o = d->out();
   const int B = 2 * c->cfg.max_batch;
   int* hc = c->h_counts;
@@ -360,8 +381,8 @@ int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, 
   if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return fail(c, AIRFE_ERR_INVALID); }
   if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return fail(c, AIRFE_ERR_INVALID); }
   cudaSetDevice(c->device);
+  int nmax = 0;
   {
-    int nmax = 0;
     for (int p = 0; p < pairs; ++p) { nmax = n0[p] > nmax ? n0[p] : nmax; nmax = n1[p] > nmax ? n1[p] : nmax; }
     if (sgm) c->sg_use = (c->sg_small && nmax <= 512) ? c->sg_small.get() : c->sg.get();
     else c->lg_use = (c->lg_small && nmax <= 512) ? c->lg_small.get() : c->lg.get();
@@ -382,7 +403,7 @@ int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, 
       cudaMemcpyAsync(c->d_mfeat + (size_t)s * kKpCap * 259, c->h_mfeat + (size_t)s * kKpCap * 259, (size_t)c->h_mn[s] * 259 * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(c->d_mn, c->h_mn, 8 * pairs, cudaMemcpyHostToDevice, st);
   const bool dense = getenv("AIRFE_DEBUG_DENSE") != nullptr;
-  if (sgm ? !c->sg_use->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm) : !c->lg_use->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm)) return fail(c, AIRFE_ERR_CUDA);
+  if (sgm ? !c->sg_use->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm, nullptr, nmax) : !c->lg_use->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm)) return fail(c, AIRFE_ERR_CUDA);
   return fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, zero.data(), matcher);
 }
 
@@ -419,9 +440,12 @@ int airfe_stereo_device(airfe_ctx* c, int net, int matcher, int pairs, const voi
   if ((sgm && !c->sg) || (!sgm && (matcher != AIRFE_MATCHER_LIGHTGLUE || !c->lg))) { set_error("matcher %d not enabled in this context", matcher); return fail(c, AIRFE_ERR_INVALID); }
   if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return fail(c, AIRFE_ERR_INVALID); }
   cudaSetDevice(c->device);
-  if (!d->run((const uint8_t*)d_images, 2 * pairs, w, h, stride, img_stride, lines != 0, junctions != 0, c->stream)) return fail(c, AIRFE_ERR_CUDA);
+  RemapMaps rm; bool rm_err;
+  const RemapMaps* rmp = remap_for(c, w, h, true, &rm, &rm_err);
+  if (rm_err) return fail(c, AIRFE_ERR_INVALID);
+  if (!d->run((const uint8_t*)d_images, 2 * pairs, w, h, stride, img_stride, lines != 0, junctions != 0, c->stream, rmp)) return fail(c, AIRFE_ERR_CUDA);
   const DetectOutputs& o = d->out();
-  if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream)) return fail(c, AIRFE_ERR_CUDA);
+  if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream, false, nullptr, c->cfg.max_keypoints) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream)) return fail(c, AIRFE_ERR_CUDA);
   return AIRFE_OK;
 }
 
@@ -501,7 +525,10 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
     }
     cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st);
   }
-  if (!d->run(c->d_img, 2 * pairs, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st)) return fail(c, AIRFE_ERR_CUDA);
+  RemapMaps rm; bool rm_err;
+  const RemapMaps* rmp = remap_for(c, w, h, true, &rm, &rm_err);
+  if (rm_err) return fail(c, AIRFE_ERR_INVALID);
+  if (!d->run(c->d_img, 2 * pairs, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st, rmp)) return fail(c, AIRFE_ERR_CUDA);
   const DetectOutputs& o = d->out();
   // detector results go home on a second stream while the matcher runs on the first (13 MB of descriptors per 16 pairs)
   cudaStream_t cs = c->copy_stream;
@@ -523,7 +550,7 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
       cudaMemcpyAsync(junc + (size_t)p * junc_cap * 259, o.junc + (size_t)(2 * p) * kKpCap * 259, (size_t)kJunc * 259 * 4, cudaMemcpyDeviceToHost, cs);
   cudaEventRecord(c->ev_copy, cs);
   if (sgm) c->sg_use = c->sg.get(); else c->lg_use = c->lg.get();     // the detector's feature sets are bounded by max_keypoints = this instance's sizing
-  if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, st) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, st)) {
+  if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, st, false, nullptr, c->cfg.max_keypoints) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, st)) {
     cudaStreamSynchronize(cs);
     return fail(c, AIRFE_ERR_CUDA);
   }
@@ -563,6 +590,62 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
   if (rc != AIRFE_OK) return fail(c, rc);
   for (int p = 0; p < pairs; ++p)
     if (hc[2 * p] < 1 || hc[2 * p + 1] < 1) n_match[p] = 0;
+  return AIRFE_OK;
+}
+
+// ---- rectification maps (Camera::UndistortImage on the device) --------------------------------------------------------------------
+int airfe_set_rectify_maps(airfe_ctx* c, int side, const float* map_x, const float* map_y, int w, int h) {
+  if (!c || side < 0 || side > 1 || !map_x || !map_y || w < 2 || h < 2) { set_error("set_rectify_maps: bad arguments"); return fail(c, AIRFE_ERR_INVALID); }
+  if (c->remap_w && (w != c->remap_w || h != c->remap_h) && c->d_rxy[1 - side]) { set_error("both cameras must share one image size"); return fail(c, AIRFE_ERR_INVALID); }
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  const size_t n = (size_t)w * h;
+  std::vector<short> xy(2 * n);
+  std::vector<unsigned short> a(n);
+  build_remap_host(map_x, map_y, w, h, xy.data(), a.data());
+  if (c->d_rxy[side]) cudaFree(c->d_rxy[side]);
+  if (c->d_ra[side]) cudaFree(c->d_ra[side]);
+  c->d_rxy[side] = nullptr; c->d_ra[side] = nullptr;
+  if (cudaMalloc(&c->d_rxy[side], 4 * n) != cudaSuccess || cudaMalloc(&c->d_ra[side], 2 * n) != cudaSuccess ||
+      cudaMemcpy(c->d_rxy[side], xy.data(), 4 * n, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(c->d_ra[side], a.data(), 2 * n, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("rectification map upload failed");
+    return fail(c, AIRFE_ERR_CUDA);
+  }
+  c->remap.side[side] = RemapSide{c->d_rxy[side], c->d_ra[side]};
+  c->remap_w = w; c->remap_h = h;
+  return AIRFE_OK;
+}
+int airfe_set_rectify(airfe_ctx* c, int mode) {
+  if (!c || mode < 0 || mode > 2) { set_error("set_rectify: mode must be 0, 1 or 2"); return fail(c, AIRFE_ERR_INVALID); }
+  if (mode && !c->d_rxy[0]) { set_error("set_rectify: no left / mono camera map installed"); return fail(c, AIRFE_ERR_INVALID); }
+  if (mode == 2 && !c->d_rxy[1]) { set_error("set_rectify: mode 2 needs the right-camera map"); return fail(c, AIRFE_ERR_INVALID); }
+  c->remap.mode = mode;
+  return AIRFE_OK;
+}
+int airfe_undistort(airfe_ctx* c, int side, const uint8_t* raw, int w, int h, int stride, uint8_t* rect, int rect_stride) {
+  if (!c || side < 0 || side > 1 || !raw || !rect || stride < w || rect_stride < w) { set_error("undistort: bad arguments"); return fail(c, AIRFE_ERR_INVALID); }
+  if (!c->d_rxy[side] || w != c->remap_w || h != c->remap_h) { set_error("undistort: no %dx%d map for side %d", w, h, side); return fail(c, AIRFE_ERR_INVALID); }
+  cudaSetDevice(c->device);
+  const size_t need = (size_t)h * stride;
+  if (need > c->h_img_bytes && !grow_image_staging(c, need)) return fail(c, AIRFE_ERR_CUDA);
+  if ((size_t)w * h > c->d_rect_bytes) {
+    if (c->d_rect) cudaFree(c->d_rect);
+    c->d_rect = nullptr; c->d_rect_bytes = 0;
+    if (cudaMalloc(&c->d_rect, (size_t)w * h) != cudaSuccess) { cudaGetLastError(); c->d_rect = nullptr; set_error("undistort: allocation failed"); return fail(c, AIRFE_ERR_CUDA); }
+    c->d_rect_bytes = (size_t)w * h;
+  }
+  memcpy(c->h_img, raw, need);
+  cudaStream_t st = c->stream;
+  cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st);
+  RemapMaps m = c->remap;
+  m.side[0] = c->remap.side[side];
+  m.mode = 1;
+  launch_remap_u8(c->d_img, w, h, stride, 0, 1, m, c->d_rect, st);
+  if (cudaMemcpy2DAsync(rect, rect_stride, c->d_rect, w, w, h, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+    set_error("undistort failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(c, AIRFE_ERR_CUDA);
+  }
   return AIRFE_OK;
 }
 
@@ -669,7 +752,7 @@ int airfe_reloc_match(airfe_ctx* c, int matcher, const float* query_feat, const 
   const int B = c->cfg.max_batch;
   for (int j0 = 0; j0 < n_jobs; j0 += B) {
     const int P = n_jobs - j0 < B ? n_jobs - j0 : B;
-    if (sgm ? !c->sg->run(nullptr, c->d_rn + 2 * j0, 0, P, false, st, false, c->d_rptr + 2 * j0)
+    if (sgm ? !c->sg->run(nullptr, c->d_rn + 2 * j0, 0, P, false, st, false, c->d_rptr + 2 * j0, -1)
             : !c->lg->run(nullptr, c->d_rn + 2 * j0, 0, P, false, st, false, c->d_rptr + 2 * j0))
       return fail(c, AIRFE_ERR_CUDA);
     const int* d_count = sgm ? c->sg->out().m_count : c->lg->out().count;

@@ -3,6 +3,7 @@
 // accesses where the layout allows), warp-shuffle reductions, no tensor cores.
 #include "kernels.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace airfe {
 
@@ -32,8 +33,33 @@ void build_resize_tables_host(int src_w, int src_h, int* sx, int* a0, int* a1, i
   }
 }
 
+// cv::remap, CV_8UC1, INTER_LINEAR, BORDER_CONSTANT(0): one rectified pixel (src/camera.cc:163).  Restated from OpenCV's remapBilinear with the
+// FixedPtCast<int, uchar, 15> cast: bilinear weights (32 - fx)(32 - fy) * 32 etc. are exact in the 15-bit table, so no table is needed.
+void build_remap_host(const float* map_x, const float* map_y, int w, int h, short* xy, unsigned short* a) {
+  auto sat16 = [](int v) { return (short)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v)); };
+  for (long long i = 0; i < (long long)w * h; ++i) {
+    const int sx = (int)lrintf(map_x[i] * 32.f), sy = (int)lrintf(map_y[i] * 32.f);      // cvRound: round half to even
+    xy[2 * i] = sat16(sx >> 5);
+    xy[2 * i + 1] = sat16(sy >> 5);
+    a[i] = (unsigned short)(((sy & 31) << 5) | (sx & 31));
+  }
+}
+__device__ __forceinline__ int remap_px(const uint8_t* __restrict__ img, int w, int h, int stride, const RemapSide m, int r, int c) {
+  const long long i = (long long)r * w + c;
+  const short2 xy = *reinterpret_cast<const short2*>(m.xy + 2 * i);
+  const int a = m.a[i];
+  const int sx = xy.x, sy = xy.y, fx = a & 31, fy = a >> 5;
+  if (sx >= w || sx + 1 < 0 || sy >= h || sy + 1 < 0) return 0;
+  const bool x0 = sx >= 0, x1 = sx + 1 < w, y0 = sy >= 0, y1 = sy + 1 < h;
+  const uint8_t* p = img + (long long)sy * stride + sx;
+  const int v00 = (x0 && y0) ? p[0] : 0, v01 = (x1 && y0) ? p[1] : 0, v10 = (x0 && y1) ? p[stride] : 0, v11 = (x1 && y1) ? p[stride + 1] : 0;
+  const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+  return (v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11 + (1 << 14)) >> 15;
+}
+
+template <bool REMAP>
 __global__ void resize_kernel(const uint8_t* __restrict__ src, int src_w, int src_h, int src_stride, long long src_img_stride,
-                              ResizeTables t, __half* __restrict__ dst, uint8_t* __restrict__ dst_u8) {
+                              ResizeTables t, __half* __restrict__ dst, uint8_t* __restrict__ dst_u8, RemapMaps maps) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -42,8 +68,17 @@ __global__ void resize_kernel(const uint8_t* __restrict__ src, int src_w, int sr
   const int s0 = t.sx[x], s1 = min(s0 + 1, src_w - 1);
   const int a0 = t.a0[x], a1 = t.a1[x];
   const int r0 = min(max(t.sy[y], 0), src_h - 1), r1 = min(max(t.sy[y] + 1, 0), src_h - 1);
-  const int h0 = (int)img[(long long)r0 * src_stride + s0] * a0 + (int)img[(long long)r0 * src_stride + s1] * a1;
-  const int h1 = (int)img[(long long)r1 * src_stride + s0] * a0 + (int)img[(long long)r1 * src_stride + s1] * a1;
+  int p00, p01, p10, p11;
+  if (REMAP) {       // the four pixels of the RECTIFIED image this output needs, computed from the raw frame on the fly
+    const RemapSide m = maps.side[maps.mode == 2 ? (b & 1) : 0];
+    p00 = remap_px(img, src_w, src_h, src_stride, m, r0, s0); p01 = remap_px(img, src_w, src_h, src_stride, m, r0, s1);
+    p10 = remap_px(img, src_w, src_h, src_stride, m, r1, s0); p11 = remap_px(img, src_w, src_h, src_stride, m, r1, s1);
+  } else {
+    p00 = img[(long long)r0 * src_stride + s0]; p01 = img[(long long)r0 * src_stride + s1];
+    p10 = img[(long long)r1 * src_stride + s0]; p11 = img[(long long)r1 * src_stride + s1];
+  }
+  const int h0 = p00 * a0 + p01 * a1;
+  const int h1 = p10 * a0 + p11 * a1;
   int v = (((t.b0[y] * (h0 >> 4)) >> 16) + ((t.b1[y] * (h1 >> 4)) >> 16) + 2) >> 2;
   v = min(max(v, 0), 255);
   const long long o = ((long long)b * 512 + y) * 512 + x;
@@ -53,9 +88,20 @@ __global__ void resize_kernel(const uint8_t* __restrict__ src, int src_w, int sr
 }
 
 void launch_resize_u8_to_f16(const uint8_t* src, int src_w, int src_h, int src_stride, long long src_img_stride, int batch,
-                             ResizeTables t, __half* dst, uint8_t* dst_u8, cudaStream_t st) {
+                             ResizeTables t, __half* dst, uint8_t* dst_u8, cudaStream_t st, const RemapMaps* remap) {
   dim3 grid(512 / 128, 512, batch);
-  resize_kernel<<<grid, 128, 0, st>>>(src, src_w, src_h, src_stride, src_img_stride, t, dst, dst_u8);
+  if (remap && remap->mode) resize_kernel<true><<<grid, 128, 0, st>>>(src, src_w, src_h, src_stride, src_img_stride, t, dst, dst_u8, *remap);
+  else resize_kernel<false><<<grid, 128, 0, st>>>(src, src_w, src_h, src_stride, src_img_stride, t, dst, dst_u8, RemapMaps{});
+}
+
+__global__ void remap_kernel(const uint8_t* __restrict__ src, int w, int h, int stride, long long img_stride, RemapMaps maps, uint8_t* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  if (x >= w) return;
+  const RemapSide m = maps.side[maps.mode == 2 ? (b & 1) : 0];
+  dst[((long long)b * h + y) * w + x] = (uint8_t)remap_px(src + (long long)b * img_stride, w, h, stride, m, y, x);
+}
+void launch_remap_u8(const uint8_t* src, int w, int h, int stride, long long img_stride, int batch, RemapMaps maps, uint8_t* dst, cudaStream_t st) {
+  remap_kernel<<<dim3((w + 127) / 128, h, batch), 128, 0, st>>>(src, w, h, stride, img_stride, maps, dst);
 }
 
 // =====================================================================================================================
@@ -327,7 +373,167 @@ __global__ void nms_round_kernel(const float* __restrict__ heat, const uint8_t* 
   }
 }
 
+
+// ---- K5 fused: the whole simple_nms (initial 9x9 maximum test + two suppression rounds = five max-pool passes in the graph) in ONE kernel ----
+// A CTA produces a 64 x 64 output tile from the heat map on tile + 20 pixels (each of the five 9x9 pools eats 4 pixels of halo) held in
+// shared memory; every 9-tap max / OR is separable and register-blocked (a thread computes 8 consecutive outputs from 16 inputs with a
+// log-step window: 5.6 ops and 2 shared-memory reads per output instead of 9 and 9).  Exactly the arithmetic of the three-kernel version
+// (float equality on the unmodified heat values, -inf / 0 outside the image), one read of the heat map and one write of the scores instead
+// of three passes over (S, M) -- 0.50 -> see profiles/ for the measured time per 64 frames.
+constexpr int kNmsT = 64;                  // output tile
+constexpr int kNmsR = 20;                  // halo
+constexpr int kNmsW = kNmsT + 2 * kNmsR;   // 104
+constexpr int kNmsP = kNmsW + 1;           // float pitch 105 (odd: lanes that walk down a column of rows hit distinct banks)
+constexpr int kNmsThreads = 256;
+
+// out[i] = max(in[i .. i+8]) for i = 0..7 from 16 inputs
+__device__ __forceinline__ void win9_max(const float (&in)[16], float (&out)[8]) {
+  float a[15], b[13], c[9];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) a[i] = fmaxf(in[i], in[i + 1]);
+#pragma unroll
+  for (int i = 0; i < 13; ++i) b[i] = fmaxf(a[i], a[i + 2]);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c[i] = fmaxf(b[i], b[i + 4]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = fmaxf(c[i], in[i + 8]);
+}
+__device__ __forceinline__ void win9_or(const uint32_t (&in)[16], uint32_t (&out)[8]) {
+  uint32_t a[15], b[13], c[9];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) a[i] = in[i] | in[i + 1];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) b[i] = a[i] | a[i + 2];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c[i] = b[i] | b[i + 4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = c[i] | in[i + 8];
+}
+
+// Horizontal 9-max of src (rows [y0, y0 + nrows), output columns [x0, x0 + ncols), ncols % 8 == 0; window = columns x .. x+8 of src) -> dst.
+// Work item = (row, block of 8 columns); lanes walk rows.  src / dst are region-relative with pitch kNmsP.
+template <class LoadF>
+__device__ __forceinline__ void row_pass_max(LoadF load, float* dst, int y0, int nrows, int x0, int ncols) {
+  const int nblk = ncols >> 3;
+  for (int it = threadIdx.x; it < nrows * nblk; it += kNmsThreads) {
+    const int r = y0 + it % nrows, c = x0 + (it / nrows) * 8;
+    float in[16], out[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) in[i] = load(r, c + i);
+    win9_max(in, out);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[r * kNmsP + c + i] = out[i];
+  }
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 2) nms_fused_kernel(const float* __restrict__ heat, float* __restrict__ scores) {
+  extern __shared__ __align__(16) uint8_t nms_smem[];
+  float* S = reinterpret_cast<float*>(nms_smem);              // [104][105]  heat on tile + 20 (-inf outside the image)
+  float* T = S + kNmsW * kNmsP;                               // [104][105]  row-pass scratch
+  uint8_t* M = reinterpret_cast<uint8_t*>(T + kNmsW * kNmsP); // [104][104]  running maximum mask
+  uint8_t* U = M + kNmsW * kNmsW;                             // [104][104]  suppression mask of the current round
+  uint8_t* B = reinterpret_cast<uint8_t*>(T);                 // [104][104]  row-pass scratch (bytes): never live at the same time as T
+  const int b = blockIdx.z, gx0 = blockIdx.x * kNmsT - kNmsR, gy0 = blockIdx.y * kNmsT - kNmsR;
+  const float* h = heat + (long long)b * 262144;
+  for (int i = threadIdx.x; i < kNmsW * kNmsW; i += kNmsThreads) {
+    const int y = i / kNmsW, x = i - y * kNmsW;
+    const int gy = gy0 + y, gx = gx0 + x;
+    S[y * kNmsP + x] = (gy >= 0 && gy < 512 && gx >= 0 && gx < 512) ? h[gy * 512 + gx] : -INFINITY;
+  }
+  __syncthreads();
+  auto in_img = [&](int y, int x) { const int gy = gy0 + y, gx = gx0 + x; return gy >= 0 && gy < 512 && gx >= 0 && gx < 512; };
+
+  // ---- M0 = (S == mp9(S)) on region [4, 100)^2 : rows 0..103 x output columns 4..99 (window starts at column x - 4)
+  row_pass_max([&](int r, int c) { return S[r * kNmsP + c]; }, T, 0, kNmsW, 0, 96);          // T[r][c] = max S[r][c .. c+8]  (centre c + 4)
+  __syncthreads();
+  for (int it = threadIdx.x; it < 96 * 12; it += kNmsThreads) {                              // column pass: lanes walk columns
+    const int c = it % 96, r0 = (it / 96) * 8;                                               // output rows r0+4 .. r0+11, centre column c + 4
+    float in[16], out[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) in[i] = T[(r0 + i) * kNmsP + c];
+    win9_max(in, out);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int y = r0 + 4 + i, x = c + 4;
+      M[y * kNmsW + x] = (in_img(y, x) && S[y * kNmsP + x] == out[i]) ? 1 : 0;               // outside the image the mask is 0
+    }
+  }
+  __syncthreads();
+
+  // ---- two suppression rounds; round k works on the region shrunk by 8 more pixels
+#pragma unroll 1
+  for (int round = 0; round < 2; ++round) {
+    const int m_lo = 4 + 8 * round;                  // M is valid on [m_lo, 104 - m_lo)
+    const int u_lo = m_lo + 4, u_n = kNmsW - 2 * u_lo;       // Sup on [u_lo, 104 - u_lo): 88 / 72 wide
+    const int o_lo = u_lo + 4, o_n = kNmsW - 2 * o_lo;       // new mask on [o_lo, 104 - o_lo): 80 / 64 wide
+    // Sup = mp9(M) > 0 : horizontal OR (rows m_lo .. , output columns u_lo ..), then vertical OR
+    {
+      const int nrows = kNmsW - 2 * m_lo, nblk = u_n >> 3;
+      for (int it = threadIdx.x; it < nrows * nblk; it += kNmsThreads) {
+        const int r = m_lo + it % nrows, c = u_lo + (it / nrows) * 8;
+        uint32_t in[16], out[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) in[i] = M[r * kNmsW + c - 4 + i];
+        win9_or(in, out);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) B[r * kNmsW + c + i] = (uint8_t)out[i];
+      }
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < u_n * (u_n >> 3); it += kNmsThreads) {
+      const int c = u_lo + it % u_n, r0 = u_lo + (it / u_n) * 8;
+      uint32_t in[16], out[8];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) in[i] = B[(r0 - 4 + i) * kNmsW + c];
+      win9_or(in, out);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) U[(r0 + i) * kNmsW + c] = (uint8_t)out[i];
+    }
+    __syncthreads();
+    // S' = Sup ? 0 : S (-inf outside the image); mp9(S') on [o_lo, ..): horizontal then vertical max; M |= (S' == max) & ~Sup
+    auto sprime = [&](int r, int c) { const float v = S[r * kNmsP + c]; return (v == -INFINITY) ? v : (U[r * kNmsW + c] ? 0.f : v); };
+    {
+      const int nblk = o_n >> 3;
+      for (int it = threadIdx.x; it < u_n * nblk; it += kNmsThreads) {
+        const int r = u_lo + it % u_n, c = o_lo + (it / u_n) * 8;
+        float in[16], out[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) in[i] = sprime(r, c - 4 + i);
+        win9_max(in, out);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) T[r * kNmsP + c + i] = out[i];
+      }
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < o_n * (o_n >> 3); it += kNmsThreads) {
+      const int c = o_lo + it % o_n, r0 = o_lo + (it / o_n) * 8;
+      float in[16], out[8];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) in[i] = T[(r0 - 4 + i) * kNmsP + c];
+      win9_max(in, out);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int y = r0 + i;
+        const bool su = U[y * kNmsW + c] != 0;
+        const bool nm = M[y * kNmsW + c] | ((sprime(y, c) == out[i]) && !su && in_img(y, c));
+        M[y * kNmsW + c] = nm;
+        if (round == 1) scores[(long long)b * 262144 + (gy0 + y) * 512 + gx0 + c] = nm ? S[y * kNmsP + c] : 0.f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 void launch_simple_nms(const float* heat, float* scores, uint8_t* mask_a, uint8_t* mask_b, int batch, cudaStream_t st) {
+  static const bool v1 = getenv("AIRFE_NMS_V1") != nullptr;       // the three-kernel version, kept for A/B timing and as a cross-check
+  if (!v1) {
+    constexpr int smem = 2 * kNmsW * kNmsP * 4 + 2 * kNmsW * kNmsW;      // 109 KB: two CTAs per SM
+    static bool attr_set[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!attr_set[dev]) { cudaFuncSetAttribute(nms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set[dev] = true; }
+    nms_fused_kernel<<<dim3(512 / kNmsT, 512 / kNmsT, batch), kNmsThreads, smem, st>>>(heat, scores);
+    return;
+  }
   dim3 grid(512 / NT, 512 / NT, batch);
   nms_init_kernel<<<grid, 256, 0, st>>>(heat, mask_a);
   nms_round_kernel<<<grid, 256, 0, st>>>(heat, mask_a, mask_b, nullptr);

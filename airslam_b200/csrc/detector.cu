@@ -299,11 +299,11 @@ bool Detector::build_ops(int B) {
 }
 
 bool Detector::run(const uint8_t* d_images, int B, int w, int h, int stride, long long img_stride, bool lines, bool junctions,
-                   cudaStream_t st) {
+                   cudaStream_t st, const RemapMaps* remap) {
   if (B < 1 || B > cfg_.max_batch) { set_error("batch %d outside [1,%d]", B, cfg_.max_batch); return false; }
   lines = lines && plnet_ && cfg_.enable_lines;
   if (!ensure_tables(w, h) || !build_ops(B)) return false;
-  timed("resize", st, [&] { launch_resize_u8_to_f16(d_images, w, h, stride, img_stride, B, tables_[{w, h}], x16_, nullptr, st); });
+  timed("resize", st, [&] { launch_resize_u8_to_f16(d_images, w, h, stride, img_stride, B, tables_[{w, h}], x16_, nullptr, st, remap); });
   if (!trunk_ops_[B].run(st)) return false;
   const float w_scale = (float)w / 512.f, h_scale = (float)h / 512.f;
   timed("select_keypoints", st, [&] {

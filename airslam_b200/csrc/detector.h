@@ -35,8 +35,9 @@ class Detector {
  public:
   bool init(const DetectorConfig& cfg, const std::string& weights_dir, bool use_plnet_weights);
   // images already on the device: u8 [B][h][stride]; asynchronous on `st`
+  // remap (optional): d_images are RAW camera frames; Camera::UndistortImage (cv::remap) is applied inside the resize kernel
   bool run(const uint8_t* d_images, int batch, int w, int h, int stride, long long img_stride, bool lines, bool junctions,
-           cudaStream_t st);
+           cudaStream_t st, const RemapMaps* remap = nullptr);
   const DetectOutputs& out() const { return out_; }
   double tc_flops(int batch, bool lines);
   int launches(int batch, bool lines);

@@ -159,8 +159,9 @@ bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __h
                          int cap, int slot_xor, float scale);
 bool attn_fused_enabled();
 // Append the fused LightGlue block tail (tc_ffn.cuh): x += ffn3(gelu(LN(ffn0([x | out_proj(ctx)])))); refreshes the fp16 copy of x.
+// relu = true: SuperGlue's block tail (merge + MLP with ReLU instead of LayerNorm + GELU; ln_g / ln_b unused).
 bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, const DenseW& w_out, const DenseW& w0, const DenseW& w3, const float* ln_g,
-                   const float* ln_b, const int* n, int slots, int cap);
+                   const float* ln_b, const int* n, int slots, int cap, bool relu = false);
 bool ffn_fused_enabled();
 // Append a raw tcgen05 GEMM described by `d` (attention products).
 bool add_gemm(OpList* ol, const TcGemmDesc& d, double flops, int kind = kDynNone);

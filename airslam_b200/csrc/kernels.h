@@ -9,9 +9,22 @@ namespace airfe {
 struct ResizeTables {        // device arrays of 512 entries each, built on the host by build_resize_tables()
   int* sx; int* a0; int* a1; int* sy; int* b0; int* b1;
 };
+// ---- §8f rank 1: cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) of Camera::UndistortImage (src/camera.cc:161-182) fused into K1.
+// Fixed-point form OpenCV derives from the CV_32F maps of initUndistortRectifyMap: xy = (cvRound(32 x) >> 5, cvRound(32 y) >> 5) saturated to
+// int16, a = (fy << 5) | fx with the 5 fractional bits; built on the host by build_remap_host() exactly as OpenCV's remap does.
+struct RemapSide { const short* xy; const unsigned short* a; };     // device: [h][w][2], [h][w]
+struct RemapMaps {
+  RemapSide side[2];     // 0 = left / mono camera, 1 = right camera
+  int mode;              // 0 off, 1 = every image uses side 0, 2 = image index parity selects the side (stereo batches: L, R, L, R ...)
+};
+void build_remap_host(const float* map_x, const float* map_y, int w, int h, short* xy, unsigned short* a);
+// standalone rectification (callers that want image_left_rect itself): dst [batch][h][w] u8
+void launch_remap_u8(const uint8_t* src, int w, int h, int stride, long long img_stride, int batch, RemapMaps maps, uint8_t* dst, cudaStream_t st);
+
 void build_resize_tables_host(int src_w, int src_h, int* sx, int* a0, int* a1, int* sy, int* b0, int* b1);
 void launch_resize_u8_to_f16(const uint8_t* src, int src_w, int src_h, int src_stride, long long src_img_stride, int batch,
-                             ResizeTables t, __half* dst /*[B,512,512]*/, uint8_t* dst_u8 /*optional [B,512,512]*/, cudaStream_t st);
+                             ResizeTables t, __half* dst /*[B,512,512]*/, uint8_t* dst_u8 /*optional [B,512,512]*/, cudaStream_t st,
+                             const RemapMaps* remap = nullptr /* non-null and mode != 0: src holds RAW frames, rectified on the fly */);
 
 // ---- first layer: 3x3 conv, C_in = 1 -> 64, +bias, ReLU, NHWC fp16 out (no tensor-core shape: K = 9)
 void launch_conv1a(const __half* x /*[B,512,512]*/, const __half* w /*[64][9]*/, const float* bias, __half* out /*[B,512,512,64]*/,

@@ -2,7 +2,9 @@
 // Data layout: "slot" s = 2 * pair + side owns rows [s*CAP, s*CAP + n[s]) of every [rows, C] matrix; all kernels read the
 // per-slot keypoint counts n[] from device memory, so nothing here depends on host-side knowledge of N.
 #include "match_kernels.h"
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace airfe {
 
@@ -415,6 +417,146 @@ __global__ void sg_col_pass_kernel(const float* __restrict__ Z, const int* __res
   }
 }
 
+
+// ---- K18 fused: all 2 x iters log-Sinkhorn passes of one pair in ONE kernel ------------------------------------------------------
+// The coupling matrix Z never changes during the iterations -- only u and v do -- so a thread-block CLUSTER of 8 CTAs keeps the whole
+// (M+1) x (N+1) fp32 matrix of a pair in REGISTERS (401^2 floats / (8 x 512 threads) = 52 per thread at 400 keypoints) and the 200
+// passes exchange nothing but per-column partial log-sum-exps:
+//   row i = l * 8 + rank is owned by CTA `rank`, local row l = warp * RPW + r by one warp; lane holds columns lane + 32 k (k < CPL);
+//   row pass : warp-shuffle LSE over the row -> u_i (stays in registers: only this warp's rows need it);
+//   col pass : per-thread (max, sum) over its rows -> across warps through shared memory -> across the 8 CTAs through DSMEM
+//              (double-buffered partials, one cluster barrier per iteration) -> v (every CTA computes the full v redundantly).
+// Replaces 200 kernel launches that re-read Z from L2 each time (sg_row_pass_kernel / sg_col_pass_kernel: 2.1 ms per 8 pairs).
+namespace cg = cooperative_groups;
+constexpr int kSkCluster = 8;
+
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {     // (m, s) <- logsumexp-combine, -inf safe
+  const float mm = fmaxf(m, m2);
+  const float ms = (mm == -INFINITY) ? 0.f : mm;
+  s = s * __expf(m - ms) + s2 * __expf(m2 - ms);
+  m = mm;
+}
+
+template <int CPL, int RPW, int NW>
+__global__ void __cluster_dims__(kSkCluster, 1, 1) __launch_bounds__(NW * 32, 1)
+sg_sinkhorn_cluster_kernel(const float* __restrict__ Z, const int* __restrict__ n, int cap, int iters, float* __restrict__ u_out, float* __restrict__ v_out) {
+  constexpr int COLS = 32 * CPL;
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  float2* part = reinterpret_cast<float2*>(sk_smem);            // [NW][COLS]   per-warp column partials (max, sum)
+  float2* cta_part = part + NW * COLS;                          // [2][COLS]    this CTA's column partials, double buffered, read by the whole cluster
+  float* v_s = reinterpret_cast<float*>(cta_part + 2 * COLS);   // [COLS]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int p = blockIdx.x / kSkCluster;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = n[2 * p], N = n[2 * p + 1];
+  const int ld = cap + 1;
+  if (M < 1 || N < 1 || M + 1 > kSkCluster * NW * RPW || N + 1 > COLS) return;   // uniform over the cluster: nobody reaches a barrier
+  const float norm = -logf((float)(M + N));
+  const float* z0 = Z + (long long)p * ld * ld;
+  float z[RPW][CPL];
+  float u[RPW];
+  int row[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    row[r] = (warp * RPW + r) * kSkCluster + rank;
+    u[r] = 0.f;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int j = lane + 32 * k;
+      z[r][k] = (row[r] <= M && j <= N) ? z0[(long long)row[r] * ld + j] : -INFINITY;
+    }
+  }
+  float v[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) v[k] = 0.f;
+
+  for (int it = 0; it < iters; ++it) {
+    // ---- row pass: u_i = log_mu_i - LSE_j(Z_ij + v_j)
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      if (row[r] <= M) {                       // warp-uniform
+        float t[CPL];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) { t[k] = z[r][k] + v[k]; mx = fmaxf(mx, t[k]); }
+        mx = warp_max_(mx);
+        float sm = 0.f;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) sm += expf(t[k] - mx);
+        sm = warp_sum_(sm);
+        const float log_mu = (row[r] < M) ? norm : logf((float)N) + norm;
+        u[r] = log_mu - (mx + logf(sm));
+      }
+    }
+    // ---- col pass: v_j = log_nu_j - LSE_i(Z_ij + u_i), partials: thread -> warp rows (already thread-local) -> CTA -> cluster
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      float mx = -INFINITY;
+      float t[RPW];
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) { t[r] = z[r][k] + u[r]; mx = fmaxf(mx, t[r]); }      // rows beyond M hold -inf
+      const float ms = (mx == -INFINITY) ? 0.f : mx;
+      float sm = 0.f;
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) sm += expf(t[r] - ms);
+      part[warp * COLS + lane + 32 * k] = make_float2(mx, sm);
+    }
+    __syncthreads();
+    float2* mine = cta_part + (it & 1) * COLS;
+    for (int j = threadIdx.x; j < COLS; j += NW * 32) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) mx = fmaxf(mx, part[w * COLS + j].x);
+      const float ms = (mx == -INFINITY) ? 0.f : mx;
+      float sm = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { const float2 q = part[w * COLS + j]; sm += q.y * expf(q.x - ms); }
+      mine[j] = make_float2(mx, sm);
+    }
+    cluster.sync();                            // every CTA's partials of this iteration are visible (and `part` may be rewritten)
+    for (int j = threadIdx.x; j < COLS; j += NW * 32) {
+      float2 q[kSkCluster];
+#pragma unroll
+      for (int c = 0; c < kSkCluster; ++c) q[c] = *cluster.map_shared_rank(mine + j, c);      // DSMEM, fixed rank order: deterministic
+      float mx = q[0].x;
+#pragma unroll
+      for (int c = 1; c < kSkCluster; ++c) mx = fmaxf(mx, q[c].x);
+      const float ms = (mx == -INFINITY) ? 0.f : mx;
+      float sm = 0.f;
+#pragma unroll
+      for (int c = 0; c < kSkCluster; ++c) sm += q[c].y * expf(q[c].x - ms);
+      const float log_nu = (j < N) ? norm : logf((float)M) + norm;
+      v_s[j] = (j <= N) ? log_nu - (mx + logf(sm)) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) v[k] = v_s[lane + 32 * k];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+      if (row[r] <= M) u_out[(long long)p * ld + row[r]] = u[r];
+  }
+  if (rank == 0)
+    for (int j = threadIdx.x; j <= N; j += NW * 32) v_out[(long long)p * ld + j] = v_s[j];
+  cluster.sync();                              // no CTA may exit while others still read its shared memory
+}
+
+template <int CPL, int RPW, int NW>
+static bool launch_sinkhorn_cluster(const float* Z, const int* n, int pairs, int cap, int iters, float* u, float* v, cudaStream_t st) {
+  constexpr int smem = (NW * 32 * CPL + 2 * 32 * CPL) * (int)sizeof(float2) + 32 * CPL * (int)sizeof(float);
+  static bool attr_set[kMaxDevices] = {};
+  const int dev = current_device();
+  auto kern = sg_sinkhorn_cluster_kernel<CPL, RPW, NW>;
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { cudaGetLastError(); return false; }
+    attr_set[dev] = true;
+  }
+  kern<<<pairs * kSkCluster, NW * 32, smem, st>>>(Z, n, cap, iters, u, v);
+  return cudaGetLastError() == cudaSuccess;
+}
+
 __device__ __forceinline__ float sg_score(float z, float u, float v, float norm) { return __fsub_rn(__fadd_rn(__fadd_rn(z, u), v), norm); }
 
 // decode: row / column argmax over the inner M x N block of Z + u + v - norm (strict '<' scan: first max)
@@ -548,14 +690,24 @@ __global__ void __launch_bounds__(1024) sg_decode_kernel(const int* __restrict__
   if (t == 0) m_count[p] = ws[31];
 }
 
-void launch_sg_sinkhorn_decode(const float* sim, const int* n, int pairs, int cap, float bin_score, int iters, float* Z, float* u, float* v,
+void launch_sg_sinkhorn_decode(const float* sim, const int* n, int pairs, int cap, int max_n, float bin_score, int iters, float* Z, float* u, float* v,
                                float thr, int* arg0, float* val0, int* arg1, int* idx0, int* idx1, float* ms0, float* ms1, int* m_idx,
                                float* m_score, int* m_count, float* dense_out, cudaStream_t st) {
   sg_couplings_kernel<<<dim3((cap + 1 + 127) / 128, cap + 1, pairs), 128, 0, st>>>(sim, n, cap, bin_score, Z, u, v);
-  for (int it = 0; it < iters; ++it) {
-    sg_row_pass_kernel<<<dim3((cap + 1 + 7) / 8, pairs), 256, 0, st>>>(Z, n, cap, u, v);
-    sg_col_pass_kernel<<<dim3((cap + 1 + 31) / 32, pairs), dim3(32, 8), 0, st>>>(Z, n, cap, u, v);
+  // fused: one cluster kernel runs all 2 x iters passes with Z in registers.  Size class by slot capacity: <= 415 keypoints per side
+  // (13 columns per lane) is what the configs of AirSLAM use (max_keypoints 350 .. 450 -> callers size cap accordingly); up to 512 takes the
+  // 17-column instantiation; larger capacities (the 1024-keypoint profile) keep the pass-per-launch path.  AIRFE_SINKHORN_V1=1 forces it.
+  static const bool v1 = getenv("AIRFE_SINKHORN_V1") != nullptr;
+  bool fused = false;
+  if (!v1 && cap <= 512) {
+    fused = (max_n >= 0 && max_n <= 415) ? launch_sinkhorn_cluster<13, 4, 16>(Z, n, pairs, cap, iters, u, v, st)
+                                         : launch_sinkhorn_cluster<17, 6, 12>(Z, n, pairs, cap, iters, u, v, st);
   }
+  if (!fused)
+    for (int it = 0; it < iters; ++it) {
+      sg_row_pass_kernel<<<dim3((cap + 1 + 7) / 8, pairs), 256, 0, st>>>(Z, n, cap, u, v);
+      sg_col_pass_kernel<<<dim3((cap + 1 + 31) / 32, pairs), dim3(32, 8), 0, st>>>(Z, n, cap, u, v);
+    }
   sg_rowmax_kernel<<<dim3((cap + 1 + 7) / 8, pairs), 256, 0, st>>>(Z, u, v, n, cap, arg0, val0, dense_out);
   sg_colmax_kernel<<<dim3((cap + 31) / 32, pairs), dim3(32, 8), 0, st>>>(Z, u, v, n, cap, arg1);
   sg_decode_kernel<<<pairs, 1024, 0, st>>>(arg0, val0, arg1, n, cap, thr, idx0, idx1, ms0, ms1, m_idx, m_score, m_count);

@@ -19,8 +19,10 @@ namespace airfe {
 // ---- SuperGlue (G5) ------------------------------------------------------------------------------------------------------------
 void launch_sg_prepare(const float* feat, const float* const* feat_ptrs, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, float* x,
                        __half* kin16, cudaStream_t st);
-// couplings Z [pair][cap+1][cap+1] from sim (already divided by 16) + bin score; 100 log-Sinkhorn iterations; decode
-void launch_sg_sinkhorn_decode(const float* sim, const int* n, int pairs, int cap, float bin_score, int iters, float* Z, float* u, float* v,
+// couplings Z [pair][cap+1][cap+1] from sim (already divided by 16) + bin score; 100 log-Sinkhorn iterations; decode.
+// max_n: host-side upper bound of the keypoints per slot (-1 = unknown: the slot capacity is assumed).  It only selects the size class of the
+// fused cluster kernel (<= 415: 13 columns per lane; <= 512: 17); capacities above 512 run one launch per pass.
+void launch_sg_sinkhorn_decode(const float* sim, const int* n, int pairs, int cap, int max_n, float bin_score, int iters, float* Z, float* u, float* v,
                                float thr, int* arg0, float* val0, int* arg1, int* idx0, int* idx1, float* ms0, float* ms1, int* m_idx,
                                float* m_score, int* m_count, float* dense_out, cudaStream_t st);
 }  // namespace airfe

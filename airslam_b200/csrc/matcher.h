@@ -68,8 +68,9 @@ struct SuperGlueOutputs {
 class SuperGlue {
  public:
   bool init(const MatcherConfig& cfg, const std::string& weights_dir, bool outdoor);
+  // max_n: host-side upper bound of the keypoint counts behind d_n (-1 = unknown), see launch_sg_sinkhorn_decode
   bool run(const float* d_feat, const int* d_n, int feat_cap, int pairs, bool want_dense, cudaStream_t st, bool prenormalised = false,
-           const float* const* d_feat_ptrs = nullptr);
+           const float* const* d_feat_ptrs = nullptr, int max_n = -1);
   const SuperGlueOutputs& out() const { return out_; }
   int cap() const { return cfg_.cap; }
   double tc_flops(int pairs) { return build_ops(pairs) ? ops_[pairs].tc_flops : 0.0; }

@@ -93,6 +93,10 @@ bool SuperGlue::build_ops(int P) {
     if (!add_dense(&ol, x16, Y.qkv, qkv, S, false, -1, 0, n)) return false;
     if (attn_fused_enabled() && cap <= 512) {
       if (!add_fused_attention(&ol, qkv16_, qkv16_ + 256, qkv16_ + 512, 768, ctx16_, n, S, cap, xr, 0.125f)) return false;
+      if (ffn_fused_enabled()) {          // merge + mlp.0 + ReLU + mlp.3 + residual in one kernel (tc_ffn.cuh, ReLU variant)
+        if (!add_fused_ffn(&ol, ctx16_, cat16_, x_, Y.merge, Y.mlp0, Y.mlp3, nullptr, nullptr, n, S, cap, true)) return false;
+        continue;
+      }
       if (!add_dense(&ol, ctx, Y.merge, msg16, S, false, -1, 0, n)) return false;
       if (!add_dense(&ol, cat, Y.mlp0, h16, S, true, -1, 0, n)) return false;
       if (!add_dense(&ol, h16, Y.mlp3, xf, S, false, -1, 0, n, 1.f, x_, &x16)) return false;
@@ -133,7 +137,7 @@ bool SuperGlue::build_ops(int P) {
   return true;
 }
 
-bool SuperGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bool want_dense, cudaStream_t st, bool prenorm, const float* const* d_feat_ptrs) {
+bool SuperGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bool want_dense, cudaStream_t st, bool prenorm, const float* const* d_feat_ptrs, int max_n) {
   if (P < 1 || P > cfg_.max_pairs) { set_error("pairs %d outside [1,%d]", P, cfg_.max_pairs); return false; }
   if (!build_ops(P)) return false;
   const int S = 2 * P, cap = cfg_.cap;
@@ -143,7 +147,7 @@ bool SuperGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bo
   timed("sg_prepare", st, [&] { launch_sg_prepare(d_feat, d_feat_ptrs, n_, S, cap, feat_cap, prenorm ? 0 : cfg_.image_width, prenorm ? 0 : cfg_.image_height, prenorm ? 1.f : l_inv, x_, kin16_, st); });
   if (!ops_[P].run(st)) return false;
   timed("sg_sinkhorn+decode", st, [&] {
-    launch_sg_sinkhorn_decode(sim_, n_, P, cap, bin_score_, 100, Z_, u_, v_, 0.2f, arg0_, val0_, arg1_, out_.idx0, out_.idx1, out_.ms0, out_.ms1,
+    launch_sg_sinkhorn_decode(sim_, n_, P, cap, max_n, bin_score_, 100, Z_, u_, v_, 0.2f, arg0_, val0_, arg1_, out_.idx0, out_.idx1, out_.ms0, out_.ms1,
                               out_.m_idx, out_.m_score, out_.m_count, want_dense ? out_.dense : nullptr, st);
   });
   cudaError_t e = cudaGetLastError();

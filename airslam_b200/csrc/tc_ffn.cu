@@ -16,7 +16,7 @@ bool ffn_fused_enabled() {
 static int ffn_sm_count() { return device_sm_count(); }
 
 bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, const DenseW& w_out, const DenseW& w0, const DenseW& w3, const float* ln_g,
-                   const float* ln_b, const int* n, int slots, int cap) {
+                   const float* ln_b, const int* n, int slots, int cap, bool relu) {
   if (w_out.n_rows != 256 || w_out.c_in_pad != 256 || w0.n_rows != 512 || w0.c_in_pad != 512 || w3.n_rows != 256 || w3.c_in_pad != 512) {
     set_error("add_fused_ffn: unexpected layer shapes");
     return false;
@@ -37,24 +37,26 @@ bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, con
     return make_tmap_f16(tm, w.w, 4, dims, str, box);
   };
   if (!wmap(&p.tmWo, w_out) || !wmap(&p.tmW0, w0) || !wmap(&p.tmW3, w3)) return false;
-  p.b_out = w_out.bias; p.b0 = w0.bias; p.b3 = w3.bias; p.ln_g = ln_g; p.ln_b = ln_b;
+  p.b_out = w_out.bias; p.b0 = w0.bias; p.b3 = w3.bias;
+  p.ln_g = relu ? w0.bias : ln_g; p.ln_b = relu ? w0.bias : ln_b;     // the ReLU variant stages but never reads the LayerNorm slots
   p.x = x; p.x16 = cat16; p.n = n; p.slots = slots; p.cap = cap;
   const int tiles = slots * (cap / 128);
   const int grid = tiles < ffn_sm_count() ? tiles : ffn_sm_count();
   const double fl = 2.0 * (double)slots * cap * (256.0 * 256 + 512.0 * 512 + 512.0 * 256);
   ol->tc_flops += fl;
   ol->launches += 1;
-  ol->push("tc_ffn fused block (out_proj+ffn0+LN+GELU+ffn3+residual)", fl, [p, grid](cudaStream_t st) {
-    static bool attr_set[kMaxDevices] = {};
+  ol->push(relu ? "tc_ffn fused block (merge+mlp0+ReLU+mlp3+residual)" : "tc_ffn fused block (out_proj+ffn0+LN+GELU+ffn3+residual)", fl, [p, grid, relu](cudaStream_t st) {
+    static bool attr_set[kMaxDevices][2] = {};
     const int dev = current_device();
-    if (!attr_set[dev]) {
-      if (cudaFuncSetAttribute(tc_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmemBytes) != cudaSuccess) {
+    auto kern = relu ? tc_ffn_kernel<true> : tc_ffn_kernel<false>;
+    if (!attr_set[dev][relu]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmemBytes) != cudaSuccess) {
         set_error("cudaFuncSetAttribute(tc_ffn_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
         return false;
       }
-      attr_set[dev] = true;
+      attr_set[dev][relu] = true;
     }
-    cudaError_t e = launch_pdl(tc_ffn_kernel, grid, kFfnThreads, kFfnSmemBytes, st, p);
+    cudaError_t e = launch_pdl(kern, grid, kFfnThreads, kFfnSmemBytes, st, p);
     if (e != cudaSuccess) { set_error("tc_ffn launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
   }, kDynRows);

@@ -30,6 +30,9 @@ constexpr int kFfnThreads = 320;
 constexpr int kFfnBStages = 4;
 constexpr int kFfnSmemBytes = 8 * 16384 + kFfnBStages * 16384 + (2048 + 512) * 4 + 1024 + 256;
 
+// RELU = false: LightGlue (LayerNorm + exact GELU between the two FFN GEMMs).  RELU = true: SuperGlue's MLP([x | merge(ctx)]) = 512 -> 512
+// (BatchNorm folded into the weights) -> ReLU -> 256 with the same residual: identical GEMM shapes, a one-pass phase-2 epilogue.
+template <bool RELU>
 __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_constant__ FfnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -189,6 +192,27 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
       ptx::tc_fence_after();
       const int c_lo = half * 256, c_hi = c_lo + 256;
+      if constexpr (RELU) {
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld32(trow + c, r);
+          ptx::tmem_ld_wait();
+          uint8_t* dst = sA + (c >> 6) * 16384 + row * 128;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = ch * 8 + e * 2;
+              __half2 h2 = __floats2half2_rn(fmaxf(__uint_as_float(r[j]) + s_b0[c + j], 0.f), fmaxf(__uint_as_float(r[j + 1]) + s_b0[c + j + 1], 0.f));
+              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            const int chunk = ((c & 63) >> 3) + ch;
+            *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      } else {
       float sum = 0.f;
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; c += 32) {
@@ -237,6 +261,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
           const int chunk = ((c & 63) >> 3) + ch;
           *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+      }
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();

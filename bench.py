@@ -380,7 +380,7 @@ def run_config5(args, cfg, rank, local, world, barrier, max_over_ranks):
                 "e2e": {"value": units / e2e_s, "unit": cfg["unit"], "h2d_bytes_per_step": int(cfg["units_per_step"] * NF * 259 * 4 // world),
                         "d2h_bytes_per_step": int(batches_per_step * (QB * NC * 4 + len(batches[0]["jq"]) * 4))},
                 "gpu_launches": int(args.steps * batches_per_step * ((len(batches[0]["jq"]) + 31) // 32) * 70),
-                "roofline": {"bound": "tensor", "kernel": "LightGlue stack (tc_gemm projections + tc_attn + tc_ffn), whole matcher pass", "achieved": tf * 1.0 / 1.0,
+                "roofline": {"bound": "tensor", "kernel": "LightGlue stack (tc_gemm projections + tc_attn + tc_ffn), whole matcher pass", "achieved": tf,
                              "peak": sustained * world, "unit": "TFLOP/s", "frac": tf / (sustained * world), "traffic": None,
                              "peak_source": "%s bf16_tflops_sustained x %d GPUs" % (how, world), "flops_per_pair_match": fl_pair},
                 "cpu_baseline": None}
@@ -533,7 +533,6 @@ def main():
     ev1.synchronize()
     barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    units = cfg["units_per_step"] if cfg["units_per_step"] >= P else P
     units = chunks_per_step * P
     if args.device_only:
         sampler.stop_flag = True
@@ -574,6 +573,11 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     sustained, burst, hbm, how = _peaks()
+    # which measured peak matches the regime: MEASURED_PEAKS' sustained figure was taken at ~1410 MHz (a dense cuBLAS loop under the 1 kW cap),
+    # the burst figure near the maximum clock.  This workload draws less power: judge by the SM clock actually sampled during the run.
+    clk = sampler.summary()
+    near_max = bool(clk["sm_mhz"] and clk["sm_max_mhz"] and clk["sm_mhz"] >= 0.85 * clk["sm_max_mhz"])
+    peak, peak_name = (burst, "bf16_tflops (burst)") if near_max else (sustained, "bf16_tflops_sustained")
     all_ms = sum(x[2] for x in prof)
 
     def fam(pred):
@@ -581,7 +585,7 @@ def main():
         ms = sum(x[2] for x in xs)
         fl = sum(x[1] for x in xs)
         return {"launches": len(xs), "ms_per_chunk": ms, "tflops": (fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0), "share_of_chunk": ms / all_ms if all_ms else 0.0,
-                "frac_of_sustained": (fl / (ms * 1e-3) / 1e12 / sustained if ms > 0 else 0.0), "flops_per_chunk": fl}
+                "frac_of_peak": (fl / (ms * 1e-3) / 1e12 / peak if ms > 0 else 0.0), "flops_per_chunk": fl}
     families = {"tc_conv3x3": fam(lambda n: n.startswith("tc_conv3x3")), "tc_gemm (1x1 convs, linears, G3 MLP, attention products)": fam(lambda n: n.startswith("tc_gemm")),
                 "tc_attn (fused attention)": fam(lambda n: n.startswith("tc_attn")), "tc_ffn (fused transformer block tail)": fam(lambda n: n.startswith("tc_ffn")),
                 "all tcgen05": fam(lambda n: n.startswith("tc_")), "non tensor-core kernels": fam(lambda n: not n.startswith("tc_"))}
@@ -611,17 +615,19 @@ def main():
                        "parallelism": "replica x%d (pairs sharded, no collective)" % world, "max_keypoints": cfg["max_keypoints"], "mean_keypoints": mean_kp,
                        "soak_s": args.soak, "timed_region_s": dev_ms * 1e-3,
                        "l2": "inputs rotate over %d chunks; a chunk's activations (~%.1f GB) exceed the 126 MB L2" % (nb, (0.3 if LINES else 0.1) * 2 * P)},
-            "clocks": sampler.summary(),
+            "clocks": clk,
             "e2e": {"value": world * units * args.steps / e2e_s, "unit": cfg["unit"], "h2d_bytes_per_step": h2d * chunks_per_step, "d2h_bytes_per_step": int(d2h) * chunks_per_step},
             "gpu_launches": int(launches * args.steps * chunks_per_step),
             "roofline": {"bound": "tensor", "kernel": "%s (dominant family: %d launches = %.0f%% of a chunk's kernel time)" % (dom_key, dom["launches"], 100 * dom["share_of_chunk"]),
-                         "achieved": dom["tflops"], "peak": sustained, "unit": "TFLOP/s", "frac": dom["tflops"] / sustained, "frac_of_burst_peak": dom["tflops"] / burst,
+                         "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": dom["tflops"] / peak, "frac_of_sustained_peak": dom["tflops"] / sustained,
+                         "frac_of_burst_peak": dom["tflops"] / burst,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": "%s bf16_tflops_sustained (fp16 runs on the same kind::f16 pipe); every op event-timed back to back after the %.0f s timed loops, SM clock as in `clocks`" % (how, dev_ms * 1e-3 + e2e_s),
+                         "peak_source": "%s %s: the SM clock sampled during the run (median %s of %s MHz) decides which measured peak applies; fp16 runs on the same kind::f16 pipe; every op is "
+                                        "event-timed back to back right after the %.0f s of timed loops" % (how, peak_name, clk["sm_mhz"], clk["sm_max_mhz"], dev_ms * 1e-3 + e2e_s),
                          "flops_per_launch": dom["flops_per_chunk"] / max(1, dom["launches"]), "ms_per_launch": dom["ms_per_chunk"] / max(1, dom["launches"]),
                          "flops": "algorithmic, on the rows actually processed (device-side keypoint / line counts read back)",
                          "families": families, "whole_chunk": {"tflops": sum(x[1] for x in prof) / (dev_ms * 1e-3 / (args.steps * chunks_per_step)) / 1e12,
-                                                               "frac_of_sustained": sum(x[1] for x in prof) / (dev_ms * 1e-3 / (args.steps * chunks_per_step)) / 1e12 / sustained}},
+                                                               "frac_of_peak": sum(x[1] for x in prof) / (dev_ms * 1e-3 / (args.steps * chunks_per_step)) / 1e12 / peak}},
         }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = cpu_threads()

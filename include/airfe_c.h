@@ -124,6 +124,20 @@ int airfe_detect_match_stereo_batch(airfe_ctx* ctx, int net, int matcher, int pa
                                     int* n_feat, double* lines, int line_cap, int* n_lines, float* junc, int junc_cap, int* n_junc,
                                     int* idx0, int* idx1, float* score, int match_cap, int* n_match);
 
+/* ---- image rectification on the device ----
+ * Camera::UndistortImage (src/camera.cc:161-182: cv::remap(image, rect, map1, map2, INTER_LINEAR), called once per frame on the CPU at
+ * src/map_builder.cc:43 and src/map_user.cc:108) is folded into the first kernel of the path: with maps installed and rectification
+ * enabled, every detect entry point takes the RAW camera frames and the resize kernel gathers through the maps (bit-exact with cv::remap
+ * followed by cv::resize; the rectified image is never materialised).
+ * map_x / map_y: the CV_32F maps of cv::initUndistortRectifyMap (src/camera.cc:63-66, 71-74), width x height floats each, row-major.
+ * side: 0 = left / mono camera, 1 = right camera. */
+int airfe_set_rectify_maps(airfe_ctx* ctx, int side, const float* map_x, const float* map_y, int width, int height);
+/* mode 0: off (frames are already rectified).  1: every image of a detect call belongs to camera `side 0`.  2: images alternate left, right
+ * (what the stereo entry points assume automatically once a right-camera map is installed). */
+int airfe_set_rectify(airfe_ctx* ctx, int mode);
+/* The rectified image itself, for callers that keep it (MapBuilder::AddInput stores it in the input data): rect = remap(raw). */
+int airfe_undistort(airfe_ctx* ctx, int side, const uint8_t* raw, int width, int height, int stride, uint8_t* rect, int rect_stride);
+
 /* ---- device-resident keyframe features + batched candidate matching (BASELINE.json config 5) ----
  * The reference re-uploads the same 259 x N keyframe features for every MatchingPoints call of a relocalization query
  * (MapUser::Relocalization, src/map_user.cc:363-376: up to GoodCandidateNum = 3 sequential calls) and of a loop-closure candidate

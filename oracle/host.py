@@ -49,6 +49,40 @@ def cv_resize_u8(img, dst_w=RESIZED, dst_h=RESIZED):
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
+def cv_remap_u8(img, map_x, map_y):
+    """Camera::UndistortImage, src/camera.cc:161-182: cv::remap(img, rect, map1, map2, cv::INTER_LINEAR) with CV_32F maps (camera.cc:63-66),
+    8-bit gray, default BORDER_CONSTANT(0).  Restated from OpenCV's remap: the float maps are quantised to 1/32 pixel (cvRound(32 x), round
+    half to even), the four bilinear weights are the 15-bit table entries (32-fx)(32-fy)*32 ... (exact, they sum to 2^15), and the result is
+    (sum + 2^14) >> 15.  Bit-exact against cv2 4.13 (tests/test_host_logic.py), including samples that leave the image."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    sx = np.rint(np.asarray(map_x, dtype=np.float32) * np.float32(32)).astype(np.int64)
+    sy = np.rint(np.asarray(map_y, dtype=np.float32) * np.float32(32)).astype(np.int64)
+    fx, fy = sx & 31, sy & 31
+    ix, iy = np.clip(sx >> 5, -32768, 32767), np.clip(sy >> 5, -32768, 32767)
+
+    def px(y, x):
+        ok = (x >= 0) & (x < w) & (y >= 0) & (y < h)
+        return np.where(ok, img[np.clip(y, 0, h - 1), np.clip(x, 0, w - 1)].astype(np.int64), 0)
+    v = (px(iy, ix) * ((32 - fx) * (32 - fy) * 32) + px(iy, ix + 1) * (fx * (32 - fy) * 32) + px(iy + 1, ix) * ((32 - fx) * fy * 32) +
+         px(iy + 1, ix + 1) * (fx * fy * 32) + (1 << 14)) >> 15
+    return np.clip(v, 0, 255).astype(np.uint8)
+
+
+def radtan_rectify_maps(w, h, fx, fy, cx, cy, k1, k2, p1, p2, k3=0.0, new_cx=None, new_cy=None):
+    """Synthetic stand-in for cv::initUndistortRectifyMap(K, D, I, K', size, CV_32F) (src/camera.cc:63-66) with R = identity: for every
+    rectified pixel the position in the raw (radial-tangential distorted) image.  Test / bench input generator, not on the hot path."""
+    new_cx = cx if new_cx is None else new_cx
+    new_cy = cy if new_cy is None else new_cy
+    u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    x, y = (u - new_cx) / fx, (v - new_cy) / fy
+    r2 = x * x + y * y
+    kr = 1 + ((k3 * r2 + k2) * r2 + k1) * r2
+    xd = x * kr + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+    yd = y * kr + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+    return (fx * xd + cx).astype(np.float32), (fy * yd + cy).astype(np.float32)
+
+
 def process_image(img):
     """src/plnet.cpp:246-270 == src/super_point.cpp:111-116,146-165: resize to 512x512, float(u8)/255.0 (double) -> f32."""
     r = cv_resize_u8(img)

@@ -56,6 +56,11 @@ def test_batch32_matches_equal_oracle_on_own_features(run32):
     from oracle import host, weights
     _, _, _, _, out = run32
     w = weights.load("lightglue")
+    try:      # offline analysis aid: the GPU's features / matches of pair 0 travel back with gpurun_out/
+        import os
+        np.savez(os.path.join(P.ROOT, "gpurun_out", "debug_p32_pair0.npz"), feat_l=out[0]["feat_l"], feat_r=out[0]["feat_r"], idx=out[0]["matches"][0], score=out[0]["matches"][1])
+    except Exception:
+        pass
     for k in (0, 31):
         # gate: the kernel-matched oracle mode (fp16 rounding of the attention probabilities where tc_attn.cuh does it); report: plain emul
         # (profiles/r02_attention_rounding_drift.txt explains why those two differ by ~1e-2 on ambiguous matches of real-image features)

@@ -167,3 +167,22 @@ def test_association_grid_pruning_equals_full_scan_on_kept_rows():
     # TopK padding with non-peak cells produces runs of adjacent junctions: the grid must refuse (the kernel falls back to the full scan)
     dense = np.stack([np.arange(300) % 128 + 0.5, np.arange(300) // 128 + 0.5], 1).astype(np.float32)
     assert _assoc_grid(lines, dense) is None
+
+
+def test_cv_remap_restatement_is_bit_exact_against_cv2():
+    """oracle.host.cv_remap_u8 == cv2.remap(INTER_LINEAR) on 8-bit gray with CV_32F maps (src/camera.cc:161-182), inside the image and
+    across its borders (BORDER_CONSTANT 0); the synthetic radial-tangential maps agree with cv2.initUndistortRectifyMap."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import host, synth
+    img, _, _ = synth.stereo_pair(752, 480, 77)
+    K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]])
+    D = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0])
+    newK = K.copy()
+    newK[0, 2], newK[1, 2] = 362.0, 250.0
+    m1, m2 = cv2.initUndistortRectifyMap(K, D, np.eye(3), newK, (752, 480), cv2.CV_32F)
+    assert np.array_equal(host.cv_remap_u8(img, m1, m2), cv2.remap(img, m1, m2, cv2.INTER_LINEAR))
+    for sx, ox, sy, oy in ((1.3, -100.0, 1.2, -40.0), (0.5, 300.0, 0.5, 200.0), (1.0, 0.499, 1.0, -0.501)):      # far outside / magnified / half-pixel ties
+        a, b = (m1 * sx + ox).astype(np.float32), (m2 * sy + oy).astype(np.float32)
+        assert np.array_equal(host.cv_remap_u8(img, a, b), cv2.remap(img, a, b, cv2.INTER_LINEAR))
+    mx, my = host.radtan_rectify_maps(752, 480, 458.654, 457.296, 367.215, 248.375, *D[:4], new_cx=362.0, new_cy=250.0)
+    assert np.abs(mx - m1).max() < 2e-3 and np.abs(my - m2).max() < 2e-3
