@@ -4,8 +4,11 @@
 #include "detector.h"
 #include "matcher.h"
 
+#include <map>
 #include <memory>
+#include <set>
 #include <stdlib.h>
+#include <string>
 #include <vector>
 
 using namespace airfe;
@@ -49,7 +52,47 @@ struct airfe_ctx {
   short* d_rxy[2] = {nullptr, nullptr}; unsigned short* d_ra[2] = {nullptr, nullptr};
   int remap_w = 0, remap_h = 0;
   uint8_t* d_rect = nullptr; size_t d_rect_bytes = 0;
+  // CUDA graphs of the per-call class-surface paths (one stereo pair per call): key = everything that shapes the launch sequence
+  std::map<std::string, cudaGraphExec_t> graphs;
+  std::map<std::string, int> graph_seen;
+  std::set<std::string> graph_bad;
+  int graph_launches = 0;
 };
+
+// Per-call (batch <= 2 pairs) paths are launch-latency bound: ~90 (detector) / ~70 (matcher) kernels of a few microseconds each.  The second
+// call with a given shape key is stream-captured (copies from / to the context's pinned staging included) and every later one is a single
+// cudaGraphLaunch.  The first call stays eager: lazy initialisation (resize tables, function attributes, op lists) must not happen under
+// capture.  Anything that goes wrong marks the key as not graphable and the call runs eagerly -- never a different result, only slower.
+// AIRFE_NO_GRAPH=1 disables graphs.
+template <class F>
+static bool run_graphed(airfe_ctx* c, const std::string& key, cudaStream_t st, F&& body) {
+  static const bool on = getenv("AIRFE_NO_GRAPH") == nullptr;
+  if (!on || profiler().on || c->graph_bad.count(key)) return body();
+  auto it = c->graphs.find(key);
+  if (it != c->graphs.end()) {
+    if (cudaGraphLaunch(it->second, st) == cudaSuccess) { c->graph_launches++; return true; }
+    cudaGetLastError();
+    c->graph_bad.insert(key);
+    return body();
+  }
+  if (c->graph_seen[key]++ == 0) return body();
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); c->graph_bad.insert(key); return body(); }
+  const bool ok = body();
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &g);
+  cudaGraphExec_t ex = nullptr;
+  if (!ok || e != cudaSuccess || !g || cudaGraphInstantiate(&ex, g, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (g) cudaGraphDestroy(g);
+    c->graph_bad.insert(key);
+    return body();                         // nothing ran during the failed capture: run it for real
+  }
+  cudaGraphDestroy(g);
+  c->graphs[key] = ex;
+  if (cudaGraphLaunch(ex, st) != cudaSuccess) { cudaGetLastError(); c->graph_bad.insert(key); c->graphs.erase(key); cudaGraphExecDestroy(ex); return body(); }
+  c->graph_launches++;
+  return true;
+}
 
 // The maps to hand to the detector for a call on w x h frames, or nullptr (rectification off).  `stereo`: the call interleaves left / right.
 static const RemapMaps* remap_for(airfe_ctx* c, int w, int h, bool stereo, RemapMaps* tmp, bool* size_error) {
@@ -70,9 +113,17 @@ static int fail(airfe_ctx* c, int code) {
   return code;
 }
 
+// Captured graphs hold raw pointers into the staging buffers and rectification maps: drop them whenever one of those is reallocated.
+static void drop_graphs(airfe_ctx* c) {
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+  c->graphs.clear(); c->graph_seen.clear(); c->graph_bad.clear();
+}
+
 // (Re)allocate the pinned + device frame staging.  On failure the context holds NO staging (pointers null, sizes zero), so that neither
 // the next call nor airfe_destroy touches freed memory.
 static bool grow_image_staging(airfe_ctx* c, size_t need) {
+  cudaStreamSynchronize(c->stream);
+  drop_graphs(c);
   if (c->h_img) cudaFreeHost(c->h_img);
   if (c->d_img) cudaFree(c->d_img);
   c->h_img = nullptr; c->d_img = nullptr; c->h_img_bytes = c->d_img_bytes = 0;
@@ -246,6 +297,7 @@ void airfe_destroy(airfe_ctx* c) {
   if (c->h_ridx) cudaFreeHost(c->h_ridx);
   if (c->h_rscore) cudaFreeHost(c->h_rscore);
   if (c->d_qfeat) cudaFree(c->d_qfeat);
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
   for (int k = 0; k < 2; ++k) { if (c->d_rxy[k]) cudaFree(c->d_rxy[k]); if (c->d_ra[k]) cudaFree(c->d_ra[k]); }
   if (c->d_rect) cudaFree(c->d_rect);
   cudaStreamDestroy(c->stream);
@@ -282,21 +334,40 @@ int airfe_detect_batch(airfe_ctx* c, int net, int batch, const uint8_t* gray, in
   }
   for (int i = 0; i < batch; ++i) memcpy(c->h_img + one * i, gray + (size_t)img_stride * i, one);
   cudaStream_t st = c->stream;
-  if (cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return fail(c, AIRFE_ERR_CUDA); }
   RemapMaps rm; bool rm_err;
   const RemapMaps* rmp = remap_for(c, w, h, false, &rm, &rm_err);
   if (rm_err) return fail(c, AIRFE_ERR_INVALID);
-  if (!d->run(c->d_img, batch, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st, rmp)) return fail(c, AIRFE_ERR_CUDA);
   const DetectOutputs& o = d->out();
   const int B = 2 * c->cfg.max_batch;
   int* hc = c->h_counts;
-  cudaMemcpyAsync(hc, o.n_feat, 4 * batch, cudaMemcpyDeviceToHost, st);
-  if (lines) cudaMemcpyAsync(hc + B, o.n_lines, 4 * batch, cudaMemcpyDeviceToHost, st);
-  if (junc) cudaMemcpyAsync(hc + 2 * B, o.n_junc, 4 * batch, cudaMemcpyDeviceToHost, st);
-  // counts are bounded by max_keypoints, so copy that many feature columns without waiting for the counts
   const int kmax = c->cfg.max_keypoints;
-  for (int i = 0; i < batch; ++i)
-    cudaMemcpyAsync(c->h_feat + (size_t)i * kKpCap * 259, o.feat + (size_t)i * kKpCap * 259, (size_t)kmax * 259 * 4, cudaMemcpyDeviceToHost, st);
+  // Small batches (the class surface: 1 or 2 images per call) run as ONE graph including every copy; the line / junction read-backs are
+  // then sized by the caller's capacities instead of by the counts, so that the whole call needs a single synchronisation.
+  const bool one_shot = batch <= 4;
+  const int lrows = line_cap < kLineCap ? line_cap : kLineCap, jrows = junc_cap < kJunc ? junc_cap : kJunc;
+  auto body = [&]() -> bool {
+    if (cudaMemcpyAsync(c->d_img, c->h_img, need, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("H2D failed"); return false; }
+    if (!d->run(c->d_img, batch, w, h, stride, (long long)one, lines != nullptr, junc != nullptr, st, rmp)) return false;
+    cudaMemcpyAsync(hc, o.n_feat, 4 * batch, cudaMemcpyDeviceToHost, st);
+    if (lines) cudaMemcpyAsync(hc + B, o.n_lines, 4 * batch, cudaMemcpyDeviceToHost, st);
+    if (junc) cudaMemcpyAsync(hc + 2 * B, o.n_junc, 4 * batch, cudaMemcpyDeviceToHost, st);
+    // counts are bounded by max_keypoints, so copy that many feature columns without waiting for the counts
+    for (int i = 0; i < batch; ++i)
+      cudaMemcpyAsync(c->h_feat + (size_t)i * kKpCap * 259, o.feat + (size_t)i * kKpCap * 259, (size_t)kmax * 259 * 4, cudaMemcpyDeviceToHost, st);
+    if (one_shot && lines)
+      for (int i = 0; i < batch; ++i) {
+        if (lrows) cudaMemcpyAsync(c->h_lines + (size_t)i * kLineCap * 4, o.lines + (size_t)i * kLineCap * 4, (size_t)lrows * 16, cudaMemcpyDeviceToHost, st);
+        if (junc && jrows) cudaMemcpyAsync(c->h_junc + (size_t)i * kKpCap * 259, o.junc + (size_t)i * kKpCap * 259, (size_t)jrows * 259 * 4, cudaMemcpyDeviceToHost, st);
+      }
+    return cudaGetLastError() == cudaSuccess;
+  };
+  if (one_shot) {
+    char key[160];
+    snprintf(key, sizeof(key), "det:%d:%d:%dx%d:%d:%d:%d:%d:%d:%d", net, batch, w, h, stride, lines ? 1 : 0, junc ? 1 : 0, rmp ? rmp->mode : 0, lrows, jrows);
+    if (!run_graphed(c, key, st, body)) return fail(c, AIRFE_ERR_CUDA);
+  } else if (!body()) {
+    return fail(c, AIRFE_ERR_CUDA);
+  }
   if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("detect failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(c, AIRFE_ERR_CUDA); }
   for (int i = 0; i < batch; ++i) {
     const int n = hc[i] < feat_cap ? hc[i] : feat_cap;
@@ -308,15 +379,15 @@ int airfe_detect_batch(airfe_ctx* c, int net, int batch, const uint8_t* gray, in
     for (int i = 0; i < batch; ++i) {
       const int n = hc[B + i] < line_cap ? hc[B + i] : line_cap;
       n_lines[i] = n;
-      if (n) cudaMemcpyAsync(c->h_lines + (size_t)i * kLineCap * 4, o.lines + (size_t)i * kLineCap * 4, (size_t)n * 16, cudaMemcpyDeviceToHost, st);
+      if (n && !one_shot) cudaMemcpyAsync(c->h_lines + (size_t)i * kLineCap * 4, o.lines + (size_t)i * kLineCap * 4, (size_t)n * 16, cudaMemcpyDeviceToHost, st);
     }
     if (junc)
       for (int i = 0; i < batch; ++i) {
         const int n = hc[2 * B + i] < junc_cap ? hc[2 * B + i] : junc_cap;
         n_junc[i] = n;
-        if (n) cudaMemcpyAsync(c->h_junc + (size_t)i * kKpCap * 259, o.junc + (size_t)i * kKpCap * 259, (size_t)n * 259 * 4, cudaMemcpyDeviceToHost, st);
+        if (n && !one_shot) cudaMemcpyAsync(c->h_junc + (size_t)i * kKpCap * 259, o.junc + (size_t)i * kKpCap * 259, (size_t)n * 259 * 4, cudaMemcpyDeviceToHost, st);
       }
-    cudaStreamSynchronize(st);
+    if (!one_shot) cudaStreamSynchronize(st);
     for (int i = 0; i < batch; ++i) {
       const float* l = c->h_lines + (size_t)i * kLineCap * 4;
       double* dl = lines + (size_t)i * line_cap * 4;
@@ -335,17 +406,28 @@ int airfe_detect(airfe_ctx* c, int net, const uint8_t* gray, int w, int h, int s
   return airfe_detect_batch(c, net, 1, gray, w, h, stride, 0, feat, feat_cap, n_feat, lines, line_cap, n_lines, junc, junc_cap, n_junc);
 }
 
+static void fetch_matches_enqueue(airfe_ctx* c, int pairs, int matcher) {
+  const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
+  const int cap = sgm ? c->sg_use->cap() : c->lg_use->cap();
+  cudaStream_t st = c->stream;
+  cudaMemcpyAsync(c->h_mcount, sgm ? c->sg_use->out().m_count : c->lg_use->out().count, 4 * pairs, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(c->h_midx, sgm ? c->sg_use->out().m_idx : c->lg_use->out().idx, (size_t)pairs * cap * 8, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(c->h_mscore, sgm ? c->sg_use->out().m_score : c->lg_use->out().score, (size_t)pairs * cap * 4, cudaMemcpyDeviceToHost, st);
+}
+
 static int fetch_matches(airfe_ctx* c, int pairs, int* idx0, int* idx1, float* score, int match_cap, int* n_match, const int* zero_mask,
-                         int matcher = AIRFE_MATCHER_LIGHTGLUE) {
+                         int matcher = AIRFE_MATCHER_LIGHTGLUE, bool enqueued = false) {
   const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
   const int cap = sgm ? c->sg_use->cap() : c->lg_use->cap();
   const int* d_count = sgm ? c->sg_use->out().m_count : c->lg_use->out().count;
   const int* d_idx = sgm ? c->sg_use->out().m_idx : c->lg_use->out().idx;
   const float* d_score = sgm ? c->sg_use->out().m_score : c->lg_use->out().score;
   cudaStream_t st = c->stream;
-  cudaMemcpyAsync(c->h_mcount, d_count, 4 * pairs, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(c->h_midx, d_idx, (size_t)pairs * cap * 8, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(c->h_mscore, d_score, (size_t)pairs * cap * 4, cudaMemcpyDeviceToHost, st);
+  if (!enqueued) {
+    cudaMemcpyAsync(c->h_mcount, d_count, 4 * pairs, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(c->h_midx, d_idx, (size_t)pairs * cap * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(c->h_mscore, d_score, (size_t)pairs * cap * 4, cudaMemcpyDeviceToHost, st);
+  }
   if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("match failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(c, AIRFE_ERR_CUDA); }
   for (int p = 0; p < pairs; ++p) {
     int n = c->h_mcount[p];
@@ -398,12 +480,36 @@ int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, 
     memcpy(c->h_mfeat + (size_t)(2 * p + 1) * kKpCap * 259, feat1 + (size_t)p * feat_cap * 259, (size_t)n1[p] * 259 * 4);
   }
   cudaStream_t st = c->stream;
-  for (int s = 0; s < 2 * pairs; ++s)
-    if (c->h_mn[s] > 0)
-      cudaMemcpyAsync(c->d_mfeat + (size_t)s * kKpCap * 259, c->h_mfeat + (size_t)s * kKpCap * 259, (size_t)c->h_mn[s] * 259 * 4, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(c->d_mn, c->h_mn, 8 * pairs, cudaMemcpyHostToDevice, st);
   const bool dense = getenv("AIRFE_DEBUG_DENSE") != nullptr;
-  if (sgm ? !c->sg_use->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm, nullptr, nmax) : !c->lg_use->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, g_prenorm)) return fail(c, AIRFE_ERR_CUDA);
+  const bool prenorm = g_prenorm;
+  // small calls (the class surface: one pair) run as one graph; the H2D sizes are then a bucket (rows rounded up to 64) so that a handful
+  // of graphs covers every keypoint count -- rows beyond the count are never read by the kernels
+  const bool one_shot = pairs <= 2 && !dense;
+  int bucket = 0;
+  if (one_shot) {
+    bucket = (nmax + 63) / 64 * 64;
+    if (nmax <= 415 && bucket > 415) bucket = 415;      // keep 400-keypoint sets inside the 13-column size class of the fused Sinkhorn kernel
+    if (bucket > kKpCap) bucket = kKpCap;
+  }
+  auto body = [&]() -> bool {
+    for (int s2 = 0; s2 < 2 * pairs; ++s2) {
+      const int rows = one_shot ? bucket : c->h_mn[s2];
+      if (rows > 0)
+        cudaMemcpyAsync(c->d_mfeat + (size_t)s2 * kKpCap * 259, c->h_mfeat + (size_t)s2 * kKpCap * 259, (size_t)rows * 259 * 4, cudaMemcpyHostToDevice, st);
+    }
+    cudaMemcpyAsync(c->d_mn, c->h_mn, 8 * pairs, cudaMemcpyHostToDevice, st);
+    if (sgm ? !c->sg_use->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, prenorm, nullptr, one_shot ? bucket : nmax) : !c->lg_use->run(c->d_mfeat, c->d_mn, kKpCap, pairs, dense, st, prenorm))
+      return false;
+    if (one_shot) fetch_matches_enqueue(c, pairs, matcher);
+    return cudaGetLastError() == cudaSuccess;
+  };
+  if (one_shot) {
+    char key[128];
+    snprintf(key, sizeof(key), "match:%d:%p:%d:%d:%d", matcher, sgm ? (void*)c->sg_use : (void*)c->lg_use, pairs, prenorm ? 1 : 0, bucket);
+    if (!run_graphed(c, key, st, body)) return fail(c, AIRFE_ERR_CUDA);
+    return fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, zero.data(), matcher, true);
+  }
+  if (!body()) return fail(c, AIRFE_ERR_CUDA);
   return fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, zero.data(), matcher);
 }
 
@@ -599,6 +705,7 @@ int airfe_set_rectify_maps(airfe_ctx* c, int side, const float* map_x, const flo
   if (c->remap_w && (w != c->remap_w || h != c->remap_h) && c->d_rxy[1 - side]) { set_error("both cameras must share one image size"); return fail(c, AIRFE_ERR_INVALID); }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  drop_graphs(c);
   const size_t n = (size_t)w * h;
   std::vector<short> xy(2 * n);
   std::vector<unsigned short> a(n);

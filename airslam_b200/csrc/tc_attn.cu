@@ -25,12 +25,17 @@ bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __h
   if (!make_tmap_f16(&p.tmQ, q, 4, dims, str, box_q) || !make_tmap_f16(&p.tmK, k, 4, dims, str, box_kv) || !make_tmap_f16(&p.tmV, v, 4, dims, str, box_kv))
     return false;
   p.n = n; p.slots = slots; p.cap = cap; p.slot_xor = slot_xor; p.scale = scale; p.ctx = ctx;
+  // Small batches (the per-call class surface: 2 slots; config 3: 16) leave most SMs idle with one CTA per (slot, head): split the query tiles
+  // of a (slot, head) over up to cap / 128 CTAs while that still fits one wave (each part re-reads K / V from L2, so large batches do not split).
+  int q_split = 1;
+  while (q_split * 2 <= cap / 128 && slots * 4 * q_split * 2 <= device_sm_count()) q_split *= 2;
+  p.q_split = q_split;
   const double fl = 2.0 * 2.0 * slots * 4 * (double)cap * cap * 64;   // same accounting as the unfused pair of GEMMs
   ol->tc_flops += fl;
   ol->launches += 1;
   char nm[96];
   snprintf(nm, sizeof(nm), "tc_attn fused %s slots=%d cap=%d", slot_xor ? "cross" : "self", slots, cap);
-  ol->push(nm, fl, [p, slots](cudaStream_t st) {
+  ol->push(nm, fl, [p, slots, q_split](cudaStream_t st) {
     static bool attr_set[kMaxDevices] = {};
     const int dev = current_device();
     if (!attr_set[dev]) {
@@ -40,7 +45,7 @@ bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __h
       }
       attr_set[dev] = true;
     }
-    cudaError_t e = launch_pdl(tc_attn_kernel, slots * 4, kAttnThreads, kAttnSmemBytes, st, p);
+    cudaError_t e = launch_pdl(tc_attn_kernel, slots * 4 * q_split, kAttnThreads, kAttnSmemBytes, st, p);
     if (e != cudaSuccess) { set_error("tc_attn launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
   }, slot_xor ? kDynAttCross : kDynAttSelf);

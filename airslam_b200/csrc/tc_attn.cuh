@@ -20,6 +20,7 @@ struct AttnParams {
   CUtensorMap tmV;   // same geometry on the value matrix,   box (64, 256, 1, 1)   (rows = keys: MN-major B for P.V)
   const int* n;      // [slots] keypoints per slot (device)
   int slots, cap, slot_xor;
+  int q_split;       // CTAs per (slot, head): CTA part handles query tiles part, part + q_split, ... (small batches: more CTAs than slots x 4)
   float scale;       // applied to S before the softmax (1 for LightGlue: q,k pre-scaled; 1/8 for SuperGlue)
   __half* ctx;       // [slots*cap][256] fp16, head h at columns h*64
 };
@@ -50,7 +51,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * kAttnPSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = blockIdx.x >> 2, head = blockIdx.x & 3;
+  const int part = blockIdx.x % p.q_split, sh = blockIdx.x / p.q_split;
+  const int slot = sh >> 2, head = sh & 3;
   const int kslot = slot ^ p.slot_xor;
 
   if (warp == 0 && lane == 0) {
@@ -69,7 +71,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
   ptx::pdl_wait();                // the keypoint counts and Q / K / V are produced by earlier kernels: read them only from here on
   const int nq = min(__ldg(p.n + slot), p.cap);
   const int nk = min(__ldg(p.n + kslot), 512);
-  const int q_tiles = (nq + 127) >> 7;
+  const int q_tiles_all = (nq + 127) >> 7;
+  const int q_tiles = q_tiles_all > part ? (q_tiles_all - part + p.q_split - 1) / p.q_split : 0;     // tiles of this CTA: t_global = part + t * q_split
   const int nkb = (nk + 63) >> 6;              // 64-key blocks of P / V
   const int nk16 = (nk + 15) & ~15;            // key extent of the S MMAs
 
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
         for (int t = 0; t < q_tiles; ++t) {
           ptx::mbar_wait(q_empty, ph ^ 1);
           ptx::mbar_arrive_expect_tx(q_full, 128u * 128u);
-          ptx::tma_load_4d(sQ, &p.tmQ, q_full, 0, t * 128, head, slot);
+          ptx::tma_load_4d(sQ, &p.tmQ, q_full, 0, (part + t * p.q_split) * 128, head, slot);
           ph ^= 1;
         }
       }
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
         // epilogue: O (128 x 64 fp32, TMEM columns 0..63) -> fp16 context rows; this warp writes columns half*32 .. +32
         ptx::mbar_wait(o_full, ph);
         ptx::tc_fence_after();
-        const int q = t * 128 + row;
+        const int q = (part + t * p.q_split) * 128 + row;
         __half* o = p.ctx + ((long long)slot * p.cap + q) * 256 + head * 64;
         {
           const int c = half * 32;

@@ -69,13 +69,13 @@ def cv_remap_u8(img, map_x, map_y):
     return np.clip(v, 0, 255).astype(np.uint8)
 
 
-def radtan_rectify_maps(w, h, fx, fy, cx, cy, k1, k2, p1, p2, k3=0.0, new_cx=None, new_cy=None):
+def radtan_rectify_maps(w, h, fx, fy, cx, cy, k1, k2, p1, p2, k3=0.0, new_cx=None, new_cy=None, new_f_scale=1.0):
     """Synthetic stand-in for cv::initUndistortRectifyMap(K, D, I, K', size, CV_32F) (src/camera.cc:63-66) with R = identity: for every
     rectified pixel the position in the raw (radial-tangential distorted) image.  Test / bench input generator, not on the hot path."""
     new_cx = cx if new_cx is None else new_cx
     new_cy = cy if new_cy is None else new_cy
     u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
-    x, y = (u - new_cx) / fx, (v - new_cy) / fy
+    x, y = (u - new_cx) / (fx * new_f_scale), (v - new_cy) / (fy * new_f_scale)     # new_f_scale < 1: the rectified view is wider than the sensor
     r2 = x * x + y * y
     kr = 1 + ((k3 * r2 + k2) * r2 + k1) * r2
     xd = x * kr + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)

@@ -68,7 +68,15 @@ def test_batch32_matches_equal_oracle_on_own_features(run32):
         idx_o = np.array([[a, b] for a, b, _ in m], dtype=np.int32).reshape(-1, 2)
         P.exact("P=32: LightGlue indices of pair %d == kernel-matched oracle on the same features" % k, np.array_equal(out[k]["matches"][0], idx_o))
         sc_o = np.array([1.0 - d for _, _, d in m], dtype=np.float32)
-        P.check("P=32: LightGlue scores vs kernel-matched oracle (emul='fused')", np.abs(out[k]["matches"][1] - sc_o).max(), 3e-3, "abs in probability")
+        # Real-image feature sets contain a few AMBIGUOUS matches (probability ~0.5) whose score is chaotic in the fp16 rounding pattern: on
+        # pair 0 one match reads 0.5667 (GPU) / 0.5716 (fused oracle) / 0.5498 (emul) / 0.5704 (fp32) while the other 366 agree to 1e-6.
+        # Gate: >= 99 % of the matches within 1e-3, median within 1e-5, and the worst one inside the oracle's own fp32 / emul / fused spread
+        # class (3e-2; profiles/r02_attention_rounding_drift.txt).
+        err = np.abs(out[k]["matches"][1] - sc_o)
+        P.check("P=32: LightGlue scores vs kernel-matched oracle: median", np.median(err), 1e-5, "abs in probability")
+        P.check("P=32: LightGlue scores vs kernel-matched oracle: fraction of matches off by > 1e-3", float((err > 1e-3).mean()), 0.01, "fraction")
+        P.check("P=32: LightGlue scores vs kernel-matched oracle: worst (ambiguous) match", err.max(), 3e-2, "abs in probability",
+                "bounded by the oracle's own fp32 / emul / fused spread on ambiguous matches")
         m2 = host.matching_points(out[k]["feat_l"], out[k]["feat_r"], w, 0, 752, 480, emul=True)
         idx_2 = np.array([[a, b] for a, b, _ in m2], dtype=np.int32).reshape(-1, 2)
         P.exact("P=32: LightGlue indices of pair %d == plain emul oracle" % k, np.array_equal(out[k]["matches"][0], idx_2))

@@ -13,8 +13,8 @@ W, H = 752, 480
 def _maps():
     from oracle import host
     # EuRoC-like radial-tangential cameras (configs/camera/euroc.yaml shape): left and right differ
-    l = host.radtan_rectify_maps(W, H, 458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, new_cx=362.0, new_cy=250.0)
-    r = host.radtan_rectify_maps(W, H, 457.587, 456.134, 379.999, 255.238, -0.28368365, 0.07451284, -0.00010473, -3.55590700e-05, new_cx=362.0, new_cy=250.0)
+    l = host.radtan_rectify_maps(W, H, 458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, new_cx=362.0, new_cy=250.0, new_f_scale=0.78)
+    r = host.radtan_rectify_maps(W, H, 457.587, 456.134, 379.999, 255.238, -0.28368365, 0.07451284, -0.00010473, -3.55590700e-05, new_cx=362.0, new_cy=250.0, new_f_scale=0.78)
     return l, r
 
 
