@@ -116,6 +116,12 @@ def _declare_match(L):
     L.airfe_set_rectify.restype = i32
     L.airfe_undistort.argtypes = [vp, i32, vp, i32, i32, i32, vp, i32]
     L.airfe_undistort.restype = i32
+    L.airfe_stereo_line_assoc.argtypes = [vp, i32, C.c_double, C.c_double, C.c_double, i32, i32, vp, vp, vp, vp]
+    L.airfe_stereo_line_assoc.restype = i32
+    L.airfe_bow_load.argtypes = [vp, C.c_char_p]
+    L.airfe_bow_load.restype = i32
+    L.airfe_bow_transform.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.airfe_bow_transform.restype = i32
     L.airfe_kf_reserve.argtypes = [vp, i32, i32]
     L.airfe_kf_reserve.restype = i32
     L.airfe_kf_put.argtypes = [vp, i32, vp, i32]
@@ -275,6 +281,32 @@ class Context:
             nm, fl, ms = line.split("\t")
             out.append((nm, float(fl), float(ms)))
         return out
+
+    # ---- BoW quantisation (Database::FrameToBow) ----
+    def bow_load(self, path=None):
+        self._check(lib().airfe_bow_load(self.h, (path or os.path.join(WEIGHTS_DIR, "point_voc_L4.afw")).encode()))
+
+    def bow_transform(self, feat):
+        """feat [259, N] float32 -> (word_of_feature uint32 [N], [(word id, normalised weight), ...])."""
+        import numpy as np
+        a = np.ascontiguousarray(feat.T, dtype=np.float32)
+        n = a.shape[0]
+        words = np.zeros(max(n, 1), np.uint32); ids = np.zeros(max(n, 1), np.uint32); vals = np.zeros(max(n, 1), np.float64)
+        nb = i32(0)
+        self._check(lib().airfe_bow_transform(self.h, a.ctypes.data_as(vp), n, words.ctypes.data_as(vp), ids.ctypes.data_as(vp), vals.ctypes.data_as(vp), C.byref(nb)))
+        return words[:n], list(zip(ids[:nb.value].tolist(), vals[:nb.value].tolist()))
+
+    # ---- point <-> line association + stereo line matching on the last stereo call's device-resident results ----
+    def stereo_line_assoc(self, pairs, min_x_diff, max_x_diff, max_y_diff, line_cap=256, rel_cap=32):
+        """Returns per pair (rel_left, rel_right, line_matches): rel_* = list (one per line slot) of {point index: distance}."""
+        import numpy as np
+        rn = np.zeros((2 * pairs, line_cap), np.int32)
+        ri = np.zeros((2 * pairs, line_cap, rel_cap), np.int32)
+        rd = np.zeros((2 * pairs, line_cap, rel_cap), np.float32)
+        lm = np.zeros((pairs, line_cap), np.int32)
+        q = lambda a: a.ctypes.data_as(vp)
+        self._check(lib().airfe_stereo_line_assoc(self.h, pairs, min_x_diff, max_x_diff, max_y_diff, line_cap, rel_cap, q(rn), q(ri), q(rd), q(lm)))
+        return rn, ri, rd, lm
 
     # ---- rectification (Camera::UndistortImage) fused into the first kernel ----
     def set_rectify_maps(self, side, map_x, map_y):

@@ -3,6 +3,8 @@
 #include "../../include/airfe_c.h"
 #include "detector.h"
 #include "matcher.h"
+#include "assoc_kernels.h"
+#include "bow.h"
 
 #include <map>
 #include <memory>
@@ -52,6 +54,13 @@ struct airfe_ctx {
   short* d_rxy[2] = {nullptr, nullptr}; unsigned short* d_ra[2] = {nullptr, nullptr};
   int remap_w = 0, remap_h = 0;
   uint8_t* d_rect = nullptr; size_t d_rect_bytes = 0;
+  std::unique_ptr<BowVocabulary> voc;                 // airfe_bow_load
+  float* d_bowfeat = nullptr; size_t d_bowfeat_rows = 0;
+  // point <-> line association (airfe_stereo_line_assoc): state of the last stereo call + device scratch
+  int last_net = -1, last_matcher = -1, last_pairs = 0, last_w = 0, last_h = 0;
+  int la_pairs = 0;
+  int *la_rel_n = nullptr, *la_rel_idx = nullptr, *la_cnt = nullptr, *la_row = nullptr, *la_lm = nullptr, *la_ovf = nullptr;
+  float* la_rel_dist = nullptr;
   // CUDA graphs of the per-call class-surface paths (one stereo pair per call): key = everything that shapes the launch sequence
   std::map<std::string, cudaGraphExec_t> graphs;
   std::map<std::string, int> graph_seen;
@@ -298,6 +307,15 @@ void airfe_destroy(airfe_ctx* c) {
   if (c->h_rscore) cudaFreeHost(c->h_rscore);
   if (c->d_qfeat) cudaFree(c->d_qfeat);
   for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+  c->voc.reset();
+  if (c->d_bowfeat) cudaFree(c->d_bowfeat);
+  if (c->la_rel_n) cudaFree(c->la_rel_n);
+  if (c->la_rel_idx) cudaFree(c->la_rel_idx);
+  if (c->la_rel_dist) cudaFree(c->la_rel_dist);
+  if (c->la_cnt) cudaFree(c->la_cnt);
+  if (c->la_row) cudaFree(c->la_row);
+  if (c->la_lm) cudaFree(c->la_lm);
+  if (c->la_ovf) cudaFree(c->la_ovf);
   for (int k = 0; k < 2; ++k) { if (c->d_rxy[k]) cudaFree(c->d_rxy[k]); if (c->d_ra[k]) cudaFree(c->d_ra[k]); }
   if (c->d_rect) cudaFree(c->d_rect);
   cudaStreamDestroy(c->stream);
@@ -551,7 +569,9 @@ int airfe_stereo_device(airfe_ctx* c, int net, int matcher, int pairs, const voi
   if (rm_err) return fail(c, AIRFE_ERR_INVALID);
   if (!d->run((const uint8_t*)d_images, 2 * pairs, w, h, stride, img_stride, lines != 0, junctions != 0, c->stream, rmp)) return fail(c, AIRFE_ERR_CUDA);
   const DetectOutputs& o = d->out();
+  if (sgm) c->sg_use = c->sg.get(); else c->lg_use = c->lg.get();
   if (sgm ? !c->sg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream, false, nullptr, c->cfg.max_keypoints) : !c->lg->run(o.feat, o.n_feat, kKpCap, pairs, false, c->stream)) return fail(c, AIRFE_ERR_CUDA);
+  c->last_net = net; c->last_matcher = matcher; c->last_pairs = pairs; c->last_w = w; c->last_h = h;
   return AIRFE_OK;
 }
 
@@ -694,8 +714,142 @@ int airfe_detect_match_stereo_batch(airfe_ctx* c, int net, int matcher, int pair
   }
   int rc = fetch_matches(c, pairs, idx0, idx1, score, match_cap, n_match, nullptr, matcher);   // synchronises the compute stream
   if (rc != AIRFE_OK) return fail(c, rc);
+  c->last_net = net; c->last_matcher = matcher; c->last_pairs = pairs; c->last_w = w; c->last_h = h;
   for (int p = 0; p < pairs; ++p)
     if (hc[2 * p] < 1 || hc[2 * p + 1] < 1) n_match[p] = 0;
+  return AIRFE_OK;
+}
+
+// ---- BoW quantisation (Database::FrameToBow) -------------------------------------------------------------------------------------------
+int airfe_bow_load(airfe_ctx* c, const char* path) {
+  if (!c || !path) { set_error("null argument"); return fail(c, AIRFE_ERR_INVALID); }
+  cudaSetDevice(c->device);
+  std::unique_ptr<BowVocabulary> v(new BowVocabulary);
+  const size_t len = strlen(path);
+  const bool afw = len > 4 && !strcmp(path + len - 4, ".afw");
+  if (!(afw ? v->load_afw(path) : v->load_boost_archive(path))) return fail(c, AIRFE_ERR_IO);
+  c->voc = std::move(v);
+  return AIRFE_OK;
+}
+int airfe_bow_transform(airfe_ctx* c, const float* feat, int n, unsigned int* word_of_feature, unsigned int* bow_ids, double* bow_vals, int* n_bow) {
+  if (!c || !feat || !word_of_feature || !bow_ids || !bow_vals || !n_bow || n < 0) { set_error("null argument"); return fail(c, AIRFE_ERR_INVALID); }
+  if (!c->voc) { set_error("no vocabulary: call airfe_bow_load first"); return fail(c, AIRFE_ERR_INVALID); }
+  *n_bow = 0;
+  if (n == 0) return AIRFE_OK;                                        // database.cc:60
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  BowVocabulary& v = *c->voc;
+  if (n > v.leaf_cap) {
+    cudaStreamSynchronize(st);
+    if (v.d_leaf) cudaFree(v.d_leaf);
+    v.d_leaf = nullptr; v.leaf_cap = 0;
+    if (cudaMalloc(&v.d_leaf, (size_t)n * 4) != cudaSuccess) { cudaGetLastError(); set_error("bow: allocation failed"); return fail(c, AIRFE_ERR_CUDA); }
+    v.leaf_cap = n;
+  }
+  cudaPointerAttributes pa;
+  const bool on_device = cudaPointerGetAttributes(&pa, feat) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  const float* df = feat;
+  if (!on_device) {
+    if ((size_t)n > c->d_bowfeat_rows) {
+      cudaStreamSynchronize(st);
+      if (c->d_bowfeat) cudaFree(c->d_bowfeat);
+      c->d_bowfeat = nullptr; c->d_bowfeat_rows = 0;
+      if (cudaMalloc(&c->d_bowfeat, (size_t)n * 259 * 4) != cudaSuccess) { cudaGetLastError(); set_error("bow: allocation failed"); return fail(c, AIRFE_ERR_CUDA); }
+      c->d_bowfeat_rows = n;
+    }
+    cudaMemcpyAsync(c->d_bowfeat, feat, (size_t)n * 259 * 4, cudaMemcpyHostToDevice, st);
+    df = c->d_bowfeat;
+  }
+  if (!bow_transform_device(v, df, 259, n, v.d_leaf, st)) return fail(c, AIRFE_ERR_CUDA);
+  std::vector<int> leaf(n);
+  cudaMemcpyAsync(leaf.data(), v.d_leaf, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("bow transform failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(c, AIRFE_ERR_CUDA); }
+  // database.cc:70-88 + BowVector::addWeight / normalize(L1): the reference's own double arithmetic, in feature order then map order
+  std::map<unsigned int, double> bow;
+  for (int i = 0; i < n; ++i) {
+    const int node = leaf[i];
+    const double w = (node >= 0 && node < v.n_nodes) ? v.weight[node] : 0.0;
+    if (w > 0) {
+      const unsigned int id = (unsigned int)v.word_id[node];
+      auto it = bow.lower_bound(id);
+      if (it != bow.end() && it->first == id) it->second += w; else bow.insert(it, std::make_pair(id, w));
+      word_of_feature[i] = id;
+    } else {
+      word_of_feature[i] = 0xFFFFFFFFu;                               // UINT_MAX
+    }
+  }
+  double norm = 0.0;
+  for (auto& kv : bow) norm += fabs(kv.second);
+  int k = 0;
+  for (auto& kv : bow) { bow_ids[k] = kv.first; bow_vals[k] = norm > 0.0 ? kv.second / norm : kv.second; ++k; }
+  *n_bow = k;
+  return AIRFE_OK;
+}
+
+// ---- point <-> line association + stereo line matching on the last stereo call's device-resident results ----------------------------
+int airfe_stereo_line_assoc(airfe_ctx* c, int pairs, double min_x_diff, double max_x_diff, double max_y_diff, int line_cap, int rel_cap,
+                            int* rel_n, int* rel_idx, float* rel_dist, int* line_matches) {
+  constexpr int kML = 256, kRC = 32;
+  if (!c || !rel_n || !rel_idx || !rel_dist || !line_matches || line_cap < 1 || rel_cap < 1) { set_error("null argument"); return fail(c, AIRFE_ERR_INVALID); }
+  if (c->last_net != AIRFE_NET_PLNET || pairs < 1 || pairs != c->last_pairs) { set_error("line association follows a PLNet stereo call with the same number of pairs"); return fail(c, AIRFE_ERR_INVALID); }
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  if (pairs > c->la_pairs) {
+    cudaStreamSynchronize(st);
+    int** ip[] = {&c->la_rel_n, &c->la_rel_idx, &c->la_cnt, &c->la_row, &c->la_lm, &c->la_ovf};
+    for (auto q : ip) { if (*q) cudaFree(*q); *q = nullptr; }
+    if (c->la_rel_dist) cudaFree(c->la_rel_dist);
+    c->la_rel_dist = nullptr; c->la_pairs = 0;
+    const size_t P = (size_t)pairs;
+    if (cudaMalloc(&c->la_rel_n, 2 * P * kML * 4) != cudaSuccess || cudaMalloc(&c->la_rel_idx, 2 * P * kML * kRC * 4) != cudaSuccess ||
+        cudaMalloc(&c->la_rel_dist, 2 * P * kML * kRC * 4) != cudaSuccess || cudaMalloc(&c->la_cnt, P * kML * kML * 4) != cudaSuccess ||
+        cudaMalloc(&c->la_row, P * kML * 4) != cudaSuccess || cudaMalloc(&c->la_lm, P * kML * 4) != cudaSuccess || cudaMalloc(&c->la_ovf, 4) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("line association scratch allocation failed");
+      return fail(c, AIRFE_ERR_CUDA);
+    }
+    c->la_pairs = pairs;
+  }
+  const DetectOutputs& o = c->pl->out();
+  const bool sgm = c->last_matcher == AIRFE_MATCHER_SUPERGLUE;
+  const int* m_idx = sgm ? c->sg_use->out().m_idx : c->lg_use->out().idx;
+  const int* m_count = sgm ? c->sg_use->out().m_count : c->lg_use->out().count;
+  const int m_cap = sgm ? c->sg_use->cap() : c->lg_use->cap();
+  const double ws = (double)((float)c->last_w / 512.f), hs = (double)((float)c->last_h / 512.f);
+  launch_line_assoc(o.lines, o.n_lines, kLineCap, o.feat, o.n_feat, kKpCap, ws, hs, m_idx, m_count, m_cap, pairs, min_x_diff, max_x_diff, max_y_diff, kML, kRC,
+                    c->la_rel_n, c->la_rel_idx, c->la_rel_dist, c->la_cnt, c->la_row, c->la_lm, c->la_ovf, st);
+  const int S = 2 * pairs;
+  std::vector<int> h_nl(S), h_rn((size_t)S * kML), h_lm((size_t)pairs * kML);
+  int ovf = 0;
+  cudaMemcpyAsync(h_nl.data(), o.n_lines, 4 * S, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(h_rn.data(), c->la_rel_n, (size_t)S * kML * 4, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(h_lm.data(), c->la_lm, (size_t)pairs * kML * 4, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(&ovf, c->la_ovf, 4, cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("line association failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(c, AIRFE_ERR_CUDA); }
+  std::vector<int> h_idx((size_t)kML * kRC);
+  std::vector<float> h_dist((size_t)kML * kRC);
+  for (int s2 = 0; s2 < S; ++s2) {
+    const int nl = h_nl[s2];
+    if (nl > kML || nl > line_cap) { set_error("image %d: %d lines exceed the association capacity %d", s2, nl, kML < line_cap ? kML : line_cap); return fail(c, AIRFE_ERR_CAPACITY); }
+    if (nl) {
+      cudaMemcpy(h_idx.data(), c->la_rel_idx + (size_t)s2 * kML * kRC, (size_t)nl * kRC * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(h_dist.data(), c->la_rel_dist + (size_t)s2 * kML * kRC, (size_t)nl * kRC * 4, cudaMemcpyDeviceToHost);
+    }
+    for (int i = 0; i < line_cap; ++i) rel_n[(size_t)s2 * line_cap + i] = 0;
+    for (int i = 0; i < nl; ++i) {
+      const int n = h_rn[(size_t)s2 * kML + i];
+      if (n > rel_cap) { set_error("line %d of image %d has %d points, rel_cap is %d", i, s2, n, rel_cap); return fail(c, AIRFE_ERR_CAPACITY); }
+      rel_n[(size_t)s2 * line_cap + i] = n;
+      for (int k = 0; k < n; ++k) {
+        rel_idx[((size_t)s2 * line_cap + i) * rel_cap + k] = h_idx[(size_t)i * kRC + k];
+        rel_dist[((size_t)s2 * line_cap + i) * rel_cap + k] = h_dist[(size_t)i * kRC + k];
+      }
+    }
+  }
+  if (ovf) { set_error("line association overflow (more than %d points on a line or 8 lines through a point)", kRC); return fail(c, AIRFE_ERR_CAPACITY); }
+  for (int p = 0; p < pairs; ++p)
+    for (int i = 0; i < line_cap; ++i) line_matches[(size_t)p * line_cap + i] = i < kML ? h_lm[(size_t)p * kML + i] : -1;
   return AIRFE_OK;
 }
 

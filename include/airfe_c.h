@@ -138,6 +138,31 @@ int airfe_set_rectify(airfe_ctx* ctx, int mode);
 /* The rectified image itself, for callers that keep it (MapBuilder::AddInput stores it in the input data): rect = remap(raw). */
 int airfe_undistort(airfe_ctx* ctx, int side, const uint8_t* raw, int width, int height, int stride, uint8_t* rect, int rect_stride);
 
+/* ---- point <-> line association and stereo line matching on the device ----
+ * The step right after the path in Frame::AddLeftFeatures / AddRightFeatures (src/frame.cc:121-125, 141-187):
+ *   AssignPointsToLines (src/line_processor.cc:68-120) for the left and the right image of every pair, and
+ *   MatchLines (src/line_processor.cc:122-187) on the stereo point matches that pass the disparity filter of src/frame.cc:141-155
+ *   (min_x_diff < |xl - xr| < max_x_diff, |yl - yr| <= max_y_diff: Camera::MinXDiff / MaxXDiff / MaxYDiff).
+ * It runs on the DEVICE-RESIDENT results of the last airfe_detect_match_stereo_batch / airfe_stereo_device call of this context (lines,
+ * features and matches never come back to the device).  Outputs, image slot s = 2*pair + side:
+ *   rel_n   [2*pairs][line_cap]            points on each line (std::map<int,double>::size())
+ *   rel_idx [2*pairs][line_cap][rel_cap]   their indices, ascending (map iteration order); rel_dist: double(float distance) as float
+ *   line_matches [pairs][line_cap]         index of the matched right line per left line, -1 = none
+ * Limits: 256 lines per image, 32 points per line, 8 lines per point -- beyond them the call returns AIRFE_ERR_CAPACITY. */
+int airfe_stereo_line_assoc(airfe_ctx* ctx, int pairs, double min_x_diff, double max_x_diff, double max_y_diff, int line_cap, int rel_cap,
+                            int* rel_n, int* rel_idx, float* rel_dist, int* line_matches);
+
+/* ---- BoW quantisation of keyframe descriptors on the device ----
+ * Database::FrameToBow (src/bow/database.cc:57-89): every 256-d descriptor walks the DBoW2 vocabulary tree (voc/point_voc_L4.bin, k = 10,
+ * L = 4) to its word; words accumulate their idf weight into the BowVector, which is L1-normalised (the vocabulary's L1_NORM scoring).
+ * airfe_bow_load: `path` is either the converted container weights/point_voc_L4.afw or the reference's Boost binary archive itself
+ * (what Database::LoadVocabulary reads, src/bow/database.cc:15-24); the tree stays resident on the device.
+ * airfe_bow_transform: feat259 (HOST or DEVICE pointer, column-major 259 x n as everywhere) ->
+ *   word_of_feature [n]   word id per keypoint, 0xFFFFFFFF where the word's weight is <= 0 (database.cc:76-78)
+ *   bow_ids / bow_vals    the BowVector: ascending word ids with their normalised weights (std::map order), *n_bow entries (<= n) */
+int airfe_bow_load(airfe_ctx* ctx, const char* path);
+int airfe_bow_transform(airfe_ctx* ctx, const float* feat259, int n, unsigned int* word_of_feature, unsigned int* bow_ids, double* bow_vals, int* n_bow);
+
 /* ---- device-resident keyframe features + batched candidate matching (BASELINE.json config 5) ----
  * The reference re-uploads the same 259 x N keyframe features for every MatchingPoints call of a relocalization query
  * (MapUser::Relocalization, src/map_user.cc:363-376: up to GoodCandidateNum = 3 sequential calls) and of a loop-closure candidate

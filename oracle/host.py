@@ -319,3 +319,76 @@ def matching_points(f0, f1, weights, matcher, image_width, image_height, emul=Fa
             if 0 <= i0[i] < len(i1) and i1[i0[i]] == i:
                 out.append((i, int(i0[i]), float(np.float32(1.0 - (ms0[i] + ms1[i0[i]]) / 2.0))))
     return out
+
+
+# ---- point <-> line association and stereo line matching --------------------
+def assign_points_to_lines(lines, feats):
+    """AssignPointsToLines, src/line_processor.cc:68-120.  lines [L,4] float64 (x1,y1,x2,y2), feats [259,N] float32.
+    Returns a list (one entry per line) of dicts {point index: distance} -- std::map<int,double> holding double(float(distance)).
+    std::pow(x, 2) is restated as x * x (exact square; glibc's pow returns the same value)."""
+    lines = np.asarray(lines, dtype=np.float64).reshape(-1, 4)
+    px = feats[1].astype(np.float64)
+    py = feats[2].astype(np.float64)
+    rel = []
+    for (lx1, ly1, lx2, ly2) in lines:
+        A, B = ly2 - ly1, lx1 - lx2
+        C = lx2 * ly1 - lx1 * ly2
+        D = np.sqrt(A * A + B * B)
+        min_lx, max_lx = (lx1, lx2) if lx1 <= lx2 else (lx2, lx1)
+        min_ly, max_ly = (ly1, ly2) if ly1 <= ly2 else (ly2, ly1)
+        box = ~((px < min_lx - 3) | (px > max_lx + 3) | (py < min_ly - 3) | (py > max_ly + 3))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dist = (np.abs((A * px + B * py) + C) / D).astype(np.float32)         # float pl_distance = std::abs(...) / D(i)
+        ok = box & ~(dist > np.float32(3))
+        side1 = (lx1 - px) * (lx1 - px) + (ly1 - py) * (ly1 - py)
+        side2 = (lx2 - px) * (lx2 - px) + (ly2 - py) * (ly2 - py)
+        line_side = D * D
+        ok &= (side1 <= 9) | (side2 <= 9) | ((side1 < line_side + side2) & (side2 < line_side + side1))
+        rel.append({int(j): float(dist[j]) for j in np.nonzero(ok)[0]})
+    return rel
+
+
+def filter_stereo_matches(feat_l, feat_r, matches, min_x_diff, max_x_diff, max_y_diff):
+    """Frame::AddRightFeatures, src/frame.cc:141-155: keep (q, t) with min < |xl - xr| < max and |yl - yr| <= max_y (float difference,
+    compared as double).  matches: iterable of (queryIdx, trainIdx[, ...])."""
+    out = []
+    for m in matches:
+        q, t = int(m[0]), int(m[1])
+        dx = np.float64(np.abs(np.float32(feat_l[1, q]) - np.float32(feat_r[1, t])))
+        dy = np.float64(np.abs(np.float32(feat_l[2, q]) - np.float32(feat_r[2, t])))
+        if dx > min_x_diff and dx < max_x_diff and dy <= max_y_diff:
+            out.append((q, t))
+    return out
+
+
+def match_lines(rel0, rel1, point_matches, n0, n1):
+    """MatchLines, src/line_processor.cc:122-187.  rel0 / rel1 from assign_points_to_lines, point_matches list of (queryIdx, trainIdx).
+    Returns line_matches [len(rel0)] (index into the second image's lines, -1 = none)."""
+    L0, L1 = len(rel0), len(rel1)
+    out = [-1] * L0
+    if n0 == 0 or n1 == 0 or L0 == 0 or L1 == 0:
+        return out
+    a0 = [[] for _ in range(n0)]
+    a1 = [[] for _ in range(n1)]
+    for i, r in enumerate(rel0):
+        for j in r:
+            a0[j].append(i)
+    for i, r in enumerate(rel1):
+        for j in r:
+            a1[j].append(i)
+    mm = np.zeros((L0, L1), dtype=np.int32)
+    for q, t in point_matches:
+        for l0 in a0[q]:
+            for l1 in a1[t]:
+                mm[l0, l1] += 1
+    row_loc = mm.argmax(axis=1)                   # Eigen maxCoeff(&index): first maximum
+    for j in range(L1):
+        loc = int(mm[:, j].argmax())
+        v = int(mm[loc, j])
+        if v < 2 or row_loc[loc] != j:
+            continue
+        score = np.float32(v * v) / np.float32(min(len(rel0[loc]), len(rel1[j])))
+        if np.float64(score) < 0.8:                # float score compared with the double literal
+            continue
+        out[loc] = j
+    return out

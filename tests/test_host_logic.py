@@ -186,3 +186,27 @@ def test_cv_remap_restatement_is_bit_exact_against_cv2():
         assert np.array_equal(host.cv_remap_u8(img, a, b), cv2.remap(img, a, b, cv2.INTER_LINEAR))
     mx, my = host.radtan_rectify_maps(752, 480, 458.654, 457.296, 367.215, 248.375, *D[:4], new_cx=362.0, new_cy=250.0)
     assert np.abs(mx - m1).max() < 2e-3 and np.abs(my - m2).max() < 2e-3
+
+
+def test_line_association_restatement_small_case():
+    """oracle.host.assign_points_to_lines / match_lines (src/line_processor.cc:68-187) on a case small enough to check by hand."""
+    from oracle import host
+    lines0 = np.array([[10.0, 10.0, 110.0, 10.0], [50.0, 0.0, 50.0, 100.0]])           # horizontal, vertical
+    lines1 = np.array([[5.0, 10.0, 105.0, 10.0], [45.0, 0.0, 45.0, 100.0]])            # the same, shifted 5 px left
+    f0 = np.zeros((259, 6), np.float32)
+    f0[1], f0[2] = [20, 60, 100, 50, 50, 300], [11, 9, 10, 40, 80, 300]                 # 3 on line 0, 2 on line 1 (+ (50,10)?) , 1 nowhere
+    f1 = f0.copy()
+    f1[1] -= 5
+    rel0, rel1 = host.assign_points_to_lines(lines0, f0), host.assign_points_to_lines(lines1, f1)
+    assert [sorted(r) for r in rel0] == [[0, 1, 2], [3, 4]] and [sorted(r) for r in rel1] == [[0, 1, 2], [3, 4]]
+    assert rel0[0][0] == 1.0 and rel0[0][1] == 1.0 and rel0[0][2] == 0.0 and rel0[1][3] == 0.0
+    # point (113, 10): beyond the end point but within 3 px -> side2 <= 9 keeps it; (118, 10): outside the +3 box
+    g = np.zeros((259, 2), np.float32)
+    g[1], g[2] = [113, 118], [10, 10]
+    assert [sorted(r) for r in host.assign_points_to_lines(lines0[:1], g)] == [[0]]
+    matches = [(j, j) for j in range(6)]
+    kept = host.filter_stereo_matches(f0, f1, matches, 2.0, 50.0, 2.0)
+    assert kept == matches                                                                # disparity 5 px, dy 0
+    assert host.filter_stereo_matches(f0, f1, matches, 6.0, 50.0, 2.0) == []
+    assert host.match_lines(rel0, rel1, kept, 6, 6) == [0, 1]                             # 3 votes / 3 points and 2 votes / 2 points
+    assert host.match_lines(rel0, rel1, kept[:1] + kept[3:], 6, 6) == [-1, 1]             # one vote is not enough (col_max_val < 2)
