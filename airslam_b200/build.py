@@ -99,6 +99,20 @@ def build_mock_caller():
     return out
 
 
+def build_ransac_test():
+    """g++: CPU unit test of the RANSAC hook (tests/cpp/ransac_test.cc)."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(root, "tests", "cpp", "ransac_test")
+    srcs = [os.path.join(root, "src", "frontend", "frontend.cc"), os.path.join(root, "tests", "cpp", "ransac_test.cc")]
+    deps = srcs + [os.path.join(root, "compat", "opencv2", "opencv.hpp"), LIB]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(root, "compat"), "-I" + os.path.join(root, "include")] + srcs + [
+        "-o", out, "-L" + HERE, "-lairfe", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../../airslam_b200"]
+    subprocess.check_call(cmd)
+    return out
+
+
 def build_class_bench():
     """g++: tests/cpp/class_bench.cc (bench.py --mode class) against the same class surfaces."""
     root = os.path.dirname(HERE)

@@ -23,6 +23,24 @@ static airfe_ctx* make_ctx(const airfe_config& cfg) {
   }
   return c;
 }
+// The outlier-rejection hook of PointMatcher::MatchingPoints exactly as the reference has it (src/point_matcher.cc:95-105): a host step on
+// integer-truncated keypoints through cv::findFundamentalMat(FM_RANSAC, 20, 0.99).  It depends on OpenCV's random stream, so it is outside the
+// bit-exact parity contract; against real OpenCV this calls OpenCV, in standalone builds the stand-in of compat/opencv2/opencv.hpp.
+void RejectOutliersByFundamental(const Eigen::Matrix<float, 259, Eigen::Dynamic>& features0, const Eigen::Matrix<float, 259, Eigen::Dynamic>& features1,
+                                 std::vector<cv::DMatch>& matches) {
+  std::vector<cv::Point> points0, points1;
+  for (auto& m : matches) {
+    points0.emplace_back(features0(1, m.queryIdx), features0(2, m.queryIdx));
+    points1.emplace_back(features1(1, m.trainIdx), features1(2, m.trainIdx));
+  }
+  std::vector<uchar> inliers;
+  cv::findFundamentalMat(points0, points1, cv::FM_RANSAC, 20, 0.99, inliers);
+  int j = 0;
+  for (size_t i = 0; i < matches.size(); i++) {
+    if (inliers[i]) matches[j++] = matches[i];
+  }
+  matches.resize(j);
+}
 }  // namespace airfe_cpp
 using airfe_cpp::make_ctx;
 typedef Eigen::Matrix<float, 259, Eigen::Dynamic> Features;
@@ -306,22 +324,6 @@ int PointMatcher::MatchingPoints(const Features& features0, const Features& feat
       }
     }
   }
-#ifdef AIRFE_WITH_OPENCV_CALIB3D
-  // host hook kept exactly as the reference has it (src/point_matcher.cc:95-105); compiled only against real OpenCV
-  if (outlier_rejection && matches.size() > 8) {
-    std::vector<cv::Point> points0, points1;
-    for (auto& m : matches) {
-      points0.emplace_back(features0(1, m.queryIdx), features0(2, m.queryIdx));
-      points1.emplace_back(features1(1, m.trainIdx), features1(2, m.trainIdx));
-    }
-    std::vector<uchar> inliers;
-    cv::findFundamentalMat(points0, points1, cv::FM_RANSAC, 20, 0.99, inliers);
-    int j = 0;
-    for (size_t i = 0; i < matches.size(); i++) if (inliers[i]) matches[j++] = matches[i];
-    matches.resize(j);
-  }
-#else
-  (void)outlier_rejection;   // cv::findFundamentalMat unavailable in the standalone build (no OpenCV calib3d): matches returned unfiltered
-#endif
+  if (outlier_rejection && matches.size() > 8) airfe_cpp::RejectOutliersByFundamental(features0, features1, matches);
   return matches.size();
 }

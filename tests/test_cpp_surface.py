@@ -27,6 +27,23 @@ def test_headers_keep_the_reference_surface():
         assert "#include <NvInfer" not in t and "tensorrtbuffer" not in t and "bool build();" in t and "bool infer(" in t
 
 
+def test_ransac_hook_rejects_planted_outliers():
+    """PointMatcher::MatchingPoints' outlier_rejection branch (src/point_matcher.cc:95-105) is compiled and behaves: planted outliers go,
+    planted inliers stay.  (OpenCV's own RANSAC is replaced by the deterministic stand-in of compat/opencv2/opencv.hpp in standalone builds, so
+    this is a behavioural test, not a parity test: the hook is excluded from bit-exact parity)"""
+    from airslam_b200 import build as b
+    if not b.have_nvcc():
+        pytest.skip("no nvcc on this box")
+    b.build()
+    exe = b.build_ransac_test()
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = [[int(v) for v in ln.split()] for ln in out.stdout.strip().splitlines()]
+    assert len(rows) == 2
+    for ki, ni, ko, no in rows:
+        assert ki >= 0.95 * ni and ko <= 0.3 * no, rows          # threshold 20 px is loose: outliers near an epipolar line legitimately survive
+
+
 @pytest.mark.gpu
 def test_mock_caller_equals_c_abi(tmp_path):
     from airslam_b200 import build as b, capi
