@@ -226,19 +226,14 @@ bool Detector::build_ops(int B) {
   };
   // SuperPoint trunk + heads (G1; G2 /backbone/point_detector/*)
   const Act r3 = cat2_.slice(32, 64), r5 = cat3_.slice(128, 128);
-  // Experimental (AIRFE_FUSE1A=1, off by default): conv1a computed inside the conv1b kernel so that its 32 MiB/frame output never goes to
-  // HBM.  Round 1 measured a CUDA-core (FFMA2) producer: parity-green but slower (1.38 ms vs 0.37 + 0.69 ms per 32 frames,
-  // profiles/r01_fused_conv1a_trace.txt).  The code now holds the tensor-core producer (im2col K = 16 -> three MMAs -> TMEM -> A stage),
-  // written at the end of round 1 WITHOUT a GPU: compile-checked only, to be validated (tools/probe_k16.cu first) before it is enabled.
-  static const bool fuse1a = conv3x3_halo_enabled() && getenv("AIRFE_FUSE1A") != nullptr;
-  if (fuse1a) {
-    const Conv1aFuse f{x16_, w_conv1a_, b_conv1a_};
-    if (!add_conv3x3(&t, a1_, w1b_, &r1_, &p1_, B, true, &f)) return false;                   // conv1a + conv1b (+ fused pool)
-  } else {
+  {
+    // conv1a (C_in = 1) on CUDA cores (packed FFMA2), then conv1b on tensor cores.  Computing conv1a inside the conv1b kernel was measured in
+    // round 1 with FFMA2 producer warps (slower: profiles/r01_fused_conv1a_trace.txt); the drafted tensor-core producer was never validated
+    // and has been removed from the tree.
     const __half* x = x16_; const __half* w = w_conv1a_; const float* bb = b_conv1a_; __half* o = (__half*)a1_.p;
     t.push("conv1a 1->64", 0, [=](cudaStream_t st) { launch_conv1a(x, w, bb, o, B, 512, 512, st); return true; });
     t.launches++;
-    if (!add_conv3x3(&t, a1_, w1b_, &r1_, &p1_, B, true)) return false;                       // conv1b (+ fused pool)
+    if (!add_conv3x3(&t, a1_, w1b_, plnet_ && cfg_.enable_lines ? &r1_ : nullptr, &p1_, B, true)) return false;      // conv1b (+ fused pool); only PLNet's line branch reads the full-resolution map
   }
   if (!add_conv3x3(&t, p1_, w2a_, &a2_, nullptr, B, true) || !add_conv3x3(&t, a2_, w2b_, &r3, &p2_, B, true)) return false;
   if (!add_conv3x3(&t, p2_, w3a_, &a3_, nullptr, B, true) || !add_conv3x3(&t, a3_, w3b_, &r5, &p3_, B, true)) return false;

@@ -148,10 +148,7 @@ bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int b
                const int* dyn_rows = nullptr, float scale = 1.f, const float* resid = nullptr, const Act* out2 = nullptr, const DenseExtra* ex = nullptr);
 // Append a 3x3 convolution on the halo-reuse tcgen05 kernel (tc_conv3x3.cuh); `out` and/or `pool_out` (fused 2x2 max-pool).
 // Falls back to the generic streaming-tap kernel (+ pool kernel) when AIRFE_CONV_V1 is set or the map is narrower than 8.
-// `fuse` (SuperPoint conv1a -> conv1b): the 64-channel input of this layer is relu(conv3x3(img) + bias) of a 1-channel fp16 image and is
-// computed on the fly by producer warps of the conv kernel; `in` then only describes the geometry (its pointer is not read).
-struct Conv1aFuse { const __half* img; const __half* w; const float* bias; };
-bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu, const Conv1aFuse* fuse = nullptr);
+bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu);
 bool conv3x3_halo_enabled();
 void conv3x3_set_trace(long long* dev_buf);   // authoring aid, see airfe_debug_conv_trace
 // Append fused multi-head attention (tc_attn.cuh): ctx = softmax(q k^T * scale) v per (slot, head); keys/values of slot ^ slot_xor.

@@ -20,7 +20,6 @@ void conv3x3_set_trace(long long* dev_buf) { g_conv_trace = dev_buf; }
 using ConvKernel = void (*)(const ConvParams);
 
 static ConvKernel conv_kernel_for(const ConvParams& p) {
-  if (p.img1) return tc_conv3x3_kernel<64, 2, true, true>;
   const int key = (p.kw == 32 ? 4 : 0) | (p.strips == 2 ? 2 : 0) | (p.b_resident ? 1 : 0);
   switch (key) {
     case 0: return tc_conv3x3_kernel<64, 1, false>;
@@ -35,10 +34,10 @@ static ConvKernel conv_kernel_for(const ConvParams& p) {
 }
 
 static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[kMaxDevices][9] = {};
+  static bool attr_set[kMaxDevices][8] = {};
   const int dev = current_device();
-  const int key = plan.p.img1 ? 8 : ((plan.p.kw == 32 ? 4 : 0) | (plan.p.strips == 2 ? 2 : 0) | (plan.p.b_resident ? 1 : 0));
-  const int threads = plan.p.img1 ? kConvThreadsFused : kConvThreads;
+  const int key = (plan.p.kw == 32 ? 4 : 0) | (plan.p.strips == 2 ? 2 : 0) | (plan.p.b_resident ? 1 : 0);
+  const int threads = kConvThreads;
   ConvKernel kern = conv_kernel_for(plan.p);
   if (!attr_set[dev][key]) {
     cudaFuncAttributes fa;
@@ -50,8 +49,7 @@ static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
     attr_set[dev][key] = true;
   }
   cudaError_t e;
-  static const bool trace_fused_only = getenv("AIRFE_TRACE_FUSED") != nullptr;   // authoring aid: stamp only the conv1a-fused launch of a detector run
-  if (g_conv_trace && (!trace_fused_only || plan.p.img1)) {
+  if (g_conv_trace) {
     ConvPlan traced = plan;
     traced.p.trace = g_conv_trace;
     e = launch_pdl(kern, traced.grid, threads, traced.smem_bytes, st, traced.p);
@@ -68,9 +66,8 @@ bool conv3x3_halo_enabled() {
   return v == 1;
 }
 
-bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu, const Conv1aFuse* fuse) {
+bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu) {
   if (w.taps != 9 || in.f32 || (out && out->f32) || (pool_out && pool_out->f32)) { set_error("add_conv3x3: unsupported layer"); return false; }
-  if (fuse && (!conv3x3_halo_enabled() || w.c_in != 64 || w.n_rows != 64 || (in.W % 16) || (in.H % 16))) { set_error("add_conv3x3: conv1a fusion needs the halo kernel on a 64->64 layer"); return false; }
   if (!conv3x3_halo_enabled() || in.W < 8 || (in.W % 8)) {
     // generic streaming-tap kernel (+ separate pool kernel)
     const Act* full = out;
@@ -102,6 +99,8 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   p.n_tiles = (n_valid + block_n - 1) / block_n;
   p.strips = (in.W >= 16 && 4 * conv_acc_stride(block_n) <= 512) ? 2 : 1;
   p.nacc = conv_nacc(block_n, p.strips);
+  static const int prewait = getenv("AIRFE_NO_PREWAIT") ? 0 : 1;
+  p.prewait = prewait;
   p.kw = (w.c_in_pad % 64) ? 32 : 64;
   p.kblocks = w.c_in_pad / p.kw;
   p.c_in_pad = w.c_in_pad;
@@ -132,22 +131,15 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
     uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)batch};
     uint64_t str[3] = {(uint64_t)in.ps * 2, (uint64_t)in.ps * in.W * 2, (uint64_t)in.ps * in.W * in.H * 2};
     uint32_t box[4] = {(uint32_t)p.kw, (uint32_t)(8 * p.strips + 2), (uint32_t)(kConvTH + 2), 1};
-    if (!fuse && !make_tmap_f16(&p.tmA, in.p, 4, dims, str, box, p.kw * 2)) return false;
+    if (!make_tmap_f16(&p.tmA, in.p, 4, dims, str, box, p.kw * 2)) return false;
     const uint64_t k_total = (uint64_t)9 * w.c_in_pad;
     uint64_t bd[4] = {k_total, (uint64_t)w.n_rows, 1, 1};
     uint64_t bs[3] = {k_total * 2, k_total * 2 * w.n_rows, k_total * 2 * w.n_rows};
     uint32_t bb[4] = {(uint32_t)p.kw, (uint32_t)block_n, 1, 1};
     if (!make_tmap_f16(&p.tmB, w.w, 4, bd, bs, bb, p.kw * 2)) return false;
   }
-  if (fuse) {
-    if (!p.b_resident || p.strips != 2 || p.kw != 64 || p.kblocks != 1) { set_error("add_conv3x3: conv1a fusion: unexpected plan"); return false; }
-    p.img1 = fuse->img; p.w1a = fuse->w; p.b1a = fuse->bias;
-    p.nacc = 2;                        // TMEM: 2 x 2 x 64 conv1b columns + 3 x 64 conv1a columns
-    p.stages_a = 2;                    // the A stages are written on chip: no load latency to cover, and the im2col tiles need the room
-  }
   const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
-  plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 8) * 8 + 16 +
-                    (fuse ? 1024 + 2048 + 2 * 12288 : 0);   // fused conv1a: W1 + two im2col tiles behind the barriers
+  plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 8) * 8 + 16;
   const int total = p.tiles_x * p.tiles_y * batch * p.n_tiles;
   plan.grid = total < sm_count() ? total : sm_count();
   if (in.C > w.c_in_pad || in.C < w.c_in) { set_error("add_conv3x3: activation has %d channels, weights expect %d", in.C, w.c_in); return false; }
@@ -155,7 +147,7 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   ol->tc_flops += fl;
   ol->launches += 1;
   char nm[160];
-  snprintf(nm, sizeof(nm), "tc_conv3x3 %s%d->%d @%dx%dx%d%s%s S%d%s", fuse ? "1->" : "", w.c_in, n_valid, in.W, in.H, batch, p.b_resident ? " Bres" : "", pool_out ? (out ? " +pool" : " pool-only") : "", p.strips, p.kw == 32 ? " K32" : "");
+  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d%s", w.c_in, n_valid, in.W, in.H, batch, p.b_resident ? " Bres" : "", pool_out ? (out ? " +pool" : " pool-only") : "", p.strips, p.kw == 32 ? " K32" : "");
   ol->push(nm, fl, [plan](cudaStream_t st) { return conv_launch(plan, st); });
   return true;
 }

@@ -26,6 +26,7 @@ struct ConvParams {
   int n_tiles, block_n, n_valid;
   int b_resident;
   int stages_a, stages_b;
+  int prewait;      // MMA issuer polls the barriers of unit u + 1 before it issues unit u (0: after; AIRFE_NO_PREWAIT=1, for A/B timing)
   int nacc;         // TMEM accumulator buffers (2..4): deeper than 2 hides the MMA -> epilogue -> MMA hand-shake latency on small-N layers
   const float* bias;
   int relu;
@@ -33,16 +34,10 @@ struct ConvParams {
   long long out_sb, out_sy, out_sx;
   __half* pool_out;   // fused 2x2/2 max-pool store (nullptr: skip)
   long long pool_sb, pool_sy, pool_sx;
-  // FUSE1A (SuperPoint conv1a fused into conv1b, experimental): the 64-channel input never exists in HBM.  Producer warps build the im2col
-  // tile of the 1-channel image (K = 9 -> 16), the MMA warp runs conv1a as three 128x64x16 MMAs into spare TMEM columns, and the producers
-  // move the result (+bias, ReLU, fp16) from TMEM into the swizzled A stage.  img1 = fp16 [B][H][W], w1a = fp16 [64][9], b1a = fp32 [64].
-  const __half* img1; const __half* w1a; const float* b1a;
   long long* trace;   // authoring aid (airfe_debug_conv_trace): CTA 0 writes clock64 stamps of its first 64 tiles, 8 slots per tile
 };
 
 constexpr int kConvThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
-constexpr int kConvFuseProducers = 8;                                    // FUSE1A: warps 10-17 compute the conv1a halo tile
-constexpr int kConvThreadsFused = kConvThreads + 32 * kConvFuseProducers;
 constexpr int kConvTH = 16;
 
 __host__ __device__ constexpr int conv_a_bytes(int strips, int kw = 64) { return ((8 * strips + 2) * (kConvTH + 2) * kw * 2 + 1023) / 1024 * 1024; }
@@ -62,41 +57,8 @@ __host__ __device__ inline int conv_tmem_cols(int block_n, int strips) {
 // (tools/trace_conv.py, profiles/r01_conv_trace.txt) the runtime-generic loop spent ~550 cycles of uniform-datapath
 // instructions per tap, i.e. the single issuing warp -- not the tensor pipe (48 cycles per 128x64x16 MMA in SS mode,
 // tools/probe_mma_rate.cu) -- bounded every small-N layer.
-__device__ __forceinline__ unsigned long long conv_ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long conv_pack2(float lo, float hi) {
-  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
-}
-
-// ---- FUSE1A helpers (only instantiated by the conv1a-fused kernel) ---------------------------------------------------------
-constexpr uint32_t kC1aCol = 256;                // conv1a accumulators: TMEM columns 256 .. 447 (conv1b uses 2 x 2 x 64 = 256)
-__device__ __forceinline__ uint8_t* conv_c1a_smem(uint32_t* tmem_slot) {   // W1 [64 x 16] (2 KiB) + two im2col tiles (12 KiB each) behind the TMEM slot
-  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023));
-}
-// conv1a of the k-th tile of this CTA: three 128x64x16 MMAs on im2col buffer k & 1 into the spare TMEM columns
-__device__ __forceinline__ void conv_issue_conv1a(int k, uint64_t* fbar, uint8_t* c1a, uint32_t tmem_base) {
-  const int b = k & 1;
-  ptx::mbar_wait(&fbar[b], (uint32_t)(k >> 1) & 1);            // im2col tile landed
-  ptx::tc_fence_after();
-  if (ptx::elect_one()) {
-    const uint32_t idesc1 = ptx::make_idesc_f16(128, 64, 0);
-    const uint64_t d1_const = ptx::make_smem_desc(0, 128, 256, 0);   // K-major INTERLEAVE: LBO = 128 B, SBO = 256 B
-    const uint64_t d1_w = d1_const + (ptx::smem_u32(c1a) >> 4);
-    const uint64_t d1_a = d1_const + (ptx::smem_u32(c1a + 2048 + b * 12288) >> 4);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) ptx::umma_f16(tmem_base + kC1aCol + i * 64, d1_a + (uint64_t)(i * (4096 >> 4)), d1_w, idesc1, 0);
-    ptx::umma_commit(&fbar[2 + b]);                             // im2col buffer free again
-    ptx::umma_commit(&fbar[4]);                                 // conv1a accumulators valid
-  }
-  __syncwarp();
-}
-
-template <int KW, int STRIPS, bool BRES, bool FUSE1A = false>
-__global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) tc_conv3x3_kernel(const __grid_constant__ ConvParams p) {
-  static_assert(!FUSE1A || (KW == 64 && STRIPS == 2 && BRES), "conv1a fusion is specialised for the 64->64 resident-weights layer");
+template <int KW, int STRIPS, bool BRES>
+__global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int a_bytes = conv_a_bytes(STRIPS, KW);
@@ -118,12 +80,12 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
   const int m_tiles = p.tiles_x * p.tiles_y * p.B;
   const int total_tiles = m_tiles * p.n_tiles;
   const uint32_t acc_stride = conv_acc_stride(p.block_n);
-  const uint32_t tmem_cols = FUSE1A ? 512u : conv_tmem_cols(p.block_n, STRIPS);
+  const uint32_t tmem_cols = conv_tmem_cols(p.block_n, STRIPS);
 
   if (warp == 0 && lane == 0) {
-    if (!FUSE1A) ptx::prefetch_tmap(&p.tmA);
+    ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB);
-    for (int s = 0; s < p.stages_a; ++s) { ptx::mbar_init(&full_a[s], FUSE1A ? kConvFuseProducers : 1); ptx::mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < p.stages_a; ++s) { ptx::mbar_init(&full_a[s], 1); ptx::mbar_init(&empty_a[s], 1); }
     const int nb = BRES ? 1 : p.stages_b;
     for (int s = 0; s < nb; ++s) { ptx::mbar_init(&full_b[s], 1); ptx::mbar_init(&empty_b[s], 1); }
     for (int s = 0; s < 4; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
@@ -136,25 +98,6 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
   const uint32_t tmem_base = *tmem_slot;
   __shared__ __align__(16) float s_bias[512];
   for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;   // weights: not produced by a kernel
-  // FUSE1A: conv1a bias, six extra barriers, and (in dynamic smem behind the TMEM slot) W1 [64 x 16] + two im2col tiles [384 x 16] in the
-  // K-major INTERLEAVE (no swizzle) layout: element (r, k) at (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2   (LBO = 128 B, SBO = 256 B)
-  __shared__ float s_b1a[FUSE1A ? 64 : 1];
-  __shared__ uint64_t s_fbar[FUSE1A ? 6 : 1];      // im2col full[2], im2col empty[2], conv1a acc full, conv1a acc empty
-  if constexpr (FUSE1A) {
-    uint8_t* c1a_w = conv_c1a_smem(tmem_slot);
-    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
-      const int n = i >> 4, k = i & 15;
-      *reinterpret_cast<__half*>(c1a_w + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = k < 9 ? p.w1a[n * 9 + k] : __float2half(0.f);
-    }
-    if (threadIdx.x < 64) s_b1a[threadIdx.x] = p.b1a[threadIdx.x];
-    if (threadIdx.x == 0) {
-      ptx::mbar_init(&s_fbar[0], kConvFuseProducers); ptx::mbar_init(&s_fbar[1], kConvFuseProducers);
-      ptx::mbar_init(&s_fbar[2], 1); ptx::mbar_init(&s_fbar[3], 1);
-      ptx::mbar_init(&s_fbar[4], 1); ptx::mbar_init(&s_fbar[5], kConvFuseProducers);
-      ptx::fence_barrier_init();
-    }
-    ptx::fence_proxy_async();                      // W1 was written with generic stores, tcgen05.mma reads it through the async proxy
-  }
   __syncthreads();
   ptx::pdl_launch_dependents();   // the next kernel may start its own prologue on SMs this grid has left
   ptx::pdl_wait();                // everything above overlapped the predecessor's tail; activations are touched only below
@@ -170,7 +113,7 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int t = blockIdx.x; !FUSE1A && t < total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % p.n_tiles, mt = t / p.n_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tz = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * 8 * STRIPS, y0 = ty * kConvTH;
@@ -204,37 +147,38 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
     const uint64_t da_base = da_const + (ptx::smem_u32(smem_a) >> 4);
     const uint64_t db_base = db_const + (ptx::smem_u32(smem_b) >> 4);
     const uint32_t b16 = (uint32_t)b_bytes >> 4;
-    // FUSE1A: conv1a of tile k+1 is issued ahead of the 72 conv1b MMAs of tile k, so the producers' TMEM -> A-stage pass for tile k+1 runs
-    // while the tensor pipe works on tile k
-    int kseq = 0;
-    if constexpr (FUSE1A) {
-      if ((int)blockIdx.x < total_tiles) conv_issue_conv1a(0, s_fbar, conv_c1a_smem(tmem_slot), tmem_base);
-    }
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && t / (int)gridDim.x < 64;
-      long long* trp = tr ? p.trace + (t / gridDim.x) * 8 : nullptr;
-      if constexpr (FUSE1A) {
-        if (t + (int)gridDim.x < total_tiles) {
-          ptx::mbar_wait(&s_fbar[5], (uint32_t)kseq & 1);           // producers have read tile k's conv1a accumulators out of TMEM
+    if constexpr (BRES) {
+      // Resident-weights layers (the 512 x 512 maps, N <= 64: a tile is only 36 / 72 MMAs long).  A clock64 trace of these layers
+      // (profiles/r02_conv_trace_prewait.txt) showed the tensor pipe idle for ~840 cycles at EVERY tile boundary: the issuing thread is
+      // back-pressured while it issues (so the pipe has drained when the last MMA of a tile is accepted), and only then did it poll the
+      // barriers of the next tile (accumulator free, halo tile landed) -- 20 .. 34 % of a tile's period.  The waits for unit u + 1 are
+      // therefore taken BEFORE the MMAs of unit u are issued (the resources of u + 1 never depend on u when there are >= 3 halo stages and
+      // >= 2 accumulator buffers), so that the next issue block follows the previous one back to back.
+      const bool prewait = p.prewait && p.stages_a >= 3 && p.nacc >= 2;
+      if ((int)blockIdx.x < total_tiles) { ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1); ptx::mbar_wait(&full_a[sa], pa); }
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && t / (int)gridDim.x < 64;
+        long long* trp = tr ? p.trace + (t / gridDim.x) * 8 : nullptr;
+        if (tr) { trp[1] = clock64(); trp[2] = trp[1]; }
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * STRIPS) * acc_stride;
+        const bool next_tile = t + (int)gridDim.x < total_tiles;
+        int nacc = acc + 1;
+        uint32_t nphase = acc_phase;
+        if (nacc == p.nacc) { nacc = 0; nphase ^= 1; }
+        for (int cb = 0; cb < p.kblocks; ++cb) {
+          const bool last_cb = cb == p.kblocks - 1;
+          int nsa = sa + 1;
+          uint32_t npa = pa;
+          if (nsa == p.stages_a) { nsa = 0; npa ^= 1; }
+          if (prewait) {
+            if (!last_cb) ptx::mbar_wait(&full_a[nsa], npa);
+            else if (next_tile) { ptx::mbar_wait(&tmem_empty[nacc], nphase ^ 1); ptx::mbar_wait(&full_a[nsa], npa); }
+          }
           ptx::tc_fence_after();
-          conv_issue_conv1a(kseq + 1, s_fbar, conv_c1a_smem(tmem_slot), tmem_base);
-        }
-        ++kseq;
-      }
-      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      ptx::tc_fence_after();
-      if (tr) trp[1] = clock64();
-      const uint32_t d0 = tmem_base + (uint32_t)(acc * STRIPS) * acc_stride;
-      for (int cb = 0; cb < p.kblocks; ++cb) {
-        ptx::mbar_wait(&full_a[sa], pa);
-        ptx::tc_fence_after();
-        if (tr && cb == 0) trp[2] = clock64();
-        const uint64_t da_stage = da_base + (uint64_t)((uint32_t)(sa * a_bytes) >> 4);
-        const uint32_t first = cb != 0;   // accumulate flag of the very first MMA of a tile
-        if (BRES) {
-          // resident weights: 9 taps x ksteps x STRIPS MMAs as one straight-line issue block under a single election
+          const uint64_t da_stage = da_base + (uint64_t)((uint32_t)(sa * a_bytes) >> 4);
+          const uint32_t first = cb != 0;   // accumulate flag of the very first MMA of a tile
           const uint64_t db_cb = db_base + (uint64_t)((uint32_t)(cb * 9) * b16);
-          if (ptx::elect_one()) {
+          if (ptx::elect_one()) {           // 9 taps x ksteps x STRIPS MMAs as one straight-line issue block under a single election
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const uint64_t da_tap = da_stage + (uint64_t)(((tap / 3) * HW + tap % 3) * row16);
@@ -247,12 +191,46 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
               }
             }
             ptx::umma_commit(&empty_a[sa]);
+            if (last_cb) ptx::umma_commit(&tmem_full[acc]);
           }
           __syncwarp();
-        } else {
+          if (!prewait) {
+            if (!last_cb) ptx::mbar_wait(&full_a[nsa], npa);
+            else if (next_tile) { ptx::mbar_wait(&tmem_empty[nacc], nphase ^ 1); ptx::mbar_wait(&full_a[nsa], npa); }
+          }
+          sa = nsa; pa = npa;
+        }
+        if (tr) trp[3] = clock64();
+        acc = nacc; acc_phase = nphase;
+      }
+    } else {
+    bool b_primed = false;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && t / (int)gridDim.x < 64;
+      long long* trp = tr ? p.trace + (t / gridDim.x) * 8 : nullptr;
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      if (tr) trp[1] = clock64();
+      const uint32_t d0 = tmem_base + (uint32_t)(acc * STRIPS) * acc_stride;
+      for (int cb = 0; cb < p.kblocks; ++cb) {
+        ptx::mbar_wait(&full_a[sa], pa);
+        ptx::tc_fence_after();
+        if (tr && cb == 0) trp[2] = clock64();
+        const uint64_t da_stage = da_base + (uint64_t)((uint32_t)(sa * a_bytes) >> 4);
+        const uint32_t first = cb != 0;   // accumulate flag of the very first MMA of a tile
+        {
+          // streamed weights: one (K block, tap) tile per ring stage.  As in the resident-weights path the barrier of the NEXT weight tile is
+          // polled before the MMAs of the current one are issued (the ring has >= 3 stages), so consecutive issue blocks are back to back;
+          // the first tile of the kernel is waited for here.
+          const bool pw = p.prewait && p.stages_b >= 3;
+          if (!b_primed) { ptx::mbar_wait(&full_b[sb], pb); b_primed = true; }
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            ptx::mbar_wait(&full_b[sb], pb);
+            int nsb = sb + 1;
+            uint32_t npb = pb;
+            if (nsb == p.stages_b) { nsb = 0; npb ^= 1; }
+            const bool more_b = tap < 8 || cb + 1 < p.kblocks || t + (int)gridDim.x < total_tiles;     // another weight tile follows in this CTA
+            if (pw && more_b) ptx::mbar_wait(&full_b[nsb], npb);
             ptx::tc_fence_after();
             const uint64_t db = db_base + (uint64_t)((uint32_t)sb * b16);
             const uint64_t da_tap = da_stage + (uint64_t)(((tap / 3) * HW + tap % 3) * row16);
@@ -267,7 +245,8 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
               if (tap == 8) ptx::umma_commit(&empty_a[sa]);
             }
             __syncwarp();
-            if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
+            if (!pw && more_b) ptx::mbar_wait(&full_b[nsb], npb);
+            sb = nsb; pb = npb;
           }
         }
         if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
@@ -277,93 +256,8 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
       if (tr) trp[3] = clock64();
       if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (FUSE1A && warp >= 10) {
-    // ===== conv1a producers (8 warps) =====
-    //  (1) im2col of tile k+1: row r = halo pixel (hy, hx) of the 18 x 18 tile, 9 taps of the 1-channel image (zero outside) -> 16 fp16
-    //  (2) after the MMA warp's three conv1a MMAs of tile k: TMEM -> +bias, ReLU, fp16 -> A stage (K-major SWIZZLE_128B row r), zero for
-    //      halo pixels outside the image (conv1b's padding)
-    const int ptid = threadIdx.x - kConvThreads;
-    uint8_t* c1a_im = conv_c1a_smem(tmem_slot) + 2048;
-    const int quarter = warp & 3, halfc = (warp - 10) >> 2;     // TMEM lane quarter (= warp % 4) and column half of this warp
-    int sa = 0;
-    uint32_t pa = 0;
-    auto build_im2col = [&](int t, int k) {
-      const int b = k & 1;
-      const int mt = t / p.n_tiles;
-      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tz = mt / (p.tiles_x * p.tiles_y);
-      const int x0 = tx * 8 * STRIPS, y0 = ty * kConvTH;
-      const __half* img = p.img1 + (long long)tz * p.W * p.H;
-      ptx::mbar_wait(&s_fbar[2 + b], ((uint32_t)(k >> 1) & 1) ^ 1);   // buffer released by the conv1a MMAs two tiles ago (first use passes)
-      uint8_t* im = c1a_im + b * 12288;
-      for (int r = ptid; r < 384; r += 32 * kConvFuseProducers) {
-        uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (r < HW * (kConvTH + 2)) {
-          const int hy = r / HW, hx = r - hy * HW;
-          const int cy = y0 - 1 + hy, cx = x0 - 1 + hx;
-#pragma unroll
-          for (int k9 = 0; k9 < 9; ++k9) {
-            const int iy = cy + k9 / 3 - 1, ix = cx + k9 % 3 - 1;
-            unsigned short bits = 0;
-            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) bits = reinterpret_cast<const unsigned short*>(img)[(long long)iy * p.W + ix];
-            v[k9 >> 1] |= (uint32_t)bits << ((k9 & 1) * 16);
-          }
-        }
-        uint8_t* dst = im + (r >> 3) * 256 + (r & 7) * 16;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);          // k = 0..7
-        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(v[4], v[5], v[6], v[7]);    // k = 8..15 (only k = 8 is non-zero)
-      }
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s_fbar[b]);
-    };
-    int kseq = 0;
-    if ((int)blockIdx.x < total_tiles) build_im2col(blockIdx.x, 0);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      if (t + (int)gridDim.x < total_tiles) build_im2col(t + gridDim.x, kseq + 1);
-      const int mt = t / p.n_tiles;
-      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y;
-      const int x0 = tx * 8 * STRIPS, y0 = ty * kConvTH;
-      ptx::mbar_wait(&s_fbar[4], (uint32_t)kseq & 1);             // conv1a accumulators of this tile are in TMEM
-      ptx::mbar_wait(&empty_a[sa], pa ^ 1);                       // the A stage is free
-      ptx::tc_fence_after();
-      const bool trp_on = p.trace && blockIdx.x == 0 && ptid == 0 && kseq < 64;
-      if (trp_on) p.trace[kseq * 8 + 0] = clock64();              // trace slot 0: TMEM -> A-stage pass starts
-      uint8_t* stage = smem_a + sa * a_bytes;
-#pragma unroll 1
-      for (int i = 0; i < 3; ++i) {
-        const int r = i * 128 + quarter * 32 + lane;
-        uint32_t acc32[32];
-        ptx::tmem_ld32(tmem_base + kC1aCol + i * 64 + halfc * 32 + ((uint32_t)(quarter * 32) << 16), acc32);
-        ptx::tmem_ld_wait();
-        if (r < HW * (kConvTH + 2)) {
-          const int hy = r / HW, hx = r - hy * HW;
-          const int oy = y0 - 1 + hy, ox = x0 - 1 + hx;
-          const bool in_img = oy >= 0 && oy < p.H && ox >= 0 && ox < p.W;
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {                        // four 16-byte chunks = this warp's 32 channels
-            uint32_t h[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = c4 * 8 + e * 2;
-              const float a0 = fmaxf(__uint_as_float(acc32[j]) + s_b1a[halfc * 32 + j], 0.f);
-              const float a1 = fmaxf(__uint_as_float(acc32[j + 1]) + s_b1a[halfc * 32 + j + 1], 0.f);
-              __half2 h2 = __floats2half2_rn(a0, a1);
-              h[e] = in_img ? *reinterpret_cast<uint32_t*>(&h2) : 0u;
-            }
-            const int chunk = halfc * 4 + c4;
-            *reinterpret_cast<uint4*>(stage + r * 128 + ((chunk ^ (r & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async();                                    // generic-proxy stores -> visible to tcgen05.mma (async proxy)
-      __syncwarp();
-      if (lane == 0) { ptx::mbar_arrive(&full_a[sa]); ptx::mbar_arrive(&s_fbar[5]); }
-      if (trp_on) p.trace[kseq * 8 + 6] = clock64();              // trace slot 6: A stage handed to the MMA warp
-      if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
-      ++kseq;
     }
-  } else if (!FUSE1A || warp < 10) {
+  } else {
     // ===== epilogue: 8 warps; warp (2 + e) owns TMEM lane quarter (warp & 3) and half of the work (strip, or column half) =====
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -384,7 +278,7 @@ __global__ void __launch_bounds__(FUSE1A ? kConvThreadsFused : kConvThreads, 1) 
       __half* o_full = p.out ? p.out + (long long)tz * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx : nullptr;
       __half* o_pool = p.pool_out ? p.pool_out + (long long)tz * p.pool_sb + (long long)(y >> 1) * p.pool_sy + (long long)(x >> 1) * p.pool_sx : nullptr;
       const bool pool_lane = valid && !(lane & 1) && !(lane & 8);
-      const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && (warp == 2 || (warp == 9 && !FUSE1A)) && t / (int)gridDim.x < 64;
+      const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9) && t / (int)gridDim.x < 64;
       long long* trp = tr ? p.trace + (t / gridDim.x) * 8 + (warp == 2 ? 4 : 6) : nullptr;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();

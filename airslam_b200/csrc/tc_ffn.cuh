@@ -24,6 +24,7 @@ struct FfnParams {
   __half* x16;         // fp16 copy (row stride 512 elements)
   const int* n;        // [slots]
   int slots, cap;
+  int prewait;         // MMA issuer polls the next weight tile's barrier before issuing the current one (0 with AIRFE_NO_PREWAIT=1)
 };
 
 constexpr int kFfnThreads = 320;
@@ -126,9 +127,17 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
         pepi ^= 1;
         ptx::tc_fence_after();
         const int nn = ph == 1 ? 4 : 2, nk = ph == 0 ? 4 : 8, a_first = ph == 0 ? 4 : 0;
+        // weight tiles: the barrier of the NEXT tile of the ring is polled before the MMAs of the current one are issued (the issuing thread is
+        // back-pressured, so anything it does between two issue blocks is idle time of the tensor pipe; 4 ring stages: tile u + 1 never
+        // depends on tile u).  The first tile of a row tile is waited for at the phase-1 start.
+        if (ph == 0) ptx::mbar_wait(&b_full[sb], pb);
         for (int nt = 0; nt < nn; ++nt)
           for (int kb = 0; kb < nk; ++kb) {
-            ptx::mbar_wait(&b_full[sb], pb);
+            int nsb = sb + 1;
+            uint32_t npb = pb;
+            if (nsb == kFfnBStages) { nsb = 0; npb ^= 1; }
+            const bool more = !(ph == 2 && nt == nn - 1 && kb == nk - 1);        // another weight tile of THIS row tile follows
+            if (p.prewait && more) ptx::mbar_wait(&b_full[nsb], npb);
             ptx::tc_fence_after();
             const int ntr = nt, kbr = kb;
             if (ptx::elect_one()) {
@@ -139,7 +148,8 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
               ptx::umma_commit(&b_empty[sb]);
             }
             __syncwarp();
-            if (++sb == kFfnBStages) { sb = 0; pb ^= 1; }
+            if (!p.prewait && more) ptx::mbar_wait(&b_full[nsb], npb);
+            sb = nsb; pb = npb;
           }
         if (ptx::elect_one()) {
           ptx::umma_commit(acc_full);

@@ -135,16 +135,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     constexpr uint32_t bstep = MN_MAJOR ? (2048 >> 4) : 2;
     const uint32_t stage16 = (uint32_t)stage_bytes >> 4, b16 = (uint32_t)b_bytes >> 4;
     if (BRES) { ptx::mbar_wait(bres_bar, 0); ptx::tc_fence_after(); }
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      if (p.dyn_w) {
-        const int mt = t / p.n_tiles;
-        if ((mt % tiles_x) * p.tw >= __ldg(p.dyn_w + (mt / (tiles_x * p.tiles_y)) * p.tb * p.dyn_w_stride)) continue;
-      }
-      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      ptx::tc_fence_after();
+    // The issuing thread is back-pressured while it issues, so the tensor pipe has (nearly) drained when the last MMA of a K step is accepted:
+    // whatever the thread does before the next issue block is idle time of the pipe (clock64 trace of the conv kernel,
+    // profiles/r02_conv_trace_prewait.txt: ~840 cycles per tile).  The barriers of unit u + 1 (next K step, or next tile: accumulator free +
+    // first stage landed) are therefore polled BEFORE unit u is issued; with >= 3 ring stages u + 1 never depends on u.
+    const bool prewait = p.prewait && p.stages >= 3;
+    auto tile_valid = [&](int t) {
+      if (!p.dyn_w) return true;
+      const int mt = t / p.n_tiles;
+      return (mt % tiles_x) * p.tw < __ldg(p.dyn_w + (mt / (tiles_x * p.tiles_y)) * p.tb * p.dyn_w_stride);
+    };
+    int t = blockIdx.x;
+    while (t < total_tiles && !tile_valid(t)) t += gridDim.x;
+    if (t < total_tiles) { ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1); ptx::mbar_wait(&full_bar[stage], phase); }
+    while (t < total_tiles) {
+      int tn = t + gridDim.x;
+      while (tn < total_tiles && !tile_valid(tn)) tn += gridDim.x;
       const uint32_t d_tmem = tmem_base + acc * acc_stride;
+      const int nacc = acc ^ 1;
+      const uint32_t nacc_phase = nacc == 0 ? acc_phase ^ 1 : acc_phase;
       for (int ks = 0; ks < ksteps; ++ks) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+        const bool last = ks == ksteps - 1;
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+        if (prewait) {
+          if (!last) ptx::mbar_wait(&full_bar[nstage], nphase);
+          else if (tn < total_tiles) { ptx::mbar_wait(&tmem_empty[nacc], nacc_phase ^ 1); ptx::mbar_wait(&full_bar[nstage], nphase); }
+        }
         ptx::tc_fence_after();
         const uint64_t da = da_base + (uint64_t)((uint32_t)stage * stage16);
         const uint64_t db = db_base + (uint64_t)(BRES ? (uint32_t)ks * b16 : (uint32_t)stage * stage16);
@@ -153,14 +171,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) ptx::umma_f16(d_tmem, da + 2 * k, db + bstep * k, idesc, k ? 1u : first);
           ptx::umma_commit(&empty_bar[stage]);
+          if (last) ptx::umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (!prewait) {
+          if (!last) ptx::mbar_wait(&full_bar[nstage], nphase);
+          else if (tn < total_tiles) { ptx::mbar_wait(&tmem_empty[nacc], nacc_phase ^ 1); ptx::mbar_wait(&full_bar[nstage], nphase); }
+        }
+        stage = nstage; phase = nphase;
       }
-      if (ptx::elect_one()) ptx::umma_commit(&tmem_full[acc]);
-      __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      acc = nacc; acc_phase = nacc_phase;
+      t = tn;
     }
   } else {
     // ===== epilogue: TMEM -> registers -> (+bias, ReLU) -> global =====

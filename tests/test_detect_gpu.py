@@ -84,9 +84,7 @@ def test_superpoint_stages(ctx, images):
         keep = {}
         sc_o, de_o = nets.superpoint_forward(x, w, emul=True, keep=keep)
         # conv stack: fp16 activations vs fp32-activation oracle with fp16 operand rounding
-        r1 = ctx.debug_read(capi.NET_SUPERPOINT, "relu_1", i, np.float16, (512, 512, 64)).astype(np.float32)
-        r1_o = keep["relu_1"][0].numpy().transpose(1, 2, 0)
-        P.check("G1.relu_1 (conv1a+conv1b, fp16 store)", _rel(r1, r1_o), 2e-3, "rel. to activation scale")
+        # (relu_1, conv1b's full-resolution output, is only materialised by PLNet contexts -- its line branch reads it; checked in test_plnet_stages)
         r7 = ctx.debug_read(capi.NET_SUPERPOINT, "relu_7", i, np.float16, (64, 64, 128)).astype(np.float32)
         r7_o = keep["relu_7"][0].numpy().transpose(1, 2, 0)
         P.check("G1.relu_7 (8 convs)", _rel(r7, r7_o), 5e-3, "rel. to activation scale")
@@ -136,6 +134,8 @@ def test_plnet_stages(ctx, images):
         x = host.process_image(img)
         keep = {}
         o = nets.plnet_s0_forward(x, w, emul=True, keep=keep)
+        r1 = ctx.debug_read(N, "relu_1", i, np.float16, (512, 512, 64)).astype(np.float32)
+        P.check("G2.relu_1 (conv1a+conv1b, fp16 store)", _rel(r1, keep["relu_1"][0].numpy().transpose(1, 2, 0)), 2e-3, "rel. to activation scale")
         heads9 = ctx.debug_read(N, "heads9", i, np.float32, (128, 128, 16))[..., :9]
         h_o = keep["heads9"][0].numpy().transpose(1, 2, 0)
         P.check("G2.heads9 (74 convs)", _rel(heads9, h_o), 2e-2, "rel. to activation scale")
