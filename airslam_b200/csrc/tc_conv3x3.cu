@@ -99,7 +99,7 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   p.n_tiles = (n_valid + block_n - 1) / block_n;
   p.strips = (in.W >= 16 && 4 * conv_acc_stride(block_n) <= 512) ? 2 : 1;
   p.nacc = conv_nacc(block_n, p.strips);
-  static const int prewait = getenv("AIRFE_NO_PREWAIT") ? 0 : 1;
+  static const int prewait = getenv("AIRFE_PREWAIT") ? 1 : 0;   // measured in round 2: no gain (profiles/r02_prewait_ab.txt), off by default
   p.prewait = prewait;
   p.kw = (w.c_in_pad % 64) ? 32 : 64;
   p.kblocks = w.c_in_pad / p.kw;

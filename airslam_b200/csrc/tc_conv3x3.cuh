@@ -26,7 +26,7 @@ struct ConvParams {
   int n_tiles, block_n, n_valid;
   int b_resident;
   int stages_a, stages_b;
-  int prewait;      // MMA issuer polls the barriers of unit u + 1 before it issues unit u (0: after; AIRFE_NO_PREWAIT=1, for A/B timing)
+  int prewait;      // MMA issuer polls the barriers of unit u + 1 before it issues unit u (0: after; AIRFE_PREWAIT=1 switches it on, for A/B timing)
   int nacc;         // TMEM accumulator buffers (2..4): deeper than 2 hides the MMA -> epilogue -> MMA hand-shake latency on small-N layers
   const float* bias;
   int relu;
@@ -148,12 +148,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
     const uint64_t db_base = db_const + (ptx::smem_u32(smem_b) >> 4);
     const uint32_t b16 = (uint32_t)b_bytes >> 4;
     if constexpr (BRES) {
-      // Resident-weights layers (the 512 x 512 maps, N <= 64: a tile is only 36 / 72 MMAs long).  A clock64 trace of these layers
-      // (profiles/r02_conv_trace_prewait.txt) showed the tensor pipe idle for ~840 cycles at EVERY tile boundary: the issuing thread is
-      // back-pressured while it issues (so the pipe has drained when the last MMA of a tile is accepted), and only then did it poll the
-      // barriers of the next tile (accumulator free, halo tile landed) -- 20 .. 34 % of a tile's period.  The waits for unit u + 1 are
-      // therefore taken BEFORE the MMAs of unit u are issued (the resources of u + 1 never depend on u when there are >= 3 halo stages and
-      // >= 2 accumulator buffers), so that the next issue block follows the previous one back to back.
+      // Resident-weights layers (the 512 x 512 maps, N <= 64: a tile is only 36 / 72 MMAs long).  A clock64 trace of these layers shows
+      // ~840 cycles between the last accepted MMA of a tile and the first of the next.  Hypothesis tested in round 2: the issuing thread
+      // polls the next tile's barriers only after its (back-pressured) issue block, so polling them one unit EARLIER (p.prewait) would close
+      // the gap.  Measured (profiles/r02_prewait_ab.txt): no change -- the period is set by the arrival of the halo tiles (these layers move
+      // 2.7 .. 3.8 TB/s of HBM traffic, see profiles/r02*_ncu_all_kernels_cfg2.txt), the wait merely moves.  The option stays for A/B runs.
       const bool prewait = p.prewait && p.stages_a >= 3 && p.nacc >= 2;
       if ((int)blockIdx.x < total_tiles) { ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1); ptx::mbar_wait(&full_a[sa], pa); }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {

@@ -40,7 +40,7 @@ bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, con
   p.b_out = w_out.bias; p.b0 = w0.bias; p.b3 = w3.bias;
   p.ln_g = relu ? w0.bias : ln_g; p.ln_b = relu ? w0.bias : ln_b;     // the ReLU variant stages but never reads the LayerNorm slots
   p.x = x; p.x16 = cat16; p.n = n; p.slots = slots; p.cap = cap;
-  static const int prewait = getenv("AIRFE_NO_PREWAIT") ? 0 : 1;
+  static const int prewait = getenv("AIRFE_PREWAIT") ? 1 : 0;   // measured in round 2: no gain (profiles/r02_prewait_ab.txt), off by default
   p.prewait = prewait;
   const int tiles = slots * (cap / 128);
   const int grid = tiles < ffn_sm_count() ? tiles : ffn_sm_count();

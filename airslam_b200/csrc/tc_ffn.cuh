@@ -24,7 +24,7 @@ struct FfnParams {
   __half* x16;         // fp16 copy (row stride 512 elements)
   const int* n;        // [slots]
   int slots, cap;
-  int prewait;         // MMA issuer polls the next weight tile's barrier before issuing the current one (0 with AIRFE_NO_PREWAIT=1)
+  int prewait;         // MMA issuer polls the next weight tile's barrier before issuing the current one (0 with AIRFE_PREWAIT=1 switches it on)
 };
 
 constexpr int kFfnThreads = 320;

@@ -128,7 +128,7 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  static const int prewait = getenv("AIRFE_NO_PREWAIT") ? 0 : 1;
+  static const int prewait = getenv("AIRFE_PREWAIT") ? 1 : 0;   // measured in round 2: no gain (profiles/r02_prewait_ab.txt), off by default
   p.prewait = prewait;
   plan->smem_bytes = stages * (p.b_resident ? kABytes : kABytes + b_bytes) + (p.b_resident ? panel : 0) + 1024 /*align slack*/ + (2 * stages + 5) * 8 + 16;
   int grid = total < num_sms() ? total : num_sms();

@@ -135,10 +135,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     constexpr uint32_t bstep = MN_MAJOR ? (2048 >> 4) : 2;
     const uint32_t stage16 = (uint32_t)stage_bytes >> 4, b16 = (uint32_t)b_bytes >> 4;
     if (BRES) { ptx::mbar_wait(bres_bar, 0); ptx::tc_fence_after(); }
-    // The issuing thread is back-pressured while it issues, so the tensor pipe has (nearly) drained when the last MMA of a K step is accepted:
-    // whatever the thread does before the next issue block is idle time of the pipe (clock64 trace of the conv kernel,
-    // profiles/r02_conv_trace_prewait.txt: ~840 cycles per tile).  The barriers of unit u + 1 (next K step, or next tile: accumulator free +
-    // first stage landed) are therefore polled BEFORE unit u is issued; with >= 3 ring stages u + 1 never depends on u.
+    // Optional (p.prewait, off by default): poll the barriers of unit u + 1 (next K step, or next tile: accumulator free + first stage landed)
+    // BEFORE unit u is issued; with >= 3 ring stages u + 1 never depends on u.  Tested in round 2 against the idea that post-issue polling
+    // idles the tensor pipe: no gain (profiles/r02_prewait_ab.txt) -- these GEMMs wait for data, not for the issuing thread.
     const bool prewait = p.prewait && p.stages >= 3;
     auto tile_valid = [&](int t) {
       if (!p.dyn_w) return true;

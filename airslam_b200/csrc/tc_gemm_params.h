@@ -34,7 +34,7 @@ struct TcGemmParams {
   long long out_sb, out_sy, out_sx;
   int n_valid;
   int stages;
-  int prewait;      // MMA issuer polls the barriers of unit u + 1 before it issues unit u (see tc_gemm.cuh); 0 with AIRFE_NO_PREWAIT=1
+  int prewait;      // MMA issuer polls the barriers of unit u + 1 before it issues unit u (see tc_gemm.cuh); 0 with AIRFE_PREWAIT=1 switches it on
   int b_resident;   // whole [block_n x K] weight panel of this CTA's (fixed) N tile stays in shared memory; the ring then holds A only
   int dyn_w_stride; // index = tile batch * dyn_w_stride
   const int* dyn_w;  // optional: per-batch-index valid W (rows of a plain GEMM), read from device memory (tb must be 1)
