@@ -152,8 +152,9 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
 bool conv3x3_halo_enabled();
 void conv3x3_set_trace(long long* dev_buf);   // authoring aid, see airfe_debug_conv_trace
 // Append fused multi-head attention (tc_attn.cuh): ctx = softmax(q k^T * scale) v per (slot, head); keys/values of slot ^ slot_xor.
+// row_off (optional, device int[slots + 1]): packed row layout, slot s at rows [row_off[s], row_off[s] + n[s]).
 bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __half* v, long long row_stride, __half* ctx, const int* n, int slots,
-                         int cap, int slot_xor, float scale);
+                         int cap, int slot_xor, float scale, const int* row_off = nullptr);
 bool attn_fused_enabled();
 // Append the fused LightGlue block tail (tc_ffn.cuh): x += ffn3(gelu(LN(ffn0([x | out_proj(ctx)])))); refreshes the fp16 copy of x.
 // relu = true: SuperGlue's block tail (merge + MLP with ReLU instead of LayerNorm + GELU; ln_g / ln_b unused).

@@ -23,7 +23,17 @@ __device__ __forceinline__ float warp_max_(float v) {
 // NormalizeKeypoints (src/point_matcher.cc:39-48): (x - width/2) * L_inv with integer width/2; L_inv = float(1.0/max(w,h)*scale).
 // `feat_ptrs` (optional): per-slot base pointers instead of the dense [slot][feat_cap][259] array -- relocalization jobs pair a query
 // with a keyframe of the device-resident cache without copying either (airfe_reloc_match).
-__global__ void lg_prepare_kernel(const float* __restrict__ feat, const float* const* __restrict__ feat_ptrs, const int* __restrict__ n, int cap, int feat_cap, int width, int height,
+// `row_off` (optional): PACKED row layout -- slot s owns rows [row_off[s], row_off[s] + n[s]) of every [rows, C] matrix instead of
+// [s * cap, ...): the row GEMMs and the fused block tail then process sum(n) rows instead of slots x cap (400 of 512 rows used at 400 keypoints).
+__global__ void lg_offsets_kernel(const int* __restrict__ n, int slots, int cap, int* __restrict__ row_off /*[slots + 1]*/) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int s = 0; s < slots; ++s) { row_off[s] = acc; acc += min(max(n[s], 0), cap); }
+    row_off[slots] = acc;
+  }
+}
+
+__global__ void lg_prepare_kernel(const float* __restrict__ feat, const float* const* __restrict__ feat_ptrs, const int* __restrict__ n, const int* __restrict__ row_off, int cap, int feat_cap, int width, int height,
                                   float l_inv, const __half* __restrict__ wr /*[32][2]*/, float* __restrict__ x, __half* __restrict__ cat16,
                                   float* __restrict__ rot /*[slots][cap][64] cos | sin interleaved as (cos,sin) per freq*/) {
   const int s = blockIdx.y;
@@ -33,7 +43,7 @@ __global__ void lg_prepare_kernel(const float* __restrict__ feat, const float* c
   const float* f = feat_ptrs ? feat_ptrs[s] + (long long)r * 259 : feat + ((long long)s * feat_cap + r) * 259;
   const float kx = __fmul_rn(__fsub_rn(f[1], (float)(width / 2)), l_inv);
   const float ky = __fmul_rn(__fsub_rn(f[2], (float)(height / 2)), l_inv);
-  const long long row = (long long)s * cap + r;
+  const long long row = row_off ? (long long)row_off[s] + r : (long long)s * cap + r;
   // descriptors: fp32 residual stream + fp16 operand copy (cols 0..255 of the [x | msg] concat buffer)
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -132,16 +142,20 @@ __global__ void ln_gelu_kernel(const float* __restrict__ h, const float* __restr
 }
 
 // ---- K15: log assignment.  sim fp32 [pair][cap][cap] (rows = image 0, cols = image 1); z = matchability logit ------------------
+// x may be packed (row_off != nullptr); logsig is always slot-padded ([slot][cap]), like sim.  With md16_pad != nullptr the kernel also copies the
+// packed final-projection rows md16 into the slot-padded operand of the similarity GEMM.
 __global__ void matchability_kernel(const float* __restrict__ x, const __half* __restrict__ w /*[256]*/, float bias, const int* __restrict__ n,
-                                    int cap, float* __restrict__ logsig) {
+                                    const int* __restrict__ row_off, int cap, float* __restrict__ logsig, const __half* __restrict__ md16, __half* __restrict__ md16_pad) {
   const int s = blockIdx.y;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= n[s]) return;
   const long long row = (long long)s * cap + r;
+  const long long xrow = row_off ? (long long)row_off[s] + r : row;
+  if (md16_pad) *reinterpret_cast<uint4*>(md16_pad + row * 256 + lane * 8) = *reinterpret_cast<const uint4*>(md16 + xrow * 256 + lane * 8);
   float acc = 0.f;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc += __half2float(__float2half_rn(x[row * 256 + lane * 8 + e])) * __half2float(w[lane * 8 + e]);
+  for (int e = 0; e < 8; ++e) acc += __half2float(__float2half_rn(x[xrow * 256 + lane * 8 + e])) * __half2float(w[lane * 8 + e]);
   acc = warp_sum_(acc) + bias;
   // logsigmoid(z) = min(z,0) - log1p(exp(-|z|))
   if (lane == 0) logsig[row] = fminf(acc, 0.f) - log1pf(expf(-fabsf(acc)));
@@ -294,9 +308,10 @@ __global__ void __launch_bounds__(1024) lg_filter_kernel(const int* __restrict__
 }
 
 // ---- launchers ------------------------------------------------------------------------------------------------------------------
-void launch_lg_prepare(const float* feat, const float* const* feat_ptrs, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, const __half* wr,
+void launch_lg_prepare(const float* feat, const float* const* feat_ptrs, const int* n, int* row_off, int slots, int cap, int feat_cap, int width, int height, float l_inv, const __half* wr,
                        float* x, __half* cat16, float* rot, cudaStream_t st) {
-  lg_prepare_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(feat, feat_ptrs, n, cap, feat_cap, width, height, l_inv, wr, x, cat16, rot);
+  if (row_off) lg_offsets_kernel<<<1, 32, 0, st>>>(n, slots, cap, row_off);
+  lg_prepare_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(feat, feat_ptrs, n, row_off, cap, feat_cap, width, height, l_inv, wr, x, cat16, rot);
 }
 void launch_lg_rotary(const float* qkv, const float* rot, const int* n, int slots, int cap, __half* q16, __half* k16, __half* v16, cudaStream_t st) {
   lg_rotary_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(qkv, rot, n, cap, q16, k16, v16, 0.35355339059327379f /* 64^-1/4 */);
@@ -307,10 +322,13 @@ void launch_softmax_rows(const float* S, __half* P, const int* n, int slots, int
 void launch_ln_gelu(const float* h, const float* gamma, const float* beta, const int* n, int slots, int cap, __half* out, cudaStream_t st) {
   ln_gelu_kernel<<<dim3((cap + 7) / 8, slots), 256, 0, st>>>(h, gamma, beta, n, cap, out);
 }
-void launch_lg_assignment(const float* sim, const float* x, const __half* wm, float bm, const int* n, int pairs, int cap, float* logsig,
+void launch_lg_matchability(const float* x, const __half* wm, float bm, const int* n, const int* row_off, int pairs, int cap, float* logsig, const __half* md16,
+                            __half* md16_pad, cudaStream_t st) {
+  matchability_kernel<<<dim3((cap + 7) / 8, 2 * pairs), 256, 0, st>>>(x, wm, bm, n, row_off, cap, logsig, md16, md16_pad);
+}
+void launch_lg_assignment(const float* sim, const int* n, int pairs, int cap, float* logsig,
                           float* lse, int* row_arg, float* row_val, int* col_arg, float thr, int* m_idx, float* m_score, int* m_count,
                           float* scores_out, cudaStream_t st) {
-  matchability_kernel<<<dim3((cap + 7) / 8, 2 * pairs), 256, 0, st>>>(x, wm, bm, n, cap, logsig);
   row_lse_kernel<<<dim3((cap + 7) / 8, pairs), 256, 0, st>>>(sim, n, cap, lse);
   col_lse_kernel<<<dim3((cap + 31) / 32, pairs), dim3(32, 8), 0, st>>>(sim, n, cap, lse);
   lg_rowmax_kernel<<<dim3((cap + 7) / 8, pairs), 256, 0, st>>>(sim, lse, logsig, n, cap, row_arg, row_val, scores_out);

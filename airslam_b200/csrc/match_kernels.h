@@ -4,12 +4,16 @@
 
 namespace airfe {
 
-void launch_lg_prepare(const float* feat, const float* const* feat_ptrs /* optional per-slot bases */, const int* n, int slots, int cap, int feat_cap, int width, int height, float l_inv, const __half* wr,
+// row_off (optional, device int[slots + 1], written here): packed row layout, see lg_offsets_kernel
+void launch_lg_prepare(const float* feat, const float* const* feat_ptrs /* optional per-slot bases */, const int* n, int* row_off, int slots, int cap, int feat_cap, int width, int height, float l_inv, const __half* wr,
                        float* x, __half* cat16, float* rot, cudaStream_t st);
 void launch_lg_rotary(const float* qkv, const float* rot, const int* n, int slots, int cap, __half* q16, __half* k16, __half* v16, cudaStream_t st);
 void launch_softmax_rows(const float* S, __half* P, const int* n, int slots, int cap, int col_xor, cudaStream_t st);
 void launch_ln_gelu(const float* h, const float* gamma, const float* beta, const int* n, int slots, int cap, __half* out, cudaStream_t st);
-void launch_lg_assignment(const float* sim, const float* x, const __half* wm, float bm, const int* n, int pairs, int cap, float* logsig,
+// matchability logits of the final state x (packed when row_off != nullptr) -> logsig [slot][cap]; optionally unpacks md16 (packed) -> md16_pad
+void launch_lg_matchability(const float* x, const __half* wm, float bm, const int* n, const int* row_off, int pairs, int cap, float* logsig, const __half* md16,
+                            __half* md16_pad, cudaStream_t st);
+void launch_lg_assignment(const float* sim, const int* n, int pairs, int cap, float* logsig,
                           float* lse, int* row_arg, float* row_val, int* col_arg, float thr, int* m_idx, float* m_score, int* m_count,
                           float* scores_out, cudaStream_t st);
 

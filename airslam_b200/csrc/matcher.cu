@@ -23,7 +23,7 @@ bool LightGlue::init(const MatcherConfig& cfg, const std::string& wdir) {
   const int S = 2 * cfg.max_pairs, cap = cfg.cap;
   const size_t R = (size_t)S * cap;
   size_t bytes = (size_t)64 << 20;                                  // weights (23 MB fp16) + slack
-  bytes += R * (256 * 4 + 512 * 2 + 768 * 4 + 4 * 256 * 2 + 512 * 4 + 512 * 2 + 64 * 4 + 256 * 2 + 64);
+  bytes += R * (256 * 4 + 512 * 2 + 768 * 4 + 4 * 256 * 2 + 512 * 4 + 512 * 2 + 64 * 4 + 256 * 2 + 256 * 2 + 64);
   bytes += (size_t)S * 4 * cap * cap * 6 + (size_t)cfg.max_pairs * cap * cap * 8 + (size_t)cfg.max_pairs * cap * 32 + (1 << 20);
   if (!arena_.init(bytes)) return false;
   Arena* ar = &arena_;
@@ -88,6 +88,12 @@ bool LightGlue::init(const MatcherConfig& cfg, const std::string& wdir) {
   row_arg_ = ar->alloc_n<int>((size_t)cfg.max_pairs * cap);
   col_arg_ = ar->alloc_n<int>((size_t)cfg.max_pairs * cap);
   n_ = ar->alloc_n<int>(S);
+  row_off_ = ar->alloc_n<int>(S + 1);
+  md16_pad_ = ar->alloc_n<__half>(R * 256);
+  // Packed rows (slot s at rows [row_off[s], +n[s]) instead of [s * cap, ...)): the row GEMMs, the fused block tails and the attention row
+  // tiles then cover sum(n) rows instead of slots x cap -- at 400 keypoints 200 instead of 256 row tiles per 32 pairs.  Needs the fused
+  // attention / FFN kernels (cap <= 512); AIRFE_LG_PADDED=1 keeps the slot-padded layout for A/B runs.
+  packed_ = attn_fused_enabled() && ffn_fused_enabled() && cap <= 512 && getenv("AIRFE_LG_PADDED") == nullptr && getenv("AIRFE_LG_UNFUSED_PROJ") == nullptr;
   out_.idx = ar->alloc_n<int>((size_t)cfg.max_pairs * cap * 2);
   out_.score = ar->alloc_n<float>((size_t)cfg.max_pairs * cap);
   out_.count = ar->alloc_n<int>(cfg.max_pairs);
@@ -98,17 +104,22 @@ bool LightGlue::build_ops(int P) {
   if (ops_.count(P)) return true;
   OpList ol;
   const int S = 2 * P, cap = cfg_.cap;
-  auto rows = [&](void* p, int C, int ps, bool f32) { Act a; a.p = p; a.C = C; a.H = 1; a.W = cap; a.ps = ps; a.f32 = f32; return a; };
+  // packed: ONE matrix of S * cap rows whose valid extent row_off[S] is read on the device; padded: S slots of cap rows with n[s] valid each
+  const int RW = packed_ ? S * cap : cap;      // rows per "batch" of the row GEMMs
+  const int RB = packed_ ? 1 : S;              // batches
+  auto rows = [&](void* p, int C, int ps, bool f32) { Act a; a.p = p; a.C = C; a.H = 1; a.W = RW; a.ps = ps; a.f32 = f32; return a; };
   const Act x16 = rows(cat16_, 256, 512, false), msg16 = rows(cat16_ + 256, 256, 512, false), cat = rows(cat16_, 512, 512, false);
   const Act xf = rows(x_, 256, 256, true), qkv = rows(qkv_, 768, 768, true), q16 = rows(q16_, 256, 256, false), v16 = rows(v16_, 256, 256, false);
   const Act ctx = rows(ctx16_, 256, 256, false), hf = rows(h_, 512, 512, true), h16 = rows(h16_, 512, 512, false), md = rows(md16_, 256, 256, false);
   const float sc = 0.35355339059327379f;   // 64^-1/4
   const int* n = n_;
+  const int* nrow = packed_ ? row_off_ + S : n_;                    // valid rows per batch of the row GEMMs (device)
+  const int* roff = packed_ ? row_off_ : nullptr;
   const size_t Rall = (size_t)2 * cfg_.max_pairs * cap;             // rows of the q / k / v matrices as allocated
   static const bool fused_proj = getenv("AIRFE_LG_UNFUSED_PROJ") == nullptr;
 
   auto attention = [&](const __half* qa, const __half* kb, const __half* vb, int xr) -> bool {
-    if (attn_fused_enabled() && cap <= 512) return add_fused_attention(&ol, qa, kb, vb, 256, ctx16_, n, S, cap, xr, 1.f);
+    if (attn_fused_enabled() && cap <= 512) return add_fused_attention(&ol, qa, kb, vb, 256, ctx16_, n, S, cap, xr, 1.f, roff);
     // unfused path (cap > 512): S[s][h] = Q_s,h . K_(s^xr),h^T (fp32 in HBM), softmax rows, ctx_s = P . V_(s^xr)
     TcGemmDesc d;
     d.a = qa; d.a_C = 64; d.W = cap; d.H = 4; d.B = S; d.a_sx = 256; d.a_sy = 64; d.a_sb = (long long)cap * 256;
@@ -129,7 +140,7 @@ bool LightGlue::build_ops(int P) {
     return add_gemm(&ol, e, 2.0 * S * 4 * (double)cap * cap * 64, xr ? kDynAttCross : kDynAttSelf);
   };
   auto ffn = [&](const DenseW& w_out, const DenseW& w0, const DenseW& w3, const float* g, const float* b) -> bool {
-    if (ffn_fused_enabled()) return add_fused_ffn(&ol, ctx16_, cat16_, x_, w_out, w0, w3, g, b, n, S, cap);
+    if (ffn_fused_enabled()) return add_fused_ffn(&ol, ctx16_, cat16_, x_, w_out, w0, w3, g, b, nrow, RB, RW);
     if (!add_dense(&ol, ctx, w_out, msg16, S, false, -1, 0, n)) return false;                     // msg -> [x | msg] operand buffer
     if (!add_dense(&ol, cat, w0, hf, S, false, -1, 0, n)) return false;
     {
@@ -146,7 +157,7 @@ bool LightGlue::build_ops(int P) {
       // own matrices.  (The unfused path wrote 50 MB of fp32 qkv and re-read it in a separate rotary kernel.)
       DenseExtra ex;
       ex.scale_cols = 512; ex.rot = rot_; ex.rot_cols = 512; ex.out_split = 256; ex.out_split_stride = (long long)Rall * 256;
-      if (!add_dense(&ol, x16, Y.qkv, rows(q16_, 768, 256, false), S, false, -1, 0, n, sc, nullptr, nullptr, &ex)) return false;
+      if (!add_dense(&ol, x16, Y.qkv, rows(q16_, 768, 256, false), RB, false, -1, 0, nrow, sc, nullptr, nullptr, &ex)) return false;
     } else {
       if (!add_dense(&ol, x16, Y.qkv, qkv, S, false, -1, 0, n)) return false;
       const float* qp = qkv_; const float* rp = rot_; __half* q = q16_; __half* k = k16_; __half* v = v16_;
@@ -157,18 +168,26 @@ bool LightGlue::build_ops(int P) {
     if (fused_proj) {
       DenseExtra ex;
       ex.scale_cols = 256; ex.out_split = 256; ex.out_split_stride = (long long)Rall * 512;   // section 0 -> q16_, section 1 -> v16_
-      if (!add_dense(&ol, x16, Y.c_qv, rows(q16_, 512, 256, false), S, false, -1, 0, n, sc, nullptr, nullptr, &ex)) return false;
+      if (!add_dense(&ol, x16, Y.c_qv, rows(q16_, 512, 256, false), RB, false, -1, 0, nrow, sc, nullptr, nullptr, &ex)) return false;
     } else {
       if (!add_dense(&ol, x16, Y.c_qk, q16, S, false, -1, 0, n, sc)) return false;
       if (!add_dense(&ol, x16, Y.c_v, v16, S, false, -1, 0, n)) return false;
     }
     if (!attention(q16_, q16_, v16_, 1) || !ffn(Y.c_out, Y.c_ffn0, Y.c_ffn3, Y.c_ln_g, Y.c_ln_b)) return false;
   }
-  if (!add_dense(&ol, x16, final_, md, S, false, -1, 0, n, 0.25f)) return false;                 // / 256^(1/4)
+  if (!add_dense(&ol, x16, final_, md, RB, false, -1, 0, nrow, 0.25f)) return false;             // / 256^(1/4)
   {
+    // matchability logits of the final state + (packed layout) the slot-padded copy of md the similarity GEMM reads
+    const float* xs = x_; const __half* wm = wm_; const float bm = bm_; float* ls = logsig_; const __half* mdp = md16_; __half* mdo = packed_ ? md16_pad_ : nullptr;
+    const int* ro = roff;
+    ol.push("lg_matchability", 0, [=](cudaStream_t st) { launch_lg_matchability(xs, wm, bm, n, ro, P, cap, ls, mdp, mdo, st); return true; });
+    ol.launches++;
+  }
+  {
+    const __half* mdsrc = packed_ ? md16_pad_ : md16_;
     TcGemmDesc d;
-    d.a = md16_; d.a_C = 256; d.W = cap; d.H = 1; d.B = P; d.a_sx = 256; d.a_sy = 0; d.a_sb = 2ll * cap * 256;
-    d.bw = md16_ + (size_t)cap * 256; d.k_total = 256; d.n_rows = cap; d.bw_sn = 256; d.b_batches = P > 1 ? P : 0; d.bw_sbatch = 2ll * cap * 256;
+    d.a = mdsrc; d.a_C = 256; d.W = cap; d.H = 1; d.B = P; d.a_sx = 256; d.a_sy = 0; d.a_sb = 2ll * cap * 256;
+    d.bw = mdsrc + (size_t)cap * 256; d.k_total = 256; d.n_rows = cap; d.bw_sn = 256; d.b_batches = P > 1 ? P : 0; d.bw_sbatch = 2ll * cap * 256;
     d.taps = 1; d.c_in_pad = 256; d.block_n = 128; d.out_f32 = 1; d.out = sim_; d.out_sb = (long long)cap * cap; d.out_sy = 0; d.out_sx = cap;
     d.n_valid = cap; d.tw = 128; d.th = 1; d.tb = 1; d.dyn_w = n; d.dyn_w_stride = 2;
     if (!add_gemm(&ol, d, 2.0 * P * (double)cap * cap * 256, kDynSim)) return false;
@@ -185,10 +204,10 @@ bool LightGlue::run(const float* d_feat, const int* d_n, int feat_cap, int P, bo
   // float L_inv = 1.0 / std::max(width, height) * scale;  scale = 0.5 for LightGlue (src/point_matcher.cc:43,58)
   const float l_inv = (float)(1.0 / (double)(cfg_.image_width > cfg_.image_height ? cfg_.image_width : cfg_.image_height) * (double)0.5f);
   // prenormalised input: (x - 0) * 1 reproduces the value bit for bit
-  timed("lg_prepare", st, [&] { launch_lg_prepare(d_feat, d_feat_ptrs, n_, S, cap, feat_cap, prenorm ? 0 : cfg_.image_width, prenorm ? 0 : cfg_.image_height, prenorm ? 1.f : l_inv, wr_, x_, cat16_, rot_, st); });
+  timed("lg_prepare", st, [&] { launch_lg_prepare(d_feat, d_feat_ptrs, n_, packed_ ? row_off_ : nullptr, S, cap, feat_cap, prenorm ? 0 : cfg_.image_width, prenorm ? 0 : cfg_.image_height, prenorm ? 1.f : l_inv, wr_, x_, cat16_, rot_, st); });
   if (!ops_[P].run(st)) return false;
   timed("lg_assignment+filter", st, [&] {
-    launch_lg_assignment(sim_, x_, wm_, bm_, n_, P, cap, logsig_, lse_, row_arg_, row_val_, col_arg_, 0.1f, out_.idx, out_.score, out_.count,
+    launch_lg_assignment(sim_, n_, P, cap, logsig_, lse_, row_arg_, row_val_, col_arg_, 0.1f, out_.idx, out_.score, out_.count,
                          want_dense ? out_.dense : nullptr, st);
   });
   cudaError_t e = cudaGetLastError();

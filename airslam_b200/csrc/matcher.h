@@ -45,6 +45,9 @@ class LightGlue {
   __half *cat16_ = nullptr, *q16_ = nullptr, *k16_ = nullptr, *v16_ = nullptr, *P_ = nullptr, *ctx16_ = nullptr, *h16_ = nullptr, *md16_ = nullptr;
   int *row_arg_ = nullptr, *col_arg_ = nullptr;
   int* n_ = nullptr;   // [2*max_pairs] keypoint counts per slot (device copy owned by the matcher: plans bake this pointer)
+  int* row_off_ = nullptr;     // [2*max_pairs + 1] packed row offsets (prefix sums of n_), written by lg_offsets_kernel every run
+  __half* md16_pad_ = nullptr; // slot-padded copy of the final projection (operand of the similarity GEMM) in packed mode
+  bool packed_ = false;
   MatchOutputs out_;
 };
 

@@ -15,16 +15,17 @@ bool attn_fused_enabled() {
 
 // q, k, v: fp16 matrices with `row_stride` elements per keypoint row, head h at columns h*64; slot s at rows [s*cap, (s+1)*cap).
 bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __half* v, long long row_stride, __half* ctx, const int* n, int slots,
-                         int cap, int slot_xor, float scale) {
+                         int cap, int slot_xor, float scale, const int* row_off) {
   if (cap > 512 || cap % 128) { set_error("fused attention supports cap <= 512"); return false; }
   AttnParams p;
   memset(&p, 0, sizeof(p));
-  uint64_t dims[4] = {64, (uint64_t)cap, 4, (uint64_t)slots};
-  uint64_t str[3] = {(uint64_t)row_stride * 2, 64 * 2, (uint64_t)cap * row_stride * 2};
+  // packed layout: one "slot" of slots * cap rows; the kernel adds the slot's row base to the row coordinate
+  uint64_t dims[4] = {64, row_off ? (uint64_t)cap * slots : (uint64_t)cap, 4, row_off ? 1u : (uint64_t)slots};
+  uint64_t str[3] = {(uint64_t)row_stride * 2, 64 * 2, (uint64_t)cap * row_stride * 2 * (row_off ? slots : 1)};
   uint32_t box_q[4] = {64, 128, 1, 1}, box_kv[4] = {64, 256, 1, 1};
   if (!make_tmap_f16(&p.tmQ, q, 4, dims, str, box_q) || !make_tmap_f16(&p.tmK, k, 4, dims, str, box_kv) || !make_tmap_f16(&p.tmV, v, 4, dims, str, box_kv))
     return false;
-  p.n = n; p.slots = slots; p.cap = cap; p.slot_xor = slot_xor; p.scale = scale; p.ctx = ctx;
+  p.n = n; p.slots = slots; p.cap = cap; p.slot_xor = slot_xor; p.scale = scale; p.ctx = ctx; p.row_off = row_off;
   // Small batches (the per-call class surface: 2 slots; config 3: 16) leave most SMs idle with one CTA per (slot, head): split the query tiles
   // of a (slot, head) over up to cap / 128 CTAs while that still fits one wave (each part re-reads K / V from L2, so large batches do not split).
   int q_split = 1;

@@ -20,6 +20,7 @@ struct AttnParams {
   CUtensorMap tmV;   // same geometry on the value matrix,   box (64, 256, 1, 1)   (rows = keys: MN-major B for P.V)
   const int* n;      // [slots] keypoints per slot (device)
   int slots, cap, slot_xor;
+  const int* row_off; // optional packed layout: slot s owns rows [row_off[s], +n[s]) of the q / k / v / ctx matrices (tensor maps then have ONE slot of slots*cap rows)
   int q_split;       // CTAs per (slot, head): CTA part handles query tiles part, part + q_split, ... (small batches: more CTAs than slots x 4)
   float scale;       // applied to S before the softmax (1 for LightGlue: q,k pre-scaled; 1/8 for SuperGlue)
   __half* ctx;       // [slots*cap][256] fp16, head h at columns h*64
@@ -69,6 +70,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   ptx::pdl_launch_dependents();   // programmatic dependent launch: see launch_pdl (common.h)
   ptx::pdl_wait();                // the keypoint counts and Q / K / V are produced by earlier kernels: read them only from here on
+  const int q_row0 = p.row_off ? __ldg(p.row_off + slot) : 0, k_row0 = p.row_off ? __ldg(p.row_off + kslot) : 0;   // packed: row bases inside the single slot
+  const int q_slot = p.row_off ? 0 : slot, k_slot = p.row_off ? 0 : kslot;
   const int nq = min(__ldg(p.n + slot), p.cap);
   const int nk = min(__ldg(p.n + kslot), 512);
   const int q_tiles_all = (nq + 127) >> 7;
@@ -82,17 +85,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
         // ===== TMA producer =====
         const uint32_t kv_rows = (nk > 256) ? 512u : 256u;
         ptx::mbar_arrive_expect_tx(kv_full, 2u * kv_rows * 128u);
-        ptx::tma_load_4d(sK, &p.tmK, kv_full, 0, 0, head, kslot);
-        ptx::tma_load_4d(sV, &p.tmV, kv_full, 0, 0, head, kslot);
+        ptx::tma_load_4d(sK, &p.tmK, kv_full, 0, k_row0, head, k_slot);      // packed: rows beyond nk belong to the next slot -- masked by the softmax
+        ptx::tma_load_4d(sV, &p.tmV, kv_full, 0, k_row0, head, k_slot);
         if (nk > 256) {
-          ptx::tma_load_4d(sK + 256 * 128, &p.tmK, kv_full, 0, 256, head, kslot);
-          ptx::tma_load_4d(sV + 256 * 128, &p.tmV, kv_full, 0, 256, head, kslot);
+          ptx::tma_load_4d(sK + 256 * 128, &p.tmK, kv_full, 0, k_row0 + 256, head, k_slot);
+          ptx::tma_load_4d(sV + 256 * 128, &p.tmV, kv_full, 0, k_row0 + 256, head, k_slot);
         }
         uint32_t ph = 0;
         for (int t = 0; t < q_tiles; ++t) {
           ptx::mbar_wait(q_empty, ph ^ 1);
           ptx::mbar_arrive_expect_tx(q_full, 128u * 128u);
-          ptx::tma_load_4d(sQ, &p.tmQ, q_full, 0, (part + t * p.q_split) * 128, head, slot);
+          ptx::tma_load_4d(sQ, &p.tmQ, q_full, 0, q_row0 + (part + t * p.q_split) * 128, head, q_slot);
           ph ^= 1;
         }
       }
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
         ptx::mbar_wait(o_full, ph);
         ptx::tc_fence_after();
         const int q = (part + t * p.q_split) * 128 + row;
-        __half* o = p.ctx + ((long long)slot * p.cap + q) * 256 + head * 64;
+        __half* o = p.ctx + ((p.row_off ? (long long)q_row0 : (long long)slot * p.cap) + q) * 256 + head * 64;
         {
           const int c = half * 32;
           uint32_t r[32];
