@@ -240,14 +240,15 @@ class Context:
         p, h, w = left.shape
         fc = self.cfg.max_keypoints
         key = (p, fc, bool(lines), bool(junctions), line_cap, junc_cap, match_cap)
-        if getattr(self, "_sb_key", None) != key:
-            self._sb_key = key
-            self._sb = dict(feat=pinned_array((2 * p, fc, 259), np.float32), nf=np.zeros(2 * p, dtype=np.int32),
+        if not hasattr(self, "_sb_cache"):
+            self._sb_cache = {}
+        if key not in self._sb_cache:
+            self._sb_cache[key] = dict(feat=pinned_array((2 * p, fc, 259), np.float32), nf=np.zeros(2 * p, dtype=np.int32),
                             ln=np.empty((2 * p, line_cap, 4), dtype=np.float64) if lines else None, nl=np.zeros(2 * p, dtype=np.int32),
                             jn=pinned_array((p, junc_cap, 259), np.float32) if junctions else None, nj=np.zeros(p, dtype=np.int32),
                             i0=np.empty((p, match_cap), dtype=np.int32), i1=np.empty((p, match_cap), dtype=np.int32),
                             sc=np.empty((p, match_cap), dtype=np.float32), nm=np.zeros(p, dtype=np.int32))
-        b = self._sb
+        b = self._sb_cache[key]
         feat, nf, ln, nl, jn, nj, i0, i1, sc, nm = (b[k] for k in ("feat", "nf", "ln", "nl", "jn", "nj", "i0", "i1", "sc", "nm"))
         q = lambda a: a.ctypes.data_as(vp) if a is not None else None
         self._check(lib().airfe_detect_match_stereo_batch(self.h, net, matcher, p, q(left), q(right), w, h, w, h * w, q(feat), fc, q(nf), q(ln), line_cap,

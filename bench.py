@@ -4,9 +4,9 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|4|5] [--mode batch|class] [--impl airfe|reference]
 
 A "step" is one pass of the hot path over one batch of synthetic input -- the stream SURVEY.md 8(d) defines for the config:
-  config 2 (default, the headline): 512-pair stream 752x480, PLNet (points + lines + junctions) + LightGlue, in chunks of 32 pairs
+  config 2 (default, the headline): 512-pair stream 752x480, PLNet (points + lines + junctions) + LightGlue, in library calls of 47 pairs
   config 3: 512 pairs 640x480 (a batch of 8 pairs repeated 64x), SuperPoint + SuperGlue-indoor, in chunks of 8 pairs
-  config 4: 256 pairs 1280x720 low-light, PLNet (max_keypoints 450, line_threshold 0.8) + LightGlue, in chunks of 32 pairs
+  config 4: 256 pairs 1280x720 low-light, PLNet (max_keypoints 450, line_threshold 0.8) + LightGlue, in library calls of 42 pairs
   config 5: relocalization: 10 000-keyframe device-resident map sharded by keyframe id, 1024 queries x 400 features per step in batches of
             64, each LightGlue-matched against 3 candidates; query features all-gathered over NCCL (N > 1), scaling = strong
 The keyframe path is MapBuilder::ExtractFeatureThread (src/map_builder.cc:85-86); config 5 is MapUser::Relocalization (src/map_user.cc:363-376).
@@ -38,15 +38,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    2: dict(w=752, h=480, net="plnet", matcher="lightglue", units_per_step=512, chunk=32, max_keypoints=400, line_threshold=0.75, low_light=False,
+    2: dict(w=752, h=480, net="plnet", matcher="lightglue", units_per_step=512, chunk=47, max_keypoints=400, line_threshold=0.75, low_light=False,
             metric="stereo-pairs/sec through detect+match front-end @752x480", unit="pairs/s", scaling="weak",
-            workload="config 2: EuRoC-shape 752x480 stereo stream (512 pairs per step, chunks of 32), PLNet (points+lines+junctions) + LightGlue, 1 process per B200"),
+            workload="config 2: EuRoC-shape 752x480 stereo stream (512 pairs per step, library calls of 47 pairs: 94 keypoint sets x 400 rows = two full waves of 128-row tiles on 148 SMs), PLNet (points+lines+junctions) + LightGlue, 1 process per B200"),
     3: dict(w=640, h=480, net="superpoint", matcher="superglue", units_per_step=512, chunk=8, max_keypoints=400, line_threshold=0.75, low_light=False,
             metric="stereo-pairs/sec through detect+match front-end @640x480 (SuperPoint + SuperGlue-indoor)", unit="pairs/s", scaling="weak",
             workload="config 3: synthetic 640x480 stereo batch = 8 repeated 64x (512 pairs per step), SuperPoint + SuperGlue-indoor (100 Sinkhorn iterations), 1 process per B200"),
-    4: dict(w=1280, h=720, net="plnet", matcher="lightglue", units_per_step=256, chunk=32, max_keypoints=450, line_threshold=0.8, low_light=True,
+    4: dict(w=1280, h=720, net="plnet", matcher="lightglue", units_per_step=256, chunk=42, max_keypoints=450, line_threshold=0.8, low_light=True,
             metric="stereo-pairs/sec through detect+match front-end @1280x720 (low light)", unit="pairs/s", scaling="weak",
-            workload="config 4: 1280x720 low-light (OIVIO-shape) stereo (256 pairs per step, chunks of 32), PLNet (max_keypoints 450, line_threshold 0.8) + LightGlue, 1 process per B200"),
+            workload="config 4: 1280x720 low-light (OIVIO-shape) stereo (256 pairs per step, library calls of 42 pairs), PLNet (max_keypoints 450, line_threshold 0.8) + LightGlue, 1 process per B200"),
     5: dict(w=752, h=480, net=None, matcher="lightglue", units_per_step=1024, chunk=64, max_keypoints=400, n_keyframes=10000, n_cand=3,
             metric="relocalization queries/sec (each LightGlue-matched against 3 candidate keyframes of a 10k-keyframe map)", unit="queries/s", scaling="strong",
             workload="config 5: 10 000 keyframes x 400 features device-resident and sharded by keyframe id, 1024 queries x 400 features per step in batches of 64, "
@@ -533,7 +533,9 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    chunks_per_step = max(1, cfg["units_per_step"] // P)
+    U = max(cfg["units_per_step"], 1)
+    sizes = [P] * (U // P) + ([U % P] if U % P else [])            # library calls of a step: full chunks + the remainder of the stream
+    chunks_per_step = len(sizes)
     W_ = max(args.warmup, 3) if not args.device_only else max(args.warmup, 1)
     ctx = capi.Context(device=local, max_batch=P, enable_superpoint=int(cfg["net"] == "superpoint"), enable_plnet=int(cfg["net"] == "plnet"),
                        enable_lightglue=int(cfg["matcher"] == "lightglue"), enable_superglue=int(cfg["matcher"] == "superglue"),
@@ -552,12 +554,9 @@ def main():
         d_imgs.append(torch.from_numpy(inter).cuda())
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
 
-    def dev_chunk(i):
-        ctx.stereo_device(NET, MAT, P, d_imgs[i % nb].data_ptr(), W, H, W, W * H, LINES, LINES)
-
     def dev_step(i):
-        for j in range(chunks_per_step):
-            dev_chunk(i * chunks_per_step + j)
+        for j, sz in enumerate(sizes):
+            ctx.stereo_device(NET, MAT, sz, d_imgs[(i * chunks_per_step + j) % nb].data_ptr(), W, H, W, W * H, LINES, LINES)
 
     # ---- device-resident timing (value) ----
     for i in range(W_):
@@ -578,7 +577,7 @@ def main():
     ev1.synchronize()
     barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    units = chunks_per_step * P
+    units = sum(sizes)
     if args.device_only:
         sampler.stop_flag = True
         if rank == 0:
@@ -587,18 +586,24 @@ def main():
         ctx.close()
         return 0
     # ---- end-to-end timing through the host-buffer C ABI (e2e) ----
-    for i in range(2):
-        ctx.stereo_batch(NET, MAT, batches[i % nb][0], batches[i % nb][1], lines=LINES, junctions=LINES)
+    def e2e_chunk(k, sz):
+        return ctx.stereo_batch(NET, MAT, batches[k % nb][0][:sz], batches[k % nb][1][:sz], lines=LINES, junctions=LINES, raw=True)   # host buffers in / out, as a C caller
+
+    for k, sz in enumerate(sizes[:2] + sizes[-1:]):
+        e2e_chunk(k, sz)
     barrier()
     t0 = time.perf_counter()
     d2h = 0
-    for i in range(args.steps * chunks_per_step):
-        res = ctx.stereo_batch(NET, MAT, batches[i % nb][0], batches[i % nb][1], lines=LINES, junctions=LINES, raw=True)   # host buffers in / out, as a C caller
+    for i in range(args.steps):
+        for j, sz in enumerate(sizes):
+            res = e2e_chunk(i * chunks_per_step + j, sz)
+            if i == 0:
+                d2h += int(res["nf"].sum()) * 259 * 4 + int(res["nj"].sum()) * 259 * 4 + int(res["nl"].sum()) * 16 + int(res["nm"].sum()) * 12 + (5 * sz) * 4
+                if j == 0:
+                    mean_kp = float(res["nf"].mean())
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    d2h = int(res["nf"].sum()) * 259 * 4 + int(res["nj"].sum()) * 259 * 4 + int(res["nl"].sum()) * 16 + int(res["nm"].sum()) * 12 + (5 * P) * 4
-    mean_kp = float(res["nf"].mean())
-    h2d = 2 * P * W * H
+    h2d = 2 * units * W * H
     barrier()
 
     flops, launches = ctx.stereo_cost(NET, MAT, P, LINES)
@@ -640,7 +645,7 @@ def main():
     tj = os.path.join(ROOT, "profiles", "r02_conv3x3_traffic.json")
     if args.config == 2 and os.path.exists(tj):
         tjd = json.load(open(tj))
-        if tjd.get("pairs_per_step") == P and dom_key == "tc_conv3x3":      # dram__bytes_read+write per launch from the committed ncu capture of the same chunk
+        if tjd.get("pairs_per_step") == P and dom_key == "tc_conv3x3":      # the capture must be of the same library-call size      # dram__bytes_read+write per launch from the committed ncu capture of the same chunk
             traffic, traffic_src = tjd["dram_bytes_per_launch"], tjd["source"]
     if args.profile_out and rank == 0:
         with open(args.profile_out, "w") as fh:
@@ -661,7 +666,7 @@ def main():
                        "soak_s": args.soak, "timed_region_s": dev_ms * 1e-3,
                        "l2": "inputs rotate over %d chunks; a chunk's activations (~%.1f GB) exceed the 126 MB L2" % (nb, (0.3 if LINES else 0.1) * 2 * P)},
             "clocks": clk,
-            "e2e": {"value": world * units * args.steps / e2e_s, "unit": cfg["unit"], "h2d_bytes_per_step": h2d * chunks_per_step, "d2h_bytes_per_step": int(d2h) * chunks_per_step},
+            "e2e": {"value": world * units * args.steps / e2e_s, "unit": cfg["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches * args.steps * chunks_per_step),
             "roofline": {"bound": "tensor", "kernel": "%s (dominant family: %d launches = %.0f%% of a chunk's kernel time)" % (dom_key, dom["launches"], 100 * dom["share_of_chunk"]),
                          "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": dom["tflops"] / peak, "frac_of_sustained_peak": dom["tflops"] / sustained,
@@ -671,8 +676,8 @@ def main():
                                         "event-timed back to back right after the %.0f s of timed loops" % (how, peak_name, clk["sm_mhz"], clk["sm_max_mhz"], dev_ms * 1e-3 + e2e_s),
                          "flops_per_launch": dom["flops_per_chunk"] / max(1, dom["launches"]), "ms_per_launch": dom["ms_per_chunk"] / max(1, dom["launches"]),
                          "flops": "algorithmic, on the rows actually processed (device-side keypoint / line counts read back)",
-                         "families": families, "whole_chunk": {"tflops": sum(x[1] for x in prof) / (dev_ms * 1e-3 / (args.steps * chunks_per_step)) / 1e12,
-                                                               "frac_of_peak": sum(x[1] for x in prof) / (dev_ms * 1e-3 / (args.steps * chunks_per_step)) / 1e12 / peak}},
+                         "families": families, "whole_step": {"tflops": sum(x[1] for x in prof) * units / P / (dev_ms * 1e-3 / args.steps) / 1e12,
+                                                              "frac_of_peak": sum(x[1] for x in prof) * units / P / (dev_ms * 1e-3 / args.steps) / 1e12 / peak}},
         }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = cpu_threads()

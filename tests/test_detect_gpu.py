@@ -1,5 +1,10 @@
 """Stage-wise + end-to-end GPU parity of the detector (SuperPoint G1, PLNet G2+G3) against the oracle.
 
+Every dense tolerance below is <= 2x the error MEASURED on B200 (profiles/r02_parity_errors.json keeps the measured value next to it).  Dense
+conv stacks are compared relative to the activation scale max|x| (G2 activations reach several hundred): the absolute 1e-3 of SURVEY 8c is
+met on everything that leaves the path (descriptors 2e-4, heat map 2e-7, line scores 8e-5, match probabilities 4e-4) while intermediate feature
+maps carry the fp16 storage rounding of 70 stacked layers (measured <= 2.4e-3 of the scale at the deepest tap).
+
 Discrete stages (NMS, top-k, association, unique pairs, line acceptance) are compared EXACTLY against the oracle
 stage applied to the GPU's own upstream tensor; dense stages are compared with the precision-matched ("emul":
 fp16 operands, fp32 accumulate) oracle within the tolerances written below.  End-to-end agreement with the pure
@@ -67,7 +72,7 @@ def assert_junctions(tag, got, exp):
     """exact count, (x, y) and order; scores exact; descriptors <= 1e-5."""
     P.exact(tag + ".count+xy+score", got.shape == exp.shape and np.array_equal(got[:3], exp[:3]))
     if exp.shape[1]:
-        P.check(tag + ".descriptors", np.abs(got[3:] - exp[3:]).max(), 1e-5)
+        P.check(tag + ".descriptors", np.abs(got[3:] - exp[3:]).max(), 2e-7)
 
 
 def test_superpoint_stages(ctx, images):
@@ -87,18 +92,18 @@ def test_superpoint_stages(ctx, images):
         # (relu_1, conv1b's full-resolution output, is only materialised by PLNet contexts -- its line branch reads it; checked in test_plnet_stages)
         r7 = ctx.debug_read(capi.NET_SUPERPOINT, "relu_7", i, np.float16, (64, 64, 128)).astype(np.float32)
         r7_o = keep["relu_7"][0].numpy().transpose(1, 2, 0)
-        P.check("G1.relu_7 (8 convs)", _rel(r7, r7_o), 5e-3, "rel. to activation scale")
+        P.check("G1.relu_7 (8 convs)", _rel(r7, r7_o), 1e-3, "rel. to activation scale")
         logits = ctx.debug_read(capi.NET_SUPERPOINT, "logits", i, np.float32, (64, 64, 80))[..., :65]
         lg_o = keep["logits"][0].numpy().transpose(1, 2, 0)
-        P.check("G1.logits (convPb)", _rel(logits, lg_o), 5e-3, "rel. to activation scale")
+        P.check("G1.logits (convPb)", _rel(logits, lg_o), 1e-3, "rel. to activation scale")
         draw = ctx.debug_read(capi.NET_SUPERPOINT, "desc_raw", i, np.float32, (64, 64, 256))
         dr_o = keep["desc_raw"][0].numpy().transpose(1, 2, 0)
-        P.check("G1.desc_raw (convDb)", _rel(draw, dr_o), 5e-3, "rel. to activation scale")
+        P.check("G1.desc_raw (convDb)", _rel(draw, dr_o), 1.6e-3, "rel. to activation scale")
         # K4 softmax + depth-to-space on OUR logits
         heat = ctx.debug_read(capi.NET_SUPERPOINT, "heat", i, np.float32, (512, 512))
         prob = torch.softmax(torch.from_numpy(logits), dim=-1)[..., :64].numpy()
         heat_o = prob.reshape(64, 64, 8, 8).transpose(0, 2, 1, 3).reshape(512, 512)
-        P.check("K4.heat (softmax+d2s on own logits)", np.abs(heat - heat_o).max(), 1e-6)
+        P.check("K4.heat (softmax+d2s on own logits)", np.abs(heat - heat_o).max(), 4e-7)
         # K5 NMS on OUR heat: exact
         scores = ctx.debug_read(capi.NET_SUPERPOINT, "scores", i, np.float32, (512, 512))
         sc_ref = nets.simple_nms(torch.from_numpy(heat)[None])[0].numpy()
@@ -112,7 +117,7 @@ def test_superpoint_stages(ctx, images):
         # K7+K8 descriptors from OUR dense map at OUR keypoints: 1e-5 abs
         d = draw / np.maximum(np.sqrt((draw * draw).sum(-1, keepdims=True)), 1e-12)
         desc_ref = host.extract_descriptors(_nhwc_to_nchw(d), pts)
-        P.check("K7+K8.sampled descriptors (own dense map)", np.abs(feat[3:] - desc_ref).max(), 1e-5)
+        P.check("K7+K8.sampled descriptors (own dense map)", np.abs(feat[3:] - desc_ref).max(), 2e-7)
         # end to end vs the pure oracle (emul mode): set overlap of keypoints, descriptor distance on the common ones
         f_o = host.keypoints_decoder(sc_o[0].numpy(), de_o[0].numpy(), CFG["keypoint_threshold"], CFG["remove_borders"], CFG["max_keypoints"])
         ours = {(int(a), int(b)): k for k, (a, b) in enumerate(zip(pts[1], pts[2]))}
@@ -120,7 +125,7 @@ def test_superpoint_stages(ctx, images):
         P.report("G1.e2e keypoint overlap vs emul oracle", len(common) / max(1, f_o.shape[1]), "fraction", "reported, not a gate beyond 0.95")
         assert len(common) >= 0.95 * f_o.shape[1], "keypoint overlap %d / %d" % (len(common), f_o.shape[1])
         dd = max(np.abs(feat[3:, a] - f_o[3:, b]).max() for a, b in common)
-        P.check("G1.e2e descriptors on common keypoints", dd, 3e-3)
+        P.check("G1.e2e descriptors on common keypoints", dd, 5e-4)
 
 
 def test_plnet_stages(ctx, images):
@@ -135,24 +140,24 @@ def test_plnet_stages(ctx, images):
         keep = {}
         o = nets.plnet_s0_forward(x, w, emul=True, keep=keep)
         r1 = ctx.debug_read(N, "relu_1", i, np.float16, (512, 512, 64)).astype(np.float32)
-        P.check("G2.relu_1 (conv1a+conv1b, fp16 store)", _rel(r1, keep["relu_1"][0].numpy().transpose(1, 2, 0)), 2e-3, "rel. to activation scale")
+        P.check("G2.relu_1 (conv1a+conv1b, fp16 store)", _rel(r1, keep["relu_1"][0].numpy().transpose(1, 2, 0)), 8e-4, "rel. to activation scale")
         heads9 = ctx.debug_read(N, "heads9", i, np.float32, (128, 128, 16))[..., :9]
         h_o = keep["heads9"][0].numpy().transpose(1, 2, 0)
-        P.check("G2.heads9 (74 convs)", _rel(heads9, h_o), 2e-2, "rel. to activation scale")
+        P.check("G2.heads9 (74 convs)", _rel(heads9, h_o), 5e-3, "rel. to activation scale")
         loi = ctx.debug_read(N, "loi", i, np.float32, (128, 128, 128))
-        P.check("G2.loi_features", _rel(loi, o["loi_features"][0].numpy().transpose(1, 2, 0)), 2e-2, "rel. to activation scale")
+        P.check("G2.loi_features", _rel(loi, o["loi_features"][0].numpy().transpose(1, 2, 0)), 2e-3, "rel. to activation scale")
         ta = ctx.debug_read(N, "thinaux", i, np.float32, (128, 128, 8))
         ta_o = np.concatenate([o["loi_features_thin"][0].numpy(), o["loi_features_aux"][0].numpy()]).transpose(1, 2, 0)
-        P.check("G2.thin/aux", _rel(ta, ta_o), 2e-2, "rel. to activation scale")
+        P.check("G2.thin/aux", _rel(ta, ta_o), 1.5e-3, "rel. to activation scale")
         # K9 decode on OUR heads: lines within 1e-3 grid units; junction indices exact given our jloc
         dec = nets.hafm_decode(torch.from_numpy(np.ascontiguousarray(heads9.transpose(2, 0, 1)))[None])
         lines = ctx.debug_read(N, "lines_pred", i, np.float32, (3 * 128 * 128, 4))
         # tan() near pi/2 amplifies 1-ulp differences of sin/cos/tan between CUDA libm and the CPU: loose max, tight median
         dl = np.abs(lines - dec["lines_pred"].numpy())
-        P.check("K9.lines_pred max (own heads; tan near pi/2)", dl.max(), 2e-2, "grid units")
+        P.check("K9.lines_pred max (own heads; tan near pi/2)", dl.max(), 2e-3, "grid units")
         P.check("K9.lines_pred median", np.median(dl), 1e-5, "grid units")
         jloc = ctx.debug_read(N, "jloc", i, np.float32, (128, 128))
-        P.check("K9.jloc", np.abs(jloc - dec["jloc"][0, 0].numpy()).max(), 1e-6)
+        P.check("K9.jloc", np.abs(jloc - dec["jloc"][0, 0].numpy()).max(), 3e-7)
         joff = dec["joff"]
         ja = nets.junctions_and_association(torch.from_numpy(lines), torch.from_numpy(jloc)[None, None], joff)
         jidx = ctx.debug_read(N, "junc_idx", i, np.int32, (300,))
@@ -189,9 +194,9 @@ def test_plnet_stages(ctx, images):
                                         loi.transpose(2, 0, 1)[None], ta.transpose(2, 0, 1)[None, :4], ta.transpose(2, 0, 1)[None, 4:], w,
                                         emul=True, keep=kp2)
         f496 = ctx.debug_read(N, "feat496", i, np.float16, (16384, 512))[:nu, :496].astype(np.float32)
-        P.check("K11.feat496 (LOI gather, fp16 store)", _rel(f496, kp2["feat"].numpy()), 4e-3, "rel. to activation scale")
+        P.check("K11.feat496 (LOI gather, fp16 store)", _rel(f496, kp2["feat"].numpy()), 6e-4, "rel. to activation scale")
         ls = ctx.debug_read(N, "line_score", i, np.float32, (16384,))[:nu]
-        P.check("G3.scores_line (own inputs)", np.abs(ls - sl.numpy()).max(), 5e-3)
+        P.check("G3.scores_line (own inputs)", np.abs(ls - sl.numpy()).max(), 2e-4)
         # K12 acceptance on OUR scores: exact line list
         adj_g = ctx.debug_read(N, "lines_adjusted", i, np.float32, (16384, 4))[:nu]
         P.exact("G3.lines_adjusted", np.array_equal(adj_g, adj.numpy()))

@@ -1,4 +1,8 @@
-"""GPU parity of the LightGlue device pipeline against the oracle (precision-matched 'emul' mode) and of the
+"""Tolerances are <= 2x the error measured on B200 (profiles/r02_parity_errors.json).  SuperGlue's 18 layers + 100 Sinkhorn iterations reach
+2.1e-3 in match probability against the kernel-matched oracle -- above the 1e-3 of SURVEY 8c, inside the fp16-operand drift class that App. D
+measured for the reference's own FP16 engines (4.1e-3 vs fp32); indices are identical.
+
+GPU parity of the LightGlue device pipeline against the oracle (precision-matched 'emul' mode) and of the
 mutual-NN filter (exact, on the GPU's own score matrix).  Also the stereo (detect -> match) entry point."""
 import os
 
@@ -46,14 +50,14 @@ def test_lightglue_scores_and_matches(ctx):
         P.report("G4.match score drift vs plain emul oracle", np.abs(res[i][1] - sc_e).max(), "abs in probability")
         # dense log-scores: compare where it matters (exp(score) > 1e-4) in probability space, tolerance 1e-3 abs
         big = (dense_o > np.log(1e-4)) | (dense > np.log(1e-4))
-        P.check("G4.dense assignment probabilities (exp of log-scores > 1e-4)", np.abs(np.exp(dense[big]) - np.exp(dense_o[big])).max(), 2e-3, "abs in probability")
+        P.check("G4.dense assignment probabilities (exp of log-scores > 1e-4)", np.abs(np.exp(dense[big]) - np.exp(dense_o[big])).max(), 8e-4, "abs in probability")
         # filter on OUR dense matrix: exact indices, scores 1e-6
         idx_g, sc_g = host.filter_matches(dense)
         P.exact("K16.filter_matches indices (own matrix)", np.array_equal(res[i][0], idx_g))
-        P.check("K16.filter_matches scores (own matrix)", np.abs(res[i][1] - sc_g).max(), 1e-6)
+        P.check("K16.filter_matches scores (own matrix)", np.abs(res[i][1] - sc_g).max(), 4e-7)
         # vs the pure oracle: identical match indices, scores within 2e-3
         P.exact("G4.match indices vs kernel-matched oracle (same features)", np.array_equal(res[i][0], idx_o))
-        P.check("G4.match scores vs kernel-matched oracle", np.abs(res[i][1] - sc_o).max(), 2e-3, "abs in probability")
+        P.check("G4.match scores vs kernel-matched oracle", np.abs(res[i][1] - sc_o).max(), 8e-4, "abs in probability")
         # planted correspondences are recovered
         good = (perm[res[i][0][:, 1]] == res[i][0][:, 0]).mean()
         assert good > 0.95
@@ -122,16 +126,16 @@ def test_superglue_scores_decode_and_matches(ctx_sg):
         # 2e-3 relative on the dustbin row / column (values up to N)
         di, do = dense[:n0, :n1], dense_o[:n0, :n1]
         big = (do > np.log(1e-4)) | (di > np.log(1e-4))
-        P.check("G5.dense match block probabilities", np.abs(np.exp(di[big]) - np.exp(do[big])).max(), 5e-3, "abs in probability")
+        P.check("G5.dense match block probabilities", np.abs(np.exp(di[big]) - np.exp(do[big])).max(), 4e-3, "abs in probability")
         for g_, o_ in ((dense[n0, :], dense_o[n0, :]), (dense[:, n1], dense_o[:, n1])):
-            P.check("G5.dustbin row / column (values up to N)", (np.abs(np.exp(g_) - np.exp(o_)) / (1.0 + np.exp(o_))).max(), 5e-3, "abs / (1 + value)")
+            P.check("G5.dustbin row / column (values up to N)", (np.abs(np.exp(g_) - np.exp(o_)) / (1.0 + np.exp(o_))).max(), 2.5e-3, "abs / (1 + value)")
         # decode on OUR matrix: exact
         i0_g, i1_g, m0_g, m1_g = host.superglue_decode(dense)
         P.exact("K19.superglue decode indices (own matrix)", np.array_equal(raw[i][0], i0_g) and np.array_equal(raw[i][1], i1_g))
-        P.check("K19.superglue decode mscores (own matrix)", max(np.abs(raw[i][2] - m0_g).max(), np.abs(raw[i][3] - m1_g).max()), 1e-6)
+        P.check("K19.superglue decode mscores (own matrix)", max(np.abs(raw[i][2] - m0_g).max(), np.abs(raw[i][3] - m1_g).max()), 3e-7)
         # vs the pure oracle
         P.exact("G5.indices0/1 vs kernel-matched oracle (same features)", np.array_equal(raw[i][0], i0_o) and np.array_equal(raw[i][1], i1_o))
-        P.check("G5.mscores0 vs kernel-matched oracle", np.abs(raw[i][2] - m0_o).max(), 5e-3, "abs in probability")
+        P.check("G5.mscores0 vs kernel-matched oracle", np.abs(raw[i][2] - m0_o).max(), 4e-3, "abs in probability")
         # PointMatcher::MatchingPoints semantics on top of it
         exp = [(k, int(i0_g[k])) for k in range(n0) if 0 <= i0_g[k] < n1 and i1_g[i0_g[k]] == k]
         assert [tuple(r) for r in mm[i][0]] == exp
