@@ -78,6 +78,8 @@ def _declare_frame(L):
     L.airfe_destroy.argtypes = [vp]
     L.airfe_debug_conv_trace.argtypes = [vp]
     L.airfe_debug_conv_trace.restype = None
+    L.airfe_debug_match_trace.argtypes = [vp]
+    L.airfe_debug_match_trace.restype = None
     L.airfe_stream.argtypes = [vp]
     L.airfe_stream.restype = vp
     L.airfe_detect_batch.argtypes = [vp, i32, i32, vp, i32, i32, i32, i64, vp, i32, vp, vp, i32, vp, vp, i32, vp]

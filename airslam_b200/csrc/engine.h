@@ -150,6 +150,8 @@ bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int b
 // Falls back to the generic streaming-tap kernel (+ pool kernel) when AIRFE_CONV_V1 is set or the map is narrower than 8.
 bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu);
 bool conv3x3_halo_enabled();
+void match_set_trace(long long* dev_buf);      // authoring aid, see airfe_debug_match_trace
+long long* match_trace_buf();
 void conv3x3_set_trace(long long* dev_buf);   // authoring aid, see airfe_debug_conv_trace
 // Append fused multi-head attention (tc_attn.cuh): ctx = softmax(q k^T * scale) v per (slot, head); keys/values of slot ^ slot_xor.
 // row_off (optional, device int[slots + 1]): packed row layout, slot s at rows [row_off[s], row_off[s] + n[s]).

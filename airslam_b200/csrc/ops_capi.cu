@@ -39,5 +39,6 @@ int airfe_op_conv3x3(const void* in, int C, int W, int H, int B, long long in_ps
 }
 
 void airfe_debug_conv_trace(long long* dev_buf) { conv3x3_set_trace(dev_buf); }
+void airfe_debug_match_trace(long long* dev_buf) { match_set_trace(dev_buf); }
 
 }  // extern "C"

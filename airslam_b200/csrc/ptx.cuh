@@ -72,6 +72,22 @@ __device__ __forceinline__ void ld_global_256f(const void* p, float (&v)[8]) {
                : "memory");
 }
 
+// Non-volatile variant for loads that the compiler may batch / hoist (no ordering against other memory operations is implied: use it only
+// for data this thread does not write before the load, or whose later store depends on the loaded value).
+__device__ __forceinline__ void ld_global_256f_nv(const void* p, float (&v)[8]) {
+  asm("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+      : "l"(p));
+}
+
+// exp2 on the special-function unit (MUFU.EX2), flush-to-zero: the callers feed arguments <= 0 whose results are rounded to fp16 or
+// multiplied into O(1) values, so results below 2^-126 are irrelevant.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---- programmatic dependent launch (see launch_pdl in common.h) -----------------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

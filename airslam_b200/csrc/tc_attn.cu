@@ -46,7 +46,9 @@ bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __h
       }
       attr_set[dev] = true;
     }
-    cudaError_t e = launch_pdl(tc_attn_kernel, slots * 4 * q_split, kAttnThreads, kAttnSmemBytes, st, p);
+    AttnParams pp = p;
+    pp.trace = match_trace_buf() ? match_trace_buf() + 1024 : nullptr;    // authoring aid, normally nullptr
+    cudaError_t e = launch_pdl(tc_attn_kernel, slots * 4 * q_split, kAttnThreads, kAttnSmemBytes, st, pp);
     if (e != cudaSuccess) { set_error("tc_attn launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
   }, slot_xor ? kDynAttCross : kDynAttSelf);

@@ -24,6 +24,7 @@ struct AttnParams {
   int q_split;       // CTAs per (slot, head): CTA part handles query tiles part, part + q_split, ... (small batches: more CTAs than slots x 4)
   float scale;       // applied to S before the softmax (1 for LightGlue: q,k pre-scaled; 1/8 for SuperGlue)
   __half* ctx;       // [slots*cap][256] fp16, head h at columns h*64
+  long long* trace;  // authoring aid (airfe_debug_match_trace): CTA 0 writes clock64 stamps of its query tiles, 16 slots per tile
 };
 
 constexpr int kAttnThreads = 320;
@@ -115,9 +116,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
       uint32_t ph = 0;
       uint32_t pph = 0;   // phase bit per P ring slot
       for (int t = 0; t < q_tiles; ++t) {
+        long long* trp = (p.trace && blockIdx.x == 0 && lane == 0 && t < 8) ? p.trace + t * 16 : nullptr;
+        if (trp) trp[0] = clock64();             // MMA warp reaches the tile (K / V landed)
         ptx::mbar_wait(q_full, ph);
         ptx::mbar_wait(s_free, ph ^ 1);          // TMEM free again (previous tile's O has been read)
         ptx::tc_fence_after();
+        if (trp) trp[1] = clock64();             // Q landed, TMEM free
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, dq + 2 * k, dk + 2 * k, idesc_lo, k != 0);
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
           __syncwarp();
           pph ^= 1u << ps;
         }
+        if (trp) trp[2] = clock64();             // last P.V block issued
         ph ^= 1;
       }
     } else {
@@ -156,75 +161,103 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
       uint32_t eph = 0;   // phase bit per P ring slot (a slot always belongs to the same half: slot parity == block parity)
       const float sc2 = p.scale * 1.4426950408889634f;      // exp(x) = exp2(x * log2 e): one FFMA + MUFU.EX2 per element
       for (int t = 0; t < q_tiles; ++t) {
+        long long* tre = (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && t < 8) ? p.trace + t * 16 + 4 : nullptr;
         ptx::mbar_wait(s_full, ph);
         ptx::tc_fence_after();
-        // pass 1: row max over this half's key blocks (raw scores; scale > 0 so the max commutes with it)
-        float mx = -INFINITY;
-        for (int kb = half; kb < nkb; kb += 2) {
+        if (tre) tre[0] = clock64();             // S complete
+        // pass 1: row max over this half's key blocks (raw scores; scale > 0 so the max commutes with it).  Both passes walk the 32-column
+        // groups of this thread's blocks (kb = half, half + 2, ...; two groups per 64-key block) with double-buffered TMEM loads: group i + 1 is
+        // in flight while group i is reduced.  (First version: load, wait, reduce -- the ~300-cycle load latency was exposed 14 times per
+        // pass and the exp pass took 7.4 k cycles per 128-query tile, 70 % of the kernel: profiles/r02c_match_trace.txt.)
+        uint32_t rr[2][32];
+        const int nblk = nkb > half ? (nkb - half + 1) >> 1 : 0;          // 64-key blocks of this half
+        auto col_of = [&](int i) { return (half + 2 * (i >> 1)) * 64 + (i & 1) * 32; };
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        auto max_group = [&](const uint32_t (&r)[32], int c) {
+          if (c + 32 <= nk) {
 #pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
-            const int c = kb * 64 + hc * 32;
-            if (c >= nk) break;
-            uint32_t r[32];
-            ptx::tmem_ld32(trow + c, r);
+            for (int i = 0; i < 32; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1])); }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx0 = fmaxf(mx0, (c + i < nk) ? __uint_as_float(r[i]) : -INFINITY);
+          }
+        };
+        {
+          int n_it = 2 * nblk;
+          while (n_it > 0 && col_of(n_it - 1) >= nk) --n_it;                 // groups entirely beyond the last key hold no scores
+          if (n_it > 0) ptx::tmem_ld32(trow + col_of(0), rr[0]);
+          for (int i = 0; i < n_it; i += 2) {
             ptx::tmem_ld_wait();
-            if (c + 32 <= nk) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < nk) ? __uint_as_float(r[i]) : -INFINITY);
+            if (i + 1 < n_it) ptx::tmem_ld32(trow + col_of(i + 1), rr[1]);
+            max_group(rr[0], col_of(i));
+            if (i + 1 < n_it) {
+              ptx::tmem_ld_wait();
+              if (i + 2 < n_it) ptx::tmem_ld32(trow + col_of(i + 2), rr[0]);
+              max_group(rr[1], col_of(i + 1));
             }
           }
         }
-        sRed[half * 128 + row] = mx;
+        sRed[half * 128 + row] = fmaxf(mx0, mx1);
+        if (nblk > 0) ptx::tmem_ld32(trow + col_of(0), rr[0]);               // first group of pass 2: in flight across the barrier
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float m2 = fmaxf(sRed[row], sRed[128 + row]) * sc2;
-        // pass 2: e = exp(s - max) once per element: accumulate the row sum in fp32 and hand fp16(e) to the tensor core through
-        // shared memory (K-major SWIZZLE_128B, 64 keys per block); the 1/sum normalisation is applied to O in the epilogue.
-        float sum = 0.f;
-        for (int kb = half; kb < nkb; kb += 2) {
+        if (tre) tre[1] = clock64();             // pass 1 (row max) done
+        // pass 2: e = exp(s - max) once per element: accumulate the row sum in fp32 (four partial sums) and hand fp16(e) to the tensor core
+        // through shared memory (K-major SWIZZLE_128B, 64 keys per block); the 1/sum normalisation is applied to O in the epilogue.
+        float sm[4] = {0.f, 0.f, 0.f, 0.f};
+        auto exp_group = [&](const uint32_t (&r)[32], int i) {
+          const int kb = half + 2 * (i >> 1), hc = i & 1;
           const int ps = kb & (kAttnPSlots - 1);
-          ptx::mbar_wait(&p_empty[ps], ((eph >> ps) & 1) ^ 1);     // slot free (first use of a fresh barrier passes immediately)
+          if (hc == 0) ptx::mbar_wait(&p_empty[ps], ((eph >> ps) & 1) ^ 1);     // slot free (first use of a fresh barrier passes immediately)
           uint8_t* prow = sP + ps * 16384 + row * 128;
+          const int c0 = kb * 64 + hc * 32;
+          float e[32];
+          if (c0 + 32 <= nk) {
 #pragma unroll
-          for (int hc = 0; hc < 2; ++hc) {
-            const int c0 = kb * 64 + hc * 32;
-            uint32_t r[32];
-            ptx::tmem_ld32(trow + c0, r);
-            ptx::tmem_ld_wait();
-            float e[32];
-            if (c0 + 32 <= nk) {
+            for (int j = 0; j < 32; ++j) { e[j] = ptx::ex2_approx(fmaf(__uint_as_float(r[j]), sc2, -m2)); sm[j & 3] += e[j]; }
+          } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) { e[i] = exp2f(fmaf(__uint_as_float(r[i]), sc2, -m2)); sum += e[i]; }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) { e[i] = (c0 + i < nk) ? exp2f(fmaf(__uint_as_float(r[i]), sc2, -m2)) : 0.f; sum += e[i]; }
-            }
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {       // 4 chunks of 8 keys (16 bytes)
-              uint32_t pk[4];
-#pragma unroll
-              for (int q2 = 0; q2 < 4; ++q2) {
-                __half2 h2 = __floats2half2_rn(e[ch * 8 + q2 * 2], e[ch * 8 + q2 * 2 + 1]);
-                pk[q2] = *reinterpret_cast<uint32_t*>(&h2);
-              }
-              const int chunk = hc * 4 + ch;
-              *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
+            for (int j = 0; j < 32; ++j) { e[j] = (c0 + j < nk) ? ptx::ex2_approx(fmaf(__uint_as_float(r[j]), sc2, -m2)) : 0.f; sm[j & 3] += e[j]; }
           }
-          ptx::fence_proxy_async();                // generic-proxy smem writes -> visible to the tensor core (async proxy)
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&p_full[ps]);
-          eph ^= 1u << ps;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {       // 4 chunks of 8 keys (16 bytes)
+            uint32_t pk[4];
+#pragma unroll
+            for (int q2 = 0; q2 < 4; ++q2) {
+              __half2 h2 = __floats2half2_rn(e[ch * 8 + q2 * 2], e[ch * 8 + q2 * 2 + 1]);
+              pk[q2] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            const int chunk = hc * 4 + ch;
+            *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          if (hc == 1) {
+            ptx::fence_proxy_async();                // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&p_full[ps]);
+            eph ^= 1u << ps;
+          }
+        };
+        {
+          const int n_it = 2 * nblk;                                         // every 64-key block is written completely (keys >= nk as zeros)
+          for (int i = 0; i < n_it; i += 2) {
+            ptx::tmem_ld_wait();
+            ptx::tmem_ld32(trow + col_of(i + 1), rr[1]);
+            exp_group(rr[0], i);
+            ptx::tmem_ld_wait();
+            if (i + 2 < n_it) ptx::tmem_ld32(trow + col_of(i + 2), rr[0]);
+            exp_group(rr[1], i + 1);
+          }
         }
+        const float sum = (sm[0] + sm[1]) + (sm[2] + sm[3]);
         sRed[256 + half * 128 + row] = sum;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float inv = 1.f / (sRed[256 + row] + sRed[384 + row]);
+        if (tre) tre[2] = clock64();             // pass 2 (exp, P blocks) done
         // epilogue: O (128 x 64 fp32, TMEM columns 0..63) -> fp16 context rows; this warp writes columns half*32 .. +32
         ptx::mbar_wait(o_full, ph);
         ptx::tc_fence_after();
+        if (tre) tre[3] = clock64();             // O complete
         const int q = (part + t * p.q_split) * 128 + row;
         __half* o = p.ctx + ((p.row_off ? (long long)q_row0 : (long long)slot * p.cap) + q) * 256 + head * 64;
         {
@@ -248,6 +281,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(s_free);
+        if (tre) tre[4] = clock64();             // context stored
         ph ^= 1;
       }
     }

@@ -2,6 +2,7 @@
 #include "common.h"
 #include "engine.h"
 #include "tc_conv3x3.cuh"
+#include "tc_conv3x3_fold.cuh"
 
 #include <stdlib.h>
 
@@ -19,7 +20,16 @@ void conv3x3_set_trace(long long* dev_buf) { g_conv_trace = dev_buf; }
 
 using ConvKernel = void (*)(const ConvParams);
 
+static int conv_key(const ConvParams& p) {
+  if (p.fold) return 8 + (p.kw == 32 ? 2 : 0) + (p.block_n == 64 ? 1 : 0);
+  return (p.kw == 32 ? 4 : 0) | (p.strips == 2 ? 2 : 0) | (p.b_resident ? 1 : 0);
+}
+
 static ConvKernel conv_kernel_for(const ConvParams& p) {
+  if (p.fold) {
+    if (p.kw == 64) return p.block_n == 64 ? tc_conv3x3_fold_kernel<64, 64> : tc_conv3x3_fold_kernel<64, 32>;
+    return p.block_n == 64 ? tc_conv3x3_fold_kernel<32, 64> : tc_conv3x3_fold_kernel<32, 32>;
+  }
   const int key = (p.kw == 32 ? 4 : 0) | (p.strips == 2 ? 2 : 0) | (p.b_resident ? 1 : 0);
   switch (key) {
     case 0: return tc_conv3x3_kernel<64, 1, false>;
@@ -34,9 +44,9 @@ static ConvKernel conv_kernel_for(const ConvParams& p) {
 }
 
 static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[kMaxDevices][8] = {};
+  static bool attr_set[kMaxDevices][12] = {};
   const int dev = current_device();
-  const int key = (plan.p.kw == 32 ? 4 : 0) | (plan.p.strips == 2 ? 2 : 0) | (plan.p.b_resident ? 1 : 0);
+  const int key = conv_key(plan.p);
   const int threads = kConvThreads;
   ConvKernel kern = conv_kernel_for(plan.p);
   if (!attr_set[dev][key]) {
@@ -58,6 +68,15 @@ static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
   }
   if (e != cudaSuccess) { set_error("tc_conv3x3 launch failed: %s", cudaGetErrorString(e)); return false; }
   return true;
+}
+
+// kx-folded variant (tc_conv3x3_fold.cuh) for resident-weights small-N layers.  Measured on B200 (profiles/r02c_fold_ab.txt, 16 frames of
+// 512 x 512): 64->32 0.234 -> 0.176 ms, but 32->32 pool-only 0.150 -> 0.188, 64->64 0.296 -> 0.319, 64->64 + pool 0.349 -> 0.401: the fold cuts the
+// MMA time by 1.3-1.9x and triples the accumulator columns the epilogue has to read, shift and add, so it only pays where the nine-tap kernel
+// is furthest below the tensor roofline.  Default: C_in = 64 -> C_out = 32 only.  AIRFE_CONV_FOLD=0: never, =2: every eligible layer (tests, A/B).
+static int conv3x3_fold_mode() {
+  const char* e = getenv("AIRFE_CONV_FOLD");   // read at plan time (not cached: the operator tests switch it between calls)
+  return e ? atoi(e) : 1;
 }
 
 bool conv3x3_halo_enabled() {
@@ -127,7 +146,30 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
     if (p.stages_b > 12) p.stages_b = 12;
     if (p.stages_b < 3) { set_error("add_conv3x3: shared memory budget too small"); return false; }
   }
-  {
+  const int fold_mode = conv3x3_fold_mode();
+  if (fold_mode && p.b_resident && p.kblocks == 1 && p.n_tiles == 1 && (block_n == 32 || block_n == 64) && (fold_mode == 2 || (block_n == 32 && p.kw == 64))) {
+    // kx taps folded into N (tc_conv3x3_fold.cuh): tiles of 14 output columns x 16 rows, one TMEM buffer of 3N columns per 8-row strip
+    p.fold = 1;
+    p.strips = kFoldStrips;
+    p.tiles_x = (in.W + kFoldTX - 1) / kFoldTX;
+    p.tiles_y = (in.H + 8 * kFoldStrips - 1) / (8 * kFoldStrips);
+    p.nacc = fold_nbuf(block_n);
+    const int fa = fold_a_bytes(p.kw), fb = 9 * block_n * p.kw * 2;
+    p.stages_a = (budget - fb) / fa;
+    if (p.stages_a > 4) p.stages_a = 4;
+    uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)batch};
+    uint64_t str[3] = {(uint64_t)in.ps * 2, (uint64_t)in.ps * in.W * 2, (uint64_t)in.ps * in.W * in.H * 2};
+    uint32_t box[4] = {(uint32_t)p.kw, 16, (uint32_t)(8 * kFoldStrips + 2), 1};
+    if (!make_tmap_f16(&p.tmA, in.p, 4, dims, str, box, p.kw * 2)) return false;
+    const uint64_t k_total = (uint64_t)9 * w.c_in_pad;
+    uint64_t bd[4] = {k_total, (uint64_t)w.n_rows, 1, 1};
+    uint64_t bs[3] = {k_total * 2, k_total * 2 * w.n_rows, k_total * 2 * w.n_rows};
+    uint32_t bb[4] = {(uint32_t)p.kw, (uint32_t)block_n, 1, 1};
+    if (!make_tmap_f16(&p.tmB, w.w, 4, bd, bs, bb, p.kw * 2)) return false;
+    plan.smem_bytes = p.stages_a * fa + fb + 1024 + (2 * p.stages_a + 1 + 8) * 8 + 16;
+    const int total = p.tiles_x * p.tiles_y * batch;
+    plan.grid = total < sm_count() ? total : sm_count();
+  } else {
     uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)batch};
     uint64_t str[3] = {(uint64_t)in.ps * 2, (uint64_t)in.ps * in.W * 2, (uint64_t)in.ps * in.W * in.H * 2};
     uint32_t box[4] = {(uint32_t)p.kw, (uint32_t)(8 * p.strips + 2), (uint32_t)(kConvTH + 2), 1};
@@ -138,16 +180,18 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
     uint32_t bb[4] = {(uint32_t)p.kw, (uint32_t)block_n, 1, 1};
     if (!make_tmap_f16(&p.tmB, w.w, 4, bd, bs, bb, p.kw * 2)) return false;
   }
-  const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
-  plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 8) * 8 + 16;
-  const int total = p.tiles_x * p.tiles_y * batch * p.n_tiles;
-  plan.grid = total < sm_count() ? total : sm_count();
+  if (!p.fold) {
+    const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
+    plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 8) * 8 + 16;
+    const int total = p.tiles_x * p.tiles_y * batch * p.n_tiles;
+    plan.grid = total < sm_count() ? total : sm_count();
+  }
   if (in.C > w.c_in_pad || in.C < w.c_in) { set_error("add_conv3x3: activation has %d channels, weights expect %d", in.C, w.c_in); return false; }
   const double fl = 2.0 * (double)in.W * in.H * batch * (double)n_valid * 9 * w.c_in;
   ol->tc_flops += fl;
   ol->launches += 1;
   char nm[160];
-  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d%s", w.c_in, n_valid, in.W, in.H, batch, p.b_resident ? " Bres" : "", pool_out ? (out ? " +pool" : " pool-only") : "", p.strips, p.kw == 32 ? " K32" : "");
+  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d%s", w.c_in, n_valid, in.W, in.H, batch, p.fold ? " Bres kx-fold" : (p.b_resident ? " Bres" : ""), pool_out ? (out ? " +pool" : " pool-only") : "", p.strips, p.kw == 32 ? " K32" : "");
   ol->push(nm, fl, [plan](cudaStream_t st) { return conv_launch(plan, st); });
   return true;
 }

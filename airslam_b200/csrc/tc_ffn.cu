@@ -15,6 +15,10 @@ bool ffn_fused_enabled() {
 
 static int ffn_sm_count() { return device_sm_count(); }
 
+static long long* g_match_trace = nullptr;
+long long* match_trace_buf() { return g_match_trace; }
+void match_set_trace(long long* dev_buf) { g_match_trace = dev_buf; }
+
 bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, const DenseW& w_out, const DenseW& w0, const DenseW& w3, const float* ln_g,
                    const float* ln_b, const int* n, int slots, int cap, bool relu) {
   if (w_out.n_rows != 256 || w_out.c_in_pad != 256 || w0.n_rows != 512 || w0.c_in_pad != 512 || w3.n_rows != 256 || w3.c_in_pad != 512) {
@@ -58,7 +62,9 @@ bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, con
       }
       attr_set[dev][relu] = true;
     }
-    cudaError_t e = launch_pdl(kern, grid, kFfnThreads, kFfnSmemBytes, st, p);
+    FfnParams pp = p;
+    pp.trace = g_match_trace;                      // authoring aid, normally nullptr
+    cudaError_t e = launch_pdl(kern, grid, kFfnThreads, kFfnSmemBytes, st, pp);
     if (e != cudaSuccess) { set_error("tc_ffn launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
   }, kDynRows);

@@ -4,7 +4,7 @@
 //   phase 2  h   = [x | msg] . W0^T + b0      (K = 512, N = 512)   accumulators fill all 512 TMEM columns
 //            LayerNorm(512, eps 1e-5) + exact GELU over TMEM rows -> fp16 -> shared memory (overwrites [x | msg])
 //   phase 3  y   = gelu . W3^T + b3           (K = 512, N = 256)   x += y  (fp32 residual stream + fp16 operand copy to HBM)
-// Weights (896 KB per tile) stream from L2 through a 4-stage TMA ring of [128 x 64] tiles.  The unfused path needed four GEMM
+// Weights (896 KB per tile) stream from L2 through a 5-stage TMA ring of [128 x 64] tiles.  The unfused path needed four GEMM
 // launches + one LayerNorm launch per block and moved msg / h / gelu(h) through HBM.
 //   warp 0: TMA producer   warp 1: MMA issuer   warps 2-9: epilogues / LayerNorm: two warps per TMEM lane quarter, each thread owns one
 //   keypoint row and one half of the columns; the LayerNorm statistics of the two halves meet in shared memory (named barrier 1)
@@ -24,11 +24,12 @@ struct FfnParams {
   __half* x16;         // fp16 copy (row stride 512 elements)
   const int* n;        // [slots]
   int slots, cap;
+  long long* trace;    // authoring aid (airfe_debug_match_trace): CTA 0 writes clock64 stamps of its first 8 row tiles, 16 slots per tile
   int prewait;         // MMA issuer polls the next weight tile's barrier before issuing the current one (0 with AIRFE_PREWAIT=1 switches it on)
 };
 
 constexpr int kFfnThreads = 320;
-constexpr int kFfnBStages = 4;
+constexpr int kFfnBStages = 5;      // 16 KiB weight tiles in flight per SM (224.5 KiB of shared memory in total)
 constexpr int kFfnSmemBytes = 8 * 16384 + kFfnBStages * 16384 + (2048 + 512) * 4 + 1024 + 256;
 
 // RELU = false: LightGlue (LayerNorm + exact GELU between the two FFN GEMMs).  RELU = true: SuperGlue's MLP([x | merge(ctx)]) = 512 -> 512
@@ -116,9 +117,12 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
     const uint32_t idesc = ptx::make_idesc_f16(128, 128, 0);
     const uint64_t da0 = d_const + (ptx::smem_u32(sA) >> 4);
     int sb = 0; uint32_t pb = 0, pt = 0, pepi = 0;
+    int tcount = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int slot = t / tiles_per_slot, r0 = (t % tiles_per_slot) * 128;
       if (r0 >= __ldg(p.n + slot)) continue;
+      long long* trp = (p.trace && blockIdx.x == 0 && lane == 0 && tcount < 8) ? p.trace + tcount * 16 : nullptr;
+      ++tcount;
       for (int ph = 0; ph < 3; ++ph) {
         // operands ready?  phase 1: ctx tile landed and the previous tile's last epilogue released TMEM; phase 2: msg written + x tile
         // landed; phase 3: gelu(h) written.  epi_done completes once per phase (three times per tile).
@@ -126,6 +130,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
         else { ptx::mbar_wait(epi_done, pepi ^ 1); if (ph == 1) ptx::mbar_wait(x_full, pt); }
         pepi ^= 1;
         ptx::tc_fence_after();
+        if (trp) trp[2 * ph] = clock64();             // operands of this phase ready
         const int nn = ph == 1 ? 4 : 2, nk = ph == 0 ? 4 : 8, a_first = ph == 0 ? 4 : 0;
         // weight tiles: the barrier of the NEXT tile of the ring is polled before the MMAs of the current one are issued (the issuing thread is
         // back-pressured, so anything it does between two issue blocks is idle time of the tensor pipe; 4 ring stages: tile u + 1 never
@@ -156,6 +161,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
           if (ph == 2) ptx::umma_commit(a_free);
         }
         __syncwarp();
+        if (trp) trp[2 * ph + 1] = clock64();         // all MMAs of this phase issued
       }
       pt ^= 1;
     }
@@ -166,15 +172,19 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
     const int row = quarter * 32 + lane;
     const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
     uint32_t pacc = 0;
+    int tcount = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int slot = t / tiles_per_slot, r0 = (t % tiles_per_slot) * 128;
       const int ns = __ldg(p.n + slot);
       if (r0 >= ns) continue;
+      long long* tre = (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tcount < 8) ? p.trace + tcount * 16 + 6 : nullptr;
+      ++tcount;
       const bool valid = (r0 + row) < ns;
       const long long grow = (long long)slot * p.cap + r0 + row;
       // ---- phase 1 epilogue: msg = acc + b_out -> fp16 -> A blocks 4..7 (this warp: columns half*128 .. +128) ----
       ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
       ptx::tc_fence_after();
+      if (tre) tre[0] = clock64();                    // phase-1 accumulators complete
 #pragma unroll 1
       for (int c = half * 128; c < half * 128 + 128; c += 32) {
         uint32_t r[32];
@@ -198,9 +208,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(epi_done);
+      if (tre) tre[1] = clock64();                    // phase-1 epilogue done (msg in shared memory)
       // ---- phase 2 epilogue: LayerNorm + GELU over 512 columns (this warp: columns half*256 .. +256) -> fp16 -> A blocks 0..7 ----
       ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
       ptx::tc_fence_after();
+      if (tre) tre[2] = clock64();                    // phase-2 accumulators complete
       const int c_lo = half * 256, c_hi = c_lo + 256;
       if constexpr (RELU) {
 #pragma unroll 1
@@ -223,35 +235,52 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
           }
         }
       } else {
+      // Three passes over this thread's 256 accumulator columns (mean, variance, normalise + GELU).  The TMEM loads are double-buffered:
+      // the load of block i + 1 is in flight while block i is reduced.  The loops are unrolled by two only (static register-set indices):
+      // fully unrolled, the kernel grew to 170 KB of SASS and ran 30 % SLOWER (instruction-cache misses, profiles/r02c_match_trace.txt).
+      uint32_t rr[2][32];
       float sum = 0.f;
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(trow + c, r);
-        ptx::tmem_ld_wait();
+      auto sum_blk = [&](const uint32_t (&r)[32], int c) {
+        float part = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += __uint_as_float(r[j]) + s_b0[c + j];
+        for (int j = 0; j < 32; ++j) part += __uint_as_float(r[j]) + s_b0[c + j];
+        sum += part;
+      };
+      ptx::tmem_ld32(trow + c_lo, rr[0]);
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; c += 64) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld32(trow + c + 32, rr[1]);
+        sum_blk(rr[0], c);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld32(trow + (c + 64 < c_hi ? c + 64 : c_lo), rr[0]);         // last iteration: first block of the next pass
+        sum_blk(rr[1], c + 32);
       }
       sRed[half * 128 + row] = sum;
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tre) tre[3] = clock64();                    // LayerNorm pass 1 (mean) done
       const float mean = (sRed[row] + sRed[128 + row]) * (1.f / 512.f);      // low half + high half: the same order in both warps
       float var = 0.f;
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(trow + c, r);
-        ptx::tmem_ld_wait();
+      auto var_blk = [&](const uint32_t (&r)[32], int c) {
+        float part = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(r[j]) + s_b0[c + j] - mean; var = fmaf(d, d, var); }
+        for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(r[j]) + s_b0[c + j] - mean; part = fmaf(d, d, part); }
+        var += part;
+      };
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; c += 64) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld32(trow + c + 32, rr[1]);
+        var_blk(rr[0], c);
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld32(trow + (c + 64 < c_hi ? c + 64 : c_lo), rr[0]);
+        var_blk(rr[1], c + 32);
       }
       sRed[256 + half * 128 + row] = var;
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tre) tre[4] = clock64();                    // pass 2 (variance) done
       const float rstd = 1.f / sqrtf((sRed[256 + row] + sRed[384 + row]) * (1.f / 512.f) + 1e-5f);
-#pragma unroll 1
-      for (int c = c_lo; c < c_hi; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(trow + c, r);
-        ptx::tmem_ld_wait();
+      auto gelu_blk = [&](const uint32_t (&r)[32], int c) {
         uint8_t* dst = sA + (c >> 6) * 16384 + row * 128;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -271,40 +300,71 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
           const int chunk = ((c & 63) >> 3) + ch;
           *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+      };
+#pragma unroll 1
+      for (int c = c_lo; c < c_hi; c += 64) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld32(trow + c + 32, rr[1]);
+        gelu_blk(rr[0], c);
+        ptx::tmem_ld_wait();
+        if (c + 64 < c_hi) ptx::tmem_ld32(trow + c + 64, rr[0]);
+        gelu_blk(rr[1], c + 32);
       }
       }
       ptx::fence_proxy_async();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(epi_done);
+      if (tre) tre[5] = clock64();                    // phase-2 epilogue done (gelu(h) in shared memory)
       // ---- phase 3 epilogue: x += acc + b3 ; fp32 residual + fp16 operand copy (this warp: columns half*128 .. +128) ----
       ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
       ptx::tc_fence_after();
+      if (tre) tre[6] = clock64();                    // phase-3 accumulators complete
+      // The residual rows come from L2 (written by the previous block's launch).  All four 32-byte loads of a 32-column group are issued
+      // together and the next group's loads fly while this one is summed and stored: the first version issued them one at a time between
+      // dependent stores -- sixteen serialised L2 round trips, 27.8 k cycles per tile (profiles/r02c_match_trace.txt).
       float* xr = p.x + grow * 256;
       __half* x16r = p.x16 + grow * 512;
-#pragma unroll 1
-      for (int c = half * 128; c < half * 128 + 128; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(trow + c, r);
-        ptx::tmem_ld_wait();
+      const int c3 = half * 128;
+      float xv[2][4][8];
+      uint32_t r3[2][32];
+      auto ld_x = [&](float (&dstv)[4][8], int c) {
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float v[8];
-            ptx::ld_global_256f(xr + c + j, v);      // rows are 1 KiB, c + j a multiple of 8 floats: 32-byte aligned
+          for (int j = 0; j < 4; ++j) ptx::ld_global_256f_nv(xr + c + 8 * j, dstv[j]);      // rows are 1 KiB, columns multiples of 8 floats: 32-byte aligned
+        }
+      };
+      auto add_store = [&](const float (&xin)[4][8], const uint32_t (&r)[32], int c) {
+        if (valid) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += __uint_as_float(r[j + e]) + s_b3[c + j + e];
-            ptx::st_global_256f(xr + c + j, v);
+          for (int j = 0; j < 4; ++j) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = xin[j][e] + (__uint_as_float(r[8 * j + e]) + s_b3[c + 8 * j + e]);
+            ptx::st_global_256f(xr + c + 8 * j, v);
             uint32_t h[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) { __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]); h[e] = *reinterpret_cast<uint32_t*>(&h2); }
-            *reinterpret_cast<uint4*>(x16r + c + j) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(x16r + c + 8 * j) = make_uint4(h[0], h[1], h[2], h[3]);
           }
         }
+      };
+      ld_x(xv[0], c3);
+      ptx::tmem_ld32(trow + c3, r3[0]);
+#pragma unroll 1
+      for (int c = c3; c < c3 + 128; c += 64) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld32(trow + c + 32, r3[1]);
+        ld_x(xv[1], c + 32);
+        add_store(xv[0], r3[0], c);
+        ptx::tmem_ld_wait();
+        if (c + 64 < c3 + 128) { ptx::tmem_ld32(trow + c + 64, r3[0]); ld_x(xv[0], c + 64); }
+        add_store(xv[1], r3[1], c + 32);
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(epi_done);
+      if (tre) tre[7] = clock64();                    // phase-3 epilogue done (x stored)
     }
   }
 

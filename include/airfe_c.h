@@ -203,6 +203,10 @@ long long airfe_debug_read(airfe_ctx* ctx, int net, const char* name, int index,
  * epilogue start / end of the first and last epilogue warp).  NULL switches tracing off.  See tools/trace_conv.py. */
 void airfe_debug_conv_trace(long long* dev_buf);
 
+/* Same for the fused matcher kernels: `dev_buf` (>= 2048 int64) receives, from CTA 0 of every following launch, 16 stamps per row tile of
+ * tc_ffn at [0, 128) and 16 stamps per query tile of tc_attn at [1024, 1152).  See tools/trace_match.py. */
+void airfe_debug_match_trace(long long* dev_buf);
+
 /* The CUDA stream all work of this context is issued on (cudaStream_t), for event timing by the caller. */
 void* airfe_stream(airfe_ctx* ctx);
 

@@ -188,6 +188,22 @@ def test_conv3x3_halo_matches_torch(cfg):
     assert torch.equal(pool.float(), ref_pool)     # pooling the fp16-rounded values is exact
 
 
+@pytest.mark.parametrize("cfg", [(2, 64, 64, 64, 64), (1, 48, 40, 64, 32), (2, 32, 32, 32, 32), (1, 40, 72, 32, 64)])
+def test_conv3x3_kx_fold_all_instantiations(cfg, monkeypatch):
+    """AIRFE_CONV_FOLD=2 routes every eligible layer (C_in <= 64, C_out = 32 / 64) through tc_conv3x3_fold_kernel<KW, N> -- by default only
+    64 -> 32 uses it (csrc/tc_conv3x3.cu).  Full store, fused 2x2 max-pool and ragged tiles (width not a multiple of 14, height not of 16)."""
+    monkeypatch.setenv("AIRFE_CONV_FOLD", "2")
+    b, h, w, cin, cout = cfg
+    x, wt, bias = _mk(b, h, w, cin, cout, 3, seed=(hash(cfg) & 0xFFFF) + 11)
+    full, pool = run_conv_halo(x, wt, bias, True, want_full=True, want_pool=True)
+    _close(full, ref_conv(x, wt, bias, True).half())
+    ref_pool = F.max_pool2d(full.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert torch.equal(pool.float(), ref_pool)
+    monkeypatch.setenv("AIRFE_CONV_FOLD", "0")
+    full0, pool0 = run_conv_halo(x, wt, bias, True, want_full=True, want_pool=True)
+    _close(full0, full)       # nine-tap kernel vs folded kernel: same values up to the fp32 summation order
+
+
 def test_conv3x3_halo_pool_only_and_channel_offset():
     x, wt, bias = _mk(1, 64, 64, 64, 32, 3, seed=21)
     _, pool = run_conv_halo(x, wt, bias, True, want_full=False, want_pool=True)
