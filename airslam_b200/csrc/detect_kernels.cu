@@ -111,6 +111,7 @@ void launch_remap_u8(const uint8_t* src, int w, int h, int stride, long long img
 // Thread = (8 pixels along x, group of 8 output channels): consecutive threads write consecutive 16-byte vectors of one pixel.
 // =====================================================================================================================
 constexpr int kC1Px = 8;
+constexpr int kC1Rows = 8;   // image rows per block
 __device__ __forceinline__ unsigned long long ffma2_(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
@@ -119,7 +120,7 @@ __device__ __forceinline__ unsigned long long ffma2_(unsigned long long a, unsig
 __device__ __forceinline__ unsigned long long pack2_(float lo, float hi) {
   return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
-__global__ void __launch_bounds__(256) conv1a_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(128, 3) conv1a_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
                                                      __half* __restrict__ out, int H, int W, long long total) {
   __shared__ float2 sw2[8 * 4 * 9];   // [channel group][channel pair][tap] = (w of channel 2p, w of channel 2p+1)
   __shared__ float2 sb2[32];
@@ -129,64 +130,72 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const __half* __restrict__ 
   }
   if (threadIdx.x < 32) sb2[threadIdx.x] = make_float2(bias[2 * threadIdx.x], bias[2 * threadIdx.x + 1]);
   __syncthreads();
-  // grid = (threads along a row / 256, H, batch): no integer divisions on the index path
+  // grid = (threads along a row / 256, H / kC1Rows, batch): no integer divisions on the index path.  A block walks kC1Rows consecutive image
+  // rows: the weight staging above and the block launch are paid once per 8 rows instead of once per row (they were ~25 % of a one-row
+  // block's life), and the three input rows slide through registers, so each input row is loaded once instead of three times.
   const int tix = blockIdx.x * blockDim.x + threadIdx.x;
   if (tix >= W) return;                            // W / 8 pixel groups x 8 channel groups = W threads per row
   const int cg = tix & 7;
   const int x0 = (tix >> 3) * kC1Px;
-  const int yy = blockIdx.y;
+  const int y_begin = blockIdx.y * kC1Rows;
   const long long img = blockIdx.z;
   const __half* xi = x + img * (long long)W * H;
   // inputs: per row one aligned 16-byte vector (x0 is a multiple of 8) plus the two halo pixels; each value duplicated into a float2
   unsigned long long in2[3][kC1Px + 2];
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int y2 = yy + ky - 1;
+  auto load_row = [&](unsigned long long (&dst)[kC1Px + 2], int y2) {
     const bool rv = (y2 >= 0) && (y2 < H);
-    const __half* rp = xi + (long long)(rv ? y2 : yy) * W + x0;
+    const __half* rp = xi + (long long)(rv ? y2 : 0) * W + x0;
     uint4 v = *reinterpret_cast<const uint4*>(rp);
     const __half hl = (x0 > 0) ? rp[-1] : __float2half(0.f);
     const __half hr = (x0 + kC1Px < W) ? rp[kC1Px] : __float2half(0.f);
     if (!rv) v = make_uint4(0, 0, 0, 0);
     const __half2* v2 = reinterpret_cast<const __half2*>(&v);
     const float fl = rv ? __half2float(hl) : 0.f, fr = rv ? __half2float(hr) : 0.f;
-    in2[ky][0] = pack2_(fl, fl);
-    in2[ky][kC1Px + 1] = pack2_(fr, fr);
+    dst[0] = pack2_(fl, fl);
+    dst[kC1Px + 1] = pack2_(fr, fr);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float2 f = __half22float2(v2[q]);
-      in2[ky][1 + 2 * q] = pack2_(f.x, f.x);
-      in2[ky][2 + 2 * q] = pack2_(f.y, f.y);
+      dst[1 + 2 * q] = pack2_(f.x, f.x);
+      dst[2 + 2 * q] = pack2_(f.y, f.y);
     }
-  }
-  uint32_t packed[kC1Px][4];
+  };
+  load_row(in2[0], y_begin - 1);
+  load_row(in2[1], y_begin);
+#pragma unroll 1
+  for (int yy = y_begin; yy < y_begin + kC1Rows && yy < H; ++yy) {
+    load_row(in2[2], yy + 1);
+    uint32_t packed[kC1Px][4];
 #pragma unroll
-  for (int jp = 0; jp < 4; ++jp) {
-    unsigned long long wp[9];
+    for (int jp = 0; jp < 4; ++jp) {
+      unsigned long long wp[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { const float2 t = sw2[(cg * 4 + jp) * 9 + k]; wp[k] = pack2_(t.x, t.y); }
-    const float2 bb = sb2[cg * 4 + jp];
-    const unsigned long long b2 = pack2_(bb.x, bb.y);
+      for (int k = 0; k < 9; ++k) { const float2 t = sw2[(cg * 4 + jp) * 9 + k]; wp[k] = pack2_(t.x, t.y); }
+      const float2 bb = sb2[cg * 4 + jp];
+      const unsigned long long b2 = pack2_(bb.x, bb.y);
 #pragma unroll
-    for (int px = 0; px < kC1Px; ++px) {
-      unsigned long long acc = b2;                 // bias folded into the accumulator
+      for (int px = 0; px < kC1Px; ++px) {
+        unsigned long long acc = b2;                 // bias folded into the accumulator
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) acc = ffma2_(in2[ky][px + kx], wp[ky * 3 + kx], acc);
-      const float a0 = fmaxf(__uint_as_float((unsigned)(acc & 0xffffffffu)), 0.f), a1 = fmaxf(__uint_as_float((unsigned)(acc >> 32)), 0.f);
-      __half2 h2 = __floats2half2_rn(a0, a1);
-      packed[px][jp] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int kx = 0; kx < 3; ++kx) acc = ffma2_(in2[ky][px + kx], wp[ky * 3 + kx], acc);
+        const float a0 = fmaxf(__uint_as_float((unsigned)(acc & 0xffffffffu)), 0.f), a1 = fmaxf(__uint_as_float((unsigned)(acc >> 32)), 0.f);
+        __half2 h2 = __floats2half2_rn(a0, a1);
+        packed[px][jp] = *reinterpret_cast<uint32_t*>(&h2);
+      }
     }
-  }
-  __half* o = out + ((img * H + yy) * (long long)W + x0) * 64 + cg * 8;
+    __half* o = out + ((img * H + yy) * (long long)W + x0) * 64 + cg * 8;
 #pragma unroll
-  for (int px = 0; px < kC1Px; ++px)
-    *reinterpret_cast<uint4*>(o + (long long)px * 64) = make_uint4(packed[px][0], packed[px][1], packed[px][2], packed[px][3]);
+    for (int px = 0; px < kC1Px; ++px)
+      *reinterpret_cast<uint4*>(o + (long long)px * 64) = make_uint4(packed[px][0], packed[px][1], packed[px][2], packed[px][3]);
+#pragma unroll
+    for (int j = 0; j < kC1Px + 2; ++j) { in2[0][j] = in2[1][j]; in2[1][j] = in2[2][j]; }
+  }
 }
 
 void launch_conv1a(const __half* x, const __half* w, const float* bias, __half* out, int batch, int H, int W, cudaStream_t st) {
-  conv1a_kernel<<<dim3((W + 255) / 256, H, batch), 256, 0, st>>>(x, w, bias, out, H, W, 0);
+  conv1a_kernel<<<dim3((W + 127) / 128, (H + kC1Rows - 1) / kC1Rows, batch), 128, 0, st>>>(x, w, bias, out, H, W, 0);
 }
 
 // =====================================================================================================================

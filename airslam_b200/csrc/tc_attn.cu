@@ -37,18 +37,20 @@ bool add_fused_attention(OpList* ol, const __half* q, const __half* k, const __h
   char nm[96];
   snprintf(nm, sizeof(nm), "tc_attn fused %s slots=%d cap=%d", slot_xor ? "cross" : "self", slots, cap);
   ol->push(nm, fl, [p, slots, q_split](cudaStream_t st) {
-    static bool attr_set[kMaxDevices] = {};
+    static bool attr_set[kMaxDevices][2] = {};
+    static const int wide = getenv("AIRFE_ATTN_NP") ? (atoi(getenv("AIRFE_ATTN_NP")) == 4) : 0;   // AIRFE_ATTN_NP=4: sixteen softmax warps.  Measured equal to eight (80 vs 82 us per launch, profiles/r02c_lightglue_ab.txt): the exp pass is bound by the XU pipe (MUFU.EX2 + fp16 conversions: 51 k exponentials per tile in ~6 k cycles), not by latency
+    auto kern = wide ? tc_attn_kernel<4> : tc_attn_kernel<2>;
     const int dev = current_device();
-    if (!attr_set[dev]) {
-      if (cudaFuncSetAttribute(tc_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes) != cudaSuccess) {
+    if (!attr_set[dev][wide]) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes) != cudaSuccess) {
         set_error("cudaFuncSetAttribute(tc_attn_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
         return false;
       }
-      attr_set[dev] = true;
+      attr_set[dev][wide] = true;
     }
     AttnParams pp = p;
     pp.trace = match_trace_buf() ? match_trace_buf() + 1024 : nullptr;    // authoring aid, normally nullptr
-    cudaError_t e = launch_pdl(tc_attn_kernel, slots * 4 * q_split, kAttnThreads, kAttnSmemBytes, st, pp);
+    cudaError_t e = launch_pdl(kern, slots * 4 * q_split, wide ? kAttnThreadsWide : kAttnThreads, kAttnSmemBytes, st, pp);
     if (e != cudaSuccess) { set_error("tc_attn launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
   }, slot_xor ? kDynAttCross : kDynAttSelf);

@@ -27,21 +27,26 @@ struct AttnParams {
   long long* trace;  // authoring aid (airfe_debug_match_trace): CTA 0 writes clock64 stamps of its query tiles, 16 slots per tile
 };
 
-constexpr int kAttnThreads = 320;
+constexpr int kAttnThreads = 320;               // NP = 2: warps 2-9 = eight softmax warps
+constexpr int kAttnThreadsWide = 576;           // NP = 4: warps 2-17 = sixteen softmax warps (four per scheduler)
 constexpr int kAttnSmemQ = 128 * 128;            // 16 KiB
 constexpr int kAttnSmemKV = 512 * 128;           // 64 KiB each
 constexpr int kAttnPSlots = 4;                   // ring of 64-key P blocks (16 KiB each)
-constexpr int kAttnSmemBytes = kAttnSmemQ + 2 * kAttnSmemKV + kAttnPSlots * 16384 + 2048 + 1024 + 256;
+constexpr int kAttnSmemBytes = kAttnSmemQ + 2 * kAttnSmemKV + kAttnPSlots * 16384 + 4096 + 1024 + 256;
 
-__global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_constant__ AttnParams p) {
+// NP = softmax warps per TMEM lane quarter (2 or 4): a thread owns one query row and every NP-th 64-key block.  The softmax is bound by
+// MUFU.EX2 (16 / clk / SM) and by instruction latency, not by the tensor pipe (ncu: issue slot 34 % busy with 2.5 resident warps per
+// scheduler), so NP = 4 doubles the warps that hide each other's latency; it runs single-buffered TMEM loads to stay under 113 registers.
+template <int NP>
+__global__ void __launch_bounds__(64 + NP * 128, 1) tc_attn_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kAttnSmemQ;
   uint8_t* sV = sK + kAttnSmemKV;
   uint8_t* sP = sV + kAttnSmemKV;
-  float* sRed = reinterpret_cast<float*>(sP + kAttnPSlots * 16384);   // row max [2][128], row sum [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 512);
+  float* sRed = reinterpret_cast<float*>(sP + kAttnPSlots * 16384);   // row max [NP][128], row sum [NP][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 1024);
   uint64_t* kv_full = bars + 0;
   uint64_t* q_full = bars + 1;
   uint64_t* q_empty = bars + 2;
@@ -60,7 +65,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmQ); ptx::prefetch_tmap(&p.tmK); ptx::prefetch_tmap(&p.tmV);
     ptx::mbar_init(kv_full, 1); ptx::mbar_init(q_full, 1); ptx::mbar_init(q_empty, 1);
-    ptx::mbar_init(s_full, 1); ptx::mbar_init(o_full, 1); ptx::mbar_init(s_free, 8);
+    ptx::mbar_init(s_full, 1); ptx::mbar_init(o_full, 1); ptx::mbar_init(s_free, 4 * NP);
     for (int i = 0; i < kAttnPSlots; ++i) { ptx::mbar_init(&p_full[i], 4); ptx::mbar_init(&p_empty[i], 1); }
     ptx::fence_barrier_init();
   }
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
     } else {
       // ===== softmax + epilogue: thread = one query row x every second 64-key block =====
       const int quarter = warp & 3;
-      const int half = (warp - 2) >> 2;
+      const int half = (warp - 2) >> 2;              // key-block residue of this warp: blocks kb = half, half + NP, ...  (0 .. NP-1)
       const int row = quarter * 32 + lane;
       const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
       uint32_t ph = 0;
@@ -170,8 +175,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
         // in flight while group i is reduced.  (First version: load, wait, reduce -- the ~300-cycle load latency was exposed 14 times per
         // pass and the exp pass took 7.4 k cycles per 128-query tile, 70 % of the kernel: profiles/r02c_match_trace.txt.)
         uint32_t rr[2][32];
-        const int nblk = nkb > half ? (nkb - half + 1) >> 1 : 0;          // 64-key blocks of this half
-        auto col_of = [&](int i) { return (half + 2 * (i >> 1)) * 64 + (i & 1) * 32; };
+        const int nblk = nkb > half ? (nkb - half + NP - 1) / NP : 0;      // 64-key blocks of this warp
+        // Rows of this warp beyond the slot's keypoint count (the last query tile of a 400-keypoint slot has 16 valid rows of 128): the warp
+        // keeps the barrier / P-slot protocol going but skips the TMEM reads, the exponentials and the shared-memory writes.  Whatever the
+        // P.V MMA then reads for those rows only reaches output rows that are never stored.
+        const bool wact = ((part + t * p.q_split) * 128 + quarter * 32) < nq;
+        auto col_of = [&](int i) { return (half + NP * (i >> 1)) * 64 + (i & 1) * 32; };
         float mx0 = -INFINITY, mx1 = -INFINITY;
         auto max_group = [&](const uint32_t (&r)[32], int c) {
           if (c + 32 <= nk) {
@@ -183,30 +192,40 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
           }
         };
         {
-          int n_it = 2 * nblk;
+          int n_it = wact ? 2 * nblk : 0;
           while (n_it > 0 && col_of(n_it - 1) >= nk) --n_it;                 // groups entirely beyond the last key hold no scores
-          if (n_it > 0) ptx::tmem_ld32(trow + col_of(0), rr[0]);
-          for (int i = 0; i < n_it; i += 2) {
-            ptx::tmem_ld_wait();
-            if (i + 1 < n_it) ptx::tmem_ld32(trow + col_of(i + 1), rr[1]);
-            max_group(rr[0], col_of(i));
-            if (i + 1 < n_it) {
+          if constexpr (NP == 2) {
+            if (n_it > 0) ptx::tmem_ld32(trow + col_of(0), rr[0]);
+            for (int i = 0; i < n_it; i += 2) {
               ptx::tmem_ld_wait();
-              if (i + 2 < n_it) ptx::tmem_ld32(trow + col_of(i + 2), rr[0]);
-              max_group(rr[1], col_of(i + 1));
+              if (i + 1 < n_it) ptx::tmem_ld32(trow + col_of(i + 1), rr[1]);
+              max_group(rr[0], col_of(i));
+              if (i + 1 < n_it) {
+                ptx::tmem_ld_wait();
+                if (i + 2 < n_it) ptx::tmem_ld32(trow + col_of(i + 2), rr[0]);
+                max_group(rr[1], col_of(i + 1));
+              }
+            }
+          } else {
+            for (int i = 0; i < n_it; ++i) {
+              ptx::tmem_ld32(trow + col_of(i), rr[0]);
+              ptx::tmem_ld_wait();
+              max_group(rr[0], col_of(i));
             }
           }
         }
         sRed[half * 128 + row] = fmaxf(mx0, mx1);
-        if (nblk > 0) ptx::tmem_ld32(trow + col_of(0), rr[0]);               // first group of pass 2: in flight across the barrier
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float m2 = fmaxf(sRed[row], sRed[128 + row]) * sc2;
+        if (NP == 2 && wact && nblk > 0) ptx::tmem_ld32(trow + col_of(0), rr[0]);       // first group of pass 2: in flight across the barrier
+        if constexpr (NP == 2) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 512;" ::: "memory");
+        float mall = fmaxf(sRed[row], sRed[128 + row]);
+        if constexpr (NP == 4) mall = fmaxf(mall, fmaxf(sRed[256 + row], sRed[384 + row]));
+        const float m2 = mall * sc2;
         if (tre) tre[1] = clock64();             // pass 1 (row max) done
         // pass 2: e = exp(s - max) once per element: accumulate the row sum in fp32 (four partial sums) and hand fp16(e) to the tensor core
         // through shared memory (K-major SWIZZLE_128B, 64 keys per block); the 1/sum normalisation is applied to O in the epilogue.
         float sm[4] = {0.f, 0.f, 0.f, 0.f};
         auto exp_group = [&](const uint32_t (&r)[32], int i) {
-          const int kb = half + 2 * (i >> 1), hc = i & 1;
+          const int kb = half + NP * (i >> 1), hc = i & 1;
           const int ps = kb & (kAttnPSlots - 1);
           if (hc == 0) ptx::mbar_wait(&p_empty[ps], ((eph >> ps) & 1) ^ 1);     // slot free (first use of a fresh barrier passes immediately)
           uint8_t* prow = sP + ps * 16384 + row * 128;
@@ -239,20 +258,40 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
           }
         };
         {
-          const int n_it = 2 * nblk;                                         // every 64-key block is written completely (keys >= nk as zeros)
-          for (int i = 0; i < n_it; i += 2) {
-            ptx::tmem_ld_wait();
-            ptx::tmem_ld32(trow + col_of(i + 1), rr[1]);
-            exp_group(rr[0], i);
-            ptx::tmem_ld_wait();
-            if (i + 2 < n_it) ptx::tmem_ld32(trow + col_of(i + 2), rr[0]);
-            exp_group(rr[1], i + 1);
+          const int n_it = wact ? 2 * nblk : 0;                              // every 64-key block is written completely (keys >= nk as zeros)
+          if (!wact) {
+            for (int b2 = 0; b2 < nblk; ++b2) {                              // protocol only: wait for the slot, hand it over unwritten
+              const int ps = (half + NP * b2) & (kAttnPSlots - 1);
+              ptx::mbar_wait(&p_empty[ps], ((eph >> ps) & 1) ^ 1);
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&p_full[ps]);
+              eph ^= 1u << ps;
+            }
+          }
+          if constexpr (NP == 2) {
+            for (int i = 0; i < n_it; i += 2) {
+              ptx::tmem_ld_wait();
+              ptx::tmem_ld32(trow + col_of(i + 1), rr[1]);
+              exp_group(rr[0], i);
+              ptx::tmem_ld_wait();
+              if (i + 2 < n_it) ptx::tmem_ld32(trow + col_of(i + 2), rr[0]);
+              exp_group(rr[1], i + 1);
+            }
+          } else {
+            for (int i = 0; i < n_it; ++i) {
+              ptx::tmem_ld32(trow + col_of(i), rr[0]);
+              ptx::tmem_ld_wait();
+              exp_group(rr[0], i);
+            }
           }
         }
         const float sum = (sm[0] + sm[1]) + (sm[2] + sm[3]);
-        sRed[256 + half * 128 + row] = sum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float inv = 1.f / (sRed[256 + row] + sRed[384 + row]);
+        sRed[NP * 128 + half * 128 + row] = sum;
+        if constexpr (NP == 2) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 512;" ::: "memory");
+        float sall = sRed[NP * 128 + row] + sRed[NP * 128 + 128 + row];        // the same order in every warp of the row
+        if constexpr (NP == 4) sall += sRed[NP * 128 + 256 + row] + sRed[NP * 128 + 384 + row];
+        const float inv = 1.f / sall;
         if (tre) tre[2] = clock64();             // pass 2 (exp, P blocks) done
         // epilogue: O (128 x 64 fp32, TMEM columns 0..63) -> fp16 context rows; this warp writes columns half*32 .. +32
         ptx::mbar_wait(o_full, ph);
@@ -260,7 +299,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
         if (tre) tre[3] = clock64();             // O complete
         const int q = (part + t * p.q_split) * 128 + row;
         __half* o = p.ctx + ((p.row_off ? (long long)q_row0 : (long long)slot * p.cap) + q) * 256 + head * 64;
-        {
+        if constexpr (NP == 2) {
           const int c = half * 32;
           uint32_t r[32];
           ptx::tmem_ld32(trow + c, r);
@@ -276,6 +315,20 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attn_kernel(const __grid_c
               }
               ptx::st_global_256(o + c + i, h);       // ctx rows are 512 B, head * 64 + c + i a multiple of 16 halves: 32-byte aligned
             }
+          }
+        } else {
+          const int c = half * 16;
+          uint32_t r[16];
+          ptx::tmem_ld16(trow + c, r);
+          ptx::tmem_ld_wait();
+          if (q < nq) {
+            uint32_t h[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              __half2 h2 = __floats2half2_rn(__uint_as_float(r[2 * e]) * inv, __uint_as_float(r[2 * e + 1]) * inv);
+              h[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            ptx::st_global_256(o + c, h);
           }
         }
         ptx::tc_fence_before();

@@ -21,14 +21,18 @@ void conv3x3_set_trace(long long* dev_buf) { g_conv_trace = dev_buf; }
 using ConvKernel = void (*)(const ConvParams);
 
 static int conv_key(const ConvParams& p) {
-  if (p.fold) return 8 + (p.kw == 32 ? 2 : 0) + (p.block_n == 64 ? 1 : 0);
+  if (p.fold) return 8 + (p.fold == 2 ? 4 : 0) + (p.kw == 32 ? 2 : 0) + (p.block_n == 64 ? 1 : 0);
   return (p.kw == 32 ? 4 : 0) | (p.strips == 2 ? 2 : 0) | (p.b_resident ? 1 : 0);
 }
 
 static ConvKernel conv_kernel_for(const ConvParams& p) {
+  if (p.fold == 2) {
+    if (p.kw == 64) return p.block_n == 64 ? tc_conv3x3_fold_kernel<64, 64, true> : tc_conv3x3_fold_kernel<64, 32, true>;
+    return p.block_n == 64 ? tc_conv3x3_fold_kernel<32, 64, true> : tc_conv3x3_fold_kernel<32, 32, true>;
+  }
   if (p.fold) {
-    if (p.kw == 64) return p.block_n == 64 ? tc_conv3x3_fold_kernel<64, 64> : tc_conv3x3_fold_kernel<64, 32>;
-    return p.block_n == 64 ? tc_conv3x3_fold_kernel<32, 64> : tc_conv3x3_fold_kernel<32, 32>;
+    if (p.kw == 64) return p.block_n == 64 ? tc_conv3x3_fold_kernel<64, 64, false> : tc_conv3x3_fold_kernel<64, 32, false>;
+    return p.block_n == 64 ? tc_conv3x3_fold_kernel<32, 64, false> : tc_conv3x3_fold_kernel<32, 32, false>;
   }
   const int key = (p.kw == 32 ? 4 : 0) | (p.strips == 2 ? 2 : 0) | (p.b_resident ? 1 : 0);
   switch (key) {
@@ -44,10 +48,10 @@ static ConvKernel conv_kernel_for(const ConvParams& p) {
 }
 
 static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[kMaxDevices][12] = {};
+  static bool attr_set[kMaxDevices][16] = {};
   const int dev = current_device();
   const int key = conv_key(plan.p);
-  const int threads = kConvThreads;
+  const int threads = plan.p.fold == 2 ? kFoldWideThreads : kConvThreads;
   ConvKernel kern = conv_kernel_for(plan.p);
   if (!attr_set[dev][key]) {
     cudaFuncAttributes fa;
@@ -71,9 +75,10 @@ static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
 }
 
 // kx-folded variant (tc_conv3x3_fold.cuh) for resident-weights small-N layers.  Measured on B200 (profiles/r02c_fold_ab.txt, 16 frames of
-// 512 x 512): 64->32 0.234 -> 0.176 ms, but 32->32 pool-only 0.150 -> 0.188, 64->64 0.296 -> 0.319, 64->64 + pool 0.349 -> 0.401: the fold cuts the
-// MMA time by 1.3-1.9x and triples the accumulator columns the epilogue has to read, shift and add, so it only pays where the nine-tap kernel
-// is furthest below the tensor roofline.  Default: C_in = 64 -> C_out = 32 only.  AIRFE_CONV_FOLD=0: never, =2: every eligible layer (tests, A/B).
+// 512 x 512, nine-tap -> folded with 16 epilogue warps): 64->32 0.233 -> 0.182 ms, 32->32 pool-only 0.150 -> 0.137, 64->64 pool-only 0.284 -> 0.284,
+// 64->64 0.295 -> 0.326, 64->64 + pool 0.348 -> 0.351: the fold cuts the MMA time by 1.3-1.9x and triples the accumulator columns the epilogue has
+// to read, shift and add (the folded kernel is bound by the epilogue's instruction issue), so it pays for C_out = 32 and not for C_out = 64.
+// Default: C_out = 32 layers.  AIRFE_CONV_FOLD=0: never, =2: every eligible layer (tests, A/B).
 static int conv3x3_fold_mode() {
   const char* e = getenv("AIRFE_CONV_FOLD");   // read at plan time (not cached: the operator tests switch it between calls)
   return e ? atoi(e) : 1;
@@ -147,9 +152,13 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
     if (p.stages_b < 3) { set_error("add_conv3x3: shared memory budget too small"); return false; }
   }
   const int fold_mode = conv3x3_fold_mode();
-  if (fold_mode && p.b_resident && p.kblocks == 1 && p.n_tiles == 1 && (block_n == 32 || block_n == 64) && (fold_mode == 2 || (block_n == 32 && p.kw == 64))) {
+  // the folded kernel has no partial-chunk store path: the layer's channel count must equal the N tile and every store must be 32-byte aligned
+  const bool fold_aligned = n_valid == block_n && (!out || (((uintptr_t)out->p & 31) == 0 && out->ps % 16 == 0)) &&
+                            (!pool_out || (((uintptr_t)pool_out->p & 31) == 0 && pool_out->ps % 16 == 0));
+  if (fold_mode && fold_aligned && p.b_resident && p.kblocks == 1 && p.n_tiles == 1 && (block_n == 32 || block_n == 64) && (fold_mode == 2 || block_n == 32)) {
     // kx taps folded into N (tc_conv3x3_fold.cuh): tiles of 14 output columns x 16 rows, one TMEM buffer of 3N columns per 8-row strip
-    p.fold = 1;
+    static const int wide = getenv("AIRFE_FOLD_WIDE") ? atoi(getenv("AIRFE_FOLD_WIDE")) : 1;   // 16 epilogue warps (0: the 8-warp software-pipelined epilogue, for A/B timing)
+    p.fold = wide ? 2 : 1;
     p.strips = kFoldStrips;
     p.tiles_x = (in.W + kFoldTX - 1) / kFoldTX;
     p.tiles_y = (in.H + 8 * kFoldStrips - 1) / (8 * kFoldStrips);

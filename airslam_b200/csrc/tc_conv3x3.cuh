@@ -25,7 +25,7 @@ struct ConvParams {
   int tiles_x, tiles_y, B, W, H;
   int n_tiles, block_n, n_valid;
   int b_resident;
-  int fold;         // 1: kx taps folded into N (tc_conv3x3_fold.cuh); tiles are 14 output columns x 16 rows
+  int fold;         // 1 / 2: kx taps folded into N (tc_conv3x3_fold.cuh; 2 = sixteen epilogue warps); tiles are 14 output columns x 16 rows
   int stages_a, stages_b;
   int prewait;      // MMA issuer polls the barriers of unit u + 1 before it issues unit u (0: after; AIRFE_PREWAIT=1 switches it on, for A/B timing)
   int nacc;         // TMEM accumulator buffers (2..4): deeper than 2 hides the MMA -> epilogue -> MMA hand-shake latency on small-N layers

@@ -28,8 +28,14 @@ constexpr int kFoldStrips = 2;   // strips of 8 rows per halo tile
 __host__ __device__ constexpr int fold_a_bytes(int kw) { return 16 * (8 * kFoldStrips + 2) * kw * 2; }   // 36 KiB (KW = 64) / 18 KiB (KW = 32)
 __host__ __device__ constexpr int fold_nbuf(int n) { return n == 64 ? 2 : 4; }
 
-template <int KW, int N>
-__global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_fold_kernel(const __grid_constant__ ConvParams p) {
+constexpr int kFoldWideThreads = 576;   // WIDE: warps 2-17 = sixteen epilogue warps (four per TMEM lane quarter / scheduler)
+
+// WIDE = false: 8 epilogue warps, each software-pipelines its (strip, chunk) items (register double buffer).
+// WIDE = true : 16 epilogue warps, one (strip, chunk group) per warp and tile, no intra-warp pipelining: the epilogue of this kernel is
+//               issue / latency bound (ncu: 2.5 resident warps per scheduler, issue slot 47 % busy, stalls = fixed-latency waits and the
+//               shuffle / store scoreboard), which more resident warps hide directly.
+template <int KW, int N, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? kFoldWideThreads : kConvThreads, 1) tc_conv3x3_fold_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int S = kFoldStrips;
@@ -137,6 +143,90 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_fold_kernel(const 
       }
       if (trp) trp[3] = clock64();
       sa = nsa; pa = npa;
+    }
+  } else if constexpr (WIDE) {
+    // ===== epilogue, 16 warps: warp -> TMEM lane quarter (warp & 3), strip of the tile ((warp - 2) >> 3) and chunk group (((warp - 2) >> 2) & 1) =====
+    // This epilogue is instruction-issue bound (one item = 16 channels x 32 pixels costs ~160 essential instructions: 3 TMEM loads, 32
+    // shuffles, 48 adds, ReLU, packing, the store), so everything else is kept out of the per-tile path: the tile coordinates advance
+    // incrementally (no division), the thread's store offset inside a tile is computed once, and the host only selects this kernel for
+    // layers whose channel count equals N and whose rows are 32-byte aligned (no partial-chunk store path).
+    const int quarter = warp & 3;
+    const int g = (warp - 2) >> 2;                     // 0..3
+    const int s_mine = g >> 1;
+    constexpr int CPW = N / 32;                        // chunks of 16 output channels per warp: 1 (N = 32) or 2 (N = 64)
+    const int c_begin = (g & 1) * CPW;
+    const int xx = lane & 15;
+    const int yr = 8 * s_mine + 2 * quarter + (lane >> 4);          // row inside the 16-row tile
+    const uint32_t lane_sel = uint32_t(quarter * 32) << 16;
+    const bool x_ok = (xx >= 1) && (xx <= kFoldTX);
+    const bool pool_sel = (xx & 1) && !(lane & 16);                 // x even (tiles start at even columns), y even
+    const long long off_full = (long long)yr * p.out_sy + (long long)(xx - 1) * p.out_sx + c_begin * 16;
+    const long long off_pool = (long long)(yr >> 1) * p.pool_sy + (long long)((xx - 1) >> 1) * p.pool_sx + c_begin * 16;
+    // tile coordinates of t = blockIdx.x, then += gridDim.x per iteration with carries
+    const int txy = p.tiles_x * p.tiles_y;
+    int tz = (int)blockIdx.x / txy, ty = ((int)blockIdx.x % txy) / p.tiles_x, tx = (int)blockIdx.x % p.tiles_x;
+    const int dz = (int)gridDim.x / txy, dy = ((int)gridDim.x % txy) / p.tiles_x, dx = (int)gridDim.x % p.tiles_x;
+    int gi = s_mine;                                   // global strip counter of this warp's strip: buffer gi % NB, phase (gi / NB) & 1
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, gi += S) {
+      const int x = tx * kFoldTX - 1 + xx;
+      const int y = ty * (8 * S) + yr;
+      const bool valid = x_ok && (x < p.W) && (y < p.H);
+      __half* o_full = p.out + ((long long)tz * p.out_sb + (long long)(ty * (8 * S)) * p.out_sy + (long long)(tx * kFoldTX) * p.out_sx + off_full);
+      __half* o_pool = p.pool_out + ((long long)tz * p.pool_sb + (long long)(ty * (4 * S)) * p.pool_sy + (long long)(tx * (kFoldTX / 2)) * p.pool_sx + off_pool);
+      const int buf = gi % NB;
+      ptx::mbar_wait(&tmem_full[buf], (uint32_t)(gi / NB) & 1u);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < CPW; ++ci) {
+        uint32_t q[3][16];
+        const uint32_t ta = tmem_base + (uint32_t)(buf * ACC) + lane_sel + (uint32_t)((c_begin + ci) * 16);
+        ptx::tmem_ld16(ta, q[0]);
+        ptx::tmem_ld16(ta + N, q[1]);
+        ptx::tmem_ld16(ta + 2 * N, q[2]);
+        ptx::tmem_ld_wait();
+        if (ci == CPW - 1) {                           // last load from this strip's buffer has landed: hand it back before processing
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+        }
+        uint32_t h[8];
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + (c_begin + ci) * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 bb = b4[i];
+          float f[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(q[0][4 * i + e]), 1);
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(q[2][4 * i + e]), 1);
+            f[e] = (left + __uint_as_float(q[1][4 * i + e])) + right;
+          }
+          f[0] += bb.x; f[1] += bb.y; f[2] += bb.z; f[3] += bb.w;
+          if (p.relu) { f[0] = fmaxf(f[0], 0.f); f[1] = fmaxf(f[1], 0.f); f[2] = fmaxf(f[2], 0.f); f[3] = fmaxf(f[3], 0.f); }
+          __half2 ha = __floats2half2_rn(f[0], f[1]), hb = __floats2half2_rn(f[2], f[3]);
+          h[2 * i] = *reinterpret_cast<uint32_t*>(&ha);
+          h[2 * i + 1] = *reinterpret_cast<uint32_t*>(&hb);
+        }
+        if (p.out && valid) ptx::st_global_256(o_full + ci * 16, h);
+        if (p.pool_out) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __half2 a = *reinterpret_cast<__half2*>(&h[i]);
+            uint32_t o1 = __shfl_down_sync(0xffffffffu, h[i], 1);
+            a = __hmax2(a, *reinterpret_cast<__half2*>(&o1));
+            uint32_t cur = *reinterpret_cast<uint32_t*>(&a);
+            uint32_t o16 = __shfl_xor_sync(0xffffffffu, cur, 16);
+            a = __hmax2(a, *reinterpret_cast<__half2*>(&o16));
+            h[i] = *reinterpret_cast<uint32_t*>(&a);
+          }
+          if (valid && pool_sel) ptx::st_global_256(o_pool + ci * 16, h);
+        }
+      }
+      tx += dx;
+      if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+      ty += dy;
+      if (ty >= p.tiles_y) { ty -= p.tiles_y; ++tz; }
+      tz += dz;
     }
   } else {
     // ===== epilogue: 8 warps per strip; warp -> TMEM lane quarter (warp & 3) and channel half =====

@@ -204,10 +204,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       if (p.dyn_w && tx * p.tw >= vW) continue;
       const bool valid = (x < vW) && (y < p.H) && (b < p.B);
       const long long off = (long long)b * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx;
+      const int n0 = nt * p.block_n;
+      // fused rotary embedding: the cos / sin values of this keypoint for chunk cc + 1 are fetched while chunk cc is processed, the first
+      // chunk's before the accumulator wait (ncu source view of the Wqkv GEMM: 30 % of the warp samples sat on the first FMUL after these
+      // loads when they were issued at the point of use)
+      float4 rv[2][4];
+      const float* rot_row = p.rot ? p.rot + ((long long)b * p.W + x) * 64 : nullptr;
+      auto rot_fetch = [&](float4 (&dst)[4], int nb) {
+        if (rot_row && valid && nb < p.rot_cols) {
+          const float4* r4 = reinterpret_cast<const float4*>(rot_row + (nb & 63));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = __ldg(r4 + i);
+        }
+      };
+      rot_fetch(rv[0], n0 + c_begin * 16);
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(quarter * 32) << 16);
-      const int n0 = nt * p.block_n;
       uint32_t rr[2][16];
       if (c_begin < c_end) ptx::tmem_ld16(taddr + c_begin * 16, rr[0]);
 #pragma unroll 1
@@ -217,7 +230,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
         if (cq + u >= c_end) break;
         const int c = (cq + u) * 16;
         ptx::tmem_ld_wait();
-        if (cq + u + 1 < c_end) ptx::tmem_ld16(taddr + c + 16, rr[u ^ 1]);
+        if (cq + u + 1 < c_end) { ptx::tmem_ld16(taddr + c + 16, rr[u ^ 1]); rot_fetch(rv[u ^ 1], n0 + c + 16); }
         const uint32_t (&r)[16] = rr[u];
         float v[16];
         float bsm[16];
@@ -238,10 +251,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
         if (p.rot && nbase < p.rot_cols && valid) {
           // fused rotary embedding: adjacent columns (2j, 2j+1) of a 64-wide head rotate by the keypoint's angle j;
           // rot[row][2j] = cos, rot[row][2j+1] = sin  (lg_prepare_kernel), rows are (b, x) of the H == 1 layout
-          const float4* r4 = reinterpret_cast<const float4*>(p.rot + ((long long)b * p.W + x) * 64 + (nbase & 63));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 cs = __ldg(r4 + i);
+            const float4 cs = rv[u][i];
             const float a0 = v[4 * i], a1 = v[4 * i + 1], a2 = v[4 * i + 2], a3 = v[4 * i + 3];
             v[4 * i] = a0 * cs.x - a1 * cs.y;     v[4 * i + 1] = a1 * cs.x + a0 * cs.y;
             v[4 * i + 2] = a2 * cs.z - a3 * cs.w; v[4 * i + 3] = a3 * cs.z + a2 * cs.w;
