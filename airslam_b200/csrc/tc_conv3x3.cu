@@ -21,11 +21,13 @@ void conv3x3_set_trace(long long* dev_buf) { g_conv_trace = dev_buf; }
 using ConvKernel = void (*)(const ConvParams);
 
 static int conv_key(const ConvParams& p) {
+  if (p.fold == 2 && p.kblocks == 2) return 16;
   if (p.fold) return 8 + (p.fold == 2 ? 4 : 0) + (p.kw == 32 ? 2 : 0) + (p.block_n == 64 ? 1 : 0);
   return (p.kw == 32 ? 4 : 0) | (p.strips == 2 ? 2 : 0) | (p.b_resident ? 1 : 0);
 }
 
 static ConvKernel conv_kernel_for(const ConvParams& p) {
+  if (p.fold == 2 && p.kblocks == 2) return tc_conv3x3_fold_kernel<64, 32, true, 1, 2>;
   if (p.fold == 2) {
     if (p.kw == 64) return p.block_n == 64 ? tc_conv3x3_fold_kernel<64, 64, true> : tc_conv3x3_fold_kernel<64, 32, true>;
     return p.block_n == 64 ? tc_conv3x3_fold_kernel<32, 64, true> : tc_conv3x3_fold_kernel<32, 32, true>;
@@ -48,7 +50,7 @@ static ConvKernel conv_kernel_for(const ConvParams& p) {
 }
 
 static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[kMaxDevices][16] = {};
+  static bool attr_set[kMaxDevices][17] = {};
   const int dev = current_device();
   const int key = conv_key(plan.p);
   const int threads = plan.p.fold == 2 ? kFoldWideThreads : kConvThreads;
@@ -152,23 +154,33 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
     if (p.stages_b < 3) { set_error("add_conv3x3: shared memory budget too small"); return false; }
   }
   const int fold_mode = conv3x3_fold_mode();
-  // the folded kernel has no partial-chunk store path: the layer's channel count must equal the N tile and every store must be 32-byte aligned
-  const bool fold_aligned = n_valid == block_n && (!out || (((uintptr_t)out->p & 31) == 0 && out->ps % 16 == 0)) &&
-                            (!pool_out || (((uintptr_t)pool_out->p & 31) == 0 && pool_out->ps % 16 == 0));
-  if (fold_mode && fold_aligned && p.b_resident && p.kblocks == 1 && p.n_tiles == 1 && (block_n == 32 || block_n == 64) && (fold_mode == 2 || block_n == 32)) {
-    // kx taps folded into N (tc_conv3x3_fold.cuh): tiles of 14 output columns x 16 rows, one TMEM buffer of 3N columns per 8-row strip
+  // The folded kernel has no partial-chunk store path: the layer's channel count must be a whole number of N tiles and every store 32-byte aligned.
+  const bool fold_aligned = (!out || (((uintptr_t)out->p & 31) == 0 && out->ps % 16 == 0)) && (!pool_out || (((uintptr_t)pool_out->p & 31) == 0 && pool_out->ps % 16 == 0));
+  int fold_n = 0, fold_s = kFoldStrips, fold_kb = 1;
+  if (fold_mode && fold_aligned && n_valid == n16) {
+    if (p.kblocks == 1 && (n16 == 32 || (n16 == 64 && fold_mode == 2))) fold_n = n16;                       // C_in <= 64: one resident N tile
+    else if (p.kblocks == 2 && p.kw == 64 && n16 == 64 && (fold_mode == 2 || (in.W >= 32 && in.H >= 32))) {   // the choice must not depend on the batch: a pair inside a batch is bit-identical to the same pair alone     // C_in = 128 -> 64: two resident N tiles of 32, one-strip halo tiles
+      static const int kb2 = getenv("AIRFE_CONV_FOLD_KB2") ? atoi(getenv("AIRFE_CONV_FOLD_KB2")) : 1;      // 0: keep the nine-tap kernel for these layers (A/B timing)
+      if (kb2) { fold_n = 32; fold_s = 1; fold_kb = 2; }
+    }
+  }
+  if (fold_n) {
+    // kx taps folded into N (tc_conv3x3_fold.cuh): tiles of 14 output columns x 8S rows, one TMEM buffer of 3N columns per 8-row strip
     static const int wide = getenv("AIRFE_FOLD_WIDE") ? atoi(getenv("AIRFE_FOLD_WIDE")) : 1;   // 16 epilogue warps (0: the 8-warp software-pipelined epilogue, for A/B timing)
-    p.fold = wide ? 2 : 1;
-    p.strips = kFoldStrips;
+    p.fold = (wide || fold_kb == 2) ? 2 : 1;
+    p.block_n = block_n = fold_n;
+    p.n_tiles = n_valid / fold_n;
+    p.b_resident = 1;
+    p.strips = fold_s;
     p.tiles_x = (in.W + kFoldTX - 1) / kFoldTX;
-    p.tiles_y = (in.H + 8 * kFoldStrips - 1) / (8 * kFoldStrips);
+    p.tiles_y = (in.H + 8 * fold_s - 1) / (8 * fold_s);
     p.nacc = fold_nbuf(block_n);
-    const int fa = fold_a_bytes(p.kw), fb = 9 * block_n * p.kw * 2;
+    const int fa = fold_kb * fold_a_bytes(p.kw, fold_s), fb = 9 * fold_kb * block_n * p.kw * 2;
     p.stages_a = (budget - fb) / fa;
     if (p.stages_a > 4) p.stages_a = 4;
     uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)batch};
     uint64_t str[3] = {(uint64_t)in.ps * 2, (uint64_t)in.ps * in.W * 2, (uint64_t)in.ps * in.W * in.H * 2};
-    uint32_t box[4] = {(uint32_t)p.kw, 16, (uint32_t)(8 * kFoldStrips + 2), 1};
+    uint32_t box[4] = {(uint32_t)p.kw, 16, (uint32_t)(8 * fold_s + 2), 1};
     if (!make_tmap_f16(&p.tmA, in.p, 4, dims, str, box, p.kw * 2)) return false;
     const uint64_t k_total = (uint64_t)9 * w.c_in_pad;
     uint64_t bd[4] = {k_total, (uint64_t)w.n_rows, 1, 1};
@@ -176,8 +188,9 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
     uint32_t bb[4] = {(uint32_t)p.kw, (uint32_t)block_n, 1, 1};
     if (!make_tmap_f16(&p.tmB, w.w, 4, bd, bs, bb, p.kw * 2)) return false;
     plan.smem_bytes = p.stages_a * fa + fb + 1024 + (2 * p.stages_a + 1 + 8) * 8 + 16;
-    const int total = p.tiles_x * p.tiles_y * batch;
+    const int total = p.tiles_x * p.tiles_y * batch * p.n_tiles;
     plan.grid = total < sm_count() ? total : sm_count();
+    plan.grid -= plan.grid % p.n_tiles;                  // a CTA keeps one N tile resident: t % n_tiles must not change as t += grid
   } else {
     uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)batch};
     uint64_t str[3] = {(uint64_t)in.ps * 2, (uint64_t)in.ps * in.W * 2, (uint64_t)in.ps * in.W * in.H * 2};
@@ -200,7 +213,7 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   ol->tc_flops += fl;
   ol->launches += 1;
   char nm[160];
-  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d%s", w.c_in, n_valid, in.W, in.H, batch, p.fold ? " Bres kx-fold" : (p.b_resident ? " Bres" : ""), pool_out ? (out ? " +pool" : " pool-only") : "", p.strips, p.kw == 32 ? " K32" : "");
+  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d%s", w.c_in, n_valid, in.W, in.H, batch, p.fold ? (p.kblocks == 2 ? " Bres kx-fold 2xN32" : " Bres kx-fold") : (p.b_resident ? " Bres" : ""), pool_out ? (out ? " +pool" : " pool-only") : "", p.strips, p.kw == 32 ? " K32" : "");
   ol->push(nm, fl, [plan](cudaStream_t st) { return conv_launch(plan, st); });
   return true;
 }

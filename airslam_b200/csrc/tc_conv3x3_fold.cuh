@@ -25,7 +25,7 @@ namespace airfe {
 constexpr int kFoldTX = 14;      // valid output columns per tile (16 loaded)
 constexpr int kFoldStrips = 2;   // strips of 8 rows per halo tile
 
-__host__ __device__ constexpr int fold_a_bytes(int kw) { return 16 * (8 * kFoldStrips + 2) * kw * 2; }   // 36 KiB (KW = 64) / 18 KiB (KW = 32)
+__host__ __device__ constexpr int fold_a_bytes(int kw, int strips = kFoldStrips) { return 16 * (8 * strips + 2) * kw * 2; }   // one K block of a halo tile: 36 KiB (KW = 64, 2 strips), 18 KiB (KW = 32), 20 KiB (KW = 64, 1 strip)
 __host__ __device__ constexpr int fold_nbuf(int n) { return n == 64 ? 2 : 4; }
 
 constexpr int kFoldWideThreads = 576;   // WIDE: warps 2-17 = sixteen epilogue warps (four per TMEM lane quarter / scheduler)
@@ -34,20 +34,25 @@ constexpr int kFoldWideThreads = 576;   // WIDE: warps 2-17 = sixteen epilogue w
 // WIDE = true : 16 epilogue warps, one (strip, chunk group) per warp and tile, no intra-warp pipelining: the epilogue of this kernel is
 //               issue / latency bound (ncu: 2.5 resident warps per scheduler, issue slot 47 % busy, stalls = fixed-latency waits and the
 //               shuffle / store scoreboard), which more resident warps hide directly.
-template <int KW, int N, bool WIDE>
+// S  = strips of 8 rows per halo tile (2; 1 for the two-K-block variant, whose halo tile is twice as deep)
+// KB = K blocks of 64 input channels (1; 2 = C_in 128: both K blocks of a tile form one stage and a strip accumulates over 2 x 3 x 4 MMAs).
+//      With KB = 2 the layer's 64 output channels are TWO resident N tiles of 32 (p.n_tiles = 2; a CTA keeps the N tile blockIdx.x % 2, the grid
+//      is even): 9 x 128 x 64 fp16 weights (147 KB) do not fit next to the halo ring, 9 x 128 x 32 do.  WIDE only.
+template <int KW, int N, bool WIDE, int S = kFoldStrips, int KB = 1>
 __global__ void __launch_bounds__(WIDE ? kFoldWideThreads : kConvThreads, 1) tc_conv3x3_fold_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(WIDE || (S == kFoldStrips && KB == 1), "the 8-warp epilogue exists for the one-K-block, two-strip shape only");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int S = kFoldStrips;
-  constexpr int a_bytes = fold_a_bytes(KW);
+  constexpr int a_one = fold_a_bytes(KW, S);   // one K block of the halo tile
+  constexpr int a_bytes = KB * a_one;          // ring stage
   constexpr int rowb = KW * 2;                 // bytes per pixel row
   constexpr int b_bytes = N * rowb;            // one tap's weights: N rows (a multiple of 1 KiB for every instantiation)
   constexpr int NB = fold_nbuf(N);
   constexpr int ACC = 3 * N;                   // TMEM columns per strip
-  static_assert(b_bytes % 1024 == 0 && a_bytes % 1024 == 0, "operand blocks must keep the 1 KiB swizzle phase");
+  static_assert(b_bytes % 1024 == 0 && a_one % 1024 == 0, "operand blocks must keep the 1 KiB swizzle phase");
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.stages_a * a_bytes;
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem_b + 9 * b_bytes);
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem_b + 9 * KB * b_bytes);
   uint64_t* empty_a = full_a + p.stages_a;
   uint64_t* full_b = empty_a + p.stages_a;
   uint64_t* tmem_full = full_b + 1;
@@ -55,7 +60,8 @@ __global__ void __launch_bounds__(WIDE ? kFoldWideThreads : kConvThreads, 1) tc_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_x * p.tiles_y * p.B;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.B * p.n_tiles;      // t = m tile * n_tiles + n tile; the N tile of a CTA never changes
+  const int nt0 = (int)blockIdx.x % p.n_tiles;
   constexpr uint32_t tmem_cols = 512;          // 2 x 192 or 4 x 96 columns: the next power of two
 
   if (warp == 0 && lane == 0) {
@@ -72,7 +78,7 @@ __global__ void __launch_bounds__(WIDE ? kFoldWideThreads : kConvThreads, 1) tc_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   __shared__ __align__(16) float s_bias[64];
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_bias[i] = (p.bias && i < p.n_valid) ? p.bias[i] : 0.f;   // weights: not produced by a kernel
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_bias[i] = (p.bias && i < N && nt0 * N + i < p.n_valid) ? p.bias[nt0 * N + i] : 0.f;   // weights: not produced by a kernel
   __syncthreads();
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();                // activations are touched only below
@@ -80,16 +86,19 @@ __global__ void __launch_bounds__(WIDE ? kFoldWideThreads : kConvThreads, 1) tc_
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer: the nine weight taps once, then one halo tile per output tile =====
-      ptx::mbar_arrive_expect_tx(&full_b[0], (uint32_t)(9 * b_bytes));
-      for (int tap = 0; tap < 9; ++tap) ptx::tma_load_4d(smem_b + tap * b_bytes, &p.tmB, &full_b[0], tap * p.c_in_pad, 0, 0, 0);
+      ptx::mbar_arrive_expect_tx(&full_b[0], (uint32_t)(9 * KB * b_bytes));
+      for (int cb = 0; cb < KB; ++cb)
+        for (int tap = 0; tap < 9; ++tap) ptx::tma_load_4d(smem_b + (cb * 9 + tap) * b_bytes, &p.tmB, &full_b[0], tap * p.c_in_pad + cb * KW, nt0 * N, 0, 0);
       int sa = 0;
       uint32_t pa = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, tz = t / (p.tiles_x * p.tiles_y);
+        const int mt = t / p.n_tiles;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tz = mt / (p.tiles_x * p.tiles_y);
         ptx::mbar_wait(&empty_a[sa], pa ^ 1);
         if (p.trace && blockIdx.x == 0 && t / (int)gridDim.x < 64) p.trace[(t / gridDim.x) * 8 + 0] = clock64();
         ptx::mbar_arrive_expect_tx(&full_a[sa], (uint32_t)a_bytes);
-        ptx::tma_load_4d(smem_a + sa * a_bytes, &p.tmA, &full_a[sa], 0, tx * kFoldTX - 1, ty * 8 * S - 1, tz);
+#pragma unroll
+        for (int cb = 0; cb < KB; ++cb) ptx::tma_load_4d(smem_a + sa * a_bytes + cb * a_one, &p.tmA, &full_a[sa], cb * KW, tx * kFoldTX - 1, ty * 8 * S - 1, tz);
         if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
       }
     }
@@ -121,12 +130,14 @@ __global__ void __launch_bounds__(WIDE ? kFoldWideThreads : kConvThreads, 1) tc_
         const uint32_t d0 = tmem_base + (uint32_t)(buf * ACC);
         if (ptx::elect_one()) {
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const uint64_t da = da_stage + (uint64_t)((uint32_t)(8 * s + ky) * row16);
-            const uint64_t db = db_base + (uint64_t)((uint32_t)(3 * ky) * b16);
+          for (int cb = 0; cb < KB; ++cb)
 #pragma unroll
-            for (int k = 0; k < ksteps; ++k) ptx::umma_f16(d0, da + 2 * k, db + 2 * k, idesc, (ky | k) ? 1u : 0u);
-          }
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint64_t da = da_stage + (uint64_t)((uint32_t)(cb * (a_one >> 4)) + (uint32_t)(8 * s + ky) * row16);
+              const uint64_t db = db_base + (uint64_t)((uint32_t)(cb * 9 + 3 * ky) * b16);
+#pragma unroll
+              for (int k = 0; k < ksteps; ++k) ptx::umma_f16(d0, da + 2 * k, db + 2 * k, idesc, (cb | ky | k) ? 1u : 0u);
+            }
           if (s == S - 1) ptx::umma_commit(&empty_a[sa]);
           ptx::umma_commit(&tmem_full[buf]);
         }
@@ -151,23 +162,29 @@ __global__ void __launch_bounds__(WIDE ? kFoldWideThreads : kConvThreads, 1) tc_
     // incrementally (no division), the thread's store offset inside a tile is computed once, and the host only selects this kernel for
     // layers whose channel count equals N and whose rows are 32-byte aligned (no partial-chunk store path).
     const int quarter = warp & 3;
-    const int g = (warp - 2) >> 2;                     // 0..3
-    const int s_mine = g >> 1;
+    const int g = (warp - 2) >> 2;                     // 0..3: chunk group g & 1, strip-sequence parity g >> 1
+    // The CTA's strips form one sequence gi = tile iteration * S + strip; this warp serves the strips with gi % 2 == g >> 1:
+    // S = 2: strip (g >> 1) of every tile; S = 1: every second tile.
+    constexpr int iter_step = (S == 1) ? 2 : 1;
+    const int s_mine = (S == 2) ? (g >> 1) : 0;
+    const int first_iter = (S == 1) ? (g >> 1) : 0;
     constexpr int CPW = N / 32;                        // chunks of 16 output channels per warp: 1 (N = 32) or 2 (N = 64)
     const int c_begin = (g & 1) * CPW;
     const int xx = lane & 15;
-    const int yr = 8 * s_mine + 2 * quarter + (lane >> 4);          // row inside the 16-row tile
+    const int yr = 8 * s_mine + 2 * quarter + (lane >> 4);          // row inside the 8S-row tile
     const uint32_t lane_sel = uint32_t(quarter * 32) << 16;
     const bool x_ok = (xx >= 1) && (xx <= kFoldTX);
     const bool pool_sel = (xx & 1) && !(lane & 16);                 // x even (tiles start at even columns), y even
-    const long long off_full = (long long)yr * p.out_sy + (long long)(xx - 1) * p.out_sx + c_begin * 16;
-    const long long off_pool = (long long)(yr >> 1) * p.pool_sy + (long long)((xx - 1) >> 1) * p.pool_sx + c_begin * 16;
-    // tile coordinates of t = blockIdx.x, then += gridDim.x per iteration with carries
+    const long long off_full = (long long)yr * p.out_sy + (long long)(xx - 1) * p.out_sx + nt0 * N + c_begin * 16;
+    const long long off_pool = (long long)(yr >> 1) * p.pool_sy + (long long)((xx - 1) >> 1) * p.pool_sx + nt0 * N + c_begin * 16;
+    // m-tile coordinates of this warp's first tile, then += (m tiles per step) with carries: no division on the per-tile path
     const int txy = p.tiles_x * p.tiles_y;
-    int tz = (int)blockIdx.x / txy, ty = ((int)blockIdx.x % txy) / p.tiles_x, tx = (int)blockIdx.x % p.tiles_x;
-    const int dz = (int)gridDim.x / txy, dy = ((int)gridDim.x % txy) / p.tiles_x, dx = (int)gridDim.x % p.tiles_x;
-    int gi = s_mine;                                   // global strip counter of this warp's strip: buffer gi % NB, phase (gi / NB) & 1
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, gi += S) {
+    const int gm = (int)gridDim.x / p.n_tiles;         // m-tile stride of one CTA iteration (the grid is a multiple of n_tiles)
+    const int m0 = (int)blockIdx.x / p.n_tiles + first_iter * gm, dm = iter_step * gm;
+    int tz = m0 / txy, ty = (m0 % txy) / p.tiles_x, tx = m0 % p.tiles_x;
+    const int dz = dm / txy, dy = (dm % txy) / p.tiles_x, dx = dm % p.tiles_x;
+    int gi = first_iter * S + s_mine;                  // position of this warp's strip in the CTA's strip sequence: buffer gi % NB, phase (gi / NB) & 1
+    for (int t = blockIdx.x + first_iter * gridDim.x; t < total_tiles; t += iter_step * gridDim.x, gi += 2) {
       const int x = tx * kFoldTX - 1 + xx;
       const int y = ty * (8 * S) + yr;
       const bool valid = x_ok && (x < p.W) && (y < p.H);

@@ -642,11 +642,14 @@ def main():
     dom_key = max((k for k in families if k not in ("all tcgen05", "non tensor-core kernels")), key=lambda k: families[k]["ms_per_chunk"])
     dom = families[dom_key]
     traffic, traffic_src = None, None
-    tj = os.path.join(ROOT, "profiles", "r02_conv3x3_traffic.json")
-    if args.config == 2 and os.path.exists(tj):
-        tjd = json.load(open(tj))
-        if tjd.get("pairs_per_step") == P and dom_key == "tc_conv3x3":      # the capture must be of the same library-call size      # dram__bytes_read+write per launch from the committed ncu capture of the same chunk
-            traffic, traffic_src = tjd["dram_bytes_per_launch"], tjd["source"]
+    import glob
+    if args.config == 2 and dom_key == "tc_conv3x3":
+        # dram__bytes_read + write per launch from the newest committed ncu capture of the SAME library-call size (tools/ncu_summarize.py all)
+        for tj in sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*conv3x3_traffic*.json")), reverse=True):
+            tjd = json.load(open(tj))
+            if tjd.get("pairs_per_step") == P:
+                traffic, traffic_src = tjd["dram_bytes_per_launch"], tjd["source"]
+                break
     if args.profile_out and rank == 0:
         with open(args.profile_out, "w") as fh:
             fh.write("# per-op CUDA-event profile of one %d-pair chunk (config %d, mean of %d chunks after the timed loops); tensor-core share %.1f%%; FLOPs on the rows actually processed\n"

@@ -188,10 +188,11 @@ def test_conv3x3_halo_matches_torch(cfg):
     assert torch.equal(pool.float(), ref_pool)     # pooling the fp16-rounded values is exact
 
 
-@pytest.mark.parametrize("cfg", [(2, 64, 64, 64, 64), (1, 48, 40, 64, 32), (2, 32, 32, 32, 32), (1, 40, 72, 32, 64)])
+@pytest.mark.parametrize("cfg", [(2, 64, 64, 64, 64), (1, 48, 40, 64, 32), (2, 32, 32, 32, 32), (1, 40, 72, 32, 64), (2, 40, 44, 128, 64), (1, 64, 64, 128, 64)])
 def test_conv3x3_kx_fold_all_instantiations(cfg, monkeypatch):
-    """AIRFE_CONV_FOLD=2 routes every eligible layer (C_in <= 64, C_out = 32 / 64) through tc_conv3x3_fold_kernel<KW, N> -- by default only
-    64 -> 32 uses it (csrc/tc_conv3x3.cu).  Full store, fused 2x2 max-pool and ragged tiles (width not a multiple of 14, height not of 16)."""
+    """AIRFE_CONV_FOLD=2 routes every eligible layer (C_in <= 64 with C_out = 32 / 64; C_in = 128 -> 64 as two resident N tiles of 32 with
+    two K blocks) through tc_conv3x3_fold_kernel -- by default the C_out = 32 layers and the large 128 -> 64 maps use it (csrc/tc_conv3x3.cu).
+    Full store, fused 2x2 max-pool and ragged tiles (width not a multiple of 14, height not of 8 / 16)."""
     monkeypatch.setenv("AIRFE_CONV_FOLD", "2")
     b, h, w, cin, cout = cfg
     x, wt, bias = _mk(b, h, w, cin, cout, 3, seed=(hash(cfg) & 0xFFFF) + 11)

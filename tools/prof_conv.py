@@ -45,3 +45,5 @@ for t in which:
     if t == "c128po": conv(t, B, 256, 256, 128, 128, False, True)
     if t == "c256": conv(t, B, 128, 128, 256, 320, True, False)
     if t == "c96": conv(t, B, 256, 256, 96, 128, True, False)
+    if t == "c12864": conv(t, 32, 128, 128, 128, 64, True, False)
+    if t == "c12864s": conv(t, 32, 64, 64, 128, 64, True, False)
