@@ -113,7 +113,31 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   p.dyn_w = d.dyn_w;
   p.dyn_w_stride = d.dyn_w_stride;
   const int b_bytes = tc_b_bytes(d.block_n, d.b_mn_major);
-  const int budget = 200 * 1024;
+  // TMA-store epilogue (tc_gemm.cuh): plain fp16 outputs whose N tile is a whole number of 64-column groups per epilogue warp.  Each warp's
+  // 32 tile rows must be one box of the output tensor: the tile box sides are powers of two.  Parity-green (29 operator + 17 pipeline GPU tests ran
+  // with it on) but measured SLOWER than the 256-bit STG path on every GEMM it applies to (profiles/r02c_tma_store_ab.txt: Wqkv + rotary 84 -> 88 us,
+  // to_qk_v 38 -> 41 us, G3 496->128 137 -> 149 us): the staging tiles cost one A stage and the stores were not what these kernels wait for.
+  // Off by default; AIRFE_GEMM_TMA_STORE=1 switches it on.
+  static const int tma_store_on = getenv("AIRFE_GEMM_TMA_STORE") ? atoi(getenv("AIRFE_GEMM_TMA_STORE")) : 0;
+  auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+  p.tma_store = 0;
+  if (tma_store_on && !d.out_f32 && !d.resid && !d.out2 && d.block_n % 128 == 0 && pow2(d.tw) && pow2(d.th) && pow2(d.tb) && ((uintptr_t)d.out & 15) == 0 &&
+      d.out_sx % 8 == 0 && (d.H == 1 || d.out_sy % 8 == 0) && (d.B == 1 || d.out_sb % 8 == 0) && (!d.out_split || (d.out_split % 64 == 0 && d.out_split_stride % 8 == 0))) {
+    const int bw = d.tw < 32 ? d.tw : 32, bh = d.th < 32 / bw ? d.th : 32 / bw, bbx = 32 / (bw * bh);
+    if (bbx <= d.tb) {
+      const uint64_t cols = d.out_split ? (uint64_t)d.out_split : (uint64_t)d.n_valid;
+      const uint64_t nsec = d.out_split ? (uint64_t)((d.n_valid + d.out_split - 1) / d.out_split) : 1;
+      const uint64_t sx = (uint64_t)d.out_sx * 2, sy = (d.H == 1 || d.out_sy == 0) ? sx * d.W : (uint64_t)d.out_sy * 2;
+      const uint64_t sb = (d.B == 1 || d.out_sb == 0) ? sy * d.H : (uint64_t)d.out_sb * 2;
+      const uint64_t ss = d.out_split ? (uint64_t)d.out_split_stride * 2 : sb * d.B;
+      uint64_t dims[5] = {cols, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B, nsec};
+      uint64_t str[4] = {sx, sy, sb, ss};
+      uint32_t box[5] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bbx, 1};
+      if (!make_tmap_f16(&p.tmO, d.out, 5, dims, str, box)) return false;
+      p.tma_store = 1;
+    }
+  }
+  const int budget = 200 * 1024 - (p.tma_store ? 24 * 1024 : 0);     // 32 KiB of staging tiles: 24 KiB out of the operand budget (a 128 KiB weight panel + 3 A stages still fit), 8 KiB of former slack
   const int total = p.tiles_x * p.tiles_y * p.tiles_b * p.n_tiles;
   const int panel = p.taps * p.kblocks * b_bytes;
   static const bool bres_off = getenv("AIRFE_GEMM_NO_BRES") != nullptr;
@@ -130,7 +154,7 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   p.stages = stages;
   static const int prewait = getenv("AIRFE_PREWAIT") ? 1 : 0;   // measured in round 2: no gain (profiles/r02_prewait_ab.txt), off by default
   p.prewait = prewait;
-  plan->smem_bytes = stages * (p.b_resident ? kABytes : kABytes + b_bytes) + (p.b_resident ? panel : 0) + 1024 /*align slack*/ + (2 * stages + 5) * 8 + 16;
+  plan->smem_bytes = stages * (p.b_resident ? kABytes : kABytes + b_bytes) + (p.b_resident ? panel : 0) + 1024 /*align slack*/ + (2 * stages + 5) * 8 + 16 + (p.tma_store ? kTcStoreStage + 1024 + 32 : 0);
   int grid = total < num_sms() ? total : num_sms();
   if (p.b_resident) grid = grid / p.n_tiles * p.n_tiles;   // a CTA's N tile (blockIdx % n_tiles) must never change
   plan->grid = grid;

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* bres_bar = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  uint8_t* smem_store = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~uintptr_t(1023));   // tma_store: 8 staging tiles of 4 KiB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA);
     ptx::prefetch_tmap(&p.tmB);
+    if (p.tma_store) ptx::prefetch_tmap(&p.tmO);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -189,6 +191,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     const int chunks = p.block_n / 16;
     const int c_begin = half ? (chunks + 1) / 2 : 0, c_end = half ? chunks : (chunks + 1) / 2;
     const int row = quarter * 32 + lane;
+    // tma_store: this warp's 32 rows x 64 columns go through its own 4 KiB staging tile (row = lane, 128 bytes, 16-byte pieces XOR-swizzled
+    // like SWIZZLE_128B so that the 32 lanes' 16-byte writes spread over all banks) and leave with ONE cp.async.bulk.tensor store per 64
+    // columns: full 128-byte lines instead of 32 scattered 32-byte segments per STG.256 (the LSU data pipe was 42 % busy with those).
+    uint8_t* stg = smem_store + (warp - 2) * 4096;
+    const int r0w = quarter * 32;                                       // first tile row of this warp
+    const int bx = r0w % p.tw, by = (r0w / p.tw) % p.th, bb = r0w / (p.tw * p.th);
+    bool store_pending = false;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
               for (int i = 0; i < 16; ++i) if (nbase + i < p.n_valid) o[i] = v[i];
             }
-          } else {
+          } else if (!p.tma_store) {
             __half* o = reinterpret_cast<__half*>(p.out) + off + ncol;
             if (nbase + 16 <= p.n_valid) {
               uint32_t h[8];
@@ -327,6 +336,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
             }
           }
         }
+        if (p.tma_store) {
+          // every lane stages its 16 values (rows beyond the valid extent as zeros: their positions inside the tensor may be read as padding
+          // rows of a later tile, and must stay finite), the group of four chunks = 64 columns leaves as one box
+          const int cg = (cq + u - c_begin) & 3;
+          if (cg == 0) {
+            if (store_pending) { if (lane == 0) ptx::tma_store_wait_read(); store_pending = false; }
+            __syncwarp();
+          }
+          uint32_t h[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __half2 h2 = valid ? __floats2half2_rn(v[2 * i], v[2 * i + 1]) : __floats2half2_rn(0.f, 0.f);
+            h[i] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          uint8_t* srow = stg + lane * 128;
+          *reinterpret_cast<uint4*>(srow + (((2 * cg) ^ (lane & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(srow + (((2 * cg + 1) ^ (lane & 7)) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+          if (cg == 3) {
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int n_first = nbase - 48;                                 // first column of the 64-column group
+              const int sec = p.out_split ? n_first / p.out_split : 0;
+              ptx::tma_store_5d(&p.tmO, stg, p.out_split ? n_first % p.out_split : n_first, tx * p.tw + bx, ty * p.th + by, tz * p.tb + bb, sec);
+              ptx::tma_store_commit();
+            }
+            store_pending = true;
+          }
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -336,6 +374,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     }
   }
 
+  if (p.tma_store && warp >= 2 && lane == 0) ptx::tma_store_wait_all();      // the staging tiles must outlive the bulk stores that read them
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {

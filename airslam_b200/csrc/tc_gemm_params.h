@@ -8,6 +8,7 @@ namespace airfe {
 struct TcGemmParams {
   CUtensorMap tmA;  // 4-D (C, W, H, B)   box (64, tw, th, tb)   SWIZZLE_128B
   CUtensorMap tmB;  // 4-D (K, N, Hb, Bb) box (64, block_n, 1, 1) SWIZZLE_128B  [MN-major: (N, K, Hb, Bb), box (64, 64, 1, 1)]
+  CUtensorMap tmO;  // tma_store only: 5-D (columns of a section, W, H, B, sections) of the fp16 output, box (64, bw, bh, bb, 1) = one warp's 32 rows x 64 columns
   int taps;         // 1 or 9
   int kblocks;      // 64-wide K blocks per tap
   int c_in_pad;     // kblocks * 64 (K offset between taps in Bw)
@@ -35,6 +36,7 @@ struct TcGemmParams {
   int n_valid;
   int stages;
   int prewait;      // MMA issuer polls the barriers of unit u + 1 before it issues unit u (see tc_gemm.cuh); 0 with AIRFE_PREWAIT=1 switches it on
+  int tma_store;    // epilogue stages fp16 tiles in shared memory and stores them with cp.async.bulk.tensor (plain fp16 outputs with block_n % 128 == 0)
   int b_resident;   // whole [block_n x K] weight panel of this CTA's (fixed) N tile stays in shared memory; the ring then holds A only
   int dyn_w_stride; // index = tile batch * dyn_w_stride
   const int* dyn_w;  // optional: per-batch-index valid W (rows of a plain GEMM), read from device memory (tb must be 1)
@@ -44,6 +46,7 @@ constexpr int kTcThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (t
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
+constexpr int kTcStoreStage = 8 * 4096;         // tma_store: one 32-row x 64-column fp16 staging tile (4 KiB, SWIZZLE_128B) per epilogue warp
 
 __host__ __device__ inline int tc_b_bytes(int block_n, int mn_major) { return mn_major ? 64 * 128 : ((block_n * 128 + 1023) / 1024) * 1024; }
 __host__ __device__ inline int tc_acc_stride(int block_n) { return (block_n + 31) / 32 * 32; }
