@@ -10,8 +10,12 @@ cpu_baseline / --impl reference legs may import it; the product path
 
 Pinning status: the reference ships no tests, golden vectors or fixtures for
 this path and its arithmetic lives in TensorRT 8.6.1.6 (absent, closed source),
-so the oracle is pinned against the next best thing: a node-by-node fp32
-execution of the reference's own ONNX files (tools/onnx_interp.py, run in the
-authoring container) frozen under tests/golden/.  With respect to the
-TensorRT engines themselves: PARITY UNPINNED.
+so the oracle is pinned against executions of the reference's own ONNX files:
+(1) by an EXTERNAL runtime, OpenCV DNN 4.13, on static-shape sub-graphs cut byte
+for byte out of the shipped files (tools/onnx_cut.py, tools/make_cv2dnn_golden.py
+-> tests/golden/cv2dnn_*.npz, tests/test_oracle_cv2dnn.py): the dense part of
+G1-G3, the whole LightGlue graph, SuperGlue up to the similarity matrix;
+(2) by the node-by-node interpreter tools/onnx_interp.py for what cv2.dnn cannot
+import (integer / logical tails, Sinkhorn loop) -> tests/golden/g*.npz.
+With respect to the TensorRT engines themselves: PARITY UNPINNED.
 """

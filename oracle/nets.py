@@ -5,10 +5,11 @@ compute for the corresponding shipped ONNX file (the graphs are the arithmetic
 spec; the engines are built from them at src/super_point.cpp:18-85,
 src/plnet.cpp:24-196, src/light_glue.cpp:24-118, src/super_glue.cpp:26-130 and
 executed at src/super_point.cpp:133, src/plnet.cpp:233,510,
-src/light_glue.cpp:159, src/super_glue.cpp:185).  Pinned in the authoring
-container against a node-by-node execution of the ONNX files
-(tests/test_oracle_vs_onnx.py, tools/onnx_interp.py) and, everywhere, against
-the frozen vectors in tests/golden/.
+src/light_glue.cpp:159, src/super_glue.cpp:185).  Pinned against the reference's
+ONNX files executed by OpenCV DNN (an external runtime; tests/golden/cv2dnn_*.npz,
+tests/test_oracle_cv2dnn.py) and by the node-by-node interpreter
+tools/onnx_interp.py (tests/golden/g*.npz, tests/test_oracle_golden.py; live in
+the authoring container: tests/test_oracle_vs_onnx.py).
 
 `emul=True` rounds both operands of every conv / matmul to fp16 and accumulates
 in fp32: what the tcgen05 kernels compute up to summation order (SURVEY.md §8c
