@@ -105,6 +105,9 @@ bool Detector::init(const DetectorConfig& cfg, const std::string& wdir, bool use
       if (!pack_dense(wf, a, 256, ar, &heads0_) || !pack_dense(wf, c, 320, ar, &heads2_)) return false;
     }
     if (!pack_dense(wf, {{L + "fc3.weight", L + "fc3.bias", 0}, {L + "fc4.weight", L + "fc4.bias", 0}}, 256, ar, &fc34_)) return false;
+    // fc1 (LOI features, 128) | fc3 (thin, 4) | fc4 (aux, 4) read the same fc2 map: one 256 -> 136 GEMM reads it once (AIRFE_FC134_MERGE=0: two GEMMs, A/B timing)
+    fc134_merged_ = !(getenv("AIRFE_FC134_MERGE") && atoi(getenv("AIRFE_FC134_MERGE")) == 0);
+    if (fc134_merged_ && !pack_dense(wf, {{L + "fc1.weight", L + "fc1.bias", 0}, {L + "fc3.weight", L + "fc3.bias", 0}, {L + "fc4.weight", L + "fc4.bias", 0}}, 256, ar, &fc134_)) return false;
     // stage 1 (G3) MLP
     auto p1 = [&](const std::string& name, int cin, DenseW* out) { return pack_dense(wf, {{L + "s1." + name + ".weight", L + "s1." + name + ".bias", 0}}, cin, ar, out); };
     if (!p1("fc2.0", 496, &s1_fc0_) || !p1("fc2.2", 128, &s1_fc2_) || !p1("fc2.4", 128, &s1_fc4_) || !p1("fc2_res.0", 240, &s1_res_)) return false;
@@ -121,6 +124,10 @@ bool Detector::init(const DetectorConfig& cfg, const std::string& wdir, bool use
     l1b_o_ = make_act(ar, B, 512, 512, 32);
     l2a_o_ = make_act(ar, B, 256, 256, 128);
     l2b_o_ = make_act(ar, B, 256, 256, 128);
+    // The Resize (nearest, 2x) node in front of every `deconv` conv is fused into the epilogue of the conv that produces its input: that conv
+    // stores each pixel four times, straight into the up-sampled map (the low-resolution map itself has no other reader).  AIRFE_UP2_FUSE=0
+    // keeps the separate upsample2 launches (8 per frame batch, 0.47 ms per 94 frames) for A/B timing.
+    fuse_up_ = conv3x3_halo_enabled() && !(getenv("AIRFE_UP2_FUSE") && atoi(getenv("AIRFE_UP2_FUSE")) == 0);
     for (int s = 0; s < 2; ++s) {
       int hw_ = 128;
       for (int l = 0; l < 5; ++l) {
@@ -133,15 +140,23 @@ bool Detector::init(const DetectorConfig& cfg, const std::string& wdir, bool use
       for (int u = 0; u < 4; ++u) {
         hgb_[s].up[u] = make_act(ar, B, hw_, hw_, 128);
         hgb_[s].cat[u] = make_act(ar, B, hw_, hw_, 128);   // [deconv relu (64) | skip conv relu (64)]
-        hgb_[s].u[u] = make_act(ar, B, hw_, hw_, 128);
+        if (!(fuse_up_ && u < 3)) hgb_[s].u[u] = make_act(ar, B, hw_, hw_, 128);     // fused up-sampling: decoder levels 0-2 are stored up-sampled only
         hw_ *= 2;
       }
     }
     fc2_o_ = make_act(ar, B, 128, 128, 256);
     hmid_o_ = make_act(ar, B, 128, 128, 320);
     heads9_o_ = make_act(ar, B, 128, 128, 16, true);
-    loi_o_ = make_act(ar, B, 128, 128, 128, true);
-    thinaux_o_ = make_act(ar, B, 128, 128, 8, true);
+    if (fc134_merged_) {
+      // [loi 128 | thin 4 | aux 4 | 8 GEMM padding columns] fp32 with a pixel stride of 160 floats: every pixel's LOI row starts on a 128-byte
+      // line (with the dense stride of 144 the LOI sampler touched 5 lines per pixel instead of 4 and ran 17 % slower)
+      lt_o_ = make_act(ar, B, 128, 128, 144, true, 160);
+      loi_o_ = lt_o_.slice(0, 128);
+      thinaux_o_ = lt_o_.slice(128, 8);
+    } else {
+      loi_o_ = make_act(ar, B, 128, 128, 128, true);
+      thinaux_o_ = make_act(ar, B, 128, 128, 8, true);
+    }
     lines_pred_ = ar->alloc_n<float>((size_t)B * kProp * 4);
     jloc_ = ar->alloc_n<float>((size_t)B * 16384);
     juncs_ = ar->alloc_n<float>((size_t)B * kJunc * 2);
@@ -183,8 +198,8 @@ bool Detector::init(const DetectorConfig& cfg, const std::string& wdir, bool use
     taps["stack1_out"] = {hgb_[0].u[3].p, (size_t)16384 * 128 * 2};
     taps["fc2"] = {fc2_o_.p, (size_t)16384 * 256 * 2};
     taps["heads9"] = {heads9_o_.p, (size_t)16384 * 16 * 4};
-    taps["loi"] = {loi_o_.p, (size_t)16384 * 128 * 4};
-    taps["thinaux"] = {thinaux_o_.p, (size_t)16384 * 8 * 4};
+    if (fc134_merged_) taps["loi_thinaux"] = {lt_o_.p, (size_t)16384 * 160 * 4};
+    else { taps["loi"] = {loi_o_.p, (size_t)16384 * 128 * 4}; taps["thinaux"] = {thinaux_o_.p, (size_t)16384 * 8 * 4}; }
     taps["lines_pred"] = {lines_pred_, (size_t)kProp * 4 * 4};
     taps["jloc"] = {jloc_, 16384 * 4};
     taps["juncs_pred"] = {juncs_, kJunc * 2 * 4};
@@ -260,18 +275,21 @@ bool Detector::build_ops(int B) {
     for (int s = 0; s < 2; ++s) {
       HGBuf& g = hgb_[s];
       Act in = x;
+      const bool fuse_up = fuse_up_;     // Resize nodes fused into the producing conv's store (see the buffer allocation)
       for (int lv = 0; lv < 5; ++lv) {
         if (!add_conv3x3(&l, in, hg_[s].c[lv][0], &g.a[lv], nullptr, B, true)) return false;
-        if (!add_conv3x3(&l, g.a[lv], hg_[s].c[lv][1], &g.r[lv], lv < 4 ? &g.pool[lv] : nullptr, B, true)) return false;
+        if (lv == 4 && fuse_up) { if (!add_conv3x3(&l, g.a[lv], hg_[s].c[lv][1], &g.up[0], nullptr, B, true, true)) return false; }
+        else if (!add_conv3x3(&l, g.a[lv], hg_[s].c[lv][1], &g.r[lv], lv < 4 ? &g.pool[lv] : nullptr, B, true)) return false;
         if (lv < 4) in = g.pool[lv];
       }
       Act u = g.r[4];
       for (int k = 0; k < 4; ++k) {      // k = 0: 8 -> 16 (deconv1, skip = level-3 relu), ... k = 3: 64 -> 128 (skip = level-0 relu)
-        up(&l, u, g.up[k]);
+        if (!fuse_up) up(&l, u, g.up[k]);
         const Act clo = g.cat[k].slice(0, 64), chi = g.cat[k].slice(64, 64);
         if (!add_conv3x3(&l, g.up[k], hg_[s].dec[k], &clo, nullptr, B, true)) return false;
         if (!add_conv3x3(&l, g.r[3 - k], hg_[s].aup[k], &chi, nullptr, B, true)) return false;
-        if (!add_conv3x3(&l, g.cat[k], hg_[s].bup[k], &g.u[k], nullptr, B, true)) return false;
+        if (fuse_up && k < 3) { if (!add_conv3x3(&l, g.cat[k], hg_[s].bup[k], &g.up[k + 1], nullptr, B, true, true)) return false; }
+        else if (!add_conv3x3(&l, g.cat[k], hg_[s].bup[k], &g.u[k], nullptr, B, true)) return false;
         u = g.u[k];
       }
       x = u;
@@ -279,8 +297,8 @@ bool Detector::build_ops(int B) {
     if (!add_dense(&l, x, fc2_, fc2_o_, B, false)) return false;                 // no ReLU after fc2 (graph)
     if (!add_conv3x3(&l, fc2_o_, heads0_, &hmid_o_, nullptr, B, true)) return false;   // 5 x (3x3 256->64) + ReLU
     if (!add_dense(&l, hmid_o_, heads2_, heads9_o_, B, false, 9, 16)) return false;
-    if (!add_dense(&l, fc2_o_, fc1_, loi_o_, B, false)) return false;
-    if (!add_dense(&l, fc2_o_, fc34_, thinaux_o_, B, false, 8, 16)) return false;
+    if (fc134_merged_) { if (!add_dense(&l, fc2_o_, fc134_, lt_o_, B, false, 136, 144)) return false; }
+    else if (!add_dense(&l, fc2_o_, fc1_, loi_o_, B, false) || !add_dense(&l, fc2_o_, fc34_, thinaux_o_, B, false, 8, 16)) return false;
     line_ops_[B] = std::move(l);
     OpList m;
     m.dyn_kind = kDynLines;
@@ -314,7 +332,7 @@ bool Detector::run(const uint8_t* d_images, int B, int w, int h, int stride, lon
     timed("junction_topk", st, [&] { launch_junctions(jloc_, heads, 16, cand_, cand_count_, mask_b_, juncs_, junc_idx_, B, st); });
     timed("association+unique", st, [&] { launch_association(lines_pred_, juncs_, imin_, imax_, iskeep_, pair_table_, uid_pairs_, uid_first_, n_unique_, kLineCap, B, st); });
     timed("loi_gather", st, [&] {
-      launch_loi_gather((const float*)loi_o_.p, 128, (const float*)thinaux_o_.p, 8, juncs_, lines_pred_, uid_pairs_, uid_first_, n_unique_, kLineCap,
+      launch_loi_gather((const float*)loi_o_.p, (int)loi_o_.ps, (const float*)thinaux_o_.p, (int)thinaux_o_.ps, juncs_, lines_pred_, uid_pairs_, uid_first_, n_unique_, kLineCap,
                         s1_tspan_, (__half*)feat496_.p, adj_, B, st);
     });
     if (!mlp_ops_[B].run(st)) return false;      // stage-1 MLP on tensor cores; row counts are read on the device

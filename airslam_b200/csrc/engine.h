@@ -148,7 +148,9 @@ bool add_dense(OpList* ol, const Act& in, const DenseW& w, const Act& out, int b
                const int* dyn_rows = nullptr, float scale = 1.f, const float* resid = nullptr, const Act* out2 = nullptr, const DenseExtra* ex = nullptr);
 // Append a 3x3 convolution on the halo-reuse tcgen05 kernel (tc_conv3x3.cuh); `out` and/or `pool_out` (fused 2x2 max-pool).
 // Falls back to the generic streaming-tap kernel (+ pool kernel) when AIRFE_CONV_V1 is set or the map is narrower than 8.
-bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu);
+// up2 = true: `out` is the nearest-neighbour 2x up-sampled map (out->W == 2 * in.W): the epilogue stores every pixel four times, which replaces
+// the separate upsample2 kernel between a hourglass decoder conv and the `deconv` conv that follows the Resize node (halo kernel only).
+bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu, bool up2 = false);
 bool conv3x3_halo_enabled();
 void match_set_trace(long long* dev_buf);      // authoring aid, see airfe_debug_match_trace
 long long* match_trace_buf();

@@ -92,8 +92,14 @@ bool conv3x3_halo_enabled() {
   return v == 1;
 }
 
-bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu) {
+bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, const Act* pool_out, int batch, bool relu, bool up2) {
   if (w.taps != 9 || in.f32 || (out && out->f32) || (pool_out && pool_out->f32)) { set_error("add_conv3x3: unsupported layer"); return false; }
+  if (up2) {
+    // fused nearest 2x up-sampling store: halo kernel only, whole 16-channel chunks, 32-byte aligned pixel rows of the up-sampled buffer
+    const bool ok = conv3x3_halo_enabled() && in.W >= 8 && in.W % 8 == 0 && out && !pool_out && out->W == 2 * in.W && out->H == 2 * in.H && w.n_rows % 16 == 0 &&
+                    w.n_rows > 64 && ((uintptr_t)out->p & 31) == 0 && out->ps % 16 == 0;
+    if (!ok) { set_error("add_conv3x3: layer cannot store an up-sampled map"); return false; }
+  }
   if (!conv3x3_halo_enabled() || in.W < 8 || (in.W % 8)) {
     // generic streaming-tap kernel (+ separate pool kernel)
     const Act* full = out;
@@ -134,7 +140,7 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   p.tiles_x = (in.W + 8 * p.strips - 1) / (8 * p.strips);
   p.tiles_y = (in.H + kConvTH - 1) / kConvTH;
   p.bias = w.bias; p.relu = relu;
-  if (out) { p.out = (__half*)out->p; p.out_sx = out->ps; p.out_sy = out->ps * out->W; p.out_sb = out->ps * out->W * out->H; }
+  if (out) { p.out = (__half*)out->p; p.out_sx = out->ps; p.out_sy = out->ps * out->W; p.out_sb = out->ps * out->W * out->H; p.up2 = up2 ? 1 : 0; }
   if (pool_out) { p.pool_out = (__half*)pool_out->p; p.pool_sx = pool_out->ps; p.pool_sy = pool_out->ps * pool_out->W; p.pool_sb = pool_out->ps * pool_out->W * pool_out->H; }
   const int a_bytes = conv_a_bytes(p.strips, p.kw), b_bytes = conv_b_bytes(block_n, p.kw);
   const int budget = 212 * 1024;
@@ -213,7 +219,7 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   ol->tc_flops += fl;
   ol->launches += 1;
   char nm[160];
-  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d%s", w.c_in, n_valid, in.W, in.H, batch, p.fold ? (p.kblocks == 2 ? " Bres kx-fold 2xN32" : " Bres kx-fold") : (p.b_resident ? " Bres" : ""), pool_out ? (out ? " +pool" : " pool-only") : "", p.strips, p.kw == 32 ? " K32" : "");
+  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d%s", w.c_in, n_valid, in.W, in.H, batch, p.fold ? (p.kblocks == 2 ? " Bres kx-fold 2xN32" : " Bres kx-fold") : (p.b_resident ? " Bres" : ""), pool_out ? (out ? " +pool" : " pool-only") : (up2 ? " +up2" : ""), p.strips, p.kw == 32 ? " K32" : "");
   ol->push(nm, fl, [plan](cudaStream_t st) { return conv_launch(plan, st); });
   return true;
 }

@@ -33,6 +33,8 @@ struct ConvParams {
   int relu;
   __half* out;        // full-resolution fp16 NHWC store (nullptr: skip)
   long long out_sb, out_sy, out_sx;
+  int up2;            // 1: `out` is the nearest-neighbour 2x up-sampled map (G2 hourglass decoder, Resize nodes before the `deconv` convs): pixel (y, x)
+                      // is stored at (2y, 2x), (2y, 2x+1), (2y+1, 2x), (2y+1, 2x+1); strides are those of the up-sampled buffer (32-byte aligned rows of 16 channels)
   __half* pool_out;   // fused 2x2/2 max-pool store (nullptr: skip)
   long long pool_sb, pool_sy, pool_sx;
   long long* trace;   // authoring aid (airfe_debug_conv_trace): CTA 0 writes clock64 stamps of its first 64 tiles, 8 slots per tile
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
       const int x = (tx * STRIPS + s_mine) * 8 + lx;
       const bool valid = (x < p.W) && (y < p.H);
       const int n0 = nt * p.block_n;
-      __half* o_full = p.out ? p.out + (long long)tz * p.out_sb + (long long)y * p.out_sy + (long long)x * p.out_sx : nullptr;
+      __half* o_full = p.out ? p.out + (long long)tz * p.out_sb + (long long)(y << p.up2) * p.out_sy + (long long)(x << p.up2) * p.out_sx : nullptr;
       __half* o_pool = p.pool_out ? p.pool_out + (long long)tz * p.pool_sb + (long long)(y >> 1) * p.pool_sy + (long long)(x >> 1) * p.pool_sx : nullptr;
       const bool pool_lane = valid && !(lane & 1) && !(lane & 8);
       const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9) && t / (int)gridDim.x < 64;
@@ -312,6 +314,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
             if (nbase + 16 <= p.n_valid) {
               if ((reinterpret_cast<uintptr_t>(o) & 31) == 0) {
                 ptx::st_global_256(o, h);
+                if (p.up2) {     // fused nearest 2x up-sampling (the host admits only whole, 32-byte aligned chunks): the other three copies of this pixel
+                  ptx::st_global_256(o + p.out_sx, h);
+                  ptx::st_global_256(o + p.out_sy, h);
+                  ptx::st_global_256(o + p.out_sy + p.out_sx, h);
+                }
               } else {
                 *reinterpret_cast<uint4*>(o) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4*>(o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
