@@ -105,9 +105,6 @@ bool Detector::init(const DetectorConfig& cfg, const std::string& wdir, bool use
       if (!pack_dense(wf, a, 256, ar, &heads0_) || !pack_dense(wf, c, 320, ar, &heads2_)) return false;
     }
     if (!pack_dense(wf, {{L + "fc3.weight", L + "fc3.bias", 0}, {L + "fc4.weight", L + "fc4.bias", 0}}, 256, ar, &fc34_)) return false;
-    // fc1 (LOI features, 128) | fc3 (thin, 4) | fc4 (aux, 4) read the same fc2 map: one 256 -> 136 GEMM reads it once (AIRFE_FC134_MERGE=0: two GEMMs, A/B timing)
-    fc134_merged_ = !(getenv("AIRFE_FC134_MERGE") && atoi(getenv("AIRFE_FC134_MERGE")) == 0);
-    if (fc134_merged_ && !pack_dense(wf, {{L + "fc1.weight", L + "fc1.bias", 0}, {L + "fc3.weight", L + "fc3.bias", 0}, {L + "fc4.weight", L + "fc4.bias", 0}}, 256, ar, &fc134_)) return false;
     // stage 1 (G3) MLP
     auto p1 = [&](const std::string& name, int cin, DenseW* out) { return pack_dense(wf, {{L + "s1." + name + ".weight", L + "s1." + name + ".bias", 0}}, cin, ar, out); };
     if (!p1("fc2.0", 496, &s1_fc0_) || !p1("fc2.2", 128, &s1_fc2_) || !p1("fc2.4", 128, &s1_fc4_) || !p1("fc2_res.0", 240, &s1_res_)) return false;
@@ -147,16 +144,11 @@ bool Detector::init(const DetectorConfig& cfg, const std::string& wdir, bool use
     fc2_o_ = make_act(ar, B, 128, 128, 256);
     hmid_o_ = make_act(ar, B, 128, 128, 320);
     heads9_o_ = make_act(ar, B, 128, 128, 16, true);
-    if (fc134_merged_) {
-      // [loi 128 | thin 4 | aux 4 | 8 GEMM padding columns] fp32 with a pixel stride of 160 floats: every pixel's LOI row starts on a 128-byte
-      // line (with the dense stride of 144 the LOI sampler touched 5 lines per pixel instead of 4 and ran 17 % slower)
-      lt_o_ = make_act(ar, B, 128, 128, 144, true, 160);
-      loi_o_ = lt_o_.slice(0, 128);
-      thinaux_o_ = lt_o_.slice(128, 8);
-    } else {
-      loi_o_ = make_act(ar, B, 128, 128, 128, true);
-      thinaux_o_ = make_act(ar, B, 128, 128, 8, true);
-    }
+    // fc1 (LOI features) and fc3 | fc4 (thin / aux) stay two GEMMs over the fc2 map: one merged 256 -> 136 GEMM was measured in round 2
+    // (profiles/r02e_fc134_merge_ab.txt) -- it saves a read of the fc2 map (0.41 -> 0.32 ms) but leaves thin / aux strided by the LOI row, and the
+    // LOI sampler's 240 scattered 16-byte loads per line then touch 640-byte-strided pixels instead of a compact 32-byte-per-pixel map (+0.07 .. 0.10 ms).
+    loi_o_ = make_act(ar, B, 128, 128, 128, true);
+    thinaux_o_ = make_act(ar, B, 128, 128, 8, true);
     lines_pred_ = ar->alloc_n<float>((size_t)B * kProp * 4);
     jloc_ = ar->alloc_n<float>((size_t)B * 16384);
     juncs_ = ar->alloc_n<float>((size_t)B * kJunc * 2);
@@ -198,8 +190,8 @@ bool Detector::init(const DetectorConfig& cfg, const std::string& wdir, bool use
     taps["stack1_out"] = {hgb_[0].u[3].p, (size_t)16384 * 128 * 2};
     taps["fc2"] = {fc2_o_.p, (size_t)16384 * 256 * 2};
     taps["heads9"] = {heads9_o_.p, (size_t)16384 * 16 * 4};
-    if (fc134_merged_) taps["loi_thinaux"] = {lt_o_.p, (size_t)16384 * 160 * 4};
-    else { taps["loi"] = {loi_o_.p, (size_t)16384 * 128 * 4}; taps["thinaux"] = {thinaux_o_.p, (size_t)16384 * 8 * 4}; }
+    taps["loi"] = {loi_o_.p, (size_t)16384 * 128 * 4};
+    taps["thinaux"] = {thinaux_o_.p, (size_t)16384 * 8 * 4};
     taps["lines_pred"] = {lines_pred_, (size_t)kProp * 4 * 4};
     taps["jloc"] = {jloc_, 16384 * 4};
     taps["juncs_pred"] = {juncs_, kJunc * 2 * 4};
@@ -297,8 +289,8 @@ bool Detector::build_ops(int B) {
     if (!add_dense(&l, x, fc2_, fc2_o_, B, false)) return false;                 // no ReLU after fc2 (graph)
     if (!add_conv3x3(&l, fc2_o_, heads0_, &hmid_o_, nullptr, B, true)) return false;   // 5 x (3x3 256->64) + ReLU
     if (!add_dense(&l, hmid_o_, heads2_, heads9_o_, B, false, 9, 16)) return false;
-    if (fc134_merged_) { if (!add_dense(&l, fc2_o_, fc134_, lt_o_, B, false, 136, 144)) return false; }
-    else if (!add_dense(&l, fc2_o_, fc1_, loi_o_, B, false) || !add_dense(&l, fc2_o_, fc34_, thinaux_o_, B, false, 8, 16)) return false;
+    if (!add_dense(&l, fc2_o_, fc1_, loi_o_, B, false)) return false;
+    if (!add_dense(&l, fc2_o_, fc34_, thinaux_o_, B, false, 8, 16)) return false;
     line_ops_[B] = std::move(l);
     OpList m;
     m.dyn_kind = kDynLines;

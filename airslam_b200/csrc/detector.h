@@ -64,8 +64,8 @@ class Detector {
   __half* w_conv1a_ = nullptr; float* b_conv1a_ = nullptr;
   DenseW w1b_, w2a_, w2b_, w3a_, w3b_, w4a_, w4b_, wPD_, wPb_, wDb_;
   // line branch
-  DenseW l1a_, l1b_, l2a_, l2b_, fc2_, heads0_, heads2_, fc1_, fc34_, fc134_;
-  bool fc134_merged_ = true, fuse_up_ = true;
+  DenseW l1a_, l1b_, l2a_, l2b_, fc2_, heads0_, heads2_, fc1_, fc34_;
+  bool fuse_up_ = true;
   struct HG { DenseW c[5][2], dec[4], aup[4], bup[4]; } hg_[2];
   DenseW s1_fc0_, s1_fc2_, s1_fc4_, s1_res_;
   float* s1_head_w_ = nullptr;  // [2][128] fp32
@@ -79,7 +79,7 @@ class Detector {
   uint8_t *mask_a_ = nullptr, *mask_b_ = nullptr;
   int *cand_ = nullptr, *cand_count_ = nullptr;
   // line buffers
-  Act l1a_o_, l1b_o_, l2a_o_, l2b_o_, fc2_o_, hmid_o_, heads9_o_, loi_o_, thinaux_o_, lt_o_;
+  Act l1a_o_, l1b_o_, l2a_o_, l2b_o_, fc2_o_, hmid_o_, heads9_o_, loi_o_, thinaux_o_;
   struct HGBuf { Act a[5], r[5], pool[4], up[4], cat[4], u[4]; } hgb_[2];
   float *lines_pred_ = nullptr, *juncs_ = nullptr, *jloc_ = nullptr;
   int *imin_ = nullptr, *imax_ = nullptr, *pair_table_ = nullptr, *uid_pairs_ = nullptr, *uid_first_ = nullptr, *n_unique_ = nullptr;

@@ -9,8 +9,6 @@ Discrete stages (NMS, top-k, association, unique pairs, line acceptance) are com
 stage applied to the GPU's own upstream tensor; dense stages are compared with the precision-matched ("emul":
 fp16 operands, fp32 accumulate) oracle within the tolerances written below.  End-to-end agreement with the pure
 oracle is reported as set overlap (SURVEY.md §8c tolerance statement)."""
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -146,12 +144,8 @@ def test_plnet_stages(ctx, images):
         heads9 = ctx.debug_read(N, "heads9", i, np.float32, (128, 128, 16))[..., :9]
         h_o = keep["heads9"][0].numpy().transpose(1, 2, 0)
         P.check("G2.heads9 (74 convs)", _rel(heads9, h_o), 5e-3, "rel. to activation scale")
-        if os.environ.get("AIRFE_FC134_MERGE", "1") != "0":      # fc1 | fc3 | fc4 run as one 256 -> 136 GEMM: one fp32 map, pixel stride 160
-            lt = ctx.debug_read(N, "loi_thinaux", i, np.float32, (128, 128, 160))
-            loi, ta = lt[..., :128], lt[..., 128:136]
-        else:
-            loi = ctx.debug_read(N, "loi", i, np.float32, (128, 128, 128))
-            ta = ctx.debug_read(N, "thinaux", i, np.float32, (128, 128, 8))
+        loi = ctx.debug_read(N, "loi", i, np.float32, (128, 128, 128))
+        ta = ctx.debug_read(N, "thinaux", i, np.float32, (128, 128, 8))
         P.check("G2.loi_features", _rel(loi, o["loi_features"][0].numpy().transpose(1, 2, 0)), 2e-3, "rel. to activation scale")
         ta_o = np.concatenate([o["loi_features_thin"][0].numpy(), o["loi_features_aux"][0].numpy()]).transpose(1, 2, 0)
         P.check("G2.thin/aux", _rel(ta, ta_o), 1.5e-3, "rel. to activation scale")
