@@ -11,6 +11,7 @@ namespace airfe {
 struct ConvPlan {
   ConvParams p;
   int grid = 0, smem_bytes = 0;
+  int wide = 0;       // nine-tap halo kernel with 16 epilogue warps (EW = 4)
 };
 
 static int sm_count() { return device_sm_count(); }
@@ -20,13 +21,13 @@ void conv3x3_set_trace(long long* dev_buf) { g_conv_trace = dev_buf; }
 
 using ConvKernel = void (*)(const ConvParams);
 
-static int conv_key(const ConvParams& p) {
+static int conv_key(const ConvParams& p, int wide) {
   if (p.fold == 2 && p.kblocks == 2) return 16;
   if (p.fold) return 8 + (p.fold == 2 ? 4 : 0) + (p.kw == 32 ? 2 : 0) + (p.block_n == 64 ? 1 : 0);
-  return (p.kw == 32 ? 4 : 0) | (p.strips == 2 ? 2 : 0) | (p.b_resident ? 1 : 0);
+  return (wide ? 17 : 0) + ((p.kw == 32 ? 4 : 0) | (p.strips == 2 ? 2 : 0) | (p.b_resident ? 1 : 0));
 }
 
-static ConvKernel conv_kernel_for(const ConvParams& p) {
+static ConvKernel conv_kernel_for(const ConvParams& p, int wide) {
   if (p.fold == 2 && p.kblocks == 2) return tc_conv3x3_fold_kernel<64, 32, true, 1, 2>;
   if (p.fold == 2) {
     if (p.kw == 64) return p.block_n == 64 ? tc_conv3x3_fold_kernel<64, 64, true> : tc_conv3x3_fold_kernel<64, 32, true>;
@@ -37,6 +38,18 @@ static ConvKernel conv_kernel_for(const ConvParams& p) {
     return p.block_n == 64 ? tc_conv3x3_fold_kernel<32, 64, false> : tc_conv3x3_fold_kernel<32, 32, false>;
   }
   const int key = (p.kw == 32 ? 4 : 0) | (p.strips == 2 ? 2 : 0) | (p.b_resident ? 1 : 0);
+  if (wide) {
+    switch (key) {
+      case 0: return tc_conv3x3_kernel<64, 1, false, 4>;
+      case 1: return tc_conv3x3_kernel<64, 1, true, 4>;
+      case 2: return tc_conv3x3_kernel<64, 2, false, 4>;
+      case 3: return tc_conv3x3_kernel<64, 2, true, 4>;
+      case 4: return tc_conv3x3_kernel<32, 1, false, 4>;
+      case 5: return tc_conv3x3_kernel<32, 1, true, 4>;
+      case 6: return tc_conv3x3_kernel<32, 2, false, 4>;
+      default: return tc_conv3x3_kernel<32, 2, true, 4>;
+    }
+  }
   switch (key) {
     case 0: return tc_conv3x3_kernel<64, 1, false>;
     case 1: return tc_conv3x3_kernel<64, 1, true>;
@@ -50,11 +63,11 @@ static ConvKernel conv_kernel_for(const ConvParams& p) {
 }
 
 static bool conv_launch(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set[kMaxDevices][17] = {};
+  static bool attr_set[kMaxDevices][25] = {};
   const int dev = current_device();
-  const int key = conv_key(plan.p);
-  const int threads = plan.p.fold == 2 ? kFoldWideThreads : kConvThreads;
-  ConvKernel kern = conv_kernel_for(plan.p);
+  const int key = conv_key(plan.p, plan.wide);
+  const int threads = plan.p.fold == 2 ? kFoldWideThreads : (plan.wide ? kConvWideThreads : kConvThreads);
+  ConvKernel kern = conv_kernel_for(plan.p, plan.wide);
   if (!attr_set[dev][key]) {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, kern);
@@ -209,6 +222,11 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
     if (!make_tmap_f16(&p.tmB, w.w, 4, bd, bs, bb, p.kw * 2)) return false;
   }
   if (!p.fold) {
+    // 16 epilogue warps (EW = 4).  Measured per layer on the B200 (profiles/r02e_wide_epilogue_ab.txt): -4 % on conv1b (64->64 + pool on the
+    // 512 x 512 map: the epilogue moves two full-resolution maps), +0 .. 3 % (slower) on every other nine-tap layer -> default: full-resolution maps
+    // only.  AIRFE_CONV_WIDE_MAXN=n overrides: every layer with block_n <= n (0: never).  The choice depends on the layer only, never on the batch.
+    if (getenv("AIRFE_CONV_WIDE_MAXN")) plan.wide = block_n <= atoi(getenv("AIRFE_CONV_WIDE_MAXN")) ? 1 : 0;
+    else plan.wide = (in.W >= 512 && in.H >= 512) ? 1 : 0;
     const int n_b_slots = p.b_resident ? 9 * p.kblocks : p.stages_b;
     plan.smem_bytes = p.stages_a * a_bytes + n_b_slots * b_bytes + 1024 + (2 * p.stages_a + 2 * (p.b_resident ? 1 : p.stages_b) + 8) * 8 + 16;
     const int total = p.tiles_x * p.tiles_y * batch * p.n_tiles;
@@ -219,7 +237,7 @@ bool add_conv3x3(OpList* ol, const Act& in, const DenseW& w, const Act* out, con
   ol->tc_flops += fl;
   ol->launches += 1;
   char nm[160];
-  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d%s", w.c_in, n_valid, in.W, in.H, batch, p.fold ? (p.kblocks == 2 ? " Bres kx-fold 2xN32" : " Bres kx-fold") : (p.b_resident ? " Bres" : ""), pool_out ? (out ? " +pool" : " pool-only") : (up2 ? " +up2" : ""), p.strips, p.kw == 32 ? " K32" : "");
+  snprintf(nm, sizeof(nm), "tc_conv3x3 %d->%d @%dx%dx%d%s%s S%d%s", w.c_in, n_valid, in.W, in.H, batch, p.fold ? (p.kblocks == 2 ? " Bres kx-fold 2xN32" : " Bres kx-fold") : (p.b_resident ? " Bres" : ""), pool_out ? (out ? " +pool" : " pool-only") : (up2 ? " +up2" : ""), p.strips, p.kw == 32 ? (plan.wide ? " K32 W16" : " K32") : (plan.wide ? " W16" : ""));
   ol->push(nm, fl, [plan](cudaStream_t st) { return conv_launch(plan, st); });
   return true;
 }

@@ -41,6 +41,7 @@ struct ConvParams {
 };
 
 constexpr int kConvThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int kConvWideThreads = 576;   // EW = 4: warps 2-17 epilogue (four per TMEM lane quarter = 4.5 warps per scheduler instead of 2.5)
 constexpr int kConvTH = 16;
 
 __host__ __device__ constexpr int conv_a_bytes(int strips, int kw = 64) { return ((8 * strips + 2) * (kConvTH + 2) * kw * 2 + 1023) / 1024 * 1024; }
@@ -60,8 +61,12 @@ __host__ __device__ inline int conv_tmem_cols(int block_n, int strips) {
 // (tools/trace_conv.py, profiles/r01_conv_trace.txt) the runtime-generic loop spent ~550 cycles of uniform-datapath
 // instructions per tap, i.e. the single issuing warp -- not the tensor pipe (48 cycles per 128x64x16 MMA in SS mode,
 // tools/probe_mma_rate.cu) -- bounded every small-N layer.
-template <int KW, int STRIPS, bool BRES>
-__global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __grid_constant__ ConvParams p) {
+// EW = epilogue warps per TMEM lane quarter (2 or 4).  The epilogue of the small-N / memory-heavy layers is latency-bound with two warps per
+// scheduler (ncu: 65 % of the cycles no warp eligible, stalls = fixed-latency waits + shared-memory scoreboard); EW = 4 doubles the warps
+// that hide each other's latencies at the same per-element arithmetic (results are bit-identical: a chunk of 16 channels of one pixel is
+// always processed by one thread, only the assignment of chunks / strips to warps changes).
+template <int KW, int STRIPS, bool BRES, int EW = 2>
+__global__ void __launch_bounds__(64 + 128 * EW, 1) tc_conv3x3_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int a_bytes = conv_a_bytes(STRIPS, KW);
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
     for (int s = 0; s < p.stages_a; ++s) { ptx::mbar_init(&full_a[s], 1); ptx::mbar_init(&empty_a[s], 1); }
     const int nb = BRES ? 1 : p.stages_b;
     for (int s = 0; s < nb; ++s) { ptx::mbar_init(&full_b[s], 1); ptx::mbar_init(&empty_b[s], 1); }
-    for (int s = 0; s < 4; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < 4; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4 * EW); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) { ptx::tmem_alloc(tmem_slot, tmem_cols); ptx::tmem_relinquish(); }
@@ -260,14 +265,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
     }
     }
   } else {
-    // ===== epilogue: 8 warps; warp (2 + e) owns TMEM lane quarter (warp & 3) and half of the work (strip, or column half) =====
+    // ===== epilogue: 4 * EW warps; warp (2 + e) owns TMEM lane quarter (warp & 3) and one part of the work (strip x column part) =====
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;                             // 0 .. EW - 1
     const int lx = lane & 7, ly = quarter * 4 + (lane >> 3);      // pixel of this lane inside an 8 x 16 strip
     const int chunks = p.block_n / 16;
-    const int s_mine = (STRIPS == 2) ? half : 0;
-    const int c_begin = (STRIPS == 2) ? 0 : (half ? (chunks + 1) / 2 : 0);
-    const int c_end = (STRIPS == 2) ? chunks : (half ? chunks : (chunks + 1) / 2);
+    constexpr int CP = (STRIPS == 2) ? EW / 2 : EW;               // column parts per strip
+    const int s_mine = (STRIPS == 2) ? (part & 1) : 0;
+    const int cpart = (STRIPS == 2) ? (part >> 1) : part;
+    const int c_begin = (chunks * cpart + CP - 1) / CP;
+    const int c_end = (chunks * (cpart + 1) + CP - 1) / CP;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv3x3_kernel(const __gri
       __half* o_full = p.out ? p.out + (long long)tz * p.out_sb + (long long)(y << p.up2) * p.out_sy + (long long)(x << p.up2) * p.out_sx : nullptr;
       __half* o_pool = p.pool_out ? p.pool_out + (long long)tz * p.pool_sb + (long long)(y >> 1) * p.pool_sy + (long long)(x >> 1) * p.pool_sx : nullptr;
       const bool pool_lane = valid && !(lane & 1) && !(lane & 8);
-      const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 9) && t / (int)gridDim.x < 64;
+      const bool tr = p.trace && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 1 + 4 * EW) && t / (int)gridDim.x < 64;
       long long* trp = tr ? p.trace + (t / gridDim.x) * 8 + (warp == 2 ? 4 : 6) : nullptr;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();

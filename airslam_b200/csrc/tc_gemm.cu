@@ -121,7 +121,13 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
   static const int tma_store_on = getenv("AIRFE_GEMM_TMA_STORE") ? atoi(getenv("AIRFE_GEMM_TMA_STORE")) : 0;
   auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
   p.tma_store = 0;
-  if (tma_store_on && !d.out_f32 && !d.resid && !d.out2 && d.block_n % 128 == 0 && pow2(d.tw) && pow2(d.th) && pow2(d.tb) && ((uintptr_t)d.out & 15) == 0 &&
+  // 16 epilogue warps (EW = 4).  Measured per GEMM on the B200 (profiles/r02e_wide_epilogue_ab.txt): -14 % on the 128->256 1x1 conv (N tile of 256
+  // columns), -8 % on Wqkv + fused rotary (the rotary table loads are what the two-warp epilogue waits for), neutral on the other N = 128 row GEMMs,
+  // +7 .. 18 % (slower) on narrow N tiles and on the G3 MLP -> default: N tiles of 256 columns and the rotary GEMMs.
+  // AIRFE_GEMM_WIDE=0 never, =1 every GEMM (tests, A/B).  The choice depends on the GEMM's shape only, never on the batch.
+  const int wide_mode = getenv("AIRFE_GEMM_WIDE") ? atoi(getenv("AIRFE_GEMM_WIDE")) : -1;
+  p.wide = wide_mode >= 0 ? (wide_mode == 1 ? 1 : 0) : ((d.rot || d.block_n >= 256) ? 1 : 0);
+  if (!p.wide && tma_store_on && !d.out_f32 && !d.resid && !d.out2 && d.block_n % 128 == 0 && pow2(d.tw) && pow2(d.th) && pow2(d.tb) && ((uintptr_t)d.out & 15) == 0 &&
       d.out_sx % 8 == 0 && (d.H == 1 || d.out_sy % 8 == 0) && (d.B == 1 || d.out_sb % 8 == 0) && (!d.out_split || (d.out_split % 64 == 0 && d.out_split_stride % 8 == 0))) {
     const int bw = d.tw < 32 ? d.tw : 32, bh = d.th < 32 / bw ? d.th : 32 / bw, bbx = 32 / (bw * bh);
     if (bbx <= d.tb) {
@@ -165,10 +171,12 @@ bool tc_gemm_plan(const TcGemmDesc& d, TcGemmPlan* plan) {
 using TcKernel = void (*)(const TcGemmParams);
 
 bool tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream) {
-  static bool attr_set[kMaxDevices][4] = {};
+  static bool attr_set[kMaxDevices][8] = {};
   const int dev = current_device();
-  const int key = (plan.p.b_mn_major ? 2 : 0) | (plan.p.b_resident ? 1 : 0);
-  TcKernel kern = key == 0 ? tc_gemm_kernel<false, false> : key == 1 ? tc_gemm_kernel<false, true> : key == 2 ? tc_gemm_kernel<true, false> : tc_gemm_kernel<true, true>;
+  const int key = (plan.p.wide ? 4 : 0) | (plan.p.b_mn_major ? 2 : 0) | (plan.p.b_resident ? 1 : 0);
+  static const TcKernel kerns[8] = {tc_gemm_kernel<false, false>, tc_gemm_kernel<false, true>, tc_gemm_kernel<true, false>, tc_gemm_kernel<true, true>,
+                                    tc_gemm_kernel<false, false, 4>, tc_gemm_kernel<false, true, 4>, tc_gemm_kernel<true, false, 4>, tc_gemm_kernel<true, true, 4>};
+  TcKernel kern = kerns[key];
   if (!attr_set[dev][key]) {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, kern);
@@ -179,7 +187,7 @@ bool tc_gemm_launch(const TcGemmPlan& plan, cudaStream_t stream) {
     attr_set[dev][key] = true;
   }
   if (plan.grid <= 0) return true;
-  cudaError_t e = launch_pdl(kern, plan.grid, kTcThreads, plan.smem_bytes, stream, plan.p);
+  cudaError_t e = launch_pdl(kern, plan.grid, plan.p.wide ? kTcWideThreads : kTcThreads, plan.smem_bytes, stream, plan.p);
   if (e != cudaSuccess) {
     set_error("tc_gemm launch failed: %s", cudaGetErrorString(e));
     return false;

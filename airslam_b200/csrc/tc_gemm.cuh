@@ -21,8 +21,12 @@
 
 namespace airfe {
 
-template <bool MN_MAJOR, bool BRES>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
+// EW = epilogue warps per TMEM lane quarter (2 or 4): the epilogue is latency-bound with two warps per scheduler (ncu of the Wqkv GEMM: 68 %
+// of the cycles no warp eligible; long-scoreboard waits on the rotary table and fixed-latency waits) -- EW = 4 gives each scheduler four
+// epilogue warps.  Per-element arithmetic and therefore results are identical; only the assignment of 16-column chunks to warps changes.
+// The TMA-store epilogue (off by default) exists for EW = 2 only.
+template <bool MN_MAJOR, bool BRES, int EW = 2>
+__global__ void __launch_bounds__(64 + 128 * EW, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A | B)] | barriers | tmem slot
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -56,7 +60,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 8);
+      ptx::mbar_init(&tmem_empty[s], 4 * EW);
     }
     ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
@@ -187,14 +191,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
   } else {
     // ===== epilogue: TMEM -> registers -> (+bias, ReLU) -> global =====
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;
+    constexpr int NBUF = EW == 2 ? 2 : 1;                         // register sets for the chunk pipeline
+    const int part = (warp - 2) >> 2;                             // 0 .. EW - 1: this warp's share of the tile's columns
     const int chunks = p.block_n / 16;
-    const int c_begin = half ? (chunks + 1) / 2 : 0, c_end = half ? chunks : (chunks + 1) / 2;
+    const int c_begin = (chunks * part + EW - 1) / EW, c_end = (chunks * (part + 1) + EW - 1) / EW;
     const int row = quarter * 32 + lane;
     // tma_store: this warp's 32 rows x 64 columns go through its own 4 KiB staging tile (row = lane, 128 bytes, 16-byte pieces XOR-swizzled
     // like SWIZZLE_128B so that the 32 lanes' 16-byte writes spread over all banks) and leave with ONE cp.async.bulk.tensor store per 64
     // columns: full 128-byte lines instead of 32 scattered 32-byte segments per STG.256 (the LSU data pipe was 42 % busy with those).
-    uint8_t* stg = smem_store + (warp - 2) * 4096;
+    uint8_t* stg = smem_store + ((warp - 2) & 7) * 4096;          // (tma_store is planned for EW = 2 only)
     const int r0w = quarter * 32;                                       // first tile row of this warp
     const int bx = r0w % p.tw, by = (r0w / p.tw) % p.th, bb = r0w / (p.tw * p.th);
     bool store_pending = false;
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       // fused rotary embedding: the cos / sin values of this keypoint for chunk cc + 1 are fetched while chunk cc is processed, the first
       // chunk's before the accumulator wait (ncu source view of the Wqkv GEMM: 30 % of the warp samples sat on the first FMUL after these
       // loads when they were issued at the point of use)
-      float4 rv[2][4];
+      float4 rv[NBUF][4];
       const float* rot_row = p.rot ? p.rot + ((long long)b * p.W + x) * 64 : nullptr;
       auto rot_fetch = [&](float4 (&dst)[4], int nb) {
         if (rot_row && valid && nb < p.rot_cols) {
@@ -230,17 +235,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * acc_stride + (uint32_t(quarter * 32) << 16);
-      uint32_t rr[2][16];
-      if (c_begin < c_end) ptx::tmem_ld16(taddr + c_begin * 16, rr[0]);
-#pragma unroll 1
-      for (int cq = c_begin; cq < c_end; cq += 2)
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (cq + u >= c_end) break;
-        const int c = (cq + u) * 16;
-        ptx::tmem_ld_wait();
-        if (cq + u + 1 < c_end) { ptx::tmem_ld16(taddr + c + 16, rr[u ^ 1]); rot_fetch(rv[u ^ 1], n0 + c + 16); }
-        const uint32_t (&r)[16] = rr[u];
+      uint32_t rr[NBUF][16];
+      // one 16-column chunk of this thread's row: accumulators r, rotary values rvu (fetched ahead), first column c of the tile
+      auto do_chunk = [&](const uint32_t (&r)[16], const float4 (&rvu)[4], const int c) {
         float v[16];
         float bsm[16];
         {
@@ -262,7 +259,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
           // rot[row][2j] = cos, rot[row][2j+1] = sin  (lg_prepare_kernel), rows are (b, x) of the H == 1 layout
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 cs = rv[u][i];
+            const float4 cs = rvu[i];
             const float a0 = v[4 * i], a1 = v[4 * i + 1], a2 = v[4 * i + 2], a3 = v[4 * i + 3];
             v[4 * i] = a0 * cs.x - a1 * cs.y;     v[4 * i + 1] = a1 * cs.x + a0 * cs.y;
             v[4 * i + 2] = a2 * cs.z - a3 * cs.w; v[4 * i + 3] = a3 * cs.z + a2 * cs.w;
@@ -339,7 +336,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
         if (p.tma_store) {
           // every lane stages its 16 values (rows beyond the valid extent as zeros: their positions inside the tensor may be read as padding
           // rows of a later tile, and must stay finite), the group of four chunks = 64 columns leaves as one box
-          const int cg = (cq + u - c_begin) & 3;
+          const int cg = ((c >> 4) - c_begin) & 3;
           if (cg == 0) {
             if (store_pending) { if (lane == 0) ptx::tma_store_wait_read(); store_pending = false; }
             __syncwarp();
@@ -364,6 +361,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_kernel(const __grid_con
             }
             store_pending = true;
           }
+        }
+      };
+      if constexpr (NBUF == 2) {
+        // EW = 2: the TMEM load and the rotary values of chunk cc + 1 are in flight while chunk cc is processed
+        if (c_begin < c_end) ptx::tmem_ld16(taddr + c_begin * 16, rr[0]);
+#pragma unroll 1
+        for (int cq = c_begin; cq < c_end; cq += 2)
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (cq + u >= c_end) break;
+            const int c = (cq + u) * 16;
+            ptx::tmem_ld_wait();
+            if (cq + u + 1 < c_end) { ptx::tmem_ld16(taddr + c + 16, rr[u ^ 1]); rot_fetch(rv[u ^ 1], n0 + c + 16); }
+            do_chunk(rr[u], rv[u], c);
+          }
+      } else {
+        // EW = 4: single-buffered (112 registers per thread at 576 threads); four warps per scheduler hide the load latencies instead
+#pragma unroll 1
+        for (int cc = c_begin; cc < c_end; ++cc) {
+          const int c = cc * 16;
+          if (cc != c_begin) rot_fetch(rv[0], n0 + c);
+          ptx::tmem_ld16(taddr + c, rr[0]);
+          ptx::tmem_ld_wait();
+          do_chunk(rr[0], rv[0], c);
         }
       }
       ptx::tc_fence_before();

@@ -37,12 +37,14 @@ struct TcGemmParams {
   int stages;
   int prewait;      // MMA issuer polls the barriers of unit u + 1 before it issues unit u (see tc_gemm.cuh); 0 with AIRFE_PREWAIT=1 switches it on
   int tma_store;    // epilogue stages fp16 tiles in shared memory and stores them with cp.async.bulk.tensor (plain fp16 outputs with block_n % 128 == 0)
+  int wide;         // host only: launch the EW = 4 instantiation (16 epilogue warps)
   int b_resident;   // whole [block_n x K] weight panel of this CTA's (fixed) N tile stays in shared memory; the ring then holds A only
   int dyn_w_stride; // index = tile batch * dyn_w_stride
   const int* dyn_w;  // optional: per-batch-index valid W (rows of a plain GEMM), read from device memory (tb must be 1)
 };
 
 constexpr int kTcThreads = 320;   // warp0 TMA, warp1 MMA, warps 2-9 epilogue (two per TMEM lane quarter, splitting the columns)
+constexpr int kTcWideThreads = 576;   // EW = 4: warps 2-17 epilogue
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
