@@ -110,7 +110,6 @@ void launch_remap_u8(const uint8_t* src, int w, int h, int stride, long long img
 // adjacent output channels.  That halves the issue slots and leaves the kernel bound by the FMA pipe rather than by instruction issue.
 // Thread = (8 pixels along x, group of 8 output channels): consecutive threads write consecutive 16-byte vectors of one pixel.
 // =====================================================================================================================
-constexpr int kC1Px = 8;
 constexpr int kC1Rows = 8;   // image rows per block
 __device__ __forceinline__ unsigned long long ffma2_(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long d;
@@ -120,8 +119,12 @@ __device__ __forceinline__ unsigned long long ffma2_(unsigned long long a, unsig
 __device__ __forceinline__ unsigned long long pack2_(float lo, float hi) {
   return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
-__global__ void __launch_bounds__(128, 3) conv1a_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
-                                                     __half* __restrict__ out, int H, int W, long long total) {
+// PX = pixels along x per thread (8 or 4).  PX = 8 needs 166 registers (three CTAs = 12 warps per SM); PX = 4 halves the per-thread tile
+// (in2 / packed) so that more warps are resident -- the kernel sits at ~2x its FMA floor with 12 warps.  Per output the arithmetic (bias, then the
+// nine taps in ky, kx order) is identical for both: results are bit-identical.
+template <int PX>
+__global__ void __launch_bounds__(128, PX == 8 ? 3 : 4) conv1a_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
+                                                                      __half* __restrict__ out, int H, int W, long long total) {
   __shared__ float2 sw2[8 * 4 * 9];   // [channel group][channel pair][tap] = (w of channel 2p, w of channel 2p+1)
   __shared__ float2 sb2[32];
   for (int i = threadIdx.x; i < 288; i += blockDim.x) {
@@ -130,32 +133,33 @@ __global__ void __launch_bounds__(128, 3) conv1a_kernel(const __half* __restrict
   }
   if (threadIdx.x < 32) sb2[threadIdx.x] = make_float2(bias[2 * threadIdx.x], bias[2 * threadIdx.x + 1]);
   __syncthreads();
-  // grid = (threads along a row / 256, H / kC1Rows, batch): no integer divisions on the index path.  A block walks kC1Rows consecutive image
+  // grid = (threads along a row / 128, H / kC1Rows, batch): no integer divisions on the index path.  A block walks kC1Rows consecutive image
   // rows: the weight staging above and the block launch are paid once per 8 rows instead of once per row (they were ~25 % of a one-row
   // block's life), and the three input rows slide through registers, so each input row is loaded once instead of three times.
   const int tix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tix >= W) return;                            // W / 8 pixel groups x 8 channel groups = W threads per row
+  if (tix >= W / PX * 8) return;                   // W / PX pixel groups x 8 channel groups threads per row
   const int cg = tix & 7;
-  const int x0 = (tix >> 3) * kC1Px;
+  const int x0 = (tix >> 3) * PX;
   const int y_begin = blockIdx.y * kC1Rows;
   const long long img = blockIdx.z;
   const __half* xi = x + img * (long long)W * H;
-  // inputs: per row one aligned 16-byte vector (x0 is a multiple of 8) plus the two halo pixels; each value duplicated into a float2
-  unsigned long long in2[3][kC1Px + 2];
-  auto load_row = [&](unsigned long long (&dst)[kC1Px + 2], int y2) {
+  // inputs: per row one aligned 2 * PX-byte vector (x0 is a multiple of PX) plus the two halo pixels; each value duplicated into a float2
+  unsigned long long in2[3][PX + 2];
+  auto load_row = [&](unsigned long long (&dst)[PX + 2], int y2) {
     const bool rv = (y2 >= 0) && (y2 < H);
     const __half* rp = xi + (long long)(rv ? y2 : 0) * W + x0;
-    uint4 v = *reinterpret_cast<const uint4*>(rp);
+    uint32_t v[PX / 2];
+    if constexpr (PX == 8) { const uint4 t = *reinterpret_cast<const uint4*>(rp); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else { const uint2 t = *reinterpret_cast<const uint2*>(rp); v[0] = t.x; v[1] = t.y; }
     const __half hl = (x0 > 0) ? rp[-1] : __float2half(0.f);
-    const __half hr = (x0 + kC1Px < W) ? rp[kC1Px] : __float2half(0.f);
-    if (!rv) v = make_uint4(0, 0, 0, 0);
-    const __half2* v2 = reinterpret_cast<const __half2*>(&v);
+    const __half hr = (x0 + PX < W) ? rp[PX] : __float2half(0.f);
     const float fl = rv ? __half2float(hl) : 0.f, fr = rv ? __half2float(hr) : 0.f;
     dst[0] = pack2_(fl, fl);
-    dst[kC1Px + 1] = pack2_(fr, fr);
+    dst[PX + 1] = pack2_(fr, fr);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float2 f = __half22float2(v2[q]);
+    for (int q = 0; q < PX / 2; ++q) {
+      const uint32_t vq = rv ? v[q] : 0u;
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vq));
       dst[1 + 2 * q] = pack2_(f.x, f.x);
       dst[2 + 2 * q] = pack2_(f.y, f.y);
     }
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(128, 3) conv1a_kernel(const __half* __restrict
 #pragma unroll 1
   for (int yy = y_begin; yy < y_begin + kC1Rows && yy < H; ++yy) {
     load_row(in2[2], yy + 1);
-    uint32_t packed[kC1Px][4];
+    uint32_t packed[PX][4];
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
       unsigned long long wp[9];
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(128, 3) conv1a_kernel(const __half* __restrict
       const float2 bb = sb2[cg * 4 + jp];
       const unsigned long long b2 = pack2_(bb.x, bb.y);
 #pragma unroll
-      for (int px = 0; px < kC1Px; ++px) {
+      for (int px = 0; px < PX; ++px) {
         unsigned long long acc = b2;                 // bias folded into the accumulator
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
@@ -187,15 +191,17 @@ __global__ void __launch_bounds__(128, 3) conv1a_kernel(const __half* __restrict
     }
     __half* o = out + ((img * H + yy) * (long long)W + x0) * 64 + cg * 8;
 #pragma unroll
-    for (int px = 0; px < kC1Px; ++px)
+    for (int px = 0; px < PX; ++px)
       *reinterpret_cast<uint4*>(o + (long long)px * 64) = make_uint4(packed[px][0], packed[px][1], packed[px][2], packed[px][3]);
 #pragma unroll
-    for (int j = 0; j < kC1Px + 2; ++j) { in2[0][j] = in2[1][j]; in2[1][j] = in2[2][j]; }
+    for (int j = 0; j < PX + 2; ++j) { in2[0][j] = in2[1][j]; in2[1][j] = in2[2][j]; }
   }
 }
 
 void launch_conv1a(const __half* x, const __half* w, const float* bias, __half* out, int batch, int H, int W, cudaStream_t st) {
-  conv1a_kernel<<<dim3((W + 127) / 128, (H + kC1Rows - 1) / kC1Rows, batch), 128, 0, st>>>(x, w, bias, out, H, W, 0);
+  static const int px = getenv("AIRFE_CONV1A_PX") ? atoi(getenv("AIRFE_CONV1A_PX")) : 8;     // 8 (default) or 4: A/B knob, identical results
+  if (px == 4) conv1a_kernel<4><<<dim3((W * 2 + 127) / 128, (H + kC1Rows - 1) / kC1Rows, batch), 128, 0, st>>>(x, w, bias, out, H, W, 0);
+  else conv1a_kernel<8><<<dim3((W + 127) / 128, (H + kC1Rows - 1) / kC1Rows, batch), 128, 0, st>>>(x, w, bias, out, H, W, 0);
 }
 
 // =====================================================================================================================

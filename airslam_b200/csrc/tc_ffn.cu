@@ -51,20 +51,27 @@ bool add_fused_ffn(OpList* ol, const __half* ctx16, __half* cat16, float* x, con
   const double fl = 2.0 * (double)slots * cap * (256.0 * 256 + 512.0 * 512 + 512.0 * 256);
   ol->tc_flops += fl;
   ol->launches += 1;
-  ol->push(relu ? "tc_ffn fused block (merge+mlp0+ReLU+mlp3+residual)" : "tc_ffn fused block (out_proj+ffn0+LN+GELU+ffn3+residual)", fl, [p, grid, relu](cudaStream_t st) {
-    static bool attr_set[kMaxDevices][2] = {};
+  // sixteen epilogue warps (EW = 4, tc_ffn.cuh): measured 2.14 -> 2.03 ms per 18 LightGlue launches and 0.745 -> 0.710 ms per 18 SuperGlue launches
+  // (profiles/r02e_wide_epilogue_ab.txt) -> default; AIRFE_FFN_WIDE=0 selects the eight-warp kernel (read at plan time; the choice depends on
+  // nothing else, so a pair inside a batch stays bit-identical to the same pair alone)
+  const int wide = getenv("AIRFE_FFN_WIDE") ? (atoi(getenv("AIRFE_FFN_WIDE")) ? 1 : 0) : 1;
+  ol->push(relu ? "tc_ffn fused block (merge+mlp0+ReLU+mlp3+residual)" : "tc_ffn fused block (out_proj+ffn0+LN+GELU+ffn3+residual)", fl, [p, grid, relu, wide](cudaStream_t st) {
+    static bool attr_set[kMaxDevices][4] = {};
     const int dev = current_device();
-    auto kern = relu ? tc_ffn_kernel<true> : tc_ffn_kernel<false>;
-    if (!attr_set[dev][relu]) {
+    using FfnKernel = void (*)(const FfnParams);
+    static const FfnKernel kerns[4] = {tc_ffn_kernel<false, 2>, tc_ffn_kernel<true, 2>, tc_ffn_kernel<false, 4>, tc_ffn_kernel<true, 4>};
+    const int key = (wide ? 2 : 0) | (relu ? 1 : 0);
+    FfnKernel kern = kerns[key];
+    if (!attr_set[dev][key]) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmemBytes) != cudaSuccess) {
         set_error("cudaFuncSetAttribute(tc_ffn_kernel) failed: %s", cudaGetErrorString(cudaGetLastError()));
         return false;
       }
-      attr_set[dev][relu] = true;
+      attr_set[dev][key] = true;
     }
     FfnParams pp = p;
     pp.trace = g_match_trace;                      // authoring aid, normally nullptr
-    cudaError_t e = launch_pdl(kern, grid, kFfnThreads, kFfnSmemBytes, st, pp);
+    cudaError_t e = launch_pdl(kern, grid, wide ? kFfnWideThreads : kFfnThreads, kFfnSmemBytes, st, pp);
     if (e != cudaSuccess) { set_error("tc_ffn launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
   }, kDynRows);

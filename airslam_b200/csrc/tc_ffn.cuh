@@ -29,27 +29,32 @@ struct FfnParams {
 };
 
 constexpr int kFfnThreads = 320;
-constexpr int kFfnBStages = 5;      // 16 KiB weight tiles in flight per SM (224.5 KiB of shared memory in total)
-constexpr int kFfnSmemBytes = 8 * 16384 + kFfnBStages * 16384 + (2048 + 512) * 4 + 1024 + 256;
+constexpr int kFfnWideThreads = 576;   // EW = 4: sixteen epilogue warps
+constexpr int kFfnBStages = 5;      // 16 KiB weight tiles in flight per SM (226.5 KiB of shared memory in total)
+constexpr int kFfnSmemBytes = 8 * 16384 + kFfnBStages * 16384 + (2048 + 1024) * 4 + 1024 + 256;
 
 // RELU = false: LightGlue (LayerNorm + exact GELU between the two FFN GEMMs).  RELU = true: SuperGlue's MLP([x | merge(ctx)]) = 512 -> 512
 // (BatchNorm folded into the weights) -> ReLU -> 256 with the same residual: identical GEMM shapes, a one-pass phase-2 epilogue.
-template <bool RELU>
-__global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_constant__ FfnParams p) {
+// EW = epilogue warps per TMEM lane quarter (2 or 4); a thread owns one keypoint row and 1 / EW of the columns of every phase.  The three GEMM
+// phases and their epilogues are serial per row tile (phase 2 fills all 512 TMEM columns), so during the epilogues the SM runs only these
+// warps: ncu of the EW = 2 kernel shows 2.5 warps per scheduler, 74 % of the cycles without an eligible warp and 26 % of the issue slots
+// used -- EW = 4 halves the work per thread and doubles the warps that hide each other's TMEM / global / erff latencies.
+template <bool RELU, int EW = 2>
+__global__ void __launch_bounds__(64 + 128 * EW, 1) tc_ffn_kernel(const __grid_constant__ FfnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                   // 8 K blocks of [128 rows x 64] fp16
   uint8_t* sB = sA + 8 * 16384;                         // weight ring
   float* sPar = reinterpret_cast<float*>(sB + kFfnBStages * 16384);   // b_out[256] b0[512] b3[256] g[512] beta[512]
-  float* sRed = sPar + 2048;                             // LayerNorm partials: sum[2][128], var[2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 512);
+  float* sRed = sPar + 2048;                             // LayerNorm partials: sum[EW][128], var[EW][128] (var at + 512)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 1024);
   uint64_t* b_full = bars;                              // [4]
   uint64_t* b_empty = bars + kFfnBStages;               // [4]
   uint64_t* ctx_full = bars + 2 * kFfnBStages;
   uint64_t* x_full = ctx_full + 1;
   uint64_t* a_free = ctx_full + 2;                      // all MMAs of the tile retired: A blocks may be reloaded
   uint64_t* acc_full = ctx_full + 3;                    // a GEMM phase finished: accumulators valid
-  uint64_t* epi_done = ctx_full + 4;                    // (count 8) epilogue finished with TMEM and with its smem writes
+  uint64_t* epi_done = ctx_full + 4;                    // (count 4 * EW) epilogue finished with TMEM and with its smem writes
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctx_full + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -71,7 +76,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmCtx); ptx::prefetch_tmap(&p.tmX16); ptx::prefetch_tmap(&p.tmWo); ptx::prefetch_tmap(&p.tmW0); ptx::prefetch_tmap(&p.tmW3);
     for (int i = 0; i < kFfnBStages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    ptx::mbar_init(ctx_full, 1); ptx::mbar_init(x_full, 1); ptx::mbar_init(a_free, 1); ptx::mbar_init(acc_full, 1); ptx::mbar_init(epi_done, 8);
+    ptx::mbar_init(ctx_full, 1); ptx::mbar_init(x_full, 1); ptx::mbar_init(a_free, 1); ptx::mbar_init(acc_full, 1); ptx::mbar_init(epi_done, 4 * EW);
     ptx::fence_barrier_init();
   }
   if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
@@ -166,9 +171,10 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       pt ^= 1;
     }
   } else {
-    // ===== epilogues: thread = one keypoint row x one half of the columns =====
+    // ===== epilogues: thread = one keypoint row x one part (1 / EW) of the columns =====
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;          // column part 0 .. EW - 1 (EW = 2: the low / high half)
+    constexpr int P1 = 256 / EW, P2 = 512 / EW;  // columns per thread: phases 1 and 3 (N = 256), phase 2 (N = 512)
     const int row = quarter * 32 + lane;
     const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
     uint32_t pacc = 0;
@@ -181,12 +187,12 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       ++tcount;
       const bool valid = (r0 + row) < ns;
       const long long grow = (long long)slot * p.cap + r0 + row;
-      // ---- phase 1 epilogue: msg = acc + b_out -> fp16 -> A blocks 4..7 (this warp: columns half*128 .. +128) ----
+      // ---- phase 1 epilogue: msg = acc + b_out -> fp16 -> A blocks 4..7 (this warp: columns half*P1 .. +P1) ----
       ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
       ptx::tc_fence_after();
       if (tre) tre[0] = clock64();                    // phase-1 accumulators complete
 #pragma unroll 1
-      for (int c = half * 128; c < half * 128 + 128; c += 32) {
+      for (int c = half * P1; c < half * P1 + P1; c += 32) {
         uint32_t r[32];
         ptx::tmem_ld32(trow + c, r);
         ptx::tmem_ld_wait();
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
       ptx::tc_fence_after();
       if (tre) tre[2] = clock64();                    // phase-2 accumulators complete
-      const int c_lo = half * 256, c_hi = c_lo + 256;
+      const int c_lo = half * P2, c_hi = c_lo + P2;
       if constexpr (RELU) {
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; c += 32) {
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       // Three passes over this thread's 256 accumulator columns (mean, variance, normalise + GELU).  The TMEM loads are double-buffered:
       // the load of block i + 1 is in flight while block i is reduced.  The loops are unrolled by two only (static register-set indices):
       // fully unrolled, the kernel grew to 170 KB of SASS and ran 30 % SLOWER (instruction-cache misses, profiles/r02c_match_trace.txt).
-      uint32_t rr[2][32];
+      uint32_t rr[EW == 2 ? 2 : 1][32];
       float sum = 0.f;
       auto sum_blk = [&](const uint32_t (&r)[32], int c) {
         float part = 0.f;
@@ -246,20 +252,26 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
         for (int j = 0; j < 32; ++j) part += __uint_as_float(r[j]) + s_b0[c + j];
         sum += part;
       };
-      ptx::tmem_ld32(trow + c_lo, rr[0]);
+      if constexpr (EW == 2) {
+        ptx::tmem_ld32(trow + c_lo, rr[0]);
 #pragma unroll 1
-      for (int c = c_lo; c < c_hi; c += 64) {
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld32(trow + c + 32, rr[1]);
-        sum_blk(rr[0], c);
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld32(trow + (c + 64 < c_hi ? c + 64 : c_lo), rr[0]);         // last iteration: first block of the next pass
-        sum_blk(rr[1], c + 32);
+        for (int c = c_lo; c < c_hi; c += 64) {
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld32(trow + c + 32, rr[1]);
+          sum_blk(rr[0], c);
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld32(trow + (c + 64 < c_hi ? c + 64 : c_lo), rr[0]);         // last iteration: first block of the next pass
+          sum_blk(rr[1], c + 32);
+        }
+      } else {      // EW = 4: one register set (96 registers per thread at 576 threads); the other three warps of the scheduler cover the TMEM load
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += 32) { ptx::tmem_ld32(trow + c, rr[0]); ptx::tmem_ld_wait(); sum_blk(rr[0], c); }
       }
       sRed[half * 128 + row] = sum;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * EW) : "memory");
       if (tre) tre[3] = clock64();                    // LayerNorm pass 1 (mean) done
-      const float mean = (sRed[row] + sRed[128 + row]) * (1.f / 512.f);      // low half + high half: the same order in both warps
+      // partial sums of the column parts, added in the same fixed order by every thread of the row
+      const float mean = (EW == 2 ? sRed[row] + sRed[128 + row] : (sRed[row] + sRed[128 + row]) + (sRed[256 + row] + sRed[384 + row])) * (1.f / 512.f);
       float var = 0.f;
       auto var_blk = [&](const uint32_t (&r)[32], int c) {
         float part = 0.f;
@@ -267,19 +279,25 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
         for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(r[j]) + s_b0[c + j] - mean; part = fmaf(d, d, part); }
         var += part;
       };
+      if constexpr (EW == 2) {
 #pragma unroll 1
-      for (int c = c_lo; c < c_hi; c += 64) {
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld32(trow + c + 32, rr[1]);
-        var_blk(rr[0], c);
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld32(trow + (c + 64 < c_hi ? c + 64 : c_lo), rr[0]);
-        var_blk(rr[1], c + 32);
+        for (int c = c_lo; c < c_hi; c += 64) {
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld32(trow + c + 32, rr[1]);
+          var_blk(rr[0], c);
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld32(trow + (c + 64 < c_hi ? c + 64 : c_lo), rr[0]);
+          var_blk(rr[1], c + 32);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += 32) { ptx::tmem_ld32(trow + c, rr[0]); ptx::tmem_ld_wait(); var_blk(rr[0], c); }
       }
-      sRed[256 + half * 128 + row] = var;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      sRed[512 + half * 128 + row] = var;
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * EW) : "memory");
       if (tre) tre[4] = clock64();                    // pass 2 (variance) done
-      const float rstd = 1.f / sqrtf((sRed[256 + row] + sRed[384 + row]) * (1.f / 512.f) + 1e-5f);
+      const float vsum = EW == 2 ? sRed[512 + row] + sRed[640 + row] : (sRed[512 + row] + sRed[640 + row]) + (sRed[768 + row] + sRed[896 + row]);
+      const float rstd = 1.f / sqrtf(vsum * (1.f / 512.f) + 1e-5f);
       auto gelu_blk = [&](const uint32_t (&r)[32], int c) {
         uint8_t* dst = sA + (c >> 6) * 16384 + row * 128;
 #pragma unroll
@@ -301,14 +319,19 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
           *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       };
+      if constexpr (EW == 2) {
 #pragma unroll 1
-      for (int c = c_lo; c < c_hi; c += 64) {
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld32(trow + c + 32, rr[1]);
-        gelu_blk(rr[0], c);
-        ptx::tmem_ld_wait();
-        if (c + 64 < c_hi) ptx::tmem_ld32(trow + c + 64, rr[0]);
-        gelu_blk(rr[1], c + 32);
+        for (int c = c_lo; c < c_hi; c += 64) {
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld32(trow + c + 32, rr[1]);
+          gelu_blk(rr[0], c);
+          ptx::tmem_ld_wait();
+          if (c + 64 < c_hi) ptx::tmem_ld32(trow + c + 64, rr[0]);
+          gelu_blk(rr[1], c + 32);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += 32) { ptx::tmem_ld32(trow + c, rr[0]); ptx::tmem_ld_wait(); gelu_blk(rr[0], c); }
       }
       }
       ptx::fence_proxy_async();
@@ -316,7 +339,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(epi_done);
       if (tre) tre[5] = clock64();                    // phase-2 epilogue done (gelu(h) in shared memory)
-      // ---- phase 3 epilogue: x += acc + b3 ; fp32 residual + fp16 operand copy (this warp: columns half*128 .. +128) ----
+      // ---- phase 3 epilogue: x += acc + b3 ; fp32 residual + fp16 operand copy (this warp: columns half*P1 .. +P1) ----
       ptx::mbar_wait(acc_full, pacc); pacc ^= 1;
       ptx::tc_fence_after();
       if (tre) tre[6] = clock64();                    // phase-3 accumulators complete
@@ -325,9 +348,9 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
       // dependent stores -- sixteen serialised L2 round trips, 27.8 k cycles per tile (profiles/r02c_match_trace.txt).
       float* xr = p.x + grow * 256;
       __half* x16r = p.x16 + grow * 512;
-      const int c3 = half * 128;
-      float xv[2][4][8];
-      uint32_t r3[2][32];
+      const int c3 = half * P1;
+      float xv[EW == 2 ? 2 : 1][4][8];
+      uint32_t r3[EW == 2 ? 2 : 1][32];
       auto ld_x = [&](float (&dstv)[4][8], int c) {
         if (valid) {
 #pragma unroll
@@ -349,17 +372,27 @@ __global__ void __launch_bounds__(kFfnThreads, 1) tc_ffn_kernel(const __grid_con
           }
         }
       };
-      ld_x(xv[0], c3);
-      ptx::tmem_ld32(trow + c3, r3[0]);
+      if constexpr (EW == 2) {
+        ld_x(xv[0], c3);
+        ptx::tmem_ld32(trow + c3, r3[0]);
 #pragma unroll 1
-      for (int c = c3; c < c3 + 128; c += 64) {
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld32(trow + c + 32, r3[1]);
-        ld_x(xv[1], c + 32);
-        add_store(xv[0], r3[0], c);
-        ptx::tmem_ld_wait();
-        if (c + 64 < c3 + 128) { ptx::tmem_ld32(trow + c + 64, r3[0]); ld_x(xv[0], c + 64); }
-        add_store(xv[1], r3[1], c + 32);
+        for (int c = c3; c < c3 + P1; c += 64) {
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld32(trow + c + 32, r3[1]);
+          ld_x(xv[1], c + 32);
+          add_store(xv[0], r3[0], c);
+          ptx::tmem_ld_wait();
+          if (c + 64 < c3 + P1) { ptx::tmem_ld32(trow + c + 64, r3[0]); ld_x(xv[0], c + 64); }
+          add_store(xv[1], r3[1], c + 32);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = c3; c < c3 + P1; c += 32) {
+          ld_x(xv[0], c);
+          ptx::tmem_ld32(trow + c, r3[0]);
+          ptx::tmem_ld_wait();
+          add_store(xv[0], r3[0], c);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
