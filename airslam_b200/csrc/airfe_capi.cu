@@ -615,7 +615,7 @@ int airfe_stereo_cost(airfe_ctx* c, int net, int matcher, int pairs, int lines, 
   const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
   if (!d || (sgm ? !c->sg : !c->lg)) { set_error("networks not enabled"); return fail(c, AIRFE_ERR_INVALID); }
   if (tc_flops) *tc_flops = d->tc_flops(2 * pairs, lines != 0) + (sgm ? c->sg->tc_flops(pairs) : c->lg->tc_flops(pairs));
-  if (launches) *launches = d->launches(2 * pairs, lines != 0) + (sgm ? c->sg->launches(pairs) : c->lg->launches(pairs)) + 12;
+  if (launches) *launches = d->launches(2 * pairs, lines != 0) + (sgm ? c->sg->launches(pairs) : c->lg->launches(pairs)) + (lines ? 13 : 4);    // + resize, keypoint selection (2), descriptor sampling; lines: + 9 decode / association / LOI kernels
   return AIRFE_OK;
 }
 

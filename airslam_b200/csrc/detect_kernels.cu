@@ -119,11 +119,11 @@ __device__ __forceinline__ unsigned long long ffma2_(unsigned long long a, unsig
 __device__ __forceinline__ unsigned long long pack2_(float lo, float hi) {
   return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
-// PX = pixels along x per thread (8 or 4).  PX = 8 needs 166 registers (three CTAs = 12 warps per SM); PX = 4 halves the per-thread tile
-// (in2 / packed) so that more warps are resident -- the kernel sits at ~2x its FMA floor with 12 warps.  Per output the arithmetic (bias, then the
-// nine taps in ky, kx order) is identical for both: results are bit-identical.
+// PX = pixels along x per thread.  PX = 8 needs 164 registers (three CTAs = 12 warps per SM).  A PX = 4 instantiation (128 registers, four CTAs =
+// 16 warps per SM, the weights re-read from shared memory twice as often) was measured in round 2: 0.847 -> 1.088 ms per 94 frames -- the kernel
+// is not short of warps, it is bound by the FMA pipe plus the shared-memory weight reads.  Only PX = 8 is instantiated.
 template <int PX>
-__global__ void __launch_bounds__(128, PX == 8 ? 3 : 4) conv1a_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(128, 3) conv1a_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias,
                                                                       __half* __restrict__ out, int H, int W, long long total) {
   __shared__ float2 sw2[8 * 4 * 9];   // [channel group][channel pair][tap] = (w of channel 2p, w of channel 2p+1)
   __shared__ float2 sb2[32];
@@ -199,9 +199,7 @@ __global__ void __launch_bounds__(128, PX == 8 ? 3 : 4) conv1a_kernel(const __ha
 }
 
 void launch_conv1a(const __half* x, const __half* w, const float* bias, __half* out, int batch, int H, int W, cudaStream_t st) {
-  static const int px = getenv("AIRFE_CONV1A_PX") ? atoi(getenv("AIRFE_CONV1A_PX")) : 8;     // 8 (default) or 4: A/B knob, identical results
-  if (px == 4) conv1a_kernel<4><<<dim3((W * 2 + 127) / 128, (H + kC1Rows - 1) / kC1Rows, batch), 128, 0, st>>>(x, w, bias, out, H, W, 0);
-  else conv1a_kernel<8><<<dim3((W + 127) / 128, (H + kC1Rows - 1) / kC1Rows, batch), 128, 0, st>>>(x, w, bias, out, H, W, 0);
+  conv1a_kernel<8><<<dim3((W + 127) / 128, (H + kC1Rows - 1) / kC1Rows, batch), 128, 0, st>>>(x, w, bias, out, H, W, 0);
 }
 
 // =====================================================================================================================

@@ -169,6 +169,7 @@ bool Detector::init(const DetectorConfig& cfg, const std::string& wdir, bool use
     line_score_ = ar->alloc_n<float>((size_t)B * kLineCap);
     adj_ = ar->alloc_n<float>((size_t)B * kLineCap * 4);
     junc_idx_ = ar->alloc_n<int>((size_t)B * kJunc);
+    jfeat_ = ar->alloc_n<__half>((size_t)B * kJunc * 128);      // LOI endpoint features per junction (junc_feat_kernel)
     jkp_ = ar->alloc_n<float>((size_t)B * kKpCap * 3);
     jkp_count_ = ar->alloc_n<int>(B);
     out_.lines = ar->alloc_n<float>((size_t)B * kLineCap * 4);
@@ -251,7 +252,7 @@ bool Detector::build_ops(int B) {
   {
     const float* lg = (const float*)logits_.p; float* heat = heat_; float* sc = scores_; uint8_t* ma = mask_a_; uint8_t* mb = mask_b_;
     t.push("softmax_d2s+nms", 0, [=](cudaStream_t st) { launch_softmax_d2s(lg, 80, heat, B, st); launch_simple_nms(heat, sc, ma, mb, B, st); return true; });
-    t.launches += 4;
+    t.launches += getenv("AIRFE_NMS_V1") ? 4 : 2;      // softmax + fused NMS (v1: three NMS passes)
   }
   trunk_ops_[B] = std::move(t);
 
@@ -325,7 +326,7 @@ bool Detector::run(const uint8_t* d_images, int B, int w, int h, int stride, lon
     timed("association+unique", st, [&] { launch_association(lines_pred_, juncs_, imin_, imax_, iskeep_, pair_table_, uid_pairs_, uid_first_, n_unique_, kLineCap, B, st); });
     timed("loi_gather", st, [&] {
       launch_loi_gather((const float*)loi_o_.p, (int)loi_o_.ps, (const float*)thinaux_o_.p, (int)thinaux_o_.ps, juncs_, lines_pred_, uid_pairs_, uid_first_, n_unique_, kLineCap,
-                        s1_tspan_, (__half*)feat496_.p, adj_, B, st);
+                        s1_tspan_, (__half*)feat496_.p, adj_, B, st, jfeat_);
     });
     if (!mlp_ops_[B].run(st)) return false;      // stage-1 MLP on tensor cores; row counts are read on the device
     timed("line_head+accept", st, [&] {

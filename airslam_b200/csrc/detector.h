@@ -88,6 +88,7 @@ class Detector {
   float* line_score_ = nullptr;
   float* adj_ = nullptr;
   int* junc_idx_ = nullptr;
+  __half* jfeat_ = nullptr;
   float* jkp_ = nullptr;
   int* jkp_count_ = nullptr;
   DetectOutputs out_;

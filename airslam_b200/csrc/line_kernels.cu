@@ -5,6 +5,7 @@
 // small HBM/shared-memory kernels that never leaves the device.  Arithmetic follows the ONNX graph op by op (no FMA
 // contraction where a discrete decision depends on the result: __fmul_rn / __fadd_rn).
 #include "line_kernels.h"
+#include <stdlib.h>
 #include <math.h>
 
 namespace airfe {
@@ -255,10 +256,35 @@ __device__ __forceinline__ void bil_setup(float px, float py, int& x0, int& y0, 
   w11 = (py - fy0) * (px - fx0);   // f[y1][x1]
 }
 
+// Endpoint features once per junction (300 per image) instead of once per line end (~2 x 4300 per image): a junction is an end point of ~29
+// candidate lines, and the bilinear sample of the 128-channel LOI map at a junction does not depend on the line.  One warp per junction,
+// the arithmetic of the per-line version below verbatim (results are bit-identical); the line kernel then copies two 256-byte rows.
+__global__ void junc_feat_kernel(const float* __restrict__ loi, int loi_ld, const float* __restrict__ juncs, __half* __restrict__ jf) {
+  const int b = blockIdx.y;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= kJunctions) return;
+  const float2 p = reinterpret_cast<const float2*>(juncs)[(long long)b * kJunctions + j];
+  const float* L = loi + (long long)b * 16384 * loi_ld;
+  int x0, y0, x1, y1; float w00, w10, w01, w11;
+  bil_setup(p.x, p.y, x0, y0, x1, y1, w00, w10, w01, w11);
+  const float4 a = *reinterpret_cast<const float4*>(L + (long long)(y0 * 128 + x0) * loi_ld + lane * 4);
+  const float4 c = *reinterpret_cast<const float4*>(L + (long long)(y1 * 128 + x0) * loi_ld + lane * 4);
+  const float4 d = *reinterpret_cast<const float4*>(L + (long long)(y0 * 128 + x1) * loi_ld + lane * 4);
+  const float4 g = *reinterpret_cast<const float4*>(L + (long long)(y1 * 128 + x1) * loi_ld + lane * 4);
+  const float r0 = a.x * w00 + c.x * w10 + d.x * w01 + g.x * w11;
+  const float r1 = a.y * w00 + c.y * w10 + d.y * w01 + g.y * w11;
+  const float r2 = a.z * w00 + c.z * w10 + d.z * w01 + g.z * w11;
+  const float r3 = a.w * w00 + c.w * w10 + d.w * w01 + g.w * w11;
+  __half2 h0 = __floats2half2_rn(r0, r1), h1 = __floats2half2_rn(r2, r3);
+  *reinterpret_cast<uint2*>(jf + ((long long)b * kJunctions + j) * 128 + lane * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+}
+
 __global__ void loi_gather_kernel(const float* __restrict__ loi, int loi_ld, const float* __restrict__ thinaux, int ta_ld,
                                   const float* __restrict__ juncs, const float* __restrict__ lines, const int* __restrict__ uid_pairs,
                                   const int* __restrict__ uid_first, const int* __restrict__ n_unique, int line_cap,
-                                  const float* __restrict__ tspan, __half* __restrict__ feat, float* __restrict__ adj_out) {
+                                  const float* __restrict__ tspan, __half* __restrict__ feat, float* __restrict__ adj_out,
+                                  const __half* __restrict__ jf /* junc_feat_kernel's rows, or nullptr: sample per line end */) {
   const int b = blockIdx.y;
   const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -271,6 +297,10 @@ __global__ void loi_gather_kernel(const float* __restrict__ loi, int loi_ld, con
   __half* f = feat + ub * 512;
   const float* L = loi + (long long)b * 16384 * loi_ld;
   // endpoint features: 128 channels, 4 per lane
+  if (jf) {
+    *reinterpret_cast<uint2*>(f + lane * 4) = *reinterpret_cast<const uint2*>(jf + ((long long)b * kJunctions + ja) * 128 + lane * 4);
+    *reinterpret_cast<uint2*>(f + 128 + lane * 4) = *reinterpret_cast<const uint2*>(jf + ((long long)b * kJunctions + jb) * 128 + lane * 4);
+  } else
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const float2 p = e ? pb : pa;
@@ -453,9 +483,12 @@ void launch_association(const float* lines, const float* juncs, int* imin, int* 
 }
 void launch_loi_gather(const float* loi, int loi_ld, const float* thinaux, int ta_ld, const float* juncs, const float* lines,
                        const int* uid_pairs, const int* uid_first, const int* n_unique, int line_cap, const float* tspan, __half* feat,
-                       float* adj, int batch, cudaStream_t st) {
+                       float* adj, int batch, cudaStream_t st, __half* junc_feat) {
+  static const bool use_jf = !(getenv("AIRFE_LOI_JF") && atoi(getenv("AIRFE_LOI_JF")) == 0);     // 0: per-line endpoint sampling (A/B timing; identical results)
+  __half* jf = use_jf ? junc_feat : nullptr;
+  if (jf) junc_feat_kernel<<<dim3((kJunctions * 32 + 255) / 256, batch), 256, 0, st>>>(loi, loi_ld, juncs, jf);
   loi_gather_kernel<<<dim3((line_cap * 32 + 255) / 256, batch), 256, 0, st>>>(loi, loi_ld, thinaux, ta_ld, juncs, lines, uid_pairs, uid_first,
-                                                                             n_unique, line_cap, tspan, feat, adj);
+                                                                             n_unique, line_cap, tspan, feat, adj, jf);
 }
 void launch_line_head(const float* h1, const float* h2, const float* w, const float* bias, const int* n_unique, int line_cap, float* score,
                       int batch, cudaStream_t st) {

@@ -14,7 +14,7 @@ void launch_association(const float* lines, const float* juncs, int* imin, int* 
                         int* uid_first, int* n_unique, int line_cap, int batch, cudaStream_t st);
 void launch_loi_gather(const float* loi, int loi_ld, const float* thinaux, int ta_ld, const float* juncs, const float* lines,
                        const int* uid_pairs, const int* uid_first, const int* n_unique, int line_cap, const float* tspan, __half* feat,
-                       float* adj, int batch, cudaStream_t st);
+                       float* adj, int batch, cudaStream_t st, __half* junc_feat = nullptr);
 void launch_line_head(const float* h1, const float* h2, const float* w, const float* bias, const int* n_unique, int line_cap, float* score,
                       int batch, cudaStream_t st);
 void launch_line_accept(const float* adj, const float* score, const int* n_unique, int line_cap, float line_thr, float len_thr, int border,
