@@ -286,9 +286,11 @@ __global__ void loi_gather_kernel(const float* __restrict__ loi, int loi_ld, con
                                   const float* __restrict__ tspan, __half* __restrict__ feat, float* __restrict__ adj_out,
                                   const __half* __restrict__ jf /* junc_feat_kernel's rows, or nullptr: sample per line end */) {
   const int b = blockIdx.y;
-  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (u >= n_unique[b]) return;
+  const int n_lines_b = n_unique[b];
+  // grid-stride over the image's lines: the grid holds kLineGridX blocks per image instead of one warp per CAPACITY row (16 384 rows, of which
+  // a typical image uses ~4 300: three quarters of the former 2 048 blocks per image only read the count and left)
+  for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n_lines_b; u += (gridDim.x * blockDim.x) >> 5) {
   const long long ub = (long long)b * line_cap + u;
   const int ja = uid_pairs[ub * 2], jb = uid_pairs[ub * 2 + 1];
   const float2 pa = reinterpret_cast<const float2*>(juncs)[(long long)b * kJunctions + ja];
@@ -342,6 +344,7 @@ __global__ void loi_gather_kernel(const float* __restrict__ loi, int loi_ld, con
     }
   }
   if (lane < 16) f[496 + lane] = __float2half_rn(0.f);
+  }
 }
 
 // ---- K11b: residual add + fc2_head (128 -> 2) + softmax[1]; one warp per line ------------------------------------------------
@@ -349,9 +352,9 @@ __global__ void line_head_kernel(const float* __restrict__ h1, const float* __re
                                  const float* __restrict__ bias, const int* __restrict__ n_unique, int line_cap,
                                  float* __restrict__ score) {
   const int b = blockIdx.y;
-  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (u >= n_unique[b]) return;
+  const int n_lines_b = n_unique[b];
+  for (int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n_lines_b; u += (gridDim.x * blockDim.x) >> 5) {
   const long long ub = (long long)b * line_cap + u;
   const float4 a = *reinterpret_cast<const float4*>(h1 + ub * 128 + lane * 4);
   const float4 c = *reinterpret_cast<const float4*>(h2 + ub * 128 + lane * 4);
@@ -372,6 +375,7 @@ __global__ void line_head_kernel(const float* __restrict__ h1, const float* __re
     const float m = fmaxf(l0, l1);
     const float e0 = expf(l0 - m), e1 = expf(l1 - m);
     score[ub] = e1 / (e0 + e1);
+  }
   }
 }
 
@@ -481,18 +485,21 @@ void launch_association(const float* lines, const float* juncs, int* imin, int* 
   assoc_kernel<<<dim3((kProposals + 256 * kAssocPer - 1) / (256 * kAssocPer), batch), 256, 0, st>>>(lines, juncs, imin, imax, keep, pair_table);
   unique_pairs_kernel<<<batch, 1024, 0, st>>>(imin, imax, keep, pair_table, uid_pairs, uid_first, n_unique, line_cap);
 }
+// blocks of 8 warps per image for the one-warp-per-line kernels (grid-stride over the device-side line count): 256 blocks = 2 048 lines per sweep
+static int line_grid_x(int line_cap) { const int full = (line_cap * 32 + 255) / 256; return full < 256 ? full : 256; }
+
 void launch_loi_gather(const float* loi, int loi_ld, const float* thinaux, int ta_ld, const float* juncs, const float* lines,
                        const int* uid_pairs, const int* uid_first, const int* n_unique, int line_cap, const float* tspan, __half* feat,
                        float* adj, int batch, cudaStream_t st, __half* junc_feat) {
   static const bool use_jf = !(getenv("AIRFE_LOI_JF") && atoi(getenv("AIRFE_LOI_JF")) == 0);     // 0: per-line endpoint sampling (A/B timing; identical results)
   __half* jf = use_jf ? junc_feat : nullptr;
   if (jf) junc_feat_kernel<<<dim3((kJunctions * 32 + 255) / 256, batch), 256, 0, st>>>(loi, loi_ld, juncs, jf);
-  loi_gather_kernel<<<dim3((line_cap * 32 + 255) / 256, batch), 256, 0, st>>>(loi, loi_ld, thinaux, ta_ld, juncs, lines, uid_pairs, uid_first,
+  loi_gather_kernel<<<dim3(line_grid_x(line_cap), batch), 256, 0, st>>>(loi, loi_ld, thinaux, ta_ld, juncs, lines, uid_pairs, uid_first,
                                                                              n_unique, line_cap, tspan, feat, adj, jf);
 }
 void launch_line_head(const float* h1, const float* h2, const float* w, const float* bias, const int* n_unique, int line_cap, float* score,
                       int batch, cudaStream_t st) {
-  line_head_kernel<<<dim3((line_cap * 32 + 255) / 256, batch), 256, 0, st>>>(h1, h2, w, bias, n_unique, line_cap, score);
+  line_head_kernel<<<dim3(line_grid_x(line_cap), batch), 256, 0, st>>>(h1, h2, w, bias, n_unique, line_cap, score);
 }
 void launch_line_accept(const float* adj, const float* score, const int* n_unique, int line_cap, float line_thr, float len_thr, int border,
                         uint8_t* junc_map, float* lines_out, int* n_lines, int batch, cudaStream_t st) {
