@@ -43,7 +43,7 @@ struct airfe_ctx {
   // device-resident keyframe features (airfe_kf_*) and the job tables of airfe_reloc_match
   float* kf_feat = nullptr; int* kf_n = nullptr;       // [kf_slots][kf_cap][259] on the device; counts on the host
   int kf_slots = 0, kf_cap = 0;
-  int rj_cap = 0;                                      // jobs the tables below are sized for
+  int rj_cap = 0, rj_kp_cap = 0;                       // jobs / keypoints per set the tables below are sized for
   const float** h_rptr = nullptr; const float** d_rptr = nullptr;   // [2*rj_cap] per-slot feature pointers
   int* h_rn = nullptr; int* d_rn = nullptr;            // [2*rj_cap] per-slot counts
   int* d_rcount = nullptr; int* d_ridx = nullptr; float* d_rscore = nullptr;   // per job: match count, [cap][2] indices, [cap] scores
@@ -939,7 +939,9 @@ int airfe_kf_put(airfe_ctx* c, int slot, const float* feat, int n) {
 }
 
 static bool grow_reloc_tables(airfe_ctx* c, int n_jobs, int cap) {
-  if (n_jobs <= c->rj_cap) return true;
+  if (n_jobs <= c->rj_cap && cap <= c->rj_kp_cap) return true;     // the match tables are [jobs][cap]: a matcher with a larger capacity needs them regrown too
+  if (n_jobs < c->rj_cap) n_jobs = c->rj_cap;
+  if (cap < c->rj_kp_cap) cap = c->rj_kp_cap;
   cudaStreamSynchronize(c->stream);
   if (c->h_rptr) cudaFreeHost(c->h_rptr);
   if (c->d_rptr) cudaFree(c->d_rptr);
@@ -952,7 +954,7 @@ static bool grow_reloc_tables(airfe_ctx* c, int n_jobs, int cap) {
   if (c->h_ridx) cudaFreeHost(c->h_ridx);
   if (c->h_rscore) cudaFreeHost(c->h_rscore);
   c->h_rptr = nullptr; c->d_rptr = nullptr; c->h_rn = nullptr; c->d_rn = nullptr; c->d_rcount = nullptr; c->d_ridx = nullptr; c->d_rscore = nullptr;
-  c->h_rcount = nullptr; c->h_ridx = nullptr; c->h_rscore = nullptr; c->rj_cap = 0;
+  c->h_rcount = nullptr; c->h_ridx = nullptr; c->h_rscore = nullptr; c->rj_cap = 0; c->rj_kp_cap = 0;
   const size_t J = (size_t)n_jobs;
   if (cudaMallocHost(&c->h_rptr, 2 * J * sizeof(float*)) != cudaSuccess || cudaMalloc(&c->d_rptr, 2 * J * sizeof(float*)) != cudaSuccess ||
       cudaMallocHost(&c->h_rn, 2 * J * 4) != cudaSuccess || cudaMalloc(&c->d_rn, 2 * J * 4) != cudaSuccess || cudaMalloc(&c->d_rcount, J * 4) != cudaSuccess ||
@@ -962,7 +964,7 @@ static bool grow_reloc_tables(airfe_ctx* c, int n_jobs, int cap) {
     set_error("reloc job tables (%d jobs) allocation failed", n_jobs);
     return false;
   }
-  c->rj_cap = n_jobs;
+  c->rj_cap = n_jobs; c->rj_kp_cap = cap;
   return true;
 }
 
