@@ -188,7 +188,9 @@ int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out) {
     return AIRFE_ERR_CUDA;
   }
   if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return AIRFE_ERR_CUDA; }
-  std::unique_ptr<airfe_ctx> c(new airfe_ctx);
+  // a context that fails half-way releases everything it already holds (streams, arenas, pinned staging): airfe_destroy copes with null members
+  struct Guard { airfe_ctx* p; ~Guard() { if (p) airfe_destroy(p); } airfe_ctx* operator->() const { return p; } airfe_ctx* release() { airfe_ctx* r = p; p = nullptr; return r; } };
+  Guard c{new airfe_ctx};
   c->device = device;
   c->cfg = *cfg;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -271,7 +273,7 @@ int airfe_create(const airfe_config* cfg, int device, airfe_ctx** out) {
 void airfe_destroy(airfe_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   c->sp.reset();
   c->pl.reset();
   c->lg.reset();
@@ -318,7 +320,7 @@ void airfe_destroy(airfe_ctx* c) {
   if (c->la_ovf) cudaFree(c->la_ovf);
   for (int k = 0; k < 2; ++k) { if (c->d_rxy[k]) cudaFree(c->d_rxy[k]); if (c->d_ra[k]) cudaFree(c->d_ra[k]); }
   if (c->d_rect) cudaFree(c->d_rect);
-  cudaStreamDestroy(c->stream);
+  if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev_det) cudaEventDestroy(c->ev_det);
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
@@ -490,6 +492,7 @@ int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, 
   const int cap = sgm ? c->sg_use->cap() : c->lg_use->cap();
   std::vector<int> zero(pairs, 0);
   for (int p = 0; p < pairs; ++p) {
+    if (n0[p] < 0 || n1[p] < 0) { set_error("pair %d: negative keypoint count %d/%d", p, n0[p], n1[p]); return fail(c, AIRFE_ERR_INVALID); }
     if (n0[p] > cap || n1[p] > cap || n0[p] > feat_cap || n1[p] > feat_cap) { set_error("pair %d: %d/%d keypoints exceed capacity %d", p, n0[p], n1[p], cap); return fail(c, AIRFE_ERR_CAPACITY); }
     zero[p] = (n0[p] < 1 || n1[p] < 1);
     c->h_mn[2 * p] = n0[p];
@@ -534,6 +537,8 @@ int airfe_match_batch(airfe_ctx* c, int matcher, int pairs, const float* feat0, 
 int airfe_superglue_batch(airfe_ctx* c, int pairs, const float* feat0, const int* n0, const float* feat1, const int* n1, int feat_cap,
                           int prenormalized, int* indices0, int* indices1, float* mscores0, float* mscores1, int out_cap) {
   if (!c || !c->sg) { set_error("superglue not enabled in this context"); return fail(c, AIRFE_ERR_INVALID); }
+  if (!indices0 || !indices1 || !mscores0 || !mscores1 || !n0 || !n1) { set_error("null argument"); return fail(c, AIRFE_ERR_INVALID); }
+  if (pairs < 1 || pairs > c->cfg.max_batch) { set_error("pairs %d outside [1,%d]", pairs, c->cfg.max_batch); return fail(c, AIRFE_ERR_INVALID); }
   g_prenorm = prenormalized != 0;
   std::vector<int> i0((size_t)pairs * 1024), i1((size_t)pairs * 1024), nm(pairs);
   std::vector<float> sc((size_t)pairs * 1024);
@@ -558,6 +563,7 @@ int airfe_superglue_batch(airfe_ctx* c, int pairs, const float* feat0, const int
 
 int airfe_stereo_device(airfe_ctx* c, int net, int matcher, int pairs, const void* d_images, int w, int h, int stride, long long img_stride,
                         int lines, int junctions) {
+  if (!c || !d_images) { set_error("null argument"); return fail(c, AIRFE_ERR_INVALID); }
   Detector* d = pick(c, net);
   if (!d) return fail(c, AIRFE_ERR_INVALID);
   const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
@@ -577,6 +583,7 @@ int airfe_stereo_device(airfe_ctx* c, int net, int matcher, int pairs, const voi
 
 long long airfe_profile_stereo(airfe_ctx* c, int net, int matcher, int pairs, const void* d_images, int w, int h, int stride, long long img_stride,
                                int lines, int junctions, char* out, long long cap) {
+  if (!c || !out || cap < 1) { set_error("null argument"); return fail(c, AIRFE_ERR_INVALID); }
   cudaStreamSynchronize(c->stream);
   profiler().begin();
   int rc = airfe_stereo_device(c, net, matcher, pairs, d_images, w, h, stride, img_stride, lines, junctions);
@@ -611,6 +618,7 @@ long long airfe_profile_stereo(airfe_ctx* c, int net, int matcher, int pairs, co
 }
 
 int airfe_stereo_cost(airfe_ctx* c, int net, int matcher, int pairs, int lines, double* tc_flops, int* launches) {
+  if (!c) { set_error("null argument"); return AIRFE_ERR_INVALID; }
   Detector* d = pick(c, net);
   const bool sgm = matcher == AIRFE_MATCHER_SUPERGLUE;
   if (!d || (sgm ? !c->sg : !c->lg)) { set_error("networks not enabled"); return fail(c, AIRFE_ERR_INVALID); }
@@ -827,6 +835,8 @@ int airfe_stereo_line_assoc(airfe_ctx* c, int pairs, double min_x_diff, double m
   cudaMemcpyAsync(h_lm.data(), c->la_lm, (size_t)pairs * kML * 4, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(&ovf, c->la_ovf, 4, cudaMemcpyDeviceToHost, st);
   if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("line association failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(c, AIRFE_ERR_CUDA); }
+  // overflow first: with the flag set a per-line count may exceed the kRC entries the device tables (and h_idx / h_dist below) hold per line
+  if (ovf) { set_error("line association overflow (more than %d points on a line or 8 lines through a point)", kRC); return fail(c, AIRFE_ERR_CAPACITY); }
   std::vector<int> h_idx((size_t)kML * kRC);
   std::vector<float> h_dist((size_t)kML * kRC);
   for (int s2 = 0; s2 < S; ++s2) {
@@ -839,7 +849,7 @@ int airfe_stereo_line_assoc(airfe_ctx* c, int pairs, double min_x_diff, double m
     for (int i = 0; i < line_cap; ++i) rel_n[(size_t)s2 * line_cap + i] = 0;
     for (int i = 0; i < nl; ++i) {
       const int n = h_rn[(size_t)s2 * kML + i];
-      if (n > rel_cap) { set_error("line %d of image %d has %d points, rel_cap is %d", i, s2, n, rel_cap); return fail(c, AIRFE_ERR_CAPACITY); }
+      if (n > rel_cap || n > kRC || n < 0) { set_error("line %d of image %d has %d points, rel_cap is %d", i, s2, n, rel_cap < kRC ? rel_cap : kRC); return fail(c, AIRFE_ERR_CAPACITY); }
       rel_n[(size_t)s2 * line_cap + i] = n;
       for (int k = 0; k < n; ++k) {
         rel_idx[((size_t)s2 * line_cap + i) * rel_cap + k] = h_idx[(size_t)i * kRC + k];
@@ -847,7 +857,6 @@ int airfe_stereo_line_assoc(airfe_ctx* c, int pairs, double min_x_diff, double m
       }
     }
   }
-  if (ovf) { set_error("line association overflow (more than %d points on a line or 8 lines through a point)", kRC); return fail(c, AIRFE_ERR_CAPACITY); }
   for (int p = 0; p < pairs; ++p)
     for (int i = 0; i < line_cap; ++i) line_matches[(size_t)p * line_cap + i] = i < kML ? h_lm[(size_t)p * kML + i] : -1;
   return AIRFE_OK;
