@@ -89,12 +89,31 @@ def test_g4_lightglue_whole_graph():
     assert len(idx) > 100
 
 
-def test_g5_superglue_similarity():
+def test_g5_superglue_similarity_and_sinkhorn():
+    """cv2.dnn executes the graph up to the similarity matrix and, cut at the couplings, the 100 Sinkhorn iterations ('2563' .. 'scores').  Between
+    the two sits only the dustbin Concat (restated in tools/make_cv2dnn_golden.py, pinned by the interpreter golden): so the final score matrix
+    of the fixture is the reference graph's own output on these inputs, and the oracle's WHOLE SuperGlue forward is compared with it."""
     g = np.load(os.path.join(G, "cv2dnn_g5_superglue_indoor.npz"))
     n0, n1 = _match_inputs(0.7)
     keep = {}
-    host.superglue_infer(n0, n1, weights.load("superglue_indoor"), keep=keep)
+    i0, i1, ms0, ms1, sc = host.superglue_infer(n0, n1, weights.load("superglue_indoor"), keep=keep)
     _err("g5.similarity", keep["sim"].numpy(), g["sim"], 6e-6)              # measured 5.2e-5 abs at scale 34
+    assert np.array_equal(keep["couplings"].numpy()[:-1, :-1], keep["sim"].numpy())
+    _err("g5.couplings (dustbin row / column)", keep["couplings"].numpy()[-1], g["couplings"][-1], 1e-7)
+    # the oracle's Sinkhorn alone, on the fixture's couplings: isolates the 100 iterations from the GNN's fp32 summation noise
+    z = torch.from_numpy(g["couplings"])
+    m, n = g["sim"].shape
+    norm = -torch.log(torch.tensor(float(m + n)))
+    log_mu = torch.cat([norm.expand(m), (torch.log(torch.tensor(float(n))) + norm).view(1)])
+    log_nu = torch.cat([norm.expand(n), (torch.log(torch.tensor(float(m))) + norm).view(1)])
+    own = (nets.log_sinkhorn(z, log_mu, log_nu, 100) - norm).numpy()
+    _err("g5.sinkhorn_100_iterations (same couplings)", own, g["scores"], 1e-6)     # measured 2.7e-5 abs at scale 52.5
+    # whole graph: probabilities of the assignment and the decoded matches
+    ref = g["scores"]
+    _err("g5.assignment_prob (whole graph)", np.exp(sc), np.exp(ref), 4e-8)    # measured 2.8e-6 abs at scale 145 (scores carry + log(m + n))
+    r0, r1, rm0, rm1 = host.superglue_decode(ref)
+    assert np.array_equal(i0, r0) and np.array_equal(i1, r1), "SuperGlue decode of cv2.dnn's score matrix differs from the oracle's"
+    assert (i0 >= 0).sum() > 100
 
 
 def test_zz_record():

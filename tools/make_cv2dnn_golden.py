@@ -13,7 +13,8 @@ initialisers copied as raw bytes from the reference files:
                         logits and raw descriptors                                                            [whole dense part]
   G3 plnet_s1           the verification MLP: 496-d line features -> fc2.* / fc2_res / fc2_head logits
   G4 superpoint_lightglue  WHOLE graph (keypoints / descriptors -> log-assignment scores)
-  G5 superglue_indoor   keypoint encoder + 18 GNN layers + final_proj + score einsum / sqrt(256) -> similarity matrix ('2435')
+  G5 superglue_indoor   keypoint encoder + 18 GNN layers + final_proj + score einsum / sqrt(256) -> similarity matrix ('2435');
+                        the 100 Sinkhorn iterations ('2563' .. 'scores') on the couplings built from it -> final score matrix
 
 What cv2.dnn cannot execute is exactly the integer / logical tail of G1 / G2 (3-round NMS via MaxPool+Equal+Where, HAFM decode, TopK,
 association): those are checked bit-exactly against tools/onnx_interp.py (tests/test_oracle_golden.py) and are integer arithmetic.
@@ -33,7 +34,7 @@ from oracle import host, synth  # noqa: E402
 from tools import onnx_cut, onnx_reader as R  # noqa: E402
 
 REF = "/root/reference/output/"
-OUT = os.path.join(ROOT, "tests", "golden")
+OUT = os.environ.get("AIRFE_GOLDEN_OUT", os.path.join(ROOT, "tests", "golden"))
 TMP = "/tmp/airfe_cv2dnn"
 
 
@@ -120,10 +121,23 @@ def main():
              "keypoints_1": n1[1:3].T.copy()[None], "scores_1": n1[0][None].copy(), "descriptors_1": n1[3:][None].copy()}
     o = run("superglue_indoor_sim_int32.onnx", {k: list(v.shape) for k, v in feeds.items()}, ["2435"], feeds)
     sim = o["2435"].astype(np.float32).reshape(f0.shape[1], f1.shape[1])          # einsum(mdesc0, mdesc1) / sqrt(256), before the dustbins
-    # The dustbin Concat and the 100 Sinkhorn iterations behind this tensor are built from Shape / ConstantOfShape / Expand nodes that cv2.dnn
-    # cannot import; they are log-sum-exp arithmetic on this matrix, pinned against tools/onnx_interp.py (tests/test_oracle_golden.py).
-    np.savez_compressed(os.path.join(OUT, "cv2dnn_g5_superglue_indoor.npz"), sim=sim,
-                        meta=json.dumps(dict(meta, inputs="same keypoint sets, normalize scale 0.7")))
+    # The dustbin Concat behind this tensor is built from Shape / ConstantOfShape / Expand nodes that cv2.dnn cannot import: it is restated here
+    # (three Expands of the scalar initialiser 'bin_score' + two Concats = nodes '2466'..'2498'; log_mu / log_nu = '2545' / '2559', norm = '2501')
+    # and pinned against tools/onnx_interp.py (tests/test_oracle_golden.py).  The 100 Sinkhorn iterations themselves (200 ReduceLogSumExp + Sub /
+    # Unsqueeze / Add nodes, '2563'..'scores') ARE executed by cv2.dnn, cut at those tensors with the nodes copied byte for byte.
+    m, n = sim.shape
+    bin_score = np.float32(R.load(REF + "superglue_indoor_sim_int32.onnx").init["bin_score"].reshape(()))
+    z = np.full((m + 1, n + 1), bin_score, np.float32)
+    z[:m, :n] = sim
+    norm = -np.log(np.float32(m + n))
+    log_mu = np.concatenate([np.full(m, norm, np.float32), [np.log(np.float32(n)) + norm]]).astype(np.float32)
+    log_nu = np.concatenate([np.full(n, norm, np.float32), [np.log(np.float32(m)) + norm]]).astype(np.float32)
+    feeds2 = {"2498": z[None], "2545": log_mu[None], "2559": log_nu[None], "2562": np.zeros((1, 1, n + 1), np.float32), "2501": np.array([norm], np.float32)}
+    o2 = run("superglue_indoor_sim_int32.onnx", {k: list(v.shape) for k, v in feeds2.items()}, ["scores"], feeds2)
+    scores = o2["scores"].astype(np.float32).reshape(m + 1, n + 1)
+    np.savez_compressed(os.path.join(OUT, "cv2dnn_g5_superglue_indoor.npz"), sim=sim, couplings=z, scores=scores,
+                        meta=json.dumps(dict(meta, inputs="same keypoint sets, normalize scale 0.7",
+                                             sinkhorn="nodes '2563'..'scores' (100 iterations) executed by cv2.dnn on the couplings built from cv2.dnn's own similarity matrix")))
     print("G5", sim.shape)
 
 
