@@ -69,6 +69,23 @@ def test_g2_g3_plnet_dense(image):
     _err("g3.mlp_logits", k3["logits"].numpy()[:512], g3["logits"], 1e-5)       # measured 4.5e-6 abs at scale 10
 
 
+def test_g2_hafm_decode_and_junction_nms():
+    """cv2.dnn executes the in-graph HAFM decode (head maps -> 49 152 line proposals: sigmoid, cos / sin / tan, clip, pixel grids) and the junction-heat
+    NMS (softmax, 3x3 max-pool, equal, mul) of plnet_s0.onnx, cut at the head tensor.  The oracle's decode is run on the fixture's own head maps."""
+    g2 = np.load(os.path.join(G, "cv2dnn_g2_plnet_s0.npz"))
+    g = np.load(os.path.join(G, "cv2dnn_g2_hafm_decode.npz"))
+    dec = nets.hafm_decode(torch.from_numpy(g2["heads9"])[None])
+    d = np.abs(dec["lines_pred"].numpy()[::4] - g["lines_pred"])
+    MEASURED["g2.hafm_lines_pred"] = {"max_abs_err": float(d.max()), "median_abs_err": float(np.median(d)), "frac_above_1e-4": float((d > 1e-4).mean()), "scale": 127.0,
+                                      "tol_abs": 1.2e-3}
+    # tan() near pi / 2 amplifies 1-ulp differences of the libm implementations (the GPU test gates the same way): loose max, tight bulk
+    assert d.max() <= 1.2e-3 and np.median(d) <= 1e-6 and (d > 1e-4).mean() <= 3.3e-4, (d.max(), np.median(d), (d > 1e-4).mean())      # measured 6.0e-4 / 0 / 1.6e-4 (grid units, coordinates up to 127)
+    jl = dec["jloc"][0, 0]
+    nms = (jl * (jl == torch.nn.functional.max_pool2d(jl[None, None], 3, 1, 1)[0, 0]).float()).numpy()
+    _err("g2.junction_heat_nms", nms, g["jloc_nms"], 1.2e-7)                      # measured 6.0e-8 (probabilities); 840 identical peaks
+    assert np.array_equal(nms > 0, g["jloc_nms"] > 0), "junction-heat peaks differ"
+
+
 def _match_inputs(scale):
     f0 = synth.keypoint_set(160, 752, 480, 7)
     f1, perm = synth.keypoint_set(144, 752, 480, 8, perturb_of=f0)

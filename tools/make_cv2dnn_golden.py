@@ -13,6 +13,7 @@ initialisers copied as raw bytes from the reference files:
                         logits and raw descriptors                                                            [whole dense part]
   G3 plnet_s1           the verification MLP: 496-d line features -> fc2.* / fc2_res / fc2_head logits
   G4 superpoint_lightglue  WHOLE graph (keypoints / descriptors -> log-assignment scores)
+  G2 decode             head maps -> HAFM line decode ('lines_pred') and junction-heat NMS ('/Mul_17_output_0')
   G5 superglue_indoor   keypoint encoder + 18 GNN layers + final_proj + score einsum / sqrt(256) -> similarity matrix ('2435');
                         the 100 Sinkhorn iterations ('2563' .. 'scores') on the couplings built from it -> final score matrix
 
@@ -86,6 +87,15 @@ def main():
                         aux=o["loi_features_aux"][0][:, ::2, ::2].copy(), pd_logits=o[pd_logits][0].astype(np.float32),
                         pd_desc=o[pd_desc][0][:, ::4, ::4].copy(), meta=json.dumps(dict(meta, image="same frame, resized to 512x512 by the restated cv::resize")))
     print("G2", {k: v.shape for k, v in o.items()})
+    # The in-graph HAFM decode behind the head maps (157 nodes: Sigmoid, Cos / Sin / Tan, Clip, the Range / Expand pixel grids -> 'lines_pred') and the
+    # junction-heat NMS (Softmax, 3x3 MaxPool, Equal, Mul -> '/Mul_17_output_0') run in cv2.dnn when cut at the head tensor; the TopK / GatherElements
+    # junction selection and the association behind them do not (cv2.dnn 4.13 crashes in TopK) and stay pinned by tools/onnx_interp.py.
+    h9 = np.ascontiguousarray(o[heads].astype(np.float32))
+    o_dec = run("plnet_s0.onnx", {heads: list(h9.shape)}, ["lines_pred", "/Mul_17_output_0"], {heads: h9})
+    np.savez_compressed(os.path.join(OUT, "cv2dnn_g2_hafm_decode.npz"), lines_pred=o_dec["lines_pred"].astype(np.float32)[::4].copy(),
+                        jloc_nms=o_dec["/Mul_17_output_0"].astype(np.float32).reshape(128, 128),
+                        meta=json.dumps(dict(meta, inputs="heads9 of cv2dnn_g2_plnet_s0.npz (cv2.dnn's own head maps of the same frame); lines_pred rows ::4")))
+    print("G2 decode", {k: v.shape for k, v in o_dec.items()})
 
     # ---- G3: PLNet stage 1 verification MLP on the oracle's own 496-d line features of that frame (the sampler in front of it is
     # Gather / Floor / Clip index arithmetic: checked against tools/onnx_interp.py in tests/test_oracle_golden.py)
