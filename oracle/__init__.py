@@ -14,7 +14,7 @@ so the oracle is pinned against executions of the reference's own ONNX files:
 (1) by an EXTERNAL runtime, OpenCV DNN 4.13, on static-shape sub-graphs cut byte
 for byte out of the shipped files (tools/onnx_cut.py, tools/make_cv2dnn_golden.py
 -> tests/golden/cv2dnn_*.npz, tests/test_oracle_cv2dnn.py): the dense part of
-G1-G3 (incl. the in-graph HAFM line decode and junction-heat NMS), the whole LightGlue graph, SuperGlue up to
+G1-G3 (incl. the in-graph NMS step by step, the HAFM line decode and the junction-heat NMS), the whole LightGlue graph, SuperGlue up to
 the similarity matrix and its 100 Sinkhorn iterations;
 (2) by the node-by-node interpreter tools/onnx_interp.py for what cv2.dnn cannot
 import (integer / logical tails, the dustbin concat of SuperGlue) -> tests/golden/g*.npz.

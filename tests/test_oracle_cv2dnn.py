@@ -46,6 +46,21 @@ def test_g1_superpoint_dense(image):
     _err("g1.descriptors", de[0].numpy()[:, ::2, ::2], g["desc"], 1e-5)   # measured 2.4e-6 (unit-norm descriptors)
 
 
+def test_g1_in_graph_nms_stepwise():
+    """The reference graph's simple_nms nodes (MaxPool 9x9, Equal, Cast, Greater, Where) executed by cv2.dnn on sub-graphs cut at the And / Or / Not
+    nodes (cv2.dnn has no boolean layers; those three per round are numpy in the generator): the oracle's simple_nms keeps exactly the same pixels."""
+    g1 = np.load(os.path.join(G, "cv2dnn_g1_superpoint.npz"))
+    g = np.load(os.path.join(G, "cv2dnn_g1_nms.npz"))
+    p64 = g1["prob"][:64]
+    heat = np.ascontiguousarray(p64.transpose(1, 2, 0).reshape(64, 64, 8, 8).transpose(0, 2, 1, 3).reshape(1, 512, 512))
+    ours = nets.simple_nms(torch.from_numpy(heat)).numpy()
+    mask = np.unpackbits(g["mask_bits"]).reshape(512, 512).astype(bool)
+    assert int(mask.sum()) == int(g["n_maxima"]) and mask.sum() > 1000
+    assert np.array_equal(ours[0] > 0, mask), "in-graph NMS: kept pixels differ from cv2.dnn's step-wise execution"
+    assert np.array_equal(ours[0], np.where(mask, heat[0], 0.0).astype(np.float32))
+    MEASURED["g1.nms_maxima (exact)"] = {"max_abs_err": 0.0, "scale": float(mask.sum()), "tol_abs": 0.0}
+
+
 def test_g2_g3_plnet_dense(image):
     g = np.load(os.path.join(G, "cv2dnn_g2_plnet_s0.npz"))
     w = weights.load("plnet")

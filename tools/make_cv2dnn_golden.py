@@ -13,6 +13,7 @@ initialisers copied as raw bytes from the reference files:
                         logits and raw descriptors                                                            [whole dense part]
   G3 plnet_s1           the verification MLP: 496-d line features -> fc2.* / fc2_res / fc2_head logits
   G4 superpoint_lightglue  WHOLE graph (keypoints / descriptors -> log-assignment scores)
+  G1 nms                the in-graph simple_nms, arithmetic nodes step-wise in cv2.dnn, boolean And / Or / Not in numpy -> maximum mask
   G2 decode             head maps -> HAFM line decode ('lines_pred') and junction-heat NMS ('/Mul_17_output_0')
   G5 superglue_indoor   keypoint encoder + 18 GNN layers + final_proj + score einsum / sqrt(256) -> similarity matrix ('2435');
                         the 100 Sinkhorn iterations ('2563' .. 'scores') on the couplings built from it -> final score matrix
@@ -74,6 +75,22 @@ def main():
     np.savez_compressed(os.path.join(OUT, "cv2dnn_g1_superpoint.npz"), prob=o["49"][0].astype(np.float32), desc=o["descriptors"][0][:, ::2, ::2].copy(),
                         meta=json.dumps(dict(meta, image="oracle.synth.stereo_pair(752,480,0xA175)[0] through host.process_image")))
     print("G1", o["49"].shape, o["descriptors"].shape)
+    # The in-graph NMS behind it (nodes '86'..'scores': five 9x9 MaxPools, Equal, Cast, Greater, Where, And / Or / Not) is executed STEP-WISE: cv2.dnn has
+    # no And / Or / Not layers, so every arithmetic node group (MaxPool + Equal + Cast; MaxPool + Greater + Where + MaxPool) runs in cv2.dnn on sub-graphs
+    # cut at the boolean nodes, and only the three boolean combinations per round are done here in numpy.  The heat map is the depth-to-space of
+    # cv2.dnn's own softmax output (Slice / Reshape / Transpose glue, nodes '54'..'83').
+    p64 = o["49"][0].astype(np.float32)[:64]                                                                 # drop the dustbin channel
+    heat = np.ascontiguousarray(p64.transpose(1, 2, 0).reshape(64, 64, 8, 8).transpose(0, 2, 1, 3).reshape(1, 512, 512))
+    shp, zeros = list(heat.shape), np.zeros_like(heat)
+    m = run("superpoint_v1_sim_int32.onnx", {"83": shp}, ["90"], {"83": heat})["90"].reshape(heat.shape) > 0.5        # M0 = (S == mp9(S))
+    for mask_in, mp_mask, s_out, mp_out in (("90", "93", "96", "99"), ("110", "113", "116", "119")):
+        r = run("superpoint_v1_sim_int32.onnx", {mask_in: shp, "83": shp, "85": shp}, [mp_mask, s_out, mp_out],
+                {mask_in: m.astype(np.float32), "83": heat, "85": zeros})
+        supp = r[mp_mask].reshape(heat.shape) > 0                                                            # Greater('93', 0)
+        m = m | ((r[s_out].reshape(heat.shape) == r[mp_out].reshape(heat.shape)) & ~supp)                    # Equal, Not, And, Or
+    np.savez_compressed(os.path.join(OUT, "cv2dnn_g1_nms.npz"), mask_bits=np.packbits(m[0]), n_maxima=np.int64(m.sum()),
+                        meta=json.dumps(dict(meta, what="NMS maximum mask [512][512] (np.packbits) of the heat map built from cv2dnn_g1_superpoint.npz 'prob'; scores = where(mask, heat, 0)")))
+    print("G1 nms", int(m.sum()))
 
     # ---- G2: PLNet stage 0 dense part (512x512 network input as the reference resizes to, src/plnet.cpp:246-270)
     x2 = x
