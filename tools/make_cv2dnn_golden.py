@@ -15,6 +15,7 @@ initialisers copied as raw bytes from the reference files:
   G4 superpoint_lightglue  WHOLE graph (keypoints / descriptors -> log-assignment scores)
   G1 nms                the in-graph simple_nms, arithmetic nodes step-wise in cv2.dnn, boolean And / Or / Not in numpy -> maximum mask
   G2 decode             head maps -> HAFM line decode ('lines_pred') and junction-heat NMS ('/Mul_17_output_0')
+  G2 association        squared distances line end <-> junction + column minima in cv2.dnn, arg-min / Less / And in numpy -> idx_min / idx_max / iskeep
   G5 superglue_indoor   keypoint encoder + 18 GNN layers + final_proj + score einsum / sqrt(256) -> similarity matrix ('2435');
                         the 100 Sinkhorn iterations ('2563' .. 'scores') on the couplings built from it -> final score matrix
 
@@ -113,6 +114,25 @@ def main():
                         jloc_nms=o_dec["/Mul_17_output_0"].astype(np.float32).reshape(128, 128),
                         meta=json.dumps(dict(meta, inputs="heads9 of cv2dnn_g2_plnet_s0.npz (cv2.dnn's own head maps of the same frame); lines_pred rows ::4")))
     print("G2 decode", {k: v.shape for k, v in o_dec.items()})
+    # Association (nodes 'Slice_10' .. 'iskeep'): the 300 x 49 152 squared-distance matrices of both line ends and their column minima run in cv2.dnn
+    # (Sub, Pow, ReduceSum, ReduceMin), cut at (lines_pred, juncs_pred); cv2.dnn 4.13 returns garbage from the ArgMin -> Min / Max -> Cast chain, so the
+    # arg-min (first index on ties), Min / Max / Less / And are taken here in numpy ON cv2.dnn's matrices.  juncs_pred comes from the oracle's TopK
+    # (interpreter-pinned) applied to the same head maps; lines_pred is cv2.dnn's own.
+    import torch
+    from oracle import nets as _nets
+    dec = _nets.hafm_decode(torch.from_numpy(h9))
+    lp, jp = np.ascontiguousarray(o_dec["lines_pred"].astype(np.float32)), np.ascontiguousarray(dec["juncs_pred"].numpy())
+    aouts = ["/ReduceSum_output_0", "/ReduceSum_1_output_0", "/ReduceMin_output_0", "/ReduceMin_1_output_0"]
+    oa = run("plnet_s0.onnx", {"lines_pred": list(lp.shape), "juncs_pred": list(jp.shape)}, aouts, {"lines_pred": lp, "juncs_pred": jp})
+    d1, d2 = oa[aouts[0]].reshape(300, -1), oa[aouts[1]].reshape(300, -1)
+    m1, m2 = oa[aouts[2]].reshape(-1), oa[aouts[3]].reshape(-1)
+    i1, i2 = np.argmin(d1, 0), np.argmin(d2, 0)
+    imin, imax = np.minimum(i1, i2), np.maximum(i1, i2)
+    keep = (imin < imax) & (m1 < 10.0) & (m2 < 10.0)
+    np.savez_compressed(os.path.join(OUT, "cv2dnn_g2_association.npz"), juncs_pred=jp, idx_min=imin.astype(np.uint16), idx_max=imax.astype(np.uint16),
+                        iskeep_bits=np.packbits(keep), n_keep=np.int64(keep.sum()),
+                        meta=json.dumps(dict(meta, inputs="lines_pred = cv2.dnn's HAFM decode (all 49 152 rows), juncs_pred = oracle TopK on the same head maps")))
+    print("G2 association", int(keep.sum()))
 
     # ---- G3: PLNet stage 1 verification MLP on the oracle's own 496-d line features of that frame (the sampler in front of it is
     # Gather / Floor / Clip index arithmetic: checked against tools/onnx_interp.py in tests/test_oracle_golden.py)
