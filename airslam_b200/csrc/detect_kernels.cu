@@ -57,6 +57,20 @@ __device__ __forceinline__ int remap_px(const uint8_t* __restrict__ img, int w, 
   return (v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11 + (1 << 14)) >> 15;
 }
 
+// u8 -> network input: the reference evaluates float(u8) / 255.0 in DOUBLE and stores a float (src/plnet.cpp:264); the fp16 operand rounding follows.
+// A double division per pixel on a GPU whose FP64 rate is 1/64 of FP32 made this the whole cost of the kernel, so the 256 possible results are
+// computed once per device with exactly that expression and looked up (bit-identical by construction).
+__device__ __half g_u8_to_half[256];
+__global__ void u8_lut_init_kernel() { g_u8_to_half[threadIdx.x] = __float2half_rn((float)((double)(int)threadIdx.x / 255.0)); }
+static void ensure_u8_lut() {
+  static bool done[kMaxDevices] = {};
+  const int dev = current_device();
+  if (done[dev]) return;
+  u8_lut_init_kernel<<<1, 256>>>();          // default stream + device synchronisation: once per device, at the first (eager) resize
+  cudaDeviceSynchronize();
+  done[dev] = true;
+}
+
 template <bool REMAP>
 __global__ void resize_kernel(const uint8_t* __restrict__ src, int src_w, int src_h, int src_stride, long long src_img_stride,
                               ResizeTables t, __half* __restrict__ dst, uint8_t* __restrict__ dst_u8, RemapMaps maps) {
@@ -82,14 +96,14 @@ __global__ void resize_kernel(const uint8_t* __restrict__ src, int src_w, int sr
   int v = (((t.b0[y] * (h0 >> 4)) >> 16) + ((t.b1[y] * (h1 >> 4)) >> 16) + 2) >> 2;
   v = min(max(v, 0), 255);
   const long long o = ((long long)b * 512 + y) * 512 + x;
-  // reference: float(u8) / 255.0 evaluated in double, stored as float (src/plnet.cpp:264); then the fp16 operand rounding
-  dst[o] = __float2half_rn((float)((double)v / 255.0));
+  dst[o] = g_u8_to_half[v];     // = half(float(double(v) / 255.0)), see u8_lut_init_kernel
   if (dst_u8) dst_u8[o] = (uint8_t)v;
 }
 
 void launch_resize_u8_to_f16(const uint8_t* src, int src_w, int src_h, int src_stride, long long src_img_stride, int batch,
                              ResizeTables t, __half* dst, uint8_t* dst_u8, cudaStream_t st, const RemapMaps* remap) {
   dim3 grid(512 / 128, 512, batch);
+  ensure_u8_lut();
   if (remap && remap->mode) resize_kernel<true><<<grid, 128, 0, st>>>(src, src_w, src_h, src_stride, src_img_stride, t, dst, dst_u8, *remap);
   else resize_kernel<false><<<grid, 128, 0, st>>>(src, src_w, src_h, src_stride, src_img_stride, t, dst, dst_u8, RemapMaps{});
 }
